@@ -1,0 +1,660 @@
+// C ABI of the B200-native evaluator (include/powersense_b200.h): handles, device tables, the
+// single-scenario MOI-style callbacks, the batched device-resident driver, the host-streaming
+// driver and the fixed-pattern COO -> CSC assembly.  No CPU fallback anywhere in this file: every
+// numeric result is produced by the kernels in ps_kernels.cu.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdlib>
+#include <cstring>
+#include <numeric>
+#include <string>
+#include <vector>
+
+#include "../../include/powersense_b200.h"
+#include "ps_kernels.cuh"
+
+using namespace ps;
+
+namespace {
+
+thread_local std::string g_create_error;
+
+struct DevMem {                      // owns device allocations of one object
+  std::vector<void*> ptrs;
+  cudaError_t err = cudaSuccess;
+  template <class T> T* alloc(size_t n) {
+    void* p = nullptr;
+    cudaError_t e = cudaMalloc(&p, std::max<size_t>(n, 1) * sizeof(T));
+    if (e != cudaSuccess) { if (err == cudaSuccess) err = e; return nullptr; }
+    ptrs.push_back(p);
+    return (T*)p;
+  }
+  template <class T> T* upload(const std::vector<T>& v) {
+    T* p = alloc<T>(v.size());
+    if (p && !v.empty()) {
+      cudaError_t e = cudaMemcpy(p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice);
+      if (e != cudaSuccess && err == cudaSuccess) err = e;
+    }
+    return p;
+  }
+  void release() { for (void* p : ptrs) cudaFree(p); ptrs.clear(); }
+};
+
+}  // namespace
+
+struct ps_handle {
+  Plan plan;
+  DevPlan dev{};
+  DevMem mem;
+  int device = 0;
+  std::string err;
+  ps_batch* single = nullptr;        // S = 1 batch behind the MOI-style callbacks
+  double *h_in = nullptr, *h_out = nullptr;   // pinned staging for the single-scenario calls
+  double *d_x = nullptr, *d_mu = nullptr, *d_g = nullptr, *d_J = nullptr, *d_H = nullptr, *d_scal = nullptr;
+  cudaStream_t stream = nullptr;
+};
+
+struct ps_batch {
+  ps_handle* h = nullptr;
+  int64_t S = 0;
+  DevMem mem;
+  double *d_Pd = nullptr, *d_Qd = nullptr;
+  uint8_t* d_status = nullptr;
+  double viol_tol = 1e-6;
+  int64_t launches = 0;
+  int chunk_override = 0;
+  // host-streaming state (ps_batch_eval_host)
+  int64_t stage_S = 0;
+  double *sx[2] = {nullptr, nullptr}, *smu[2] = {nullptr, nullptr}, *sg[2] = {nullptr, nullptr},
+         *sJ[2] = {nullptr, nullptr}, *sH[2] = {nullptr, nullptr}, *sscal[2] = {nullptr, nullptr};
+  cudaStream_t st_in = nullptr, st_k = nullptr, st_out = nullptr;
+  cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_k[2] = {nullptr, nullptr}, ev_out[2] = {nullptr, nullptr};
+};
+
+struct ps_csc {
+  int64_t m = 0, n = 0, nnz_coo = 0, nnz = 0;
+  std::vector<int64_t> colptr, rowval;     // 1-based (SparseMatrixCSC)
+  std::vector<int32_t> segptr, perm;       // CSC slot j sums dE[perm[segptr[j] .. segptr[j+1])]
+  int device = 0;
+  DevMem mem;
+  int32_t *d_segptr = nullptr, *d_perm = nullptr;
+  double *d_in = nullptr, *d_out = nullptr;
+  std::string err;
+};
+
+namespace {
+
+int fail(ps_handle* h, int code, const std::string& msg) {
+  if (h) h->err = msg; else g_create_error = msg;
+  return code;
+}
+int cuda_fail(ps_handle* h, cudaError_t e, const char* where) {
+  return fail(h, PS_ERR_CUDA, std::string(where) + ": " + cudaGetErrorString(e));
+}
+
+template <class T> std::vector<T> vec(const T* p, int64_t n) { return p ? std::vector<T>(p, p + n) : std::vector<T>(); }
+
+bool to_i32_csr(const int64_t* ptr, const int64_t* idx, int64_t nb, int64_t nmax, std::vector<int32_t>& optr,
+                std::vector<int32_t>& oidx) {
+  if (!ptr) return false;
+  optr.resize(nb + 1);
+  for (int64_t i = 0; i <= nb; i++) {
+    if (ptr[i] < 0 || (i && ptr[i] < ptr[i - 1])) return false;
+    optr[i] = (int32_t)ptr[i];
+  }
+  if (ptr[0] != 0) return false;
+  const int64_t n = ptr[nb];
+  if (n && !idx) return false;
+  oidx.resize(n);
+  for (int64_t q = 0; q < n; q++) {
+    if (idx[q] < 1 || idx[q] > nmax) return false;
+    oidx[q] = (int32_t)(idx[q] - 1);
+  }
+  return true;
+}
+
+int pick_chunk(const ps_batch* b, int64_t S, int ntiles) {
+  if (b->chunk_override > 0) return b->chunk_override;
+  if (const char* e = getenv("PS_CHUNK")) { const int c = atoi(e); if (c > 0) return c; }
+  // enough CTAs for ~8 waves of 148 SMs x 3 resident CTAs, while amortising per-tile constants
+  const int64_t want = 148 * 3 * 8;
+  int64_t c = (S * ntiles) / want;
+  return (int)std::max<int64_t>(1, std::min<int64_t>(16, c));
+}
+
+int do_eval(ps_batch* b, int what, int64_t s_begin, int64_t s_count, const double* x, int64_t ldx, const double* mu,
+            int64_t ldmu, double* g, int64_t ldg, double* J, int64_t ldJ, double* H, int64_t ldH, double* scalars,
+            cudaStream_t stream) {
+  ps_handle* h = b->h;
+  const Plan& P = h->plan;
+  if (s_count == 0) return PS_OK;
+  if (s_begin < 0 || s_count < 0 || s_begin + s_count > b->S) return fail(h, PS_ERR_ARG, "scenario range outside the batch");
+  if (!(what & (EV_G | EV_J | EV_H)) && !scalars) return fail(h, PS_ERR_ARG, "nothing to evaluate");
+  if (!x || ldx < P.n_var) return fail(h, PS_ERR_ARG, "x is null or ldx < n_var");
+  if ((what & EV_G) && (!g || ldg < P.m_nl)) return fail(h, PS_ERR_ARG, "g is null or ldg < m_nl");
+  if ((what & EV_J) && (!J || ldJ < P.nnzJ)) return fail(h, PS_ERR_ARG, "J is null or ldJ < nnz_jac");
+  if ((what & EV_H) && (!H || ldH < P.nnzH)) return fail(h, PS_ERR_ARG, "H is null or ldH < nnz_hess");
+  if ((what & EV_H) && (!mu || ldmu < P.m_nl)) return fail(h, PS_ERR_ARG, "mu is null or ldmu < m_nl (needed for the Hessian)");
+  if (s_count > 0x7fffffff) return fail(h, PS_ERR_ARG, "too many scenarios in one call");
+  cudaError_t e;
+  if (scalars) {
+    e = cudaMemsetAsync(scalars, 0, (size_t)s_count * NSCAL * sizeof(double), stream);
+    if (e != cudaSuccess) return cuda_fail(h, e, "cudaMemsetAsync(scalars)");
+  }
+  EvalArgs A{};
+  A.what = what; A.S = (int)s_count; A.chunk = pick_chunk(b, s_count, h->dev.ntiles);
+  A.x = x; A.ldx = ldx; A.mu = mu; A.ldmu = ldmu;
+  A.Pd = b->d_Pd ? b->d_Pd + s_begin * P.net.nbus : nullptr;
+  A.Qd = b->d_Qd ? b->d_Qd + s_begin * P.net.nbus : nullptr;
+  A.ldl = P.net.nbus;
+  A.status = b->d_status ? b->d_status + s_begin * P.net.nbr : nullptr;
+  A.ldst = P.net.nbr;
+  A.g = g; A.ldg = ldg; A.J = J; A.ldJ = ldJ; A.H = H; A.ldH = ldH;
+  A.scal = scalars; A.viol_tol = b->viol_tol;
+  e = launch_eval(h->dev, A, P.smem_doubles, stream);
+  if (e != cudaSuccess) return cuda_fail(h, e, "eval_kernel launch");
+  b->launches += 1 + (scalars ? 1 : 0);
+  return PS_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int ps_abi_version(void) { return PS_ABI_VERSION; }
+
+const char* ps_last_error(const ps_handle* h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+
+int ps_create(const ps_network* net, int formulation, int source_type, int flags, int device, ps_handle** out) {
+  if (!net || !out) return fail(nullptr, PS_ERR_ARG, "null argument");
+  *out = nullptr;
+  if (net->nbus <= 0 || net->nbr < 0 || net->ngen < 0 || net->nbss < 0 || net->n_tgh < 0)
+    return fail(nullptr, PS_ERR_ARG, "negative or zero table size");
+  if (net->nbus > (1 << 28) || net->nbr > (1 << 28) || net->ngen > (1 << 28))
+    return fail(nullptr, PS_ERR_ARG, "table too large for 32-bit device indices");
+  const int64_t nb = net->nbus, nr = net->nbr, ng = net->ngen;
+  if (nr && (!net->br_f || !net->br_t || !net->Gf || !net->Bf || !net->Gt || !net->Bt || !net->gf || !net->bf ||
+             !net->gt || !net->bt || !net->Imax))
+    return fail(nullptr, PS_ERR_ARG, "null branch table");
+  if (!net->Pd || !net->Qd || !net->Gl || !net->Bl) return fail(nullptr, PS_ERR_ARG, "null bus table");
+  HostNet hn;
+  hn.nbus = nb; hn.nbr = nr; hn.ngen = ng; hn.nbss = net->nbss; hn.n_tgh = net->n_tgh;
+  hn.f.resize(nr); hn.t.resize(nr);
+  for (int64_t k = 0; k < nr; k++) {
+    if (net->br_f[k] < 1 || net->br_f[k] > nb || net->br_t[k] < 1 || net->br_t[k] > nb)
+      return fail(nullptr, PS_ERR_NETWORK, "branch endpoint out of range");
+    hn.f[k] = (int32_t)(net->br_f[k] - 1);
+    hn.t[k] = (int32_t)(net->br_t[k] - 1);
+  }
+  hn.Gf = vec(net->Gf, nr); hn.Bf = vec(net->Bf, nr); hn.Gt = vec(net->Gt, nr); hn.Bt = vec(net->Bt, nr);
+  hn.gf = vec(net->gf, nr); hn.bf = vec(net->bf, nr); hn.gt = vec(net->gt, nr); hn.bt = vec(net->bt, nr);
+  hn.Imax = vec(net->Imax, nr);
+  hn.Pd = vec(net->Pd, nb); hn.Qd = vec(net->Qd, nb); hn.Gl = vec(net->Gl, nb); hn.Bl = vec(net->Bl, nb);
+  if (!to_i32_csr(net->gen_ptr, net->gen_idx, nb, ng, hn.gen_ptr, hn.gen_idx)) return fail(nullptr, PS_ERR_NETWORK, "bad gen adjacency list");
+  if (!to_i32_csr(net->sij_ptr, net->sij_idx, nb, nr, hn.sij_ptr, hn.sij_idx)) return fail(nullptr, PS_ERR_NETWORK, "bad Sij adjacency list");
+  if (!to_i32_csr(net->sji_ptr, net->sji_idx, nb, nr, hn.sji_ptr, hn.sji_idx)) return fail(nullptr, PS_ERR_NETWORK, "bad Sji adjacency list");
+  if (!to_i32_csr(net->sh_ptr, net->sh_idx, nb, std::max<int64_t>(net->nbss, 0), hn.sh_ptr, hn.sh_idx))
+    return fail(nullptr, PS_ERR_NETWORK, "bad shunt adjacency list");
+  hn.c0 = vec(net->c0, ng); hn.c1 = vec(net->c1, ng); hn.c2 = vec(net->c2, ng);
+  hn.cost_order = net->cost_order;
+
+  ps_handle* h = new ps_handle();
+  const std::string msg = build_plan(hn, formulation, source_type, flags, TPB, h->plan);
+  if (!msg.empty()) {
+    const bool arg = msg.rfind("unknown", 0) == 0;
+    delete h;
+    return fail(nullptr, arg ? PS_ERR_ARG : PS_ERR_NETWORK, msg);
+  }
+  const Plan& P = h->plan;
+  if (P.n_var >= (int64_t(1) << 31)) { delete h; return fail(nullptr, PS_ERR_ARG, "n_var too large for 32-bit device offsets"); }
+
+  // ---- device: there is no CPU fallback.  PS_DEVICE_NONE gives a structure-only handle (dims, bounds,
+  // sparsity structures: host logic); every evaluation entry point fails on such a handle.
+  if (device == PS_DEVICE_NONE) {
+    h->device = PS_DEVICE_NONE;
+    *out = h;
+    return PS_OK;
+  }
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0) {
+    delete h;
+    return fail(nullptr, PS_ERR_CUDA, std::string("no CUDA device available (this library has no CPU fallback): ") +
+                                          (e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0"));
+  }
+  if (device < 0) { e = cudaGetDevice(&device); if (e != cudaSuccess) { delete h; return cuda_fail(nullptr, e, "cudaGetDevice"); } }
+  if (device >= ndev) { delete h; return fail(nullptr, PS_ERR_ARG, "device ordinal out of range"); }
+  e = cudaSetDevice(device);
+  if (e != cudaSuccess) { delete h; return cuda_fail(nullptr, e, "cudaSetDevice"); }
+  cudaDeviceProp prop;
+  e = cudaGetDeviceProperties(&prop, device);
+  if (e != cudaSuccess) { delete h; return cuda_fail(nullptr, e, "cudaGetDeviceProperties"); }
+  if (prop.major != 10) {
+    delete h;
+    return fail(nullptr, PS_ERR_CUDA, "device is not sm_100 (B200): the kernels are built for sm_100a only");
+  }
+  h->device = device;
+  DevMem& M = h->mem;
+  DevPlan& D = h->dev;
+  D.form = P.form; D.src = P.src; D.flags = P.flags;
+  D.nb = (int)nb; D.nr = (int)nr; D.ng = (int)ng;
+  D.o_a = (int)P.o_a; D.o_b = (int)P.o_b; D.o_Wd = (int)P.o_Wd; D.o_Wr = (int)P.o_Wr; D.o_Wi = (int)P.o_Wi;
+  D.o_pg = (int)P.o_pg; D.o_qg = (int)P.o_qg;
+  for (int q = 0; q < 4; q++) D.o_f[q] = (int)P.o_f[q];
+  D.o_cg = (int)P.o_cg; D.o_bss = (int)P.o_bss;
+  D.bus_rows = (int)P.bus_rows;
+  D.ntiles = (int)P.tiles.size();
+  D.cost_order = P.net.cost_order;
+  D.f = M.upload(P.net.f); D.t = M.upload(P.net.t);
+  D.Gf = M.upload(P.net.Gf); D.Bf = M.upload(P.net.Bf); D.Gt = M.upload(P.net.Gt); D.Bt = M.upload(P.net.Bt);
+  D.gf = M.upload(P.net.gf); D.bf = M.upload(P.net.bf); D.gt = M.upload(P.net.gt); D.bt = M.upload(P.net.bt);
+  D.Imax = M.upload(P.net.Imax); D.Gl = M.upload(P.net.Gl); D.Bl = M.upload(P.net.Bl);
+  D.Pd0 = M.upload(P.net.Pd); D.Qd0 = M.upload(P.net.Qd);
+  D.c0 = M.upload(P.c0); D.c1 = M.upload(P.c1); D.c2 = M.upload(P.c2); D.c3 = M.upload(P.c3);
+  D.k0 = P.net.c0.empty() ? nullptr : M.upload(P.net.c0);
+  D.k1 = P.net.c1.empty() ? nullptr : M.upload(P.net.c1);
+  D.k2 = P.net.c2.empty() ? nullptr : M.upload(P.net.c2);
+  D.gen_ptr = M.upload(P.net.gen_ptr); D.gen_idx = M.upload(P.net.gen_idx);
+  D.sij_ptr = M.upload(P.net.sij_ptr); D.sij_idx = M.upload(P.net.sij_idx);
+  D.sji_ptr = M.upload(P.net.sji_ptr); D.sji_idx = M.upload(P.net.sji_idx);
+  D.sh_ptr = M.upload(P.net.sh_ptr); D.sh_idx = M.upload(P.net.sh_idx);
+  D.jptr = M.upload(P.jptr); D.hptr = M.upload(P.hptr);
+  D.bus_jpos = M.upload(P.bus_jpos); D.bus_hpos = M.upload(P.bus_hpos);
+  D.bus_jpp = M.upload(P.bus_jpp); D.bus_hpp = M.upload(P.bus_hpp);
+  D.tiles = M.upload(P.tiles);
+  // single-scenario staging
+  const int64_t n_in = P.n_var + P.m_nl, n_out = P.m_nl + P.nnzJ + P.nnzH + NSCAL;
+  h->d_x = M.alloc<double>(P.n_var); h->d_mu = M.alloc<double>(P.m_nl);
+  h->d_g = M.alloc<double>(P.m_nl); h->d_J = M.alloc<double>(P.nnzJ); h->d_H = M.alloc<double>(P.nnzH);
+  h->d_scal = M.alloc<double>(NSCAL);
+  if (M.err != cudaSuccess) { e = M.err; M.release(); delete h; return cuda_fail(nullptr, e, "device table upload"); }
+  if ((e = cudaHostAlloc((void**)&h->h_in, std::max<int64_t>(n_in, 1) * sizeof(double), cudaHostAllocDefault)) != cudaSuccess ||
+      (e = cudaHostAlloc((void**)&h->h_out, std::max<int64_t>(n_out, 1) * sizeof(double), cudaHostAllocDefault)) != cudaSuccess ||
+      (e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking)) != cudaSuccess ||
+      (e = configure_eval(P.form, P.src, P.smem_doubles)) != cudaSuccess) {
+    ps_destroy(h);
+    return cuda_fail(nullptr, e, "handle setup");
+  }
+  int rc = ps_batch_create(h, 1, &h->single);
+  if (rc != PS_OK) { g_create_error = h->err; ps_destroy(h); return rc; }
+  *out = h;
+  return PS_OK;
+}
+
+void ps_destroy(ps_handle* h) {
+  if (!h) return;
+  if (h->device == PS_DEVICE_NONE) { delete h; return; }
+  cudaSetDevice(h->device);
+  if (h->single) ps_batch_destroy(h->single);
+  if (h->stream) cudaStreamDestroy(h->stream);
+  if (h->h_in) cudaFreeHost(h->h_in);
+  if (h->h_out) cudaFreeHost(h->h_out);
+  h->mem.release();
+  delete h;
+}
+
+int ps_dims(const ps_handle* h, int64_t* n_var, int64_t* m_nl, int64_t* nnz_jac, int64_t* nnz_hess) {
+  if (!h) return PS_ERR_ARG;
+  if (n_var) *n_var = h->plan.n_var;
+  if (m_nl) *m_nl = h->plan.m_nl;
+  if (nnz_jac) *nnz_jac = h->plan.nnzJ;
+  if (nnz_hess) *nnz_hess = h->plan.nnzH;
+  return PS_OK;
+}
+
+int ps_constraint_bounds(const ps_handle* h, double* lo, double* hi) {
+  if (!h || !lo || !hi) return PS_ERR_ARG;
+  std::copy(h->plan.lo.begin(), h->plan.lo.end(), lo);
+  std::copy(h->plan.hi.begin(), h->plan.hi.end(), hi);
+  return PS_OK;
+}
+
+int ps_jacobian_structure(const ps_handle* h, int64_t* row, int64_t* col) {
+  if (!h || !row || !col) return PS_ERR_ARG;
+  std::copy(h->plan.jrow.begin(), h->plan.jrow.end(), row);
+  std::copy(h->plan.jcol.begin(), h->plan.jcol.end(), col);
+  return PS_OK;
+}
+
+int ps_hessian_structure(const ps_handle* h, int64_t* row, int64_t* col) {
+  if (!h || !row || !col) return PS_ERR_ARG;
+  std::copy(h->plan.hrow.begin(), h->plan.hrow.end(), row);
+  std::copy(h->plan.hcol.begin(), h->plan.hcol.end(), col);
+  return PS_OK;
+}
+
+int ps_variable_offsets(const ps_handle* h, int64_t out[16]) {
+  if (!h || !out) return PS_ERR_ARG;
+  const Plan& P = h->plan;
+  const int64_t v[16] = {P.o_a, P.o_b, P.o_Wd, P.o_Wr, P.o_Wi, P.o_pg, P.o_qg, P.o_f[0], P.o_f[1], P.o_f[2], P.o_f[3],
+                         P.o_cg, P.o_bss, P.o_tgh, P.n_var, P.nx_nl};
+  std::copy(v, v + 16, out);
+  return PS_OK;
+}
+
+int64_t ps_algorithmic_bytes(const ps_handle* h, int what) {
+  if (!h) return 0;
+  const Plan& P = h->plan;
+  // reads x restricted to the variables NL rows touch, mu (Hessian only), Pd/Qd (g only);
+  // writes g, J, H.  Network constants are shared by all scenarios and excluded.
+  int64_t n = P.nx_nl;
+  if (what & EV_G) n += P.m_nl + (has_bus_rows(P.form) ? 2 * P.net.nbus : 0);
+  if (what & EV_J) n += P.nnzJ;
+  if (what & EV_H) n += P.nnzH + P.m_nl;
+  return 8 * n;
+}
+
+// ---- single-scenario callbacks ------------------------------------------------------------
+static int eval_single(ps_handle* h, int what, const double* x, const double* mu, double* g, double* J, double* H,
+                       double* f) {
+  if (!h) return PS_ERR_ARG;
+  if (!x) return fail(h, PS_ERR_ARG, "x is null");
+  if (h->device == PS_DEVICE_NONE) return fail(h, PS_ERR_STATE, "structure-only handle (PS_DEVICE_NONE): no CPU fallback for evaluation");
+  const Plan& P = h->plan;
+  cudaError_t e = cudaSetDevice(h->device);
+  if (e != cudaSuccess) return cuda_fail(h, e, "cudaSetDevice");
+  if ((what & EV_H) && !mu) return fail(h, PS_ERR_ARG, "mu is null");
+  std::memcpy(h->h_in, x, (size_t)P.n_var * sizeof(double));
+  e = cudaMemcpyAsync(h->d_x, h->h_in, (size_t)P.n_var * sizeof(double), cudaMemcpyHostToDevice, h->stream);
+  if (e == cudaSuccess && (what & EV_H)) {
+    std::memcpy(h->h_in + P.n_var, mu, (size_t)P.m_nl * sizeof(double));
+    e = cudaMemcpyAsync(h->d_mu, h->h_in + P.n_var, (size_t)P.m_nl * sizeof(double), cudaMemcpyHostToDevice, h->stream);
+  }
+  if (e != cudaSuccess) return cuda_fail(h, e, "H2D copy");
+  int rc = do_eval(h->single, what, 0, 1, h->d_x, P.n_var, h->d_mu, P.m_nl, h->d_g, P.m_nl, h->d_J, P.nnzJ, h->d_H, P.nnzH,
+                   f ? h->d_scal : nullptr, h->stream);
+  if (rc != PS_OK) return rc;
+  double* ho = h->h_out;
+  if (what & EV_G) e = cudaMemcpyAsync(ho, h->d_g, (size_t)P.m_nl * sizeof(double), cudaMemcpyDeviceToHost, h->stream);
+  if (e == cudaSuccess && (what & EV_J))
+    e = cudaMemcpyAsync(ho + P.m_nl, h->d_J, (size_t)P.nnzJ * sizeof(double), cudaMemcpyDeviceToHost, h->stream);
+  if (e == cudaSuccess && (what & EV_H))
+    e = cudaMemcpyAsync(ho + P.m_nl + P.nnzJ, h->d_H, (size_t)P.nnzH * sizeof(double), cudaMemcpyDeviceToHost, h->stream);
+  if (e == cudaSuccess && f)
+    e = cudaMemcpyAsync(ho + P.m_nl + P.nnzJ + P.nnzH, h->d_scal, NSCAL * sizeof(double), cudaMemcpyDeviceToHost, h->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);   // callers read the output immediately
+  if (e != cudaSuccess) return cuda_fail(h, e, "D2H copy / kernel");
+  if (what & EV_G) std::memcpy(g, ho, (size_t)P.m_nl * sizeof(double));
+  if (what & EV_J) std::memcpy(J, ho + P.m_nl, (size_t)P.nnzJ * sizeof(double));
+  if (what & EV_H) std::memcpy(H, ho + P.m_nl + P.nnzJ, (size_t)P.nnzH * sizeof(double));
+  if (f) *f = ho[P.m_nl + P.nnzJ + P.nnzH];
+  return PS_OK;
+}
+
+int ps_eval_constraint(ps_handle* h, const double* x, double* g) {
+  if (h && !g) return fail(h, PS_ERR_ARG, "g is null");
+  return eval_single(h, EV_G, x, nullptr, g, nullptr, nullptr, nullptr);
+}
+int ps_eval_jacobian(ps_handle* h, const double* x, double* J) {
+  if (h && !J) return fail(h, PS_ERR_ARG, "J is null");
+  return eval_single(h, EV_J, x, nullptr, nullptr, J, nullptr, nullptr);
+}
+int ps_eval_hessian(ps_handle* h, const double* x, double sigma, const double* mu, double* H) {
+  (void)sigma;  // no NL objective in any Powersense OPF model (has_objective = false)
+  if (h && !H) return fail(h, PS_ERR_ARG, "H is null");
+  return eval_single(h, EV_H, x, mu, nullptr, nullptr, H, nullptr);
+}
+int ps_eval_all(ps_handle* h, const double* x, const double* mu, double* g, double* J, double* H) {
+  const int what = (g ? EV_G : 0) | (J ? EV_J : 0) | (H ? EV_H : 0);
+  if (h && !what) return fail(h, PS_ERR_ARG, "all outputs are null");
+  return eval_single(h, what, x, mu, g, J, H, nullptr);
+}
+int ps_eval_objective(ps_handle* h, const double* x, double* f) {
+  if (h && !f) return fail(h, PS_ERR_ARG, "f is null");
+  return eval_single(h, 0, x, nullptr, nullptr, nullptr, nullptr, f);
+}
+
+// ---- batched -----------------------------------------------------------------------------
+int ps_batch_create(ps_handle* h, int64_t S, ps_batch** out) {
+  if (!h || !out) return PS_ERR_ARG;
+  *out = nullptr;
+  if (S <= 0) return fail(h, PS_ERR_ARG, "S must be positive");
+  if (h->device == PS_DEVICE_NONE) return fail(h, PS_ERR_STATE, "structure-only handle (PS_DEVICE_NONE): no CPU fallback for evaluation");
+  cudaError_t e = cudaSetDevice(h->device);
+  if (e != cudaSuccess) return cuda_fail(h, e, "cudaSetDevice");
+  ps_batch* b = new ps_batch();
+  b->h = h; b->S = S;
+  *out = b;
+  return PS_OK;
+}
+
+void ps_batch_destroy(ps_batch* b) {
+  if (!b) return;
+  cudaSetDevice(b->h->device);
+  for (int q = 0; q < 2; q++) {
+    if (b->ev_in[q]) cudaEventDestroy(b->ev_in[q]);
+    if (b->ev_k[q]) cudaEventDestroy(b->ev_k[q]);
+    if (b->ev_out[q]) cudaEventDestroy(b->ev_out[q]);
+  }
+  if (b->st_in) cudaStreamDestroy(b->st_in);
+  if (b->st_k) cudaStreamDestroy(b->st_k);
+  if (b->st_out) cudaStreamDestroy(b->st_out);
+  b->mem.release();
+  delete b;
+}
+
+int ps_batch_set_loads(ps_batch* b, const double* Pd, const double* Qd) {
+  if (!b) return PS_ERR_ARG;
+  ps_handle* h = b->h;
+  if (!Pd || !Qd) return fail(h, PS_ERR_ARG, "Pd / Qd is null");
+  cudaError_t e = cudaSetDevice(h->device);
+  if (e != cudaSuccess) return cuda_fail(h, e, "cudaSetDevice");
+  const size_t n = (size_t)b->S * h->plan.net.nbus;
+  if (!b->d_Pd) { b->d_Pd = b->mem.alloc<double>(n); b->d_Qd = b->mem.alloc<double>(n); }
+  if (!b->d_Pd || !b->d_Qd) return cuda_fail(h, b->mem.err, "cudaMalloc(loads)");
+  if ((e = cudaMemcpy(b->d_Pd, Pd, n * sizeof(double), cudaMemcpyHostToDevice)) != cudaSuccess ||
+      (e = cudaMemcpy(b->d_Qd, Qd, n * sizeof(double), cudaMemcpyHostToDevice)) != cudaSuccess)
+    return cuda_fail(h, e, "cudaMemcpy(loads)");
+  return PS_OK;
+}
+
+int ps_batch_set_branch_status(ps_batch* b, const uint8_t* st) {
+  if (!b) return PS_ERR_ARG;
+  ps_handle* h = b->h;
+  cudaError_t e = cudaSetDevice(h->device);
+  if (e != cudaSuccess) return cuda_fail(h, e, "cudaSetDevice");
+  const size_t n = (size_t)b->S * h->plan.net.nbr;
+  if (!st) {                       // reset: every branch in service (the pointer stays allocated but unused)
+    if (b->d_status) { e = cudaMemset(b->d_status, 1, n); if (e != cudaSuccess) return cuda_fail(h, e, "cudaMemset(status)"); }
+    return PS_OK;
+  }
+  for (size_t q = 0; q < n; q++) if (st[q] > 1) return fail(h, PS_ERR_ARG, "branch status must be 0 or 1");
+  if (!b->d_status) b->d_status = b->mem.alloc<uint8_t>(n);
+  if (!b->d_status) return cuda_fail(h, b->mem.err, "cudaMalloc(status)");
+  if ((e = cudaMemcpy(b->d_status, st, n, cudaMemcpyHostToDevice)) != cudaSuccess) return cuda_fail(h, e, "cudaMemcpy(status)");
+  return PS_OK;
+}
+
+int ps_batch_set_viol_tol(ps_batch* b, double tol) {
+  if (!b) return PS_ERR_ARG;
+  if (!(tol >= 0.0)) return fail(b->h, PS_ERR_ARG, "tolerance must be >= 0");
+  b->viol_tol = tol;
+  return PS_OK;
+}
+
+int64_t ps_batch_launch_count(const ps_batch* b) { return b ? b->launches : 0; }
+
+int ps_batch_eval(ps_batch* b, int what, int64_t s_begin, int64_t s_count, const double* x, int64_t ldx, const double* mu,
+                  int64_t ldmu, double* g, int64_t ldg, double* J, int64_t ldJ, double* H, int64_t ldH, double* scalars,
+                  void* stream) {
+  if (!b) return PS_ERR_ARG;
+  cudaError_t e = cudaSetDevice(b->h->device);
+  if (e != cudaSuccess) return cuda_fail(b->h, e, "cudaSetDevice");
+  return do_eval(b, what, s_begin, s_count, x, ldx, mu, ldmu, g, ldg, J, ldJ, H, ldH, scalars, (cudaStream_t)stream);
+}
+
+// Host buffers: scenarios stream through two sets of device staging buffers.  Copy-in (st_in), kernel (st_k)
+// and copy-out (st_out) of consecutive chunks overlap; events order the three stages of each chunk and the reuse
+// of a staging set two chunks later.
+int ps_batch_eval_host(ps_batch* b, int what, int64_t s_begin, int64_t s_count, const double* x, int64_t ldx,
+                       const double* mu, int64_t ldmu, double* g, int64_t ldg, double* J, int64_t ldJ, double* H,
+                       int64_t ldH, double* scalars) {
+  if (!b) return PS_ERR_ARG;
+  ps_handle* h = b->h;
+  const Plan& P = h->plan;
+  if (s_count == 0) return PS_OK;
+  if (s_begin < 0 || s_count < 0 || s_begin + s_count > b->S) return fail(h, PS_ERR_ARG, "scenario range outside the batch");
+  if (!x || ldx < P.n_var) return fail(h, PS_ERR_ARG, "x is null or ldx < n_var");
+  if ((what & EV_G) && (!g || ldg < P.m_nl)) return fail(h, PS_ERR_ARG, "g is null or ldg < m_nl");
+  if ((what & EV_J) && (!J || ldJ < P.nnzJ)) return fail(h, PS_ERR_ARG, "J is null or ldJ < nnz_jac");
+  if ((what & EV_H) && (!H || ldH < P.nnzH)) return fail(h, PS_ERR_ARG, "H is null or ldH < nnz_hess");
+  if ((what & EV_H) && (!mu || ldmu < P.m_nl)) return fail(h, PS_ERR_ARG, "mu is null or ldmu < m_nl (needed for the Hessian)");
+  cudaError_t e = cudaSetDevice(h->device);
+  if (e != cudaSuccess) return cuda_fail(h, e, "cudaSetDevice");
+  if (!b->st_in) {
+    // staging chunk: ~256 MB of outputs per set
+    const int64_t per = (P.m_nl + P.nnzJ + P.nnzH + P.n_var) * 8;
+    int64_t C = std::max<int64_t>(1, std::min<int64_t>(b->S, (int64_t(256) << 20) / std::max<int64_t>(per, 1)));
+    if (const char* env = getenv("PS_STAGE")) { const int64_t c = atoll(env); if (c > 0) C = std::min<int64_t>(c, b->S); }
+    b->stage_S = C;
+    for (int q = 0; q < 2; q++) {
+      b->sx[q] = b->mem.alloc<double>((size_t)C * P.n_var); b->smu[q] = b->mem.alloc<double>((size_t)C * P.m_nl);
+      b->sg[q] = b->mem.alloc<double>((size_t)C * P.m_nl); b->sJ[q] = b->mem.alloc<double>((size_t)C * P.nnzJ);
+      b->sH[q] = b->mem.alloc<double>((size_t)C * P.nnzH); b->sscal[q] = b->mem.alloc<double>((size_t)C * NSCAL);
+    }
+    if (b->mem.err != cudaSuccess) return cuda_fail(h, b->mem.err, "cudaMalloc(staging)");
+    if ((e = cudaStreamCreateWithFlags(&b->st_in, cudaStreamNonBlocking)) != cudaSuccess ||
+        (e = cudaStreamCreateWithFlags(&b->st_k, cudaStreamNonBlocking)) != cudaSuccess ||
+        (e = cudaStreamCreateWithFlags(&b->st_out, cudaStreamNonBlocking)) != cudaSuccess)
+      return cuda_fail(h, e, "cudaStreamCreate");
+    for (int q = 0; q < 2; q++)
+      if ((e = cudaEventCreateWithFlags(&b->ev_in[q], cudaEventDisableTiming)) != cudaSuccess ||
+          (e = cudaEventCreateWithFlags(&b->ev_k[q], cudaEventDisableTiming)) != cudaSuccess ||
+          (e = cudaEventCreateWithFlags(&b->ev_out[q], cudaEventDisableTiming)) != cudaSuccess)
+        return cuda_fail(h, e, "cudaEventCreate");
+  }
+  const int64_t C = b->stage_S;
+  int64_t it = 0;
+  for (int64_t c0 = 0; c0 < s_count; c0 += C, it++) {
+    const int q = (int)(it & 1);
+    const int64_t n = std::min<int64_t>(C, s_count - c0);
+    // the staging set is free once the copy-out of chunk it-2 is done (inputs: once its kernel is done)
+    if (it >= 2) { cudaStreamWaitEvent(b->st_in, b->ev_k[q], 0); }
+    e = cudaMemcpy2DAsync(b->sx[q], P.n_var * 8, x + c0 * ldx, ldx * 8, P.n_var * 8, n, cudaMemcpyHostToDevice, b->st_in);
+    if (e == cudaSuccess && (what & EV_H))
+      e = cudaMemcpy2DAsync(b->smu[q], P.m_nl * 8, mu + c0 * ldmu, ldmu * 8, P.m_nl * 8, n, cudaMemcpyHostToDevice, b->st_in);
+    if (e != cudaSuccess) return cuda_fail(h, e, "H2D copy");
+    cudaEventRecord(b->ev_in[q], b->st_in);
+    cudaStreamWaitEvent(b->st_k, b->ev_in[q], 0);
+    if (it >= 2) cudaStreamWaitEvent(b->st_k, b->ev_out[q], 0);
+    int rc = do_eval(b, what, s_begin + c0, n, b->sx[q], P.n_var, b->smu[q], P.m_nl, b->sg[q], P.m_nl, b->sJ[q], P.nnzJ,
+                     b->sH[q], P.nnzH, scalars ? b->sscal[q] : nullptr, b->st_k);
+    if (rc != PS_OK) return rc;
+    cudaEventRecord(b->ev_k[q], b->st_k);
+    cudaStreamWaitEvent(b->st_out, b->ev_k[q], 0);
+    if (what & EV_G) e = cudaMemcpy2DAsync(g + c0 * ldg, ldg * 8, b->sg[q], P.m_nl * 8, P.m_nl * 8, n, cudaMemcpyDeviceToHost, b->st_out);
+    if (e == cudaSuccess && (what & EV_J))
+      e = cudaMemcpy2DAsync(J + c0 * ldJ, ldJ * 8, b->sJ[q], P.nnzJ * 8, P.nnzJ * 8, n, cudaMemcpyDeviceToHost, b->st_out);
+    if (e == cudaSuccess && (what & EV_H))
+      e = cudaMemcpy2DAsync(H + c0 * ldH, ldH * 8, b->sH[q], P.nnzH * 8, P.nnzH * 8, n, cudaMemcpyDeviceToHost, b->st_out);
+    if (e == cudaSuccess && scalars)
+      e = cudaMemcpyAsync(scalars + c0 * NSCAL, b->sscal[q], (size_t)n * NSCAL * 8, cudaMemcpyDeviceToHost, b->st_out);
+    if (e != cudaSuccess) return cuda_fail(h, e, "D2H copy");
+    cudaEventRecord(b->ev_out[q], b->st_out);
+  }
+  if ((e = cudaStreamSynchronize(b->st_out)) != cudaSuccess || (e = cudaStreamSynchronize(b->st_k)) != cudaSuccess ||
+      (e = cudaStreamSynchronize(b->st_in)) != cudaSuccess)
+    return cuda_fail(h, e, "pipeline synchronize");
+  return PS_OK;
+}
+
+int ps_host_alloc(void** p, int64_t bytes) {
+  if (!p || bytes < 0) return PS_ERR_ARG;
+  cudaError_t e = cudaHostAlloc(p, (size_t)std::max<int64_t>(bytes, 1), cudaHostAllocDefault);
+  if (e != cudaSuccess) { g_create_error = std::string("cudaHostAlloc: ") + cudaGetErrorString(e); return PS_ERR_CUDA; }
+  return PS_OK;
+}
+void ps_host_free(void* p) { if (p) cudaFreeHost(p); }
+
+// ---- COO -> CSC ----------------------------------------------------------------------------
+int ps_csc_create(int64_t m, int64_t n, int64_t nnz_coo, const int64_t* row, const int64_t* col, int device, ps_csc** out) {
+  if (!out) return PS_ERR_ARG;
+  *out = nullptr;
+  if (m < 0 || n < 0 || nnz_coo < 0 || (nnz_coo && (!row || !col))) return fail(nullptr, PS_ERR_ARG, "bad COO arguments");
+  if (nnz_coo >= (int64_t(1) << 31)) return fail(nullptr, PS_ERR_ARG, "COO too large");
+  for (int64_t q = 0; q < nnz_coo; q++)
+    if (row[q] < 1 || row[q] > m || col[q] < 1 || col[q] > n) return fail(nullptr, PS_ERR_ARG, "COO index out of range");
+  ps_csc* p = new ps_csc();
+  p->m = m; p->n = n; p->nnz_coo = nnz_coo;
+  // stable sort by (col, row): duplicates keep COO order, which is the order common.jl:16-18 adds them in
+  std::vector<int32_t> ord(nnz_coo);
+  std::iota(ord.begin(), ord.end(), 0);
+  std::stable_sort(ord.begin(), ord.end(), [&](int32_t a, int32_t b) {
+    return col[a] != col[b] ? col[a] < col[b] : row[a] < row[b];
+  });
+  p->perm = ord;
+  p->colptr.assign(n + 1, 0);
+  p->segptr.clear();
+  for (int64_t q = 0; q < nnz_coo; q++) {
+    const int32_t a = ord[q];
+    if (q == 0 || col[a] != col[ord[q - 1]] || row[a] != row[ord[q - 1]]) {
+      p->segptr.push_back((int32_t)q);
+      p->rowval.push_back(row[a]);
+    }
+  }
+  p->segptr.push_back((int32_t)nnz_coo);
+  p->nnz = (int64_t)p->rowval.size();
+  // SparseMatrixCSC.colptr (1-based): colptr[c] = 1 + number of stored entries in columns 1..c
+  {
+    std::vector<int64_t> cnt(n + 1, 0);
+    for (int64_t j = 0; j < p->nnz; j++) cnt[col[ord[p->segptr[j]]]]++;
+    p->colptr[0] = 1;
+    for (int64_t c = 1; c <= n; c++) p->colptr[c] = p->colptr[c - 1] + cnt[c];
+  }
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0) { delete p; return fail(nullptr, PS_ERR_CUDA, "no CUDA device available (no CPU fallback)"); }
+  if (device < 0) cudaGetDevice(&device);
+  if ((e = cudaSetDevice(device)) != cudaSuccess) { delete p; return cuda_fail(nullptr, e, "cudaSetDevice"); }
+  p->device = device;
+  p->d_segptr = p->mem.upload(p->segptr);
+  p->d_perm = p->mem.upload(p->perm);
+  p->d_in = p->mem.alloc<double>(nnz_coo);
+  p->d_out = p->mem.alloc<double>(p->nnz);
+  if (p->mem.err != cudaSuccess) { e = p->mem.err; p->mem.release(); delete p; return cuda_fail(nullptr, e, "csc upload"); }
+  *out = p;
+  return PS_OK;
+}
+
+void ps_csc_destroy(ps_csc* p) {
+  if (!p) return;
+  cudaSetDevice(p->device);
+  p->mem.release();
+  delete p;
+}
+
+int ps_csc_dims(const ps_csc* p, int64_t* nnz_csc) {
+  if (!p || !nnz_csc) return PS_ERR_ARG;
+  *nnz_csc = p->nnz;
+  return PS_OK;
+}
+
+int ps_csc_structure(const ps_csc* p, int64_t* colptr, int64_t* rowval) {
+  if (!p || !colptr || !rowval) return PS_ERR_ARG;
+  std::copy(p->colptr.begin(), p->colptr.end(), colptr);
+  std::copy(p->rowval.begin(), p->rowval.end(), rowval);
+  return PS_OK;
+}
+
+int ps_csc_assemble(ps_csc* p, const double* dE, double* nzval) {
+  if (!p || (p->nnz_coo && !dE) || (p->nnz && !nzval)) return PS_ERR_ARG;
+  if (p->nnz == 0) return PS_OK;
+  cudaError_t e = cudaSetDevice(p->device);
+  if (e == cudaSuccess) e = cudaMemcpy(p->d_in, dE, (size_t)p->nnz_coo * 8, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = launch_csc_assemble(p->d_segptr, p->d_perm, (int)p->nnz, 1, p->d_in, p->nnz_coo, p->d_out, p->nnz, nullptr);
+  if (e == cudaSuccess) e = cudaMemcpy(nzval, p->d_out, (size_t)p->nnz * 8, cudaMemcpyDeviceToHost);
+  if (e != cudaSuccess) { p->err = cudaGetErrorString(e); g_create_error = p->err; return PS_ERR_CUDA; }
+  return PS_OK;
+}
+
+int ps_csc_assemble_batch(ps_csc* p, int64_t S, const double* dE, int64_t ldE, double* nzval, int64_t ldnz, void* stream) {
+  if (!p || S < 0 || (S && (!dE || !nzval)) || ldE < p->nnz_coo || ldnz < p->nnz) return PS_ERR_ARG;
+  cudaError_t e = cudaSetDevice(p->device);
+  if (e == cudaSuccess) e = launch_csc_assemble(p->d_segptr, p->d_perm, (int)p->nnz, S, dE, ldE, nzval, ldnz, (cudaStream_t)stream);
+  if (e != cudaSuccess) { p->err = cudaGetErrorString(e); g_create_error = p->err; return PS_ERR_CUDA; }
+  return PS_OK;
+}
+
+}  // extern "C"

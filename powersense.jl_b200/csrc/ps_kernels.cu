@@ -1,0 +1,772 @@
+// Hand-written sm_100a kernels: fused evaluation of the NL constraint block g(x), its sparse
+// Jacobian and the Hessian of the Lagrangian for every AC formulation of Powersense.jl
+// (math: src/opf/formulations.jl:170-428; closed-form derivatives: SURVEY.md Appendix F),
+// batched over scenarios.
+//
+// Work decomposition: a CTA owns one *tile* -- a contiguous range of buses or of branches, i.e. a
+// contiguous range of rows and therefore of g / J / H slots in JuMP order -- and loops over a chunk
+// of scenarios.  Per-branch network constants stay in registers across the scenario loop.  For
+// each scenario every thread evaluates its unit (branch-parallel or bus-parallel, no atomics,
+// reference summation order) into a shared-memory staging tile; the tile is then streamed to HBM
+// with fully coalesced stores.  HBM traffic per scenario = reads of x / mu / loads + exactly one
+// write of every output slot.  The path is sparse FP64 and HBM-bound: no tensor cores.
+#include <cstdio>
+
+#include "ps_kernels.cuh"
+
+namespace ps {
+namespace {
+
+// ------------------------------------------------------------------------------- branch rows
+// Thread lu of a branch tile stages its rows at sG[lu*NRP + r], sJ[lu*RJP + p], sH[lu*RHP + p];
+// the strides are odd so that the 8-byte shared-memory stores of a warp are conflict free.
+template <int FORM, int SRC>
+struct Branch {
+  static constexpr BranchSlots SL = branch_slots(FORM, SRC);
+  static constexpr int NR = SL.nrows, RJ = SL.nj, RH = SL.nh;
+  static constexpr int NRP = NR | 1, RJP = RJ | 1, RHP = RH | 1;
+  static constexpr bool MP = (SRC == SRC_MATPOWER);
+  static constexpr BranchPat PAT = branch_pattern(FORM, SRC);
+  template <int R> struct Row { static constexpr int J0 = PAT.jtag0(R), H0 = PAT.htag0(R); };
+  template <int T> struct JP { static constexpr int p0 = SL.jpos[0][T], p1 = SL.jpos[1][T]; };
+  template <int T> struct HP { static constexpr int p0 = SL.hpos[0][T], p1 = SL.hpos[1][T]; };
+
+  struct Out {
+    double *g, *j, *h;     // this thread's staging rows
+    bool sw, wg, wj, wh;
+    double vmax, tol;
+    int nviol;
+    template <int R> __device__ __forceinline__ void G(double v, bool eq) {
+      if (wg) g[R] = v;
+      const double vv = eq ? fabs(v) : v;
+      vmax = fmax(vmax, vv);
+      nviol += (vv > tol) ? 1 : 0;
+    }
+    template <int T> __device__ __forceinline__ void J(double v) { j[sw ? JP<T>::p1 : JP<T>::p0] = v; }
+    template <int T> __device__ __forceinline__ void H(double v) { h[sw ? HP<T>::p1 : HP<T>::p0] = v; }
+  };
+
+  struct Cst { double gf, bf, Gf, Bf, gt, bt, Gt, Bt, Imax; double d[8]; };   // d: c0..c3 per side
+  struct In { double af, at, bf, bt, wf, wt, wr, wi, F0, F1, F2, F3, st; double mu[NR > 0 ? NR : 1]; };
+
+  static __device__ __forceinline__ Cst load_cst(const DevPlan& P, int u) {
+    Cst c;
+    c.gf = P.gf[u]; c.bf = P.bf[u]; c.Gf = P.Gf[u]; c.Bf = P.Bf[u];
+    c.gt = P.gt[u]; c.bt = P.bt[u]; c.Gt = P.Gt[u]; c.Bt = P.Bt[u]; c.Imax = P.Imax[u];
+    if constexpr (is_PN(FORM)) {
+#pragma unroll
+      for (int sd = 0; sd < 2; sd++) {
+        c.d[0 + sd] = P.c0[sd * P.nr + u]; c.d[2 + sd] = P.c1[sd * P.nr + u];
+        c.d[4 + sd] = P.c2[sd * P.nr + u]; c.d[6 + sd] = P.c3[sd * P.nr + u];
+      }
+    }
+    return c;
+  }
+
+  static __device__ __forceinline__ In load_in(const DevPlan& P, const EvalArgs& A, int s, int k, int f, int t) {
+    In in{};
+    const double* __restrict__ x = A.x + (long long)s * A.ldx;
+    in.st = A.status ? (double)A.status[(long long)s * A.ldst + k] : 1.0;
+    constexpr bool NEED_V = FORM == PBRAPV || FORM == PBRARV || is_PN(FORM) || (FORM == CBRARV && MP);
+    if constexpr (NEED_V) {
+      in.af = x[P.o_a + f]; in.at = x[P.o_a + t];
+      in.bf = x[P.o_b + f]; in.bt = x[P.o_b + t];
+    }
+    if constexpr (has_W(FORM)) { in.wf = x[P.o_Wd + f]; in.wt = x[P.o_Wd + t]; }
+    if constexpr (has_WrWi(FORM)) { in.wr = x[P.o_Wr + k]; in.wi = x[P.o_Wi + k]; }
+    if constexpr (is_PB(FORM) || is_CB(FORM)) {
+      in.F0 = x[P.o_f[0] + k]; in.F1 = x[P.o_f[1] + k]; in.F2 = x[P.o_f[2] + k]; in.F3 = x[P.o_f[3] + k];
+    }
+    if (A.what & EV_H) {
+      const double* __restrict__ mu = A.mu + (long long)s * A.ldmu + P.bus_rows + (long long)k * NR;
+#pragma unroll
+      for (int r = 0; r < NR; r++) in.mu[r] = mu[r];
+    } else {
+#pragma unroll
+      for (int r = 0; r < NR; r++) in.mu[r] = 0.0;
+    }
+    return in;
+  }
+
+  // polar flow-definition row (PBRAPV :302-305 | :366-369): row = flow - T,  T from SURVEY F.1
+  // SIDE 0: a = f ; SIDE 1: a = t.  PQ 0: P row, 1: Q row.  cs/sn = cos/sin(th_f - th_t)
+  template <int R, int SIDE, int PQ>
+  static __device__ __forceinline__ void polar_flow(Out& o, double flow, double Vf, double Vt, double cs, double sn,
+                                                    double gs, double bs, double G, double B, double mu) {
+    constexpr int J0 = Row<R>::J0, H0 = Row<R>::H0;
+    const double Va = SIDE ? Vt : Vf, Vb = SIDE ? Vf : Vt;
+    const double sd = SIDE ? -sn : sn;                       // sin(th_a - th_b)
+    const double A = G * cs + B * sd, Bt = B * cs - G * sd;
+    const double VV = Va * Vb;
+    double T, dta, dVa, dVb, haa, haVa, haVb, hVaVa, hVaVb;
+    if (PQ == 0) {
+      T = (-gs) * (Va * Va) - A * Vf * Vt;                   // :302-303
+      dta = -Bt * VV; dVa = -2.0 * gs * Va - A * Vb; dVb = -A * Va;
+      haa = A * VV; haVa = -Bt * Vb; haVb = -Bt * Va; hVaVa = -2.0 * gs; hVaVb = -A;
+    } else {
+      T = bs * (Va * Va) + Bt * Vf * Vt;                     // :304-305
+      dta = -A * VV; dVa = 2.0 * bs * Va + Bt * Vb; dVb = Bt * Va;
+      haa = -Bt * VV; haVa = -A * Vb; haVb = -A * Va; hVaVa = 2.0 * bs; hVaVb = Bt;
+    }
+    o.template G<R>(flow - T, true);
+    // J tags [flow, th_f, th_t, V_f, V_t]
+    constexpr int tTA = SIDE ? 2 : 1, tTB = SIDE ? 1 : 2, tVA = SIDE ? 4 : 3, tVB = SIDE ? 3 : 4;
+    if (o.wj) {
+      o.template J<J0 + 0>(1.0);
+      o.template J<J0 + tTA>(-dta);
+      o.template J<J0 + tTB>(dta);
+      o.template J<J0 + tVA>(-dVa);
+      o.template J<J0 + tVB>(-dVb);
+    }
+    if (o.wh) {
+      const double m = -mu;                                  // row = flow - T
+      // clique4 tags: (thf,thf)0 (tht,tht)1 (Vf,Vf)2 (Vt,Vt)3 (thf,tht)4 (thf,Vf)5 (thf,Vt)6 (tht,Vf)7 (tht,Vt)8 (Vf,Vt)9
+      constexpr int hAA = SIDE ? 1 : 0, hBB = SIDE ? 0 : 1, hVaVa_ = SIDE ? 3 : 2, hVbVb_ = SIDE ? 2 : 3;
+      constexpr int hAVa = SIDE ? 8 : 5, hAVb = SIDE ? 7 : 6, hBVa = SIDE ? 6 : 7, hBVb = SIDE ? 5 : 8;
+      o.template H<H0 + hAA>(m * haa);
+      o.template H<H0 + hBB>(m * haa);
+      o.template H<H0 + 4>(-m * haa);
+      o.template H<H0 + hAVa>(m * haVa);
+      o.template H<H0 + hAVb>(m * haVb);
+      o.template H<H0 + hBVa>(-m * haVa);
+      o.template H<H0 + hBVb>(-m * haVb);
+      o.template H<H0 + hVaVa_>(m * hVaVa);
+      o.template H<H0 + 9>(m * hVaVb);
+      o.template H<H0 + hVbVb_>(0.0);
+    }
+  }
+
+  // rectangular flow-definition row (PBRARV :309-312 | :373-376), T from SURVEY F.2
+  template <int R, int SIDE, int PQ>
+  static __device__ __forceinline__ void rect_flow(Out& o, double flow, double ra, double ia, double rb, double ib,
+                                                   double gs, double bs, double G, double B, double mu) {
+    constexpr int J0 = Row<R>::J0, H0 = Row<R>::H0;
+    const double A2 = ra * ra + ia * ia, C = ra * rb + ia * ib, S = ra * ib - ia * rb;
+    double T, dra, dia, drb, dib, hd, hC, hrib, hirb;
+    if (PQ == 0) {
+      T = ((-gs) * A2 - G * C) + B * S;                      // :309-310
+      dra = -2.0 * gs * ra - G * rb + B * ib; dia = -2.0 * gs * ia - G * ib - B * rb;
+      drb = -G * ra - B * ia; dib = -G * ia + B * ra;
+      hd = -2.0 * gs; hC = -G; hrib = B; hirb = -B;
+    } else {
+      T = (bs * A2 + B * C) + G * S;                         // :311-312
+      dra = 2.0 * bs * ra + B * rb + G * ib; dia = 2.0 * bs * ia + B * ib - G * rb;
+      drb = B * ra - G * ia; dib = B * ia + G * ra;
+      hd = 2.0 * bs; hC = B; hrib = G; hirb = -G;
+    }
+    o.template G<R>(flow - T, true);
+    // J tags [flow, vi_f, vi_t, vr_f, vr_t]
+    if (o.wj) {
+      o.template J<J0 + 0>(1.0);
+      o.template J<J0 + (SIDE ? 2 : 1)>(-dia);
+      o.template J<J0 + (SIDE ? 1 : 2)>(-dib);
+      o.template J<J0 + (SIDE ? 4 : 3)>(-dra);
+      o.template J<J0 + (SIDE ? 3 : 4)>(-drb);
+    }
+    if (o.wh) {
+      const double m = -mu;
+      // H tags: (vi_f,vi_f)0 (vi_t,vi_t)1 (vr_f,vr_f)2 (vr_t,vr_t)3 (vr_f,vr_t)4 (vi_f,vi_t)5 (vr_f,vi_t)6 (vi_f,vr_t)7
+      o.template H<H0 + (SIDE ? 1 : 0)>(m * hd);             // (ia,ia)
+      o.template H<H0 + (SIDE ? 0 : 1)>(0.0);                // (ib,ib)
+      o.template H<H0 + (SIDE ? 3 : 2)>(m * hd);             // (ra,ra)
+      o.template H<H0 + (SIDE ? 2 : 3)>(0.0);                // (rb,rb)
+      o.template H<H0 + 4>(m * hC);                          // (ra,rb)
+      o.template H<H0 + 5>(m * hC);                          // (ia,ib)
+      o.template H<H0 + (SIDE ? 7 : 6)>(m * hrib);           // (ra,ib)
+      o.template H<H0 + (SIDE ? 6 : 7)>(m * hirb);           // (ia,rb)
+    }
+  }
+
+  // L1: P^2 + Q^2 - Imax^2 [* |V_a|^2]   (:306-307,:313-314,:321-322 | :370-371,:377-378,:385-386)
+  // va, vb: V_a (polar) | (vr_a, vi_a) (rect) | Wd_a (W)
+  template <int R>
+  static __device__ __forceinline__ void limit_L1(Out& o, double Pf, double Qf, double va, double vb, double Im2, double mu) {
+    constexpr int J0 = Row<R>::J0, H0 = Row<R>::H0;
+    const double lhs = Pf * Pf + Qf * Qf;
+    double rhs = Im2;
+    if constexpr (!MP) {
+      if constexpr (FORM == PBRAPV) rhs = Im2 * (va * va);
+      else if constexpr (FORM == PBRARV) rhs = Im2 * (va * va + vb * vb);
+      else rhs = Im2 * va;
+    }
+    o.template G<R>(lhs - rhs, false);
+    if (o.wj) {
+      o.template J<J0 + 0>(2.0 * Pf);
+      o.template J<J0 + 1>(2.0 * Qf);
+      if constexpr (!MP) {
+        if constexpr (FORM == PBRAPV) o.template J<J0 + 2>(-2.0 * Im2 * va);
+        else if constexpr (FORM == PBRARV) { o.template J<J0 + 2>(-2.0 * Im2 * va); o.template J<J0 + 3>(-2.0 * Im2 * vb); }
+        else o.template J<J0 + 2>(-Im2);
+      }
+    }
+    if (o.wh) {
+      o.template H<H0 + 0>(2.0 * mu);
+      o.template H<H0 + 1>(2.0 * mu);
+      if constexpr (!MP) {
+        if constexpr (FORM == PBRAPV) o.template H<H0 + 2>(-2.0 * Im2 * mu);
+        else if constexpr (FORM == PBRARV) { o.template H<H0 + 2>(-2.0 * Im2 * mu); o.template H<H0 + 3>(-2.0 * Im2 * mu); }
+      }
+    }
+  }
+
+  // L2 / L3 (CBRARV :328-329 | :392-393 ; CBRAWV :335-336 | :399-400).  a1 = vr_a | Wd_a, a0 = vi_a
+  template <int R>
+  static __device__ __forceinline__ void limit_CB(Out& o, double Ir, double Ii, double a1, double a0, double Im2, double mm) {
+    constexpr int J0 = Row<R>::J0, H0 = Row<R>::H0;
+    const double I2 = Ir * Ir + Ii * Ii;
+    if constexpr (!MP) {
+      o.template G<R>(I2 - Im2, false);
+      if (o.wj) { o.template J<J0 + 0>(2.0 * Ir); o.template J<J0 + 1>(2.0 * Ii); }
+      if (o.wh) { o.template H<H0 + 0>(2.0 * mm); o.template H<H0 + 1>(2.0 * mm); }
+    } else if constexpr (FORM == CBRARV) {
+      const double r = a1, im = a0, A2 = r * r + im * im;
+      o.template G<R>(((Ir * Ir) * A2 + (Ii * Ii) * A2) - Im2, false);
+      if (o.wj) { o.template J<J0 + 0>(2.0 * Ir * A2); o.template J<J0 + 1>(2.0 * Ii * A2);
+                  o.template J<J0 + 2>(2.0 * r * I2); o.template J<J0 + 3>(2.0 * im * I2); }
+      if (o.wh) { o.template H<H0 + 0>(mm * 2.0 * A2); o.template H<H0 + 1>(mm * 2.0 * A2);
+                  o.template H<H0 + 2>(mm * 2.0 * I2); o.template H<H0 + 3>(mm * 2.0 * I2);
+                  o.template H<H0 + 4>(mm * 4.0 * Ir * r); o.template H<H0 + 5>(mm * 4.0 * Ir * im);
+                  o.template H<H0 + 6>(mm * 4.0 * Ii * r); o.template H<H0 + 7>(mm * 4.0 * Ii * im);
+                  o.template H<H0 + 8>(0.0); }
+    } else {
+      const double W = a1;
+      o.template G<R>(((Ir * Ir) * W + (Ii * Ii) * W) - Im2, false);
+      if (o.wj) { o.template J<J0 + 0>(2.0 * Ir * W); o.template J<J0 + 1>(2.0 * Ii * W); o.template J<J0 + 2>(I2); }
+      if (o.wh) { o.template H<H0 + 0>(mm * 2.0 * W); o.template H<H0 + 1>(mm * 2.0 * W); o.template H<H0 + 2>(0.0);
+                  o.template H<H0 + 3>(mm * 2.0 * Ir); o.template H<H0 + 4>(mm * 2.0 * Ii); }
+    }
+  }
+
+  // L4 (PNPAPV / PNRAPV :337-343 | :401-407), SURVEY F.5
+  template <int SIDE>
+  static __device__ __forceinline__ void limit_L4(Out& o, double thf, double tht, double Vf, double Vt, double gs, double bs,
+                                                  double G, double B, double y3, double th1, double th2, double Im2, double mm) {
+    constexpr int R = SIDE;
+    constexpr int J0 = Row<R>::J0, H0 = Row<R>::H0;
+    const double y1 = gs * gs + bs * bs, y2 = G * G + B * B;
+    const double Va = SIDE ? Vt : Vf, Vb = SIDE ? Vf : Vt;
+    const double psi = ((SIDE ? tht - thf : thf - tht) + th1) - th2;
+    double s, c;
+    sincos(psi, &s, &c);
+    double val, dVa, dVb, dta, hVaVa, hVaVb, hVbVb, htt, htVa, htVb;
+    if constexpr (MP) {
+      const double Va2 = Va * Va, Va3 = Va2 * Va, Vb2 = Vb * Vb;
+      val = (y1 * (Va2 * Va2) + y2 * Vb2 * Va2) + y3 * Va3 * Vb * c;
+      dVa = 4.0 * y1 * Va3 + 2.0 * y2 * Vb2 * Va + 3.0 * y3 * Va2 * Vb * c;
+      dVb = 2.0 * y2 * Vb * Va2 + y3 * Va3 * c;
+      dta = -y3 * Va3 * Vb * s;
+      hVaVa = 12.0 * y1 * Va2 + 2.0 * y2 * Vb2 + 6.0 * y3 * Va * Vb * c;
+      hVaVb = 4.0 * y2 * Va * Vb + 3.0 * y3 * Va2 * c;
+      hVbVb = 2.0 * y2 * Va2;
+      htt = -y3 * Va3 * Vb * c; htVa = -3.0 * y3 * Va2 * Vb * s; htVb = -y3 * Va3 * s;
+    } else {
+      val = (y1 * (Va * Va) + y2 * (Vb * Vb)) + y3 * Va * Vb * c;
+      dVa = 2.0 * y1 * Va + y3 * Vb * c; dVb = 2.0 * y2 * Vb + y3 * Va * c; dta = -y3 * Va * Vb * s;
+      hVaVa = 2.0 * y1; hVaVb = y3 * c; hVbVb = 2.0 * y2;
+      htt = -y3 * Va * Vb * c; htVa = -y3 * Vb * s; htVb = -y3 * Va * s;
+    }
+    o.template G<R>(val - Im2, false);
+    // J tags [th_f, th_t, V_f, V_t]
+    if (o.wj) { o.template J<J0 + (SIDE ? 1 : 0)>(dta); o.template J<J0 + (SIDE ? 0 : 1)>(-dta);
+                o.template J<J0 + (SIDE ? 3 : 2)>(dVa); o.template J<J0 + (SIDE ? 2 : 3)>(dVb); }
+    if (o.wh) {
+      o.template H<H0 + 0>(mm * htt); o.template H<H0 + 1>(mm * htt); o.template H<H0 + 4>(-mm * htt);
+      o.template H<H0 + (SIDE ? 3 : 2)>(mm * hVaVa); o.template H<H0 + (SIDE ? 2 : 3)>(mm * hVbVb);
+      o.template H<H0 + 9>(mm * hVaVb);
+      o.template H<H0 + (SIDE ? 8 : 5)>(mm * htVa);          // (th_a, V_a)
+      o.template H<H0 + (SIDE ? 7 : 6)>(mm * htVb);          // (th_a, V_b)
+      o.template H<H0 + (SIDE ? 6 : 7)>(-mm * htVa);         // (th_b, V_a)
+      o.template H<H0 + (SIDE ? 5 : 8)>(-mm * htVb);         // (th_b, V_b)
+    }
+  }
+
+  // clique4 tag of a local pair; locals 0 ra, 1 ia, 2 rb, 3 ib -> roles (AF=0 vi_f, AT=1 vi_t, BF=2 vr_f, BT=3 vr_t)
+  static constexpr int ctag(int side, int u, int v) {
+    const int m0[4] = {2, 0, 3, 1}, m1[4] = {3, 1, 2, 0};
+    int a = side ? m1[u] : m0[u], b = side ? m1[v] : m0[v];
+    if (a > b) { const int q = a; a = b; b = q; }
+    if (a == b) return a;
+    return a == 0 ? 3 + b : (a == 1 ? 5 + b : 9);
+  }
+
+  // L5 (PNRARV :344-352 | :408-414), SURVEY F.5
+  template <int SIDE>
+  static __device__ __forceinline__ void limit_L5(Out& o, double ra, double ia, double rb, double ib, double y, double Y,
+                                                  double y1, double y2, double Im2, double mm) {
+    constexpr int R = SIDE;
+    constexpr int J0 = Row<R>::J0, H0 = Row<R>::H0;
+    const double A2 = ra * ra + ia * ia, B2 = rb * rb + ib * ib, C = ra * rb + ia * ib, S = ra * ib - ia * rb;
+    const double Q = ((y1 * C + y2 * S) + y * A2) + Y * B2;
+    const double q0 = y1 * rb + y2 * ib + 2.0 * y * ra, q1 = y1 * ib - y2 * rb + 2.0 * y * ia;
+    const double q2 = y1 * ra - y2 * ia + 2.0 * Y * rb, q3 = y1 * ia + y2 * ra + 2.0 * Y * ib;
+    // J tags [vi_f, vi_t, vr_f, vr_t]; locals (ra, ia, rb, ib)
+    constexpr int t0 = SIDE ? 3 : 2, t1 = SIDE ? 1 : 0, t2 = SIDE ? 2 : 3, t3 = SIDE ? 0 : 1;
+    if constexpr (MP) {
+      o.template G<R>((((y1 * C * A2 + y2 * S * A2) + y * A2 * A2) + Y * B2 * A2) - Im2, false);
+      if (o.wj) {
+        o.template J<J0 + t0>(q0 * A2 + Q * (2.0 * ra)); o.template J<J0 + t1>(q1 * A2 + Q * (2.0 * ia));
+        o.template J<J0 + t2>(q2 * A2); o.template J<J0 + t3>(q3 * A2);
+      }
+      if (o.wh) {
+        const double a0 = 2.0 * ra, a1 = 2.0 * ia;
+        o.template H<H0 + ctag(SIDE, 0, 0)>(mm * (2.0 * y * A2 + 2.0 * q0 * a0 + 2.0 * Q));
+        o.template H<H0 + ctag(SIDE, 1, 1)>(mm * (2.0 * y * A2 + 2.0 * q1 * a1 + 2.0 * Q));
+        o.template H<H0 + ctag(SIDE, 2, 2)>(mm * (2.0 * Y * A2));
+        o.template H<H0 + ctag(SIDE, 3, 3)>(mm * (2.0 * Y * A2));
+        o.template H<H0 + ctag(SIDE, 0, 1)>(mm * (q0 * a1 + q1 * a0));
+        o.template H<H0 + ctag(SIDE, 0, 2)>(mm * (y1 * A2 + q2 * a0));
+        o.template H<H0 + ctag(SIDE, 0, 3)>(mm * (y2 * A2 + q3 * a0));
+        o.template H<H0 + ctag(SIDE, 1, 2)>(mm * (-y2 * A2 + q2 * a1));
+        o.template H<H0 + ctag(SIDE, 1, 3)>(mm * (y1 * A2 + q3 * a1));
+        o.template H<H0 + ctag(SIDE, 2, 3)>(0.0);
+      }
+    } else {
+      o.template G<R>(Q - Im2, false);
+      if (o.wj) { o.template J<J0 + t0>(q0); o.template J<J0 + t1>(q1); o.template J<J0 + t2>(q2); o.template J<J0 + t3>(q3); }
+      if (o.wh) {
+        // H tags: (vi_f,vi_f)0 (vi_t,vi_t)1 (vr_f,vr_f)2 (vr_t,vr_t)3 (vr_f,vr_t)4 (vi_f,vi_t)5 (vr_f,vi_t)6 (vi_f,vr_t)7
+        o.template H<H0 + (SIDE ? 1 : 0)>(mm * 2.0 * y);     // (ia,ia)
+        o.template H<H0 + (SIDE ? 0 : 1)>(mm * 2.0 * Y);     // (ib,ib)
+        o.template H<H0 + (SIDE ? 3 : 2)>(mm * 2.0 * y);     // (ra,ra)
+        o.template H<H0 + (SIDE ? 2 : 3)>(mm * 2.0 * Y);     // (rb,rb)
+        o.template H<H0 + 4>(mm * y1);                       // (ra,rb)
+        o.template H<H0 + 5>(mm * y1);                       // (ia,ib)
+        o.template H<H0 + (SIDE ? 7 : 6)>(mm * y2);          // (ra,ib)
+        o.template H<H0 + (SIDE ? 6 : 7)>(-mm * y2);         // (ia,rb)
+      }
+    }
+  }
+
+  static __device__ __forceinline__ void run(Out& o, const Cst& c, const In& in) {
+    const double st = in.st;
+    double Imax = c.Imax * st;
+    if (Imax == 0.0) Imax = 10000.0;                          // PowersenseData.jl:206-207
+    const double Im2 = Imax * Imax;
+    const double gf = c.gf * st, bf = c.bf * st, Gf = c.Gf * st, Bf = c.Bf * st;
+    const double gt = c.gt * st, bt = c.bt * st, Gt = c.Gt * st, Bt = c.Bt * st;
+    const double* m = in.mu;
+    if constexpr (FORM == PBRAPV) {
+      const double thf = in.af, tht = in.at, Vf = in.bf, Vt = in.bt;
+      double sn, cs;
+      sincos(thf - tht, &sn, &cs);
+      polar_flow<0, 0, 0>(o, in.F0, Vf, Vt, cs, sn, gf, bf, Gf, Bf, m[0]);
+      polar_flow<1, 1, 0>(o, in.F2, Vf, Vt, cs, sn, gt, bt, Gt, Bt, m[1]);
+      polar_flow<2, 0, 1>(o, in.F1, Vf, Vt, cs, sn, gf, bf, Gf, Bf, m[2]);
+      polar_flow<3, 1, 1>(o, in.F3, Vf, Vt, cs, sn, gt, bt, Gt, Bt, m[3]);
+      limit_L1<4>(o, in.F0, in.F1, Vf, 0.0, Im2, m[4]);
+      limit_L1<5>(o, in.F2, in.F3, Vt, 0.0, Im2, m[5]);
+    } else if constexpr (FORM == PBRARV) {
+      const double i_f = in.af, i_t = in.at, r_f = in.bf, r_t = in.bt;
+      rect_flow<0, 0, 0>(o, in.F0, r_f, i_f, r_t, i_t, gf, bf, Gf, Bf, m[0]);
+      rect_flow<1, 1, 0>(o, in.F2, r_t, i_t, r_f, i_f, gt, bt, Gt, Bt, m[1]);
+      rect_flow<2, 0, 1>(o, in.F1, r_f, i_f, r_t, i_t, gf, bf, Gf, Bf, m[2]);
+      rect_flow<3, 1, 1>(o, in.F3, r_t, i_t, r_f, i_f, gt, bt, Gt, Bt, m[3]);
+      limit_L1<4>(o, in.F0, in.F1, r_f, i_f, Im2, m[4]);
+      limit_L1<5>(o, in.F2, in.F3, r_t, i_t, Im2, m[5]);
+    } else if constexpr (FORM == PBRAWV || FORM == PNRAWV) {
+      const double Wr = in.wr, Wi = in.wi, Wf = in.wf, Wt = in.wt;
+      constexpr int J0 = Row<0>::J0, H0 = Row<0>::H0;
+      o.template G<0>((Wr * Wr + Wi * Wi) - Wf * Wt, true);     // :316 / :354
+      if (o.wj) { o.template J<J0 + 0>(2.0 * Wr); o.template J<J0 + 1>(2.0 * Wi);
+                  o.template J<J0 + 2>(-Wt); o.template J<J0 + 3>(-Wf); }
+      if (o.wh) { o.template H<H0 + 0>(2.0 * m[0]); o.template H<H0 + 1>(2.0 * m[0]);
+                  o.template H<H0 + 2>(0.0); o.template H<H0 + 3>(0.0); o.template H<H0 + 4>(-m[0]); }
+      if constexpr (FORM == PBRAWV) {
+        limit_L1<1>(o, in.F0, in.F1, Wf, 0.0, Im2, m[1]);
+        limit_L1<2>(o, in.F2, in.F3, Wt, 0.0, Im2, m[2]);
+      }
+    } else if constexpr (FORM == CBRARV) {
+      limit_CB<0>(o, in.F0, in.F1, in.bf, in.af, Im2, m[0]);
+      limit_CB<1>(o, in.F2, in.F3, in.bt, in.at, Im2, m[1]);
+    } else if constexpr (FORM == CBRAWV) {
+      limit_CB<0>(o, in.F0, in.F1, in.wf, 0.0, Im2, m[0]);
+      limit_CB<1>(o, in.F2, in.F3, in.wt, 0.0, Im2, m[1]);
+    } else if constexpr (FORM == PNPAPV || FORM == PNRAPV) {
+      const double s2 = st * st;
+      // d: [0,1] c0 = |G+jB| per side, [2,3] c1 = angle(G+jB), [4,5] c2 = y3, [6,7] c3 = angle(g_s+jb_s)
+      limit_L4<0>(o, in.af, in.at, in.bf, in.bt, gf, bf, Gf, Bf, c.d[4] * s2, c.d[6], c.d[2], Im2, m[0]);
+      limit_L4<1>(o, in.af, in.at, in.bf, in.bt, gt, bt, Gt, Bt, c.d[5] * s2, c.d[7], c.d[3], Im2, m[1]);
+    } else if constexpr (FORM == PNRARV) {
+      const double s2 = st * st;
+      // d: [0,1] y, [2,3] Y, [4,5] y1, [6,7] y2
+      limit_L5<0>(o, in.bf, in.af, in.bt, in.at, c.d[0] * s2, c.d[2] * s2, c.d[4] * s2, c.d[6] * s2, Im2, m[0]);
+      limit_L5<1>(o, in.bt, in.at, in.bf, in.af, c.d[1] * s2, c.d[3] * s2, c.d[5] * s2, c.d[7] * s2, Im2, m[1]);
+    }
+  }
+};
+
+// --------------------------------------------------------------------------- bus rows
+// Stream writer: slot positions (relative to the bus's first slot) come from the plan in emission
+// order; bit 15 = accumulate into a slot this thread has already written (duplicate variables of a
+// row: the diagonal block of PN* balances, parallel branches).  A bus's slots are private to its
+// thread, so there are no races and the accumulation order is the reference's term order.
+struct Stream {
+  double* base;
+  const uint16_t* __restrict__ pos;
+  bool on;
+  __device__ __forceinline__ void put(double v) {
+    if (on) {
+      const unsigned p = *pos;
+      double* q = base + (p & 0x7fffu);
+      *q = (p & 0x8000u) ? *q + v : v;
+    }
+    pos++;
+  }
+};
+
+struct BusOut {
+  double* g;
+  bool wg;
+  double vmax, tol;
+  int nviol;
+  __device__ __forceinline__ void G(int r, double v) {
+    if (wg) g[r] = v;
+    const double vv = fabs(v);
+    vmax = fmax(vmax, vv);
+    nviol += (vv > tol) ? 1 : 0;
+  }
+};
+
+template <int FORM>
+__device__ __forceinline__ void bus_rows(const DevPlan& P, BusOut& o, Stream& sj, Stream& sh, int i,
+                                         const double* __restrict__ x, const double* __restrict__ mu,
+                                         const double* __restrict__ Pd, const double* __restrict__ Qd,
+                                         const uint8_t* __restrict__ status) {
+  const double muP = sh.on ? mu[2 * i] : 0.0, muQ = sh.on ? mu[2 * i + 1] : 0.0;
+  double accP = 0.0, accQ = 0.0;                               // formulations.jl:171-172
+  for (int q = P.gen_ptr[i]; q < P.gen_ptr[i + 1]; q++) {      // :177-180
+    const int g = P.gen_idx[q];
+    accP = accP + x[P.o_pg + g];
+    accQ = accQ + x[P.o_qg + g];
+    sj.put(1.0);
+    sj.put(1.0);
+  }
+  double va0 = 0.0, vb0 = 0.0;                                 // own voltage: (theta_i, V_i) | (vi_i, vr_i)
+  if constexpr (FORM != PBRAPV && FORM != CBRAWV) va0 = x[P.o_a + i];
+  if constexpr (FORM != CBRAWV) vb0 = x[P.o_b + i];
+  if constexpr (FORM == CBRAWV) { va0 = x[P.o_a + i]; vb0 = x[P.o_b + i]; }
+#pragma unroll 1
+  for (int side = 0; side < 2; side++) {
+    const int32_t* __restrict__ ptr = side ? P.sji_ptr : P.sij_ptr;
+    const int32_t* __restrict__ idx = side ? P.sji_idx : P.sij_idx;
+#pragma unroll 1
+    for (int q = ptr[i]; q < ptr[i + 1]; q++) {
+      const int k = idx[q];
+      const double st = status ? (double)status[k] : 1.0;
+      if constexpr (FORM == PBRAPV || FORM == PBRARV) {        // :188-196
+        accP = accP + st * x[P.o_f[0 + 2 * side] + k];
+        accQ = accQ + st * x[P.o_f[1 + 2 * side] + k];
+        sj.put(st);
+        sj.put(st);
+      } else if constexpr (FORM == CBRARV || FORM == CBRAWV) { // :206-214  T4
+        const double Ir = x[P.o_f[0 + 2 * side] + k], Ii = x[P.o_f[1 + 2 * side] + k];
+        const double ra = vb0, ia = va0;
+        accP = (accP + st * (ra * Ir)) + st * (ia * Ii);
+        accQ = (accQ + st * (ia * Ir)) - st * (ra * Ii);
+        sj.put(st * Ir); sj.put(st * Ii); sj.put(st * ra); sj.put(st * ia);          // P: d/d(ra, ia, Ir, Ii)
+        sj.put(-st * Ii); sj.put(st * Ir); sj.put(st * ia); sj.put(-st * ra);        // Q
+        sh.put(0.0); sh.put(0.0); sh.put(st * muP); sh.put(0.0); sh.put(0.0); sh.put(st * muP);
+        sh.put(0.0); sh.put(0.0); sh.put(st * muQ); sh.put(0.0); sh.put(0.0); sh.put(-st * muQ);
+      } else if constexpr (FORM == PNPAPV || FORM == PNRAPV) { // :215-234  T2 / T1
+        const int b = side ? P.f[k] : P.t[k];
+        const double gs = st * (side ? P.gt[k] : P.gf[k]), bs = st * (side ? P.bt[k] : P.bf[k]);
+        const double thb = x[P.o_a + b], Vb = x[P.o_b + b], Va = vb0, dl = va0 - thb;
+        double A, Bt;
+        if constexpr (FORM == PNPAPV) {
+          const double Y = st * P.c0[side * P.nr + k], phi = P.c1[side * P.nr + k];
+          double s, c;
+          sincos(dl - phi, &s, &c);
+          A = Y * c; Bt = -(Y * s);
+        } else {
+          const double G = st * (side ? P.Gt[k] : P.Gf[k]), B = st * (side ? P.Bt[k] : P.Bf[k]);
+          double s, c;
+          sincos(dl, &s, &c);
+          A = G * c + B * s; Bt = B * c - G * s;
+        }
+        const double Vf = side ? Vb : Va, Vt = side ? Va : Vb;  // source order V[f]*V[t]
+        const double VV = Va * Vb;
+        accP = (accP - gs * (Va * Va)) - A * Vf * Vt;
+        accQ = (accQ + bs * (Va * Va)) + Bt * Vf * Vt;
+        // J: d/d(th_a, th_b, V_a, V_b)
+        sj.put(-Bt * VV); sj.put(Bt * VV); sj.put(-2.0 * gs * Va - A * Vb); sj.put(-A * Va);
+        sj.put(-A * VV); sj.put(A * VV); sj.put(2.0 * bs * Va + Bt * Vb); sj.put(Bt * Va);
+        // H clique order over [th_a, th_b, V_a, V_b]: aa bb VaVa VbVb ab aVa aVb bVa bVb VaVb
+        sh.put(muP * A * VV); sh.put(muP * A * VV); sh.put(muP * -2.0 * gs); sh.put(0.0); sh.put(-muP * A * VV);
+        sh.put(-muP * Bt * Vb); sh.put(-muP * Bt * Va); sh.put(muP * Bt * Vb); sh.put(muP * Bt * Va); sh.put(-muP * A);
+        sh.put(-muQ * Bt * VV); sh.put(-muQ * Bt * VV); sh.put(muQ * 2.0 * bs); sh.put(0.0); sh.put(muQ * Bt * VV);
+        sh.put(-muQ * A * Vb); sh.put(-muQ * A * Va); sh.put(muQ * A * Vb); sh.put(muQ * A * Va); sh.put(muQ * Bt);
+      } else if constexpr (FORM == PNRARV) {                   // :235-243  T3
+        const int b = side ? P.f[k] : P.t[k];
+        const double gs = st * (side ? P.gt[k] : P.gf[k]), bs = st * (side ? P.bt[k] : P.bf[k]);
+        const double G = st * (side ? P.Gt[k] : P.Gf[k]), B = st * (side ? P.Bt[k] : P.Bf[k]);
+        const double ra = vb0, ia = va0, rb = x[P.o_b + b], ib = x[P.o_a + b];
+        const double A2 = ra * ra + ia * ia, C = ra * rb + ia * ib, S = ra * ib - ia * rb;
+        accP = ((accP - gs * A2) - G * C) + B * S;
+        accQ = ((accQ + bs * A2) + B * C) + G * S;
+        // J: d/d(ra, ia, rb, ib)
+        sj.put(-2.0 * gs * ra - G * rb + B * ib); sj.put(-2.0 * gs * ia - G * ib - B * rb);
+        sj.put(-G * ra - B * ia); sj.put(-G * ia + B * ra);
+        sj.put(2.0 * bs * ra + B * rb + G * ib); sj.put(2.0 * bs * ia + B * ib - G * rb);
+        sj.put(B * ra - G * ia); sj.put(B * ia + G * ra);
+        // H: (ra,ra)(ia,ia)(rb,rb)(ib,ib)(ra,rb)(ia,ib)(ra,ib)(ia,rb)
+        sh.put(muP * -2.0 * gs); sh.put(muP * -2.0 * gs); sh.put(0.0); sh.put(0.0);
+        sh.put(-muP * G); sh.put(-muP * G); sh.put(muP * B); sh.put(-muP * B);
+        sh.put(muQ * 2.0 * bs); sh.put(muQ * 2.0 * bs); sh.put(0.0); sh.put(0.0);
+        sh.put(muQ * B); sh.put(muQ * B); sh.put(muQ * G); sh.put(-muQ * G);
+      }
+    }
+  }
+  // shunt terms :256-279
+  const double Gl = P.Gl[i], Bl = P.Bl[i];
+  const bool facts = (P.flags & FLAG_FACTS) != 0;
+  if constexpr (is_polar(FORM)) {
+    const double V = vb0, V2 = V * V;
+    accP = accP - Gl * V2;
+    accQ = accQ + Bl * V2;
+    sj.put(-2.0 * Gl * V); sj.put(2.0 * Bl * V);
+    sh.put(-2.0 * Gl * muP); sh.put(2.0 * Bl * muQ);
+    if (facts) for (int q = P.sh_ptr[i]; q < P.sh_ptr[i + 1]; q++) {
+      const double bss = x[P.o_bss + P.sh_idx[q]];
+      accQ = accQ + bss * V2;
+      sj.put(V2); sj.put(2.0 * bss * V);
+      sh.put(0.0); sh.put(2.0 * bss * muQ); sh.put(2.0 * V * muQ);
+    }
+  } else if constexpr (FORM == PBRARV || FORM == CBRARV || FORM == PNRARV) {
+    const double r = vb0, im = va0, A2 = r * r + im * im;
+    accP = accP - Gl * A2;
+    accQ = accQ + Bl * A2;
+    sj.put(-2.0 * Gl * r); sj.put(-2.0 * Gl * im); sj.put(2.0 * Bl * r); sj.put(2.0 * Bl * im);
+    sh.put(-2.0 * Gl * muP); sh.put(-2.0 * Gl * muP); sh.put(2.0 * Bl * muQ); sh.put(2.0 * Bl * muQ);
+    if (facts) for (int q = P.sh_ptr[i]; q < P.sh_ptr[i + 1]; q++) {
+      const double bss = x[P.o_bss + P.sh_idx[q]];
+      accQ = accQ + bss * A2;
+      sj.put(A2); sj.put(2.0 * bss * r); sj.put(2.0 * bss * im);
+      sh.put(0.0); sh.put(2.0 * bss * muQ); sh.put(2.0 * bss * muQ);
+      sh.put(2.0 * r * muQ); sh.put(2.0 * im * muQ); sh.put(0.0);
+    }
+  } else if constexpr (FORM == CBRAWV) {
+    const double W = x[P.o_Wd + i];
+    accP = accP - Gl * W;
+    accQ = accQ + Bl * W;
+    sj.put(-Gl); sj.put(Bl);
+    if (facts) for (int q = P.sh_ptr[i]; q < P.sh_ptr[i + 1]; q++) {
+      const double bss = x[P.o_bss + P.sh_idx[q]];
+      accQ = accQ + bss * W;
+      sj.put(W); sj.put(bss);
+      sh.put(0.0); sh.put(0.0); sh.put(muQ);
+    }
+  }
+  o.G(0, accP - Pd[i]);                                        // :291
+  o.G(1, accQ - Qd[i]);                                        // :292
+}
+
+// ------------------------------------------------------------------------------- helpers
+// stream a staged tile to HBM: consecutive threads write consecutive doubles (full 32-byte sectors)
+template <int N, int NP>
+__device__ __forceinline__ void copy_out_padded(double* __restrict__ dst, const double* tile, int n) {
+  for (int e = threadIdx.x; e < n; e += TPB) {
+    const int lu = e / N;                                      // N is a compile-time constant
+    dst[e] = tile[e + lu * (NP - N)];
+  }
+}
+__device__ __forceinline__ void copy_out(double* __restrict__ dst, const double* tile, int n) {
+  for (int e = threadIdx.x; e < n; e += TPB) dst[e] = tile[e];
+}
+
+__device__ __forceinline__ void reduce_scalars(double* scal, double vmax, int nviol) {
+  if (!scal) return;
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) {
+    vmax = fmax(vmax, __shfl_xor_sync(0xffffffffu, vmax, d));
+    nviol += __shfl_xor_sync(0xffffffffu, nviol, d);
+  }
+  if ((threadIdx.x & 31) == 0) {
+    // non-negative doubles order like their bit patterns
+    if (vmax > 0.0) atomicMax((unsigned long long*)(scal + 1), (unsigned long long)__double_as_longlong(vmax));
+    if (nviol) atomicAdd(scal + 2, (double)nviol);             // small integers: exact, order independent
+  }
+}
+
+// objective of formulations.jl:122-138: sum(cg) (obj_type = :linear) or the polynomial cost in pg
+__device__ __forceinline__ void objective_tile(const DevPlan& P, const EvalArgs& A, int s0, int s1, double* red) {
+  for (int s = s0; s < s1; s++) {
+    const double* __restrict__ x = A.x + (long long)s * A.ldx;
+    double acc = 0.0;
+    if (P.flags & FLAG_OBJ_LINEAR) {
+      for (int i = threadIdx.x; i < P.ng; i += TPB) acc += x[P.o_cg + i];
+    } else {
+      for (int i = threadIdx.x; i < P.ng; i += TPB) {
+        const double p = x[P.o_pg + i];
+        double v = P.k0 ? P.k0[i] : 0.0;
+        if (P.cost_order >= 2 && P.k1) v += P.k1[i] * p;
+        if (P.cost_order == 3 && P.k2) v += P.k2[i] * (p * p);
+        acc += v;
+      }
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, d);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double t = 0.0;
+      for (int w = 0; w < TPB / 32; w++) t += red[w];
+      A.scal[(long long)s * NSCAL + 0] = t;
+    }
+    __syncthreads();
+  }
+}
+
+template <int FORM, int SRC>
+__global__ void __launch_bounds__(TPB) eval_kernel(const __grid_constant__ DevPlan P, const __grid_constant__ EvalArgs A) {
+  extern __shared__ double smem[];
+  const Tile tl = P.tiles[blockIdx.x];
+  const int s0 = blockIdx.y * A.chunk, s1 = min(A.S, s0 + A.chunk);
+  const bool wg = (A.what & EV_G) != 0, wj = (A.what & EV_J) != 0, wh = (A.what & EV_H) != 0;
+  const int u = tl.u0 + threadIdx.x;
+  const bool act = u < tl.u1;
+
+  if (tl.kind == 1) {
+    using BR = Branch<FORM, SRC>;
+    double* sG = smem;
+    double* sJ = sG + TPB * BR::NRP;
+    double* sH = sJ + TPB * BR::RJP;
+    typename BR::Out o;
+    o.g = sG + threadIdx.x * BR::NRP; o.j = sJ + threadIdx.x * BR::RJP; o.h = sH + threadIdx.x * BR::RHP;
+    o.wg = wg; o.wj = wj; o.wh = wh; o.tol = A.viol_tol;
+    typename BR::Cst cst{};
+    typename BR::In cur{};
+    int f = 0, t = 1;
+    if (act) {
+      f = P.f[u]; t = P.t[u];
+      cst = BR::load_cst(P, u);
+      cur = BR::load_in(P, A, s0, u, f, t);
+    }
+    o.sw = f > t;
+    for (int s = s0; s < s1; s++) {
+      typename BR::In nxt{};
+      if (act && s + 1 < s1) nxt = BR::load_in(P, A, s + 1, u, f, t);   // prefetch the next scenario's inputs
+      o.vmax = 0.0; o.nviol = 0;
+      if (act) BR::run(o, cst, cur);
+      __syncthreads();
+      if (wg) copy_out_padded<BR::NR, BR::NRP>(A.g + (long long)s * A.ldg + tl.g0, sG, tl.gn);
+      if (wj) copy_out_padded<BR::RJ, BR::RJP>(A.J + (long long)s * A.ldJ + tl.j0, sJ, tl.jn);
+      if (wh) copy_out_padded<BR::RH, BR::RHP>(A.H + (long long)s * A.ldH + tl.h0, sH, tl.hn);
+      reduce_scalars(A.scal ? A.scal + (long long)s * NSCAL : nullptr, o.vmax, o.nviol);
+      __syncthreads();
+      if (s + 1 < s1) cur = nxt;
+    }
+  } else if (tl.kind == 0) {
+    if constexpr (has_bus_rows(FORM)) {
+      double* sG = smem;
+      double* sJ = sG + tl.gn;
+      double* sH = sJ + tl.jn;
+      const int jbase = act ? P.jptr[2 * u] - tl.j0 : 0, hbase = act ? P.hptr[2 * u] - tl.h0 : 0;
+      const int cj0 = act ? P.bus_jpp[u] : 0, ch0 = act ? P.bus_hpp[u] : 0;
+      BusOut o;
+      o.g = sG + 2 * threadIdx.x; o.wg = wg; o.tol = A.viol_tol;
+      for (int s = s0; s < s1; s++) {
+        o.vmax = 0.0; o.nviol = 0;
+        if (act) {
+          Stream sj{sJ + jbase, P.bus_jpos + cj0, wj}, sh{sH + hbase, P.bus_hpos + ch0, wh};
+          bus_rows<FORM>(P, o, sj, sh, u, A.x + (long long)s * A.ldx, wh ? A.mu + (long long)s * A.ldmu : nullptr,
+                         A.Pd ? A.Pd + (long long)s * A.ldl : P.Pd0, A.Qd ? A.Qd + (long long)s * A.ldl : P.Qd0,
+                         A.status ? A.status + (long long)s * A.ldst : nullptr);
+        }
+        __syncthreads();
+        if (wg) copy_out(A.g + (long long)s * A.ldg + tl.g0, sG, tl.gn);
+        if (wj) copy_out(A.J + (long long)s * A.ldJ + tl.j0, sJ, tl.jn);
+        if (wh) copy_out(A.H + (long long)s * A.ldH + tl.h0, sH, tl.hn);
+        reduce_scalars(A.scal ? A.scal + (long long)s * NSCAL : nullptr, o.vmax, o.nviol);
+        __syncthreads();
+      }
+    }
+  } else {
+    if (A.scal) objective_tile(P, A, s0, s1, smem);
+  }
+}
+
+template <int FORM>
+cudaError_t launch_form(const DevPlan& P, const EvalArgs& A, size_t smem, cudaStream_t st, dim3 grid) {
+  if (P.src == SRC_MATPOWER) eval_kernel<FORM, SRC_MATPOWER><<<grid, TPB, smem, st>>>(P, A);
+  else eval_kernel<FORM, SRC_ARPAE><<<grid, TPB, smem, st>>>(P, A);
+  return cudaGetLastError();
+}
+
+template <int FORM>
+cudaError_t configure_form(int src, size_t smem) {
+  if (src == SRC_MATPOWER)
+    return cudaFuncSetAttribute(eval_kernel<FORM, SRC_MATPOWER>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  return cudaFuncSetAttribute(eval_kernel<FORM, SRC_ARPAE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+}
+
+__global__ void __launch_bounds__(256) csc_assemble_kernel(const int32_t* __restrict__ segptr, const int32_t* __restrict__ perm,
+                                                           int nnz, const double* __restrict__ dE, long long ldE,
+                                                           double* __restrict__ nz, long long ldnz) {
+  const int j = blockIdx.x * 256 + threadIdx.x;
+  if (j >= nnz) return;
+  const int q0 = segptr[j], q1 = segptr[j + 1];
+  const long long s = blockIdx.y + (long long)blockIdx.z * gridDim.y;
+  const double* __restrict__ e = dE + s * ldE;
+  double acc = 0.0;                                           // common.jl:16-18: J[r,c] += dE[i], in COO order
+  for (int q = q0; q < q1; q++) acc += e[perm[q]];
+  nz[s * ldnz + j] = acc;
+}
+
+}  // namespace
+
+cudaError_t configure_eval(int form, int src, int64_t smem_doubles) {
+  const size_t smem = (size_t)smem_doubles * sizeof(double);
+  switch (form) {
+    case PBRAPV: return configure_form<PBRAPV>(src, smem);
+    case PBRARV: return configure_form<PBRARV>(src, smem);
+    case PBRAWV: return configure_form<PBRAWV>(src, smem);
+    case CBRARV: return configure_form<CBRARV>(src, smem);
+    case CBRAWV: return configure_form<CBRAWV>(src, smem);
+    case PNPAPV: return configure_form<PNPAPV>(src, smem);
+    case PNRAPV: return configure_form<PNRAPV>(src, smem);
+    case PNRARV: return configure_form<PNRARV>(src, smem);
+    case PNRAWV: return configure_form<PNRAWV>(src, smem);
+  }
+  return cudaErrorInvalidValue;
+}
+
+cudaError_t launch_eval(const DevPlan& P, const EvalArgs& A, int64_t smem_doubles, cudaStream_t stream) {
+  if (A.S <= 0) return cudaSuccess;
+  const size_t smem = (size_t)smem_doubles * sizeof(double);
+  const int nchunks = (A.S + A.chunk - 1) / A.chunk;
+  if (nchunks > 65535) return cudaErrorInvalidConfiguration;
+  const dim3 grid((unsigned)P.ntiles, (unsigned)nchunks);
+  switch (P.form) {
+    case PBRAPV: return launch_form<PBRAPV>(P, A, smem, stream, grid);
+    case PBRARV: return launch_form<PBRARV>(P, A, smem, stream, grid);
+    case PBRAWV: return launch_form<PBRAWV>(P, A, smem, stream, grid);
+    case CBRARV: return launch_form<CBRARV>(P, A, smem, stream, grid);
+    case CBRAWV: return launch_form<CBRAWV>(P, A, smem, stream, grid);
+    case PNPAPV: return launch_form<PNPAPV>(P, A, smem, stream, grid);
+    case PNRAPV: return launch_form<PNRAPV>(P, A, smem, stream, grid);
+    case PNRARV: return launch_form<PNRARV>(P, A, smem, stream, grid);
+    case PNRAWV: return launch_form<PNRAWV>(P, A, smem, stream, grid);
+  }
+  return cudaErrorInvalidValue;
+}
+
+cudaError_t launch_csc_assemble(const int32_t* segptr, const int32_t* perm, int nnz_csc, int64_t S, const double* dE,
+                                long long ldE, double* nz, long long ldnz, cudaStream_t stream) {
+  if (nnz_csc <= 0 || S <= 0) return cudaSuccess;
+  const unsigned gy = (unsigned)(S < 65535 ? S : 65535);
+  const unsigned gz = (unsigned)((S + gy - 1) / gy);
+  if (gz > 65535) return cudaErrorInvalidConfiguration;
+  // a partial last pass would run past S: require S to tile exactly, else launch the remainder separately
+  const int64_t full = (int64_t)gy * (gz - (S % gy ? 1 : 0));
+  if (full > 0) {
+    const dim3 grid((nnz_csc + 255) / 256, gy, (unsigned)(full / gy));
+    csc_assemble_kernel<<<grid, 256, 0, stream>>>(segptr, perm, nnz_csc, dE, ldE, nz, ldnz);
+  }
+  if (full < S) {
+    const dim3 grid((nnz_csc + 255) / 256, (unsigned)(S - full), 1);
+    csc_assemble_kernel<<<grid, 256, 0, stream>>>(segptr, perm, nnz_csc, dE + full * ldE, ldE, nz + full * ldnz, ldnz);
+  }
+  return cudaGetLastError();
+}
+
+}  // namespace ps

@@ -1,0 +1,54 @@
+// Device-side view of a Plan and the launcher interface (ps_kernels.cu).
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdint>
+
+#include "ps_plan.h"
+
+namespace ps {
+
+constexpr int TPB = 128;            // threads per CTA == units (branches / buses) per tile
+constexpr int NSCAL = 4;            // PS_NSCALARS
+
+struct DevPlan {                    // passed to kernels by value (constant bank)
+  int form, src, flags;
+  int nb, nr, ng;
+  int o_a, o_b, o_Wd, o_Wr, o_Wi, o_pg, o_qg, o_f[4], o_cg, o_bss;
+  int bus_rows;
+  int ntiles;
+  int cost_order;
+  const int32_t *f, *t;
+  const double *Gf, *Bf, *Gt, *Bt, *gf, *bf, *gt, *bt, *Imax, *Gl, *Bl, *Pd0, *Qd0;
+  const double *c0, *c1, *c2, *c3;                  // [2*nr] derived per-side constants
+  const double *k0, *k1, *k2;                       // [ng] cost coefficients (may be null)
+  const int32_t *gen_ptr, *gen_idx, *sij_ptr, *sij_idx, *sji_ptr, *sji_idx, *sh_ptr, *sh_idx;
+  const int32_t *jptr, *hptr;
+  const uint16_t *bus_jpos, *bus_hpos;
+  const int32_t *bus_jpp, *bus_hpp;
+  const Tile* tiles;
+};
+
+struct EvalArgs {
+  int what, S, chunk;
+  const double* x;  long long ldx;
+  const double* mu; long long ldmu;
+  const double* Pd; const double* Qd; long long ldl;   // per-scenario loads (nullptr -> network loads)
+  const uint8_t* status; long long ldst;               // per-scenario branch status (nullptr -> all in service)
+  double* g; long long ldg;
+  double* J; long long ldJ;
+  double* H; long long ldH;
+  double* scal;                                        // [S][NSCAL] (nullptr -> skip); must be zeroed
+  double viol_tol;
+};
+
+// launches the fused g/J/H kernel for all tiles x scenarios on `stream`
+cudaError_t launch_eval(const DevPlan& P, const EvalArgs& A, int64_t smem_doubles, cudaStream_t stream);
+// opt the kernels of one formulation into the needed dynamic shared memory (once per device)
+cudaError_t configure_eval(int form, int src, int64_t smem_doubles);
+
+// COO -> CSC assembly (replaces src/opt/algorithms/common.jl:12-20): nz[j] = sum_{q in seg j} dE[perm[q]]
+cudaError_t launch_csc_assemble(const int32_t* segptr, const int32_t* perm, int nnz_csc, int64_t S,
+                                const double* dE, long long ldE, double* nz, long long ldnz, cudaStream_t stream);
+
+}  // namespace ps

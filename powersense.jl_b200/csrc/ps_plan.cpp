@@ -1,0 +1,340 @@
+// Plan builder (host, C++): see ps_plan.h.  Everything here is structure only -- no values.
+#include "ps_plan.h"
+
+#include <algorithm>
+#include <cmath>
+#include <utility>
+
+namespace ps {
+namespace {
+
+typedef std::pair<int64_t, int64_t> pr;
+
+struct RowAcc {                       // contributions of one row in emission order
+  std::vector<int64_t> jv;
+  std::vector<pr> hp;                 // (max,min)
+  void J(int64_t v) { jv.push_back(v); }
+  void H(int64_t a, int64_t b) { hp.push_back(a >= b ? pr(a, b) : pr(b, a)); }
+  void clear() { jv.clear(); hp.clear(); }
+};
+
+struct RowCanon {                     // canonical layout of one row
+  std::vector<int64_t> cols;          // sorted unique (C.2)
+  std::vector<int64_t> verts;         // sorted unique Hessian vertices -> diagonal slots (C.3)
+  std::vector<pr> off;                // sorted unique off-diagonal (max,min)
+  std::vector<int32_t> jslot, hslot;  // per contribution
+};
+
+void canon(const RowAcc& a, RowCanon& c) {
+  c.cols = a.jv;
+  std::sort(c.cols.begin(), c.cols.end());
+  c.cols.erase(std::unique(c.cols.begin(), c.cols.end()), c.cols.end());
+  c.jslot.resize(a.jv.size());
+  for (size_t q = 0; q < a.jv.size(); q++)
+    c.jslot[q] = (int32_t)(std::lower_bound(c.cols.begin(), c.cols.end(), a.jv[q]) - c.cols.begin());
+  c.verts.clear();
+  c.off.clear();
+  for (const pr& p : a.hp) {
+    c.verts.push_back(p.first);
+    c.verts.push_back(p.second);
+    if (p.first != p.second) c.off.push_back(p);
+  }
+  std::sort(c.verts.begin(), c.verts.end());
+  c.verts.erase(std::unique(c.verts.begin(), c.verts.end()), c.verts.end());
+  std::sort(c.off.begin(), c.off.end());
+  c.off.erase(std::unique(c.off.begin(), c.off.end()), c.off.end());
+  c.hslot.resize(a.hp.size());
+  for (size_t q = 0; q < a.hp.size(); q++) {
+    const pr& p = a.hp[q];
+    if (p.first == p.second)
+      c.hslot[q] = (int32_t)(std::lower_bound(c.verts.begin(), c.verts.end(), p.first) - c.verts.begin());
+    else
+      c.hslot[q] = (int32_t)(c.verts.size() + (std::lower_bound(c.off.begin(), c.off.end(), p) - c.off.begin()));
+  }
+}
+
+void append_row(Plan& P, int64_t row, const RowCanon& c, bool eq) {
+  P.jptr.push_back((int32_t)P.jrow.size());
+  P.hptr.push_back((int32_t)P.hrow.size());
+  for (int64_t v : c.cols) { P.jrow.push_back(row + 1); P.jcol.push_back(v + 1); }
+  for (int64_t v : c.verts) { P.hrow.push_back(v + 1); P.hcol.push_back(v + 1); }
+  for (const pr& p : c.off) { P.hrow.push_back(p.first + 1); P.hcol.push_back(p.second + 1); }
+  P.lo.push_back(eq ? 0.0 : -INFINITY);
+  P.hi.push_back(0.0);
+}
+
+}  // namespace
+
+std::string build_plan(const HostNet& net, int form, int src, int flags, int tpb, Plan& P) {
+  if (form < 0 || form >= NFORM) return "unknown formulation code";
+  if (src != SRC_MATPOWER && src != SRC_ARPAE) return "unknown source_type code";
+  P = Plan();
+  P.form = form; P.src = src; P.flags = flags; P.net = net;
+  const int64_t nb = net.nbus, nr = net.nbr, ng = net.ngen;
+  for (int64_t k = 0; k < nr; k++) {
+    if (net.f[k] < 0 || net.f[k] >= nb || net.t[k] < 0 || net.t[k] >= nb) return "branch endpoint out of range";
+    if (net.f[k] == net.t[k]) return "self-loop branch (f == t) is not supported";
+  }
+  // ---- variable order (formulations.jl:20-67, :121)
+  int64_t o = 0;
+  P.o_a = o; o += nb; P.o_b = o; o += nb;
+  if (has_W(form)) { P.o_Wd = o; o += nb; }
+  if (has_WrWi(form)) { P.o_Wr = o; o += nr; P.o_Wi = o; o += nr; }
+  P.o_pg = o; o += ng; P.o_qg = o; o += ng;
+  if (is_PB(form) || is_CB(form)) for (int q = 0; q < 4; q++) { P.o_f[q] = o; o += nr; }
+  if (flags & FLAG_OBJ_LINEAR) { P.o_cg = o; o += ng; }
+  if (flags & FLAG_FACTS) { P.o_bss = o; o += net.nbss; }
+  if (flags & FLAG_OBJ_LINEAR) { P.o_tgh = o; o += net.n_tgh; }
+  P.n_var = o;
+  const bool facts = (flags & FLAG_FACTS) != 0;
+  const bool polar = is_polar(form);
+
+  // ---- bus rows (formulations.jl:170-297): emission order == the bus kernel's order
+  int64_t row = 0;
+  P.bus_jpp.assign(1, 0);
+  P.bus_hpp.assign(1, 0);
+  if (has_bus_rows(form)) {
+    RowAcc acc[2];
+    RowCanon can[2];
+    std::vector<std::pair<int, int>> sj, sh;     // streams: (row 0/1, contribution index)
+    for (int64_t i = 0; i < nb; i++) {
+      acc[0].clear(); acc[1].clear(); sj.clear(); sh.clear();
+      auto J = [&](int r, int64_t v) { sj.push_back({r, (int)acc[r].jv.size()}); acc[r].J(v); };
+      auto H = [&](int r, int64_t a, int64_t b) { sh.push_back({r, (int)acc[r].hp.size()}); acc[r].H(a, b); };
+      for (int32_t q = net.gen_ptr[i]; q < net.gen_ptr[i + 1]; q++) {              // :177-180
+        J(0, P.o_pg + net.gen_idx[q]);
+        J(1, P.o_qg + net.gen_idx[q]);
+      }
+      for (int side = 0; side < 2; side++) {
+        const std::vector<int32_t>& ptr = side ? net.sji_ptr : net.sij_ptr;
+        const std::vector<int32_t>& idx = side ? net.sji_idx : net.sij_idx;
+        for (int32_t q = ptr[i]; q < ptr[i + 1]; q++) {
+          const int64_t k = idx[q];
+          const int64_t a = side ? net.t[k] : net.f[k], b = side ? net.f[k] : net.t[k];
+          if (a != i) return "adjacency list inconsistent with branch endpoints";
+          if (form == PBRAPV || form == PBRARV) {                                  // :188-196
+            J(0, P.o_f[0 + 2 * side] + k);
+            J(1, P.o_f[1 + 2 * side] + k);
+          } else if (is_CB(form)) {                                                // :206-214
+            const int64_t ra = P.o_b + a, ia = P.o_a + a, Ir = P.o_f[0 + 2 * side] + k, Ii = P.o_f[1 + 2 * side] + k;
+            for (int r = 0; r < 2; r++) { J(r, ra); J(r, ia); J(r, Ir); J(r, Ii); }
+            H(0, ra, ra); H(0, Ir, Ir); H(0, ra, Ir); H(0, ia, ia); H(0, Ii, Ii); H(0, ia, Ii);
+            H(1, ia, ia); H(1, Ir, Ir); H(1, ia, Ir); H(1, ra, ra); H(1, Ii, Ii); H(1, ra, Ii);
+          } else if (form == PNPAPV || form == PNRAPV) {                           // :215-234
+            const int64_t v[4] = {P.o_a + a, P.o_a + b, P.o_b + a, P.o_b + b};
+            for (int r = 0; r < 2; r++) for (int q4 = 0; q4 < 4; q4++) J(r, v[q4]);
+            for (int r = 0; r < 2; r++) {
+              for (int q4 = 0; q4 < 4; q4++) H(r, v[q4], v[q4]);
+              for (int x = 0; x < 4; x++) for (int y = x + 1; y < 4; y++) H(r, v[x], v[y]);
+            }
+          } else if (form == PNRARV) {                                             // :235-243
+            const int64_t ra = P.o_b + a, ia = P.o_a + a, rb = P.o_b + b, ib = P.o_a + b;
+            for (int r = 0; r < 2; r++) { J(r, ra); J(r, ia); J(r, rb); J(r, ib); }
+            for (int r = 0; r < 2; r++) {
+              H(r, ra, ra); H(r, ia, ia); H(r, rb, rb); H(r, ib, ib);
+              H(r, ra, rb); H(r, ia, ib); H(r, ra, ib); H(r, ia, rb);
+            }
+          }
+        }
+      }
+      // shunt terms :256-279 (always emitted, even when Gl = Bl = 0)
+      if (polar) {
+        const int64_t Vi = P.o_b + i;
+        J(0, Vi); J(1, Vi); H(0, Vi, Vi); H(1, Vi, Vi);
+      } else if (form == PBRARV || form == CBRARV || form == PNRARV) {
+        const int64_t r_ = P.o_b + i, i_ = P.o_a + i;
+        for (int r = 0; r < 2; r++) { J(r, r_); J(r, i_); }
+        for (int r = 0; r < 2; r++) { H(r, r_, r_); H(r, i_, i_); }
+      } else if (form == CBRAWV) {
+        J(0, P.o_Wd + i); J(1, P.o_Wd + i);
+      }
+      if (facts) for (int32_t q = net.sh_ptr[i]; q < net.sh_ptr[i + 1]; q++) {     // :259-263,:267-271,:275-279
+        const int64_t bs = P.o_bss + net.sh_idx[q];
+        if (polar) {
+          const int64_t Vi = P.o_b + i;
+          J(1, bs); J(1, Vi); H(1, bs, bs); H(1, Vi, Vi); H(1, bs, Vi);
+        } else if (form == CBRAWV) {
+          const int64_t W = P.o_Wd + i;
+          J(1, bs); J(1, W); H(1, bs, bs); H(1, W, W); H(1, bs, W);
+        } else {
+          const int64_t r_ = P.o_b + i, i_ = P.o_a + i;
+          J(1, bs); J(1, r_); J(1, i_);
+          H(1, bs, bs); H(1, r_, r_); H(1, i_, i_); H(1, bs, r_); H(1, bs, i_); H(1, r_, i_);
+        }
+      }
+      canon(acc[0], can[0]);
+      canon(acc[1], can[1]);
+      const int64_t lenJ0 = (int64_t)can[0].cols.size(), lenH0 = (int64_t)(can[0].verts.size() + can[0].off.size());
+      const int64_t lenJ = lenJ0 + (int64_t)can[1].cols.size();
+      const int64_t lenH = lenH0 + (int64_t)(can[1].verts.size() + can[1].off.size());
+      if (lenJ >= 32768 || lenH >= 32768) return "bus degree too large for 15-bit slot positions";
+      std::vector<char> seenJ(lenJ, 0), seenH(lenH, 0);
+      for (auto& e : sj) {
+        int64_t p = (e.first ? lenJ0 : 0) + can[e.first].jslot[e.second];
+        P.bus_jpos.push_back((uint16_t)(p | (seenJ[p] ? 0x8000 : 0)));
+        seenJ[p] = 1;
+      }
+      for (auto& e : sh) {
+        int64_t p = (e.first ? lenH0 : 0) + can[e.first].hslot[e.second];
+        P.bus_hpos.push_back((uint16_t)(p | (seenH[p] ? 0x8000 : 0)));
+        seenH[p] = 1;
+      }
+      for (int64_t p = 0; p < lenH; p++) if (!seenH[p]) return "internal: Hessian slot without contribution";
+      P.bus_jpp.push_back((int32_t)P.bus_jpos.size());
+      P.bus_hpp.push_back((int32_t)P.bus_hpos.size());
+      append_row(P, row++, can[0], true);                                          // :291
+      append_row(P, row++, can[1], true);                                          // :292
+    }
+  } else {
+    P.bus_jpp.assign(nb + 1, 0);
+    P.bus_hpp.assign(nb + 1, 0);
+  }
+  P.bus_rows = row;
+
+  // ---- branch rows (formulations.jl:299-428)
+  const BranchPat pat = branch_pattern(form, src);
+  P.rows_per_branch = pat.nrows;
+  bool have_tab[2] = {false, false};
+  {
+    RowAcc acc;
+    RowCanon can;
+    for (int64_t k = 0; k < nr; k++) {
+      const int64_t f = net.f[k], t = net.t[k];
+      const int swap = f > t;
+      auto var = [&](int8_t role) -> int64_t {
+        switch (role) {
+          case R_AF: return P.o_a + f;
+          case R_AT: return P.o_a + t;
+          case R_BF: return P.o_b + f;
+          case R_BT: return P.o_b + t;
+          case R_WDF: return P.o_Wd + f;
+          case R_WDT: return P.o_Wd + t;
+          case R_WR: return P.o_Wr + k;
+          case R_WI: return P.o_Wi + k;
+          default: return P.o_f[role - R_F0] + k;
+        }
+      };
+      uint8_t jp[MAX_BR_JTAGS] = {}, hp[MAX_BR_HTAGS] = {};
+      int jbase = 0, hbase = 0, jt = 0, ht = 0;
+      for (int r = 0; r < pat.nrows; r++) {
+        const RowPat& rp = pat.rows[r];
+        acc.clear();
+        for (int q = 0; q < rp.nj; q++) acc.J(var(rp.j[q]));
+        for (int q = 0; q < rp.nh; q++) acc.H(var(rp.h[q][0]), var(rp.h[q][1]));
+        canon(acc, can);
+        if ((int)can.cols.size() != rp.nj) return "internal: duplicate Jacobian tag in a branch row";
+        if ((int)(can.verts.size() + can.off.size()) != rp.nh) return "internal: duplicate Hessian tag in a branch row";
+        for (int q = 0; q < rp.nj; q++) jp[jt++] = (uint8_t)(jbase + can.jslot[q]);
+        for (int q = 0; q < rp.nh; q++) hp[ht++] = (uint8_t)(hbase + can.hslot[q]);
+        jbase += rp.nj;
+        hbase += rp.nh;
+        append_row(P, row++, can, rp.eq != 0);
+      }
+      P.RJ = jbase; P.RH = hbase;
+      if (!have_tab[swap]) {
+        std::copy(jp, jp + MAX_BR_JTAGS, P.br_jpos[swap]);
+        std::copy(hp, hp + MAX_BR_HTAGS, P.br_hpos[swap]);
+        have_tab[swap] = true;
+      } else if (!std::equal(jp, jp + jt, P.br_jpos[swap]) || !std::equal(hp, hp + ht, P.br_hpos[swap])) {
+        return "internal: branch slot pattern is not uniform";
+      }
+    }
+    if (nr == 0) { P.RJ = pat.nj(); P.RH = pat.nh(); }
+    // the kernels use the compile-time tables of branch_slots(); they must agree with the ones
+    // derived above from the real variable indices
+    const BranchSlots sl = branch_slots(form, src);
+    if (sl.nj != P.RJ || sl.nh != P.RH || sl.nrows != pat.nrows) return "internal: branch_slots size mismatch";
+    for (int sw = 0; sw < 2; sw++) {
+      if (!have_tab[sw]) {
+        std::copy(sl.jpos[sw], sl.jpos[sw] + MAX_BR_JTAGS, P.br_jpos[sw]);
+        std::copy(sl.hpos[sw], sl.hpos[sw] + MAX_BR_HTAGS, P.br_hpos[sw]);
+      } else if (!std::equal(sl.jpos[sw], sl.jpos[sw] + P.RJ, P.br_jpos[sw]) ||
+                 !std::equal(sl.hpos[sw], sl.hpos[sw] + P.RH, P.br_hpos[sw])) {
+        return "internal: compile-time branch slot table disagrees with the variable order";
+      }
+    }
+  }
+  P.m_nl = row;
+  P.jptr.push_back((int32_t)P.jrow.size());
+  P.hptr.push_back((int32_t)P.hrow.size());
+  P.nnzJ = (int64_t)P.jrow.size();
+  P.nnzH = (int64_t)P.hrow.size();
+  if (P.nnzJ >= (int64_t(1) << 31) || P.nnzH >= (int64_t(1) << 31)) return "structure too large for 32-bit slot offsets";
+  {
+    std::vector<int64_t> u(P.jcol);
+    std::sort(u.begin(), u.end());
+    P.nx_nl = (int64_t)(std::unique(u.begin(), u.end()) - u.begin());
+  }
+
+  // ---- derived per-side constants (host-precomputed like formulations.jl:217,222,338-350)
+  P.c0.assign(2 * nr, 0.0); P.c1.assign(2 * nr, 0.0); P.c2.assign(2 * nr, 0.0); P.c3.assign(2 * nr, 0.0);
+  for (int side = 0; side < 2; side++)
+    for (int64_t k = 0; k < nr; k++) {
+      const double gs = side ? net.gt[k] : net.gf[k], bs = side ? net.bt[k] : net.bf[k];
+      const double G = side ? net.Gt[k] : net.Gf[k], B = side ? net.Bt[k] : net.Bf[k];
+      const int64_t q = side * nr + k;
+      if (form == PNPAPV || form == PNRAPV) {
+        // T2 (:217,:222): |G+jB|, angle(G+jB) in c0,c1 ; L4 (:338-342): y3 in c2, th1-th2 pieces in c3 (th1), c1 (th2)
+        P.c0[q] = std::hypot(G, B);
+        P.c1[q] = std::atan2(B, G);
+        P.c2[q] = 2.0 * std::hypot(gs, bs) * std::hypot(G, B);
+        P.c3[q] = std::atan2(bs, gs);
+      } else if (form == PNRARV) {
+        // L5 (:345-346,:349-350): y, Y, y1, y2
+        P.c0[q] = gs * gs + bs * bs;
+        P.c1[q] = G * G + B * B;
+        P.c2[q] = 2.0 * (gs * G + bs * B);
+        P.c3[q] = 2.0 * (bs * G - gs * B);
+      }
+    }
+
+  // ---- tiles
+  P.tile_units_br = tpb;
+  // bus tiles: greedy, at most tpb buses and at most `budget` staged doubles per tile
+  const int64_t budget = 8800, hard = 27000;     // doubles of staged output per CTA (~70 KB / 216 KB)
+  int64_t mx = 0;
+  P.tiles.clear();
+  if (has_bus_rows(form)) {
+    int64_t u0 = 0;
+    while (u0 < nb) {
+      int64_t u1 = u0, tot = 0;
+      while (u1 < nb && u1 - u0 < tpb) {
+        const int64_t need = 2 + (P.jptr[2 * u1 + 2] - P.jptr[2 * u1]) + (P.hptr[2 * u1 + 2] - P.hptr[2 * u1]);
+        if (need > hard) return "a bus does not fit in shared memory (bus degree too large)";
+        if (u1 > u0 && tot + need > budget) break;
+        tot += need;
+        u1++;
+      }
+      Tile t{};
+      t.kind = 0; t.u0 = (int32_t)u0; t.u1 = (int32_t)u1;
+      t.g0 = (int32_t)(2 * u0); t.gn = (int32_t)(2 * (u1 - u0));
+      t.j0 = P.jptr[2 * u0]; t.jn = P.jptr[2 * u1] - t.j0;
+      t.h0 = P.hptr[2 * u0]; t.hn = P.hptr[2 * u1] - t.h0;
+      mx = std::max<int64_t>(mx, (int64_t)t.gn + t.jn + t.hn);
+      P.tiles.push_back(t);
+      u0 = u1;
+    }
+  }
+  P.tile_units_bus = tpb;
+  P.n_bus_tiles = (int)P.tiles.size();
+  P.NRP = pat.nrows | 1; P.RJP = P.RJ | 1; P.RHP = P.RH | 1;
+  int64_t mxb = nr > 0 ? (int64_t)tpb * (P.NRP + P.RJP + P.RHP) : 0;
+  for (int64_t u0 = 0; u0 < nr; u0 += tpb) {
+    const int64_t u1 = std::min<int64_t>(nr, u0 + tpb);
+    Tile t;
+    t.kind = 1; t.u0 = (int32_t)u0; t.u1 = (int32_t)u1;
+    t.g0 = (int32_t)(P.bus_rows + u0 * pat.nrows); t.gn = (int32_t)((u1 - u0) * pat.nrows);
+    t.j0 = P.jptr[P.bus_rows] + (int32_t)(u0 * P.RJ); t.jn = (int32_t)((u1 - u0) * P.RJ);
+    t.h0 = P.hptr[P.bus_rows] + (int32_t)(u0 * P.RH); t.hn = (int32_t)((u1 - u0) * P.RH);
+    P.tiles.push_back(t);
+  }
+  {
+    Tile t{};                                      // objective scalar (formulations.jl:122-138)
+    t.kind = 2; t.u0 = 0; t.u1 = (int32_t)ng;
+    P.tiles.push_back(t);
+  }
+  P.smem_doubles = std::max<int64_t>(std::max(mx, mxb), 64);
+  return "";
+}
+
+}  // namespace ps

@@ -1,0 +1,60 @@
+// Host-side plan: variable layout, NL row order, JuMP-compatible Jacobian / Hessian structure and
+// the slot tables the kernels consume.  Built once per (network, formulation, source, flags).
+// Restates what JuMP derives from the @NL* calls of src/opf/formulations.jl:170-428
+// (structure rules: SURVEY.md Appendix C.2 / C.3).
+#pragma once
+#include <cstdint>
+#include <string>
+#include <vector>
+
+#include "ps_patterns.h"
+
+namespace ps {
+
+struct HostNet {             // deep copy of ps_network (include/powersense_b200.h)
+  int64_t nbus = 0, nbr = 0, ngen = 0, nbss = 0;
+  std::vector<int32_t> f, t;                 // 0-based
+  std::vector<double> Gf, Bf, Gt, Bt, gf, bf, gt, bt, Imax, Pd, Qd, Gl, Bl;
+  std::vector<int32_t> gen_ptr, gen_idx, sij_ptr, sij_idx, sji_ptr, sji_idx, sh_ptr, sh_idx;  // 0-based ids
+  int64_t n_tgh = 0;
+  std::vector<double> c0, c1, c2;            // objective (formulations.jl:128-138); may be empty
+  int cost_order = 0;
+};
+
+struct Tile {                // one CTA work item: a contiguous range of buses or branches
+  int32_t kind;              // 0 = bus rows, 1 = branch rows, 2 = objective scalar
+  int32_t u0, u1;            // unit range
+  int32_t g0, gn, j0, jn, h0, hn;  // output slot ranges (per scenario)
+};
+
+struct Plan {
+  int form = 0, src = 0, flags = 0;
+  HostNet net;
+  int64_t n_var = 0, m_nl = 0, nnzJ = 0, nnzH = 0;
+  // 0-based variable offsets; -1 when the block does not exist (formulations.jl:20-67, :121)
+  int64_t o_a = 0, o_b = 0, o_Wd = -1, o_Wr = -1, o_Wi = -1, o_pg = 0, o_qg = 0, o_f[4] = {-1, -1, -1, -1},
+          o_cg = -1, o_bss = -1, o_tgh = -1;
+  int64_t bus_rows = 0;      // 2*nbus or 0
+  int rows_per_branch = 0, RJ = 0, RH = 0;          // per-branch block sizes
+  std::vector<int64_t> jrow, jcol, hrow, hcol;      // 1-based structure (MOI tuples)
+  std::vector<int32_t> jptr, hptr;                  // row -> first slot
+  std::vector<double> lo, hi;                       // NLPBoundsPair per row
+  // branch position tables: [swap][tag] -> slot inside the branch's block (swap = f > t)
+  uint8_t br_jpos[2][MAX_BR_JTAGS] = {}, br_hpos[2][MAX_BR_HTAGS] = {};
+  // bus position streams (emission order of the bus kernel); bit 15 = accumulate into the slot
+  std::vector<uint16_t> bus_jpos, bus_hpos;
+  std::vector<int32_t> bus_jpp, bus_hpp;            // per-bus start in the streams (size nbus+1)
+  // derived per-side constants (side 0 = from, 1 = to), each [2*nbr]
+  std::vector<double> c0, c1, c2, c3;
+  std::vector<Tile> tiles;
+  int n_bus_tiles = 0;
+  int tile_units_bus = 0, tile_units_br = 0;
+  int64_t smem_doubles = 0;                         // max over tiles of staged outputs (padded)
+  int NRP = 0, RJP = 0, RHP = 0;                    // per-thread staging strides of a branch tile (odd)
+  int64_t nx_nl = 0;                                // variables the NL rows touch (roofline accounting)
+};
+
+// returns "" on success, else an error message
+std::string build_plan(const HostNet& net, int form, int src, int flags, int tpb, Plan& out);
+
+}  // namespace ps

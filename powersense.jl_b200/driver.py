@@ -1,0 +1,104 @@
+"""Batched scenario driver: S scenarios of one network, sharded across the ranks of one box.
+
+The reference has no scenario batching (one PowersenseData = one network + one load vector, one solve at a
+time: src/opf/formulations.jl:584-653).  Scenarios are independent units, so each rank (one process per GPU)
+owns a contiguous block and evaluates it with ps_batch_eval; there is no data-path collective.  The only
+exchange is the gather of the per-scenario scalars (objective, max NL violation, violated-row count) over
+NCCL (NVLink 5 / NVSwitch) -- `gather_scalars`.  torch is used for device memory, streams and
+torch.distributed only."""
+from __future__ import annotations
+
+from typing import Optional, Tuple
+
+import numpy as np
+
+from . import capi
+from .types import ACOPF_fromulation, EVAL_G, EVAL_H, EVAL_J
+
+
+def shard_range(S_total: int, world_size: int, rank: int) -> Tuple[int, int]:
+    """Contiguous block [begin, begin + count) of scenarios owned by `rank` (blocks differ by at most one)."""
+    if not (0 <= rank < world_size):
+        raise ValueError("rank out of range")
+    base, rem = divmod(int(S_total), int(world_size))
+    begin = rank * base + min(rank, rem)
+    return begin, base + (1 if rank < rem else 0)
+
+
+def contingency_status(nbr: int, s_begin: int, s_count: int) -> np.ndarray:
+    """N-1 branch sweep (BASELINE config 5): global scenario s opens branch s mod nbr."""
+    st = np.ones((s_count, nbr), dtype=np.uint8)
+    k = (np.arange(s_begin, s_begin + s_count) % nbr)
+    st[np.arange(s_count), k] = 0
+    return st
+
+
+class ScenarioDriver:
+    """Owns one rank's shard: the model handle, the batch and the device buffers (row-major [S_local, ld])."""
+
+    def __init__(self, data, formulation: ACOPF_fromulation, S_total: int, rank: int = 0, world_size: int = 1,
+                 device_index: Optional[int] = None, facts_bshunt: bool = True, obj_linear: bool = True,
+                 what: int = EVAL_G | EVAL_J | EVAL_H):
+        import torch
+        self.torch = torch
+        self.rank, self.world_size = rank, world_size
+        self.S_total = int(S_total)
+        self.s_begin, self.S = shard_range(S_total, world_size, rank)
+        self.device_index = rank if device_index is None else device_index
+        self.device = torch.device("cuda", self.device_index)
+        torch.cuda.set_device(self.device)
+        self.handle = capi.Handle(data, formulation.code, facts_bshunt, obj_linear, device=self.device_index)
+        self.batch = capi.Batch(self.handle, max(self.S, 1))
+        self.what = what
+        h = self.handle
+        f64 = torch.float64
+        n = max(self.S, 1)
+        self.x = torch.zeros(n, h.n_var, dtype=f64, device=self.device)
+        self.mu = torch.zeros(n, h.m_nl, dtype=f64, device=self.device) if what & EVAL_H else None
+        self.g = torch.empty(n, h.m_nl, dtype=f64, device=self.device) if what & EVAL_G else None
+        self.J = torch.empty(n, h.nnzJ, dtype=f64, device=self.device) if what & EVAL_J else None
+        self.H = torch.empty(n, h.nnzH, dtype=f64, device=self.device) if what & EVAL_H else None
+        self.scalars = torch.zeros(n, capi.PS_NSCALARS, dtype=f64, device=self.device)
+
+    def set_loads(self, Pd: np.ndarray, Qd: np.ndarray):
+        self.batch.set_loads(Pd, Qd)
+
+    def set_branch_status(self, st):
+        self.batch.set_branch_status(st)
+
+    def evaluate(self, what: Optional[int] = None):
+        """One pass of the hot path over this rank's shard (asynchronous on torch's current stream)."""
+        if self.S == 0:
+            return
+        self.batch.eval_torch(self.what if what is None else what, self.x, self.mu, self.g, self.J, self.H, self.scalars)
+
+    def gather_scalars(self):
+        """[S_total, PS_NSCALARS] on every rank.  NCCL all_gather over NVLink when world_size > 1; shards may
+        differ by one scenario, so the gather is padded to the largest shard."""
+        torch = self.torch
+        if self.world_size == 1:
+            return self.scalars[:self.S]
+        import torch.distributed as dist
+        smax = -(-self.S_total // self.world_size)
+        pad = torch.zeros(smax, capi.PS_NSCALARS, dtype=torch.float64, device=self.scalars.device)
+        pad[:self.S] = self.scalars[:self.S]
+        out = torch.empty(self.world_size * smax, capi.PS_NSCALARS, dtype=torch.float64, device=self.scalars.device)
+        dist.all_gather_into_tensor(out, pad)
+        return gather_unpad(out, self.S_total, self.world_size)
+
+    def close(self):
+        self.batch.close()
+        self.handle.close()
+
+
+def gather_unpad(padded, S_total: int, world_size: int):
+    """Drop the per-rank padding of an all_gather of ceil(S/world) rows per rank (works on torch or numpy)."""
+    smax = -(-S_total // world_size)
+    parts = []
+    for r in range(world_size):
+        _, cnt = shard_range(S_total, world_size, r)
+        parts.append(padded[r * smax:r * smax + cnt])
+    if hasattr(padded, "new_empty"):
+        import torch
+        return torch.cat(parts, dim=0)
+    return np.concatenate(parts, axis=0)

@@ -1,0 +1,280 @@
+"""GPU parity tests (run with -m gpu on a B200): the CUDA path, called through the C ABI
+(include/powersense_b200.h via powersense.jl_b200/capi.py), against the CPU oracle and the committed
+golden vectors.  Tolerance is BASELINE.json's: values within 1e-12 relative / 1e-10 absolute in FP64;
+sparsity structures and index arrays bit-exact."""
+import numpy as np
+import pytest
+
+import powersense_b200 as ps
+from powersense_b200 import capi, synth
+from oracle import c_oracle
+
+from cases import FIXTURE_CASES, load_fixture, load_golden, synthetic, tol_err
+
+pytestmark = pytest.mark.gpu
+
+FORMS = ps.ALL_FORMULATIONS
+
+
+def _torch():
+    import torch
+    assert torch.cuda.is_available(), "the gpu tests need a GPU"
+    return torch
+
+
+def _case(name):
+    return load_fixture(name) if name in FIXTURE_CASES else synthetic(name)
+
+
+def _batch_eval(h, x, mu, Pd=None, Qd=None, status=None, what=7, scal=True):
+    torch = _torch()
+    dev = torch.device("cuda:0")
+    S = x.shape[0]
+    b = capi.Batch(h, S)
+    if Pd is not None:
+        b.set_loads(Pd, Qd)
+    if status is not None:
+        b.set_branch_status(status)
+    tx, tmu = torch.from_numpy(x).to(dev), torch.from_numpy(mu).to(dev)
+    g = torch.full((S, h.m_nl), np.nan, dtype=torch.float64, device=dev)
+    J = torch.full((S, h.nnzJ), np.nan, dtype=torch.float64, device=dev)
+    H = torch.full((S, h.nnzH), np.nan, dtype=torch.float64, device=dev)
+    sc = torch.full((S, capi.PS_NSCALARS), np.nan, dtype=torch.float64, device=dev) if scal else None
+    b.eval_torch(what, tx, tmu, g, J, H, sc)
+    torch.cuda.synchronize()
+    b.close()
+    return g.cpu().numpy(), J.cpu().numpy(), H.cpu().numpy(), (sc.cpu().numpy() if scal else None)
+
+
+@pytest.mark.parametrize("F", FORMS, ids=lambda f: f.name)
+@pytest.mark.parametrize("case", FIXTURE_CASES)
+def test_golden_vectors_single_scenario(case, F):
+    """The MOI-style host-pointer callbacks against the committed golden vectors (jump_oracle)."""
+    d = load_fixture(case)
+    z = load_golden(case, F)
+    h = capi.Handle(d, F.code, device=0)
+    assert h.n_var == int(z["n_var"])
+    jr, jc = h.jacobian_structure()
+    hr, hc = h.hessian_structure()
+    assert np.array_equal(jr, z["jrow"]) and np.array_equal(jc, z["jcol"])
+    assert np.array_equal(hr, z["hrow"]) and np.array_equal(hc, z["hcol"])
+    lo, hi = h.constraint_bounds()
+    assert np.array_equal(lo, z["lo"]) and np.array_equal(hi, z["hi"])
+    g = h.eval_constraint(z["x"])
+    J = h.eval_jacobian(z["x"])
+    H = h.eval_hessian(z["x"], 1.0, z["mu"])
+    assert tol_err(g, z["g"]) <= 1.0
+    assert tol_err(J, z["J"]) <= 1.0
+    assert tol_err(H, z["H"]) <= 1.0
+    g2, J2, H2 = h.eval_all(z["x"], z["mu"])
+    assert np.array_equal(g, g2) and np.array_equal(J, J2) and np.array_equal(H, H2)
+    h.close()
+
+
+@pytest.mark.parametrize("F", FORMS, ids=lambda f: f.name)
+@pytest.mark.parametrize("case", ["case14", "case300", "case118", "arpae30", "mp40_out", "hub"])
+def test_batch_vs_oracle(case, F):
+    d = _case(case)
+    S = 5
+    x, Pd, Qd, _ = synth.scenario_batch(d, F, S, seed=7)
+    h = capi.Handle(d, F.code, device=0)
+    mu = np.random.default_rng(3).normal(size=(S, h.m_nl))
+    g, J, H, sc = _batch_eval(h, x, mu, Pd, Qd)
+    o = c_oracle.COracle(d, F.code)
+    og, oJ, oH = o.eval_batch(x, mu, Pd, Qd)
+    assert not np.isnan(g).any() and not np.isnan(J).any() and not np.isnan(H).any()
+    assert tol_err(g, og) <= 1.0
+    assert tol_err(J, oJ) <= 1.0
+    assert tol_err(H, oH) <= 1.0
+    # scalars: max violation of the NL rows (common.jl:76-98 with p = Inf) and count above tolerance
+    lo, hi = o.bounds()
+    viol = np.maximum(np.maximum(og - hi, lo - og), 0.0)
+    assert tol_err(sc[:, 1], viol.max(axis=1)) <= 1.0
+    safe = np.abs(viol - 1e-6) > 1e-9
+    assert np.array_equal(sc[:, 2], (viol > 1e-6).sum(axis=1)) or not safe.all()
+    # objective (formulations.jl:122-138, obj_type = :linear -> sum(cg))
+    off = h.variable_offsets()
+    assert tol_err(sc[:, 0], x[:, off["cg"]:off["cg"] + d.ngen].sum(axis=1)) <= 1.0
+    # batched == looped single-scenario, bitwise (network loads for the single-scenario path)
+    g1, J1, H1, _ = _batch_eval(h, x, mu)
+    for s in range(2):
+        a, b, c = h.eval_all(x[s], mu[s])
+        assert np.array_equal(a, g1[s]) and np.array_equal(b, J1[s]) and np.array_equal(c, H1[s])
+    h.close()
+
+
+@pytest.mark.parametrize("F", [ps.PBRARVmodel, ps.PNPAPVmodel, ps.CBRARVmodel, ps.PNRARVmodel], ids=lambda f: f.name)
+def test_quadratic_objective_and_flags(F):
+    d = load_fixture("case300")
+    for facts, lin in ((True, False), (False, True), (False, False)):
+        h = capi.Handle(d, F.code, facts_bshunt=facts, obj_linear=lin, device=0)
+        o = c_oracle.COracle(d, F.code, facts_bshunt=facts, obj_linear=lin)
+        assert (h.n_var, h.m_nl, h.nnzJ, h.nnzH) == (o.n_var, o.m_nl, o.nnzJ, o.nnzH)
+        x, Pd, Qd, lay = synth.scenario_batch(d, F, 3, seed=2, facts_bshunt=facts, obj_linear=lin)
+        mu = np.random.default_rng(5).normal(size=(3, h.m_nl))
+        g, J, H, sc = _batch_eval(h, x, mu, Pd, Qd)
+        og, oJ, oH = o.eval_batch(x, mu, Pd, Qd)
+        assert max(tol_err(g, og), tol_err(J, oJ), tol_err(H, oH)) <= 1.0
+        pg = x[:, lay["pg"]:lay["pg"] + d.ngen]
+        if lin:
+            obj = x[:, lay["cg"]:lay["cg"] + d.ngen].sum(axis=1)
+        else:                                   # formulations.jl:128-133 (cost_order == 3 for case300)
+            obj = (d.c2 * pg * pg + d.c1 * pg + d.c0).sum(axis=1)
+        assert np.allclose(sc[:, 0], obj, rtol=1e-12, atol=1e-9)
+        h.close()
+
+
+@pytest.mark.parametrize("F", FORMS, ids=lambda f: f.name)
+def test_contingency_status_mask(F):
+    """Per-scenario branch outages on the fixed pattern equal the oracle run on the network rebuilt with
+    that branch out of service (PowersenseData.jl:198-207: tables scaled by br_status, Imax 0 -> 10000; the
+    branch leaves Sij/Sji, GO_read2.jl:92-93), after dropping the structurally absent slots."""
+    net = synth.synth_network(40, 70, 9, seed=21, frac_parallel=0.1)
+    d = ps.create_PowersenseData(net)
+    S = 4
+    x, Pd, Qd, _ = synth.scenario_batch(d, F, S, seed=9)
+    h = capi.Handle(d, F.code, device=0)
+    mu = np.random.default_rng(1).normal(size=(S, h.m_nl))
+    out = [3, 17, 40, 69]
+    st = np.ones((S, d.nbr), dtype=np.uint8)
+    for s, k in enumerate(out):
+        st[s, k] = 0
+    g, J, H, _ = _batch_eval(h, x, mu, Pd, Qd, status=st)
+    jr, jc = h.jacobian_structure()
+    hr, hc = h.hessian_structure()
+    import copy
+    for s, k in enumerate(out):
+        net2 = copy.deepcopy(net)
+        net2.br_status = net.br_status.copy()
+        net2.br_status[k] = 0
+        d2 = ps.create_PowersenseData(net2)
+        o2 = c_oracle.COracle(d2, F.code)
+        g2, J2, H2 = o2.eval(x[s], mu[s], Pd[s], Qd[s])
+        assert tol_err(g[s], g2) <= 1.0
+        # compare as dense-by-key maps: slots absent from the outage structure must be zero on the GPU
+        r2, c2, hr2, hc2 = o2.structure()
+        ref = {}
+        for r, c, v in zip(r2, c2, J2):
+            ref[(r, c)] = v
+        for r, c, v in zip(jr, jc, J[s]):
+            assert abs(v - ref.get((r, c), 0.0)) <= 1e-10 + 1e-12 * abs(v), (F.name, s, r, c, v, ref.get((r, c)))
+        # Hessian of the Lagrangian is linear in mu: compare the weighted sum per variable pair
+        # (duplicates across row blocks summed, which is what a solver does with the COO triplets)
+        ref, acc = {}, {}
+        for a, b, v in zip(hr2, hc2, H2):
+            ref[(a, b)] = ref.get((a, b), 0.0) + v
+        for a, b, v in zip(hr, hc, H[s]):
+            acc[(a, b)] = acc.get((a, b), 0.0) + v
+        for key, v in acc.items():
+            assert abs(v - ref.get(key, 0.0)) <= 1e-9 + 1e-12 * abs(v), (F.name, s, key, v, ref.get(key))
+        for key, v in ref.items():
+            assert key in acc or abs(v) <= 1e-12
+    h.close()
+
+
+def test_view_offset_semantics():
+    """The MOI wrapper hands the evaluator views into larger arrays (MOI_wrapper.jl:967,1025,1059-1060):
+    outputs are written at the given pointer and nothing else is touched."""
+    d = load_fixture("case14")
+    F = ps.PNPAPVmodel
+    z = load_golden("case14", F)
+    h = capi.Handle(d, F.code, device=0)
+    off = 37
+    big = np.full(off + h.m_nl + 5, -7.0)
+    h.eval_constraint(z["x"], big[off:])
+    assert np.all(big[:off] == -7.0) and np.all(big[off + h.m_nl:] == -7.0)
+    assert tol_err(big[off:off + h.m_nl], z["g"]) <= 1.0
+    bigJ = np.full(off + h.nnzJ + 5, -7.0)
+    h.eval_jacobian(z["x"], bigJ[off:])
+    assert np.all(bigJ[:off] == -7.0) and np.all(bigJ[off + h.nnzJ:] == -7.0)
+    lam = np.concatenate([np.full(off, 3.0), z["mu"]])
+    bigH = np.full(off + h.nnzH + 5, -7.0)
+    h.eval_hessian(z["x"], 1.0, lam[off:], bigH[off:])
+    assert np.all(bigH[:off] == -7.0) and np.all(bigH[off + h.nnzH:] == -7.0)
+    assert tol_err(bigH[off:off + h.nnzH], z["H"]) <= 1.0
+    h.close()
+
+
+def test_errors_and_partial_what():
+    d = load_fixture("case14")
+    F = ps.PBRARVmodel
+    h = capi.Handle(d, F.code, device=0)
+    torch = _torch()
+    dev = torch.device("cuda:0")
+    x, Pd, Qd, _ = synth.scenario_batch(d, F, 3, seed=1)
+    tx = torch.from_numpy(x).to(dev)
+    b = capi.Batch(h, 3)
+    J = torch.full((3, h.nnzJ + 3), np.nan, dtype=torch.float64, device=dev)    # padded leading dimension
+    b.eval_torch(capi.EVAL_J, tx, None, None, J, None, None)
+    torch.cuda.synchronize()
+    o = c_oracle.COracle(d, F.code)
+    _, oJ, _ = o.eval_batch(x, None, None, None, what=2)
+    Jh = J.cpu().numpy()
+    assert tol_err(Jh[:, :h.nnzJ], oJ) <= 1.0 and np.isnan(Jh[:, h.nnzJ:]).all()
+    with pytest.raises(capi.PowersenseError) as e:                               # Hessian without mu
+        b.eval_torch(capi.EVAL_H, tx, None, None, None, torch.empty(3, h.nnzH, dtype=torch.float64, device=dev), None)
+    assert e.value.code == capi.PS_ERR_ARG
+    with pytest.raises(capi.PowersenseError):                                    # range outside the batch
+        b.eval_torch(capi.EVAL_J, tx, None, None, J, None, None, s_begin=2)
+    # sub-range of the batch uses that range's loads
+    b.set_loads(Pd, Qd)
+    g = torch.empty(2, h.m_nl, dtype=torch.float64, device=dev)
+    b.eval_torch(capi.EVAL_G, tx[1:], None, g, None, None, None, s_begin=1)
+    torch.cuda.synchronize()
+    og, _, _ = o.eval_batch(x[1:], None, Pd[1:], Qd[1:], what=1)
+    assert tol_err(g.cpu().numpy(), og) <= 1.0
+    b.close()
+    h.close()
+
+
+def test_host_streaming_matches_device_path():
+    d = synthetic("case118")
+    F = ps.PBRARVmodel
+    S = 37
+    x, Pd, Qd, _ = synth.scenario_batch(d, F, S, seed=4)
+    h = capi.Handle(d, F.code, device=0)
+    mu = np.random.default_rng(8).normal(size=(S, h.m_nl))
+    g0, J0, H0, sc0 = _batch_eval(h, x, mu, Pd, Qd)
+    import os
+    os.environ["PS_STAGE"] = "8"                    # force several pipeline chunks, incl. a ragged last one
+    try:
+        b = capi.Batch(h, S)
+        b.set_loads(Pd, Qd)
+        px = capi.pinned_empty((S, h.n_var)); px[:] = x
+        pmu = capi.pinned_empty((S, h.m_nl)); pmu[:] = mu
+        g, J, H = capi.pinned_empty((S, h.m_nl)), capi.pinned_empty((S, h.nnzJ)), capi.pinned_empty((S, h.nnzH))
+        sc = capi.pinned_empty((S, capi.PS_NSCALARS))
+        b.eval_host(7, px, pmu, g, J, H, sc)
+        assert np.array_equal(g, g0) and np.array_equal(J, J0) and np.array_equal(H, H0) and np.array_equal(sc, sc0)
+        # plain (pageable) numpy buffers work too
+        g2 = np.zeros((S, h.m_nl))
+        b.eval_host(1, x, None, g2, None, None, None)
+        assert np.array_equal(g2, g0)
+        b.close()
+    finally:
+        del os.environ["PS_STAGE"]
+    h.close()
+
+
+@pytest.mark.parametrize("F,case,S", [(ps.PBRARVmodel, "case13659pegase", 24), (ps.PNPAPVmodel, "case2869pegase", 48),
+                                      (ps.CBRARVmodel, "case13659pegase", 8), (ps.PNPAPVmodel, "case9241pegase", 8)],
+                         ids=lambda v: getattr(v, "name", str(v)))
+def test_full_size_cases(F, case, S):
+    """BASELINE.json's full network sizes: a few scenarios against the oracle plus size-independent
+    properties (H linear in mu; J of the flow-definition rows has +1 on the flow variable; identical
+    scenarios give identical rows)."""
+    d = synthetic(case)
+    x, Pd, Qd, _ = synth.scenario_batch(d, F, S, seed=13)
+    x[S - 1] = x[0]; Pd[S - 1] = Pd[0]; Qd[S - 1] = Qd[0]
+    h = capi.Handle(d, F.code, device=0)
+    mu = np.random.default_rng(6).normal(size=(S, h.m_nl))
+    mu[S - 1] = mu[0]
+    g, J, H, sc = _batch_eval(h, x, mu, Pd, Qd)
+    o = c_oracle.COracle(d, F.code)
+    n_chk = 3
+    og, oJ, oH = o.eval_batch(x[:n_chk], mu[:n_chk], Pd[:n_chk], Qd[:n_chk])
+    assert tol_err(g[:n_chk], og) <= 1.0 and tol_err(J[:n_chk], oJ) <= 1.0 and tol_err(H[:n_chk], oH) <= 1.0
+    assert np.array_equal(g[0], g[S - 1]) and np.array_equal(J[0], J[S - 1]) and np.array_equal(H[0], H[S - 1])
+    _, _, H2, _ = _batch_eval(h, x, 2.0 * mu, Pd, Qd, what=4, scal=False)
+    assert np.array_equal(H2, 2.0 * H)             # linearity in mu (scaling by 2 is exact in FP64)
+    h.close()

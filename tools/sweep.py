@@ -1,0 +1,60 @@
+"""Development sweep (not part of the bench contract): times ps_batch_eval for several cases /
+formulations / scenario-chunk sizes on one GPU and prints achieved algorithmic GB/s."""
+import os
+import sys
+import time
+
+import numpy as np
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch  # noqa: E402
+
+import powersense_b200 as ps  # noqa: E402
+from powersense_b200 import capi, synth  # noqa: E402
+
+
+def run(case, Fname, S, chunks, what=7, steps=5):
+    d = synth.named_case(case)
+    F = ps.BY_NAME[Fname]
+    h = capi.Handle(d, F.code, device=0)
+    b = capi.Batch(h, S)
+    dev = torch.device("cuda:0")
+    xb, Pd, Qd, _ = synth.scenario_batch(d, F, 8, seed=1)
+    x = torch.from_numpy(xb).to(dev).repeat(-(-S // 8), 1)[:S].contiguous()
+    x *= 1.0 + 1e-3 * (torch.rand_like(x) - 0.5)
+    mu = torch.randn(S, h.m_nl, dtype=torch.float64, device=dev)
+    g = torch.empty(S, h.m_nl, dtype=torch.float64, device=dev)
+    J = torch.empty(S, h.nnzJ, dtype=torch.float64, device=dev)
+    H = torch.empty(S, h.nnzH, dtype=torch.float64, device=dev)
+    sc = torch.empty(S, 4, dtype=torch.float64, device=dev)
+    ab = h.algorithmic_bytes(what)
+    for c in chunks:
+        os.environ["PS_CHUNK"] = str(c)
+        for _ in range(2):
+            b.eval_torch(what, x, mu, g, J, H, sc)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            b.eval_torch(what, x, mu, g, J, H, sc)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / steps
+        print(f"{case} {Fname} S={S} what={what} chunk={c}: {ms:.3f} ms  {S / ms * 1e3:.0f} evals/s  {ab * S / ms / 1e6:.0f} GB/s", flush=True)
+    b.close()
+    h.close()
+
+
+if __name__ == "__main__":
+    sel = sys.argv[1] if len(sys.argv) > 1 else "all"
+    if sel in ("all", "pbrarv"):
+        run("case13659pegase", "PBRARVmodel", 1024, [1, 2, 4, 8, 16, 32])
+        run("case13659pegase", "PBRARVmodel", 1024, [8], what=1)
+        run("case13659pegase", "PBRARVmodel", 1024, [8], what=2)
+        run("case13659pegase", "PBRARVmodel", 1024, [8], what=4)
+    if sel in ("all", "others"):
+        run("case13659pegase", "CBRARVmodel", 1024, [4, 16])
+        run("case2869pegase", "PNPAPVmodel", 1024, [4, 16])
+        run("case9241pegase", "PNPAPVmodel", 512, [4, 16])
+        run("case13659pegase", "PNRARVmodel", 512, [4, 16])
+        run("case13659pegase", "PBRAPVmodel", 512, [4, 16])

@@ -80,6 +80,7 @@ class COracle:
         dims = [C.c_int64() for _ in range(4)]
         L.pso_dims(self.h, *[C.byref(v) for v in dims])
         self.n_var, self.m_nl, self.nnzJ, self.nnzH = (v.value for v in dims)
+        self._has_bus_rows = formulation_code not in (2, 8)      # PBRAWV / PNRAWV have no NL bus rows
 
     def __del__(self):
         if getattr(self, "h", None):
@@ -117,3 +118,22 @@ class COracle:
         if bad:
             raise AssertionError("analytic second derivative outside the declared Hessian structure")
         return g, J, H
+
+    def condition_scale(self, x, mu=None, Pd=None, Qd=None):
+        """Per-output magnitude of the summed terms (sum of |contribution| per slot; for g the first-order
+        proxy sum_j |dg/dx_j|_abs |x_j| + |load|).  Rows such as the L4 / L5 current limits
+        (formulations.jl:338-352) subtract O(|y|^2) products to get an O(1) result: two FP64 evaluations that
+        differ only in rounding agree to ~1e-16 of this scale, not of the result.  Tests use it to state the
+        tolerance as 1e-12 relative to max(|value|, scale)."""
+        _, Ja, Ha = self.eval(x, mu, Pd, Qd, what=2 | 4 | 8)
+        jr, jc, _, _ = self.structure()
+        gs = np.zeros(self.m_nl)
+        np.add.at(gs, jr - 1, Ja * np.abs(np.asarray(x)[jc - 1]))
+        nb = len(self._keep["Pd"])
+        if True:
+            pd = np.abs(self._keep["Pd"] if Pd is None else Pd)
+            qd = np.abs(self._keep["Qd"] if Qd is None else Qd)
+            if self._has_bus_rows:
+                gs[0:2 * nb:2] += pd
+                gs[1:2 * nb:2] += qd
+        return gs, Ja, Ha

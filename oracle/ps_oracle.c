@@ -31,7 +31,7 @@
 enum { PBRAPV = 0, PBRARV, PBRAWV, CBRARV, CBRAWV, PNPAPV, PNRAPV, PNRARV, PNRAWV };
 enum { SRC_MATPOWER = 0, SRC_ARPAE = 1 };
 enum { FLAG_FACTS = 1, FLAG_OBJ_LINEAR = 2 };
-enum { EV_G = 1, EV_J = 2, EV_H = 4 };
+enum { EV_G = 1, EV_J = 2, EV_H = 4, EV_ABS = 8 };   /* EV_ABS: accumulate |contribution| per slot (condition scale) */
 
 typedef struct {
   int64_t nbus, nbr, ngen, nbss;
@@ -124,12 +124,12 @@ static void push_h(ctx *c, int64_t a, int64_t b) {
 }
 static inline void emit_j(ctx *c, int64_t var, double v) {
   if (c->mode == 0) push_j(c, var);
-  else if (c->what & EV_J) c->J[c->m->jslot[c->cj]] += v;
+  else if (c->what & EV_J) c->J[c->m->jslot[c->cj]] += (c->what & EV_ABS) ? fabs(v) : v;
   c->cj++;
 }
 static inline void emit_h(ctx *c, int64_t a, int64_t b, double v) {
   if (c->mode == 0) push_h(c, a, b);
-  else if (c->what & EV_H) c->H[c->m->hslot[c->ch]] += c->mu_row * v;
+  else if (c->what & EV_H) c->H[c->m->hslot[c->ch]] += (c->what & EV_ABS) ? fabs(c->mu_row * v) : c->mu_row * v;
   c->ch++;
 }
 /* emit sign * term: gradient for every local variable, Hessian for the declared pairs */
@@ -412,8 +412,10 @@ static void walk(ctx *c) {
           jet p1 = j_mul(j_scale(y1, C, 4), A, 4), p2 = j_mul(j_scale(y2, S, 4), A, 4);
           jet p3 = j_mul(j_scale(y, A, 4), A, 4), p4 = j_mul(j_scale(Y, Bq, 4), A, 4);
           val = p1.v + p2.v + p3.v + p4.v;
-          jet tt = j_add(j_add(j_add(p1, p2, 4), p3, 4), p4, 4);
-          emit_term(c, &tt, 1.0, 4, gid, P_CLIQUE4, 10);
+          /* one n-ary sum in the source; emitted term by term (same totals, same clique) so that the
+           * EV_ABS pass sees the cancellation between the four products */
+          emit_term(c, &p1, 1.0, 4, gid, P_CLIQUE4, 10); emit_term(c, &p2, 1.0, 4, gid, P_CLIQUE4, 10);
+          emit_term(c, &p3, 1.0, 4, gid, P_CLIQUE4, 10); emit_term(c, &p4, 1.0, 4, gid, P_CLIQUE4, 10);
         } else {
           jet p1 = j_scale(y1, C, 4), p2 = j_scale(y2, S, 4), p3 = j_scale(y, A, 4), p4 = j_scale(Y, Bq, 4);
           val = p1.v + p2.v + p3.v + p4.v;

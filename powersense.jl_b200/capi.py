@@ -11,7 +11,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libpowersense_b200.so")
+LIB_PATH = os.environ.get("PS_LIB") or os.path.join(_HERE, "libpowersense_b200.so")   # PS_LIB: development variants
 HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "powersense_b200.h")
 
 PS_OK, PS_ERR_ARG, PS_ERR_NETWORK, PS_ERR_CUDA, PS_ERR_STATE = 0, 1, 2, 3, 4

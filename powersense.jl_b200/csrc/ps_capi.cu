@@ -153,7 +153,7 @@ int do_eval(ps_batch* b, int what, int64_t s_begin, int64_t s_count, const doubl
   A.ldst = P.net.nbr;
   A.g = g; A.ldg = ldg; A.J = J; A.ldJ = ldJ; A.H = H; A.ldH = ldH;
   A.scal = scalars; A.viol_tol = b->viol_tol;
-  e = launch_eval(h->dev, A, P.smem_doubles, stream);
+  e = launch_eval(h->dev, A, P.smem_bytes, stream);
   if (e != cudaSuccess) return cuda_fail(h, e, "eval_kernel launch");
   b->launches += 1 + (scalars ? 1 : 0);
   return PS_OK;
@@ -263,6 +263,8 @@ int ps_create(const ps_network* net, int formulation, int source_type, int flags
   D.jptr = M.upload(P.jptr); D.hptr = M.upload(P.hptr);
   D.bus_jpos = M.upload(P.bus_jpos); D.bus_hpos = M.upload(P.bus_hpos);
   D.bus_jpp = M.upload(P.bus_jpp); D.bus_hpp = M.upload(P.bus_hpp);
+  D.he_ptr = M.upload(P.he_ptr); D.he_ks = M.upload(P.he_ks); D.he_other = M.upload(P.he_other);
+  D.he_c = M.upload(P.he_c); D.nhe = (int)P.he_ks.size();
   D.tiles = M.upload(P.tiles);
   // single-scenario staging
   const int64_t n_in = P.n_var + P.m_nl, n_out = P.m_nl + P.nnzJ + P.nnzH + NSCAL;
@@ -273,7 +275,7 @@ int ps_create(const ps_network* net, int formulation, int source_type, int flags
   if ((e = cudaHostAlloc((void**)&h->h_in, std::max<int64_t>(n_in, 1) * sizeof(double), cudaHostAllocDefault)) != cudaSuccess ||
       (e = cudaHostAlloc((void**)&h->h_out, std::max<int64_t>(n_out, 1) * sizeof(double), cudaHostAllocDefault)) != cudaSuccess ||
       (e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking)) != cudaSuccess ||
-      (e = configure_eval(P.form, P.src, P.smem_doubles)) != cudaSuccess) {
+      (e = configure_eval(P.form, P.src, P.smem_bytes)) != cudaSuccess) {
     ps_destroy(h);
     return cuda_fail(nullptr, e, "handle setup");
   }

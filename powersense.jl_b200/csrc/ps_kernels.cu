@@ -396,13 +396,20 @@ struct Branch {
 };
 
 // --------------------------------------------------------------------------- bus rows
-// Stream writer: slot positions (relative to the bus's first slot) come from the plan in emission
-// order; bit 15 = accumulate into a slot this thread has already written (duplicate variables of a
-// row: the diagonal block of PN* balances, parallel branches).  A bus's slots are private to its
-// thread, so there are no races and the accumulation order is the reference's term order.
+// A bus tile stages, once per CTA, everything that does not depend on the scenario in shared memory: the
+// tile's half-edge list (branch, side, other bus), the admittance entries of the PN* balances, the generator /
+// shunt lists and the slot-position streams.  Per scenario the x entries the tile reads (own voltages, the
+// flow / current variables or the neighbour voltages of every half-edge, generator injections), its
+// multipliers and loads are gathered into a double-buffered shared array with cp.async one scenario ahead,
+// so a bus thread never waits on a dependent chain of global loads.
+//
+// Stream writer: slot positions (relative to the bus's first slot) come from the plan in emission order;
+// bit 15 = accumulate into a slot this thread has already written (duplicate variables of a row: the
+// diagonal block of the nodal balances, parallel branches).  A bus's slots are private to its thread, so
+// there are no races and the accumulation order is the reference's term order.
 struct Stream {
   double* base;
-  const uint16_t* __restrict__ pos;
+  const uint16_t* pos;
   bool on;
   __device__ __forceinline__ void put(double v) {
     if (on) {
@@ -427,106 +434,112 @@ struct BusOut {
   }
 };
 
+__device__ __forceinline__ void cp_async8(void* smem_dst, const void* gsrc) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(d), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
+
+// shared-memory view of one bus tile
+struct BusTile {
+  int nbt, nhe, ngt, nsh;            // buses, half-edges, generators, switched shunts in the tile
+  int hp0, gp0, sp0, cj0, ch0;       // first global index of each list
+  int xh, xg, xw, xs_, xm, xl, nx;   // offsets inside the gathered-input array
+  double *sG, *sJ, *sH, *xb[2], *hc;
+  int *heks, *hoth, *sgen, *ssh;
+  uint16_t *jpos, *hpos;
+  uint8_t* sst;
+};
+
 template <int FORM>
-__device__ __forceinline__ void bus_rows(const DevPlan& P, BusOut& o, Stream& sj, Stream& sh, int i,
-                                         const double* __restrict__ x, const double* __restrict__ mu,
-                                         const double* __restrict__ Pd, const double* __restrict__ Qd,
-                                         const uint8_t* __restrict__ status) {
-  const double muP = sh.on ? mu[2 * i] : 0.0, muQ = sh.on ? mu[2 * i + 1] : 0.0;
+__device__ __forceinline__ void bus_rows(const DevPlan& P, const BusTile& T, const double* xs, BusOut& o, Stream& sj,
+                                         Stream& sh, int i, int lu, bool has_status) {
+  const double muP = sh.on ? xs[T.xm + 2 * lu] : 0.0, muQ = sh.on ? xs[T.xm + 2 * lu + 1] : 0.0;
   double accP = 0.0, accQ = 0.0;                               // formulations.jl:171-172
-  for (int q = P.gen_ptr[i]; q < P.gen_ptr[i + 1]; q++) {      // :177-180
-    const int g = P.gen_idx[q];
-    accP = accP + x[P.o_pg + g];
-    accQ = accQ + x[P.o_qg + g];
+  for (int q = P.gen_ptr[i] - T.gp0, q1 = P.gen_ptr[i + 1] - T.gp0; q < q1; q++) {   // :177-180
+    accP = accP + xs[T.xg + 2 * q];
+    accQ = accQ + xs[T.xg + 2 * q + 1];
     sj.put(1.0);
     sj.put(1.0);
   }
-  double va0 = 0.0, vb0 = 0.0;                                 // own voltage: (theta_i, V_i) | (vi_i, vr_i)
-  if constexpr (FORM != PBRAPV && FORM != CBRAWV) va0 = x[P.o_a + i];
-  if constexpr (FORM != CBRAWV) vb0 = x[P.o_b + i];
-  if constexpr (FORM == CBRAWV) { va0 = x[P.o_a + i]; vb0 = x[P.o_b + i]; }
+  const double va0 = xs[lu], vb0 = xs[T.nbt + lu];             // own voltage: (theta_i, V_i) | (vi_i, vr_i)
 #pragma unroll 1
-  for (int side = 0; side < 2; side++) {
-    const int32_t* __restrict__ ptr = side ? P.sji_ptr : P.sij_ptr;
-    const int32_t* __restrict__ idx = side ? P.sji_idx : P.sij_idx;
-#pragma unroll 1
-    for (int q = ptr[i]; q < ptr[i + 1]; q++) {
-      const int k = idx[q];
-      const double st = status ? (double)status[k] : 1.0;
-      if constexpr (FORM == PBRAPV || FORM == PBRARV) {        // :188-196
-        accP = accP + st * x[P.o_f[0 + 2 * side] + k];
-        accQ = accQ + st * x[P.o_f[1 + 2 * side] + k];
-        sj.put(st);
-        sj.put(st);
-      } else if constexpr (FORM == CBRARV || FORM == CBRAWV) { // :206-214  T4
-        const double Ir = x[P.o_f[0 + 2 * side] + k], Ii = x[P.o_f[1 + 2 * side] + k];
-        const double ra = vb0, ia = va0;
-        accP = (accP + st * (ra * Ir)) + st * (ia * Ii);
-        accQ = (accQ + st * (ia * Ir)) - st * (ra * Ii);
-        sj.put(st * Ir); sj.put(st * Ii); sj.put(st * ra); sj.put(st * ia);          // P: d/d(ra, ia, Ir, Ii)
-        sj.put(-st * Ii); sj.put(st * Ir); sj.put(st * ia); sj.put(-st * ra);        // Q
-        sh.put(0.0); sh.put(0.0); sh.put(st * muP); sh.put(0.0); sh.put(0.0); sh.put(st * muP);
-        sh.put(0.0); sh.put(0.0); sh.put(st * muQ); sh.put(0.0); sh.put(0.0); sh.put(-st * muQ);
-      } else if constexpr (FORM == PNPAPV || FORM == PNRAPV) { // :215-234  T2 / T1
-        const int b = side ? P.f[k] : P.t[k];
-        const double gs = st * (side ? P.gt[k] : P.gf[k]), bs = st * (side ? P.bt[k] : P.bf[k]);
-        const double thb = x[P.o_a + b], Vb = x[P.o_b + b], Va = vb0, dl = va0 - thb;
-        double A, Bt;
-        if constexpr (FORM == PNPAPV) {
-          const double Y = st * P.c0[side * P.nr + k], phi = P.c1[side * P.nr + k];
-          double s, c;
-          sincos(dl - phi, &s, &c);
-          A = Y * c; Bt = -(Y * s);
-        } else {
-          const double G = st * (side ? P.Gt[k] : P.Gf[k]), B = st * (side ? P.Bt[k] : P.Bf[k]);
-          double s, c;
-          sincos(dl, &s, &c);
-          A = G * c + B * s; Bt = B * c - G * s;
-        }
-        const double Vf = side ? Vb : Va, Vt = side ? Va : Vb;  // source order V[f]*V[t]
-        const double VV = Va * Vb;
-        accP = (accP - gs * (Va * Va)) - A * Vf * Vt;
-        accQ = (accQ + bs * (Va * Va)) + Bt * Vf * Vt;
-        // J: d/d(th_a, th_b, V_a, V_b)
-        sj.put(-Bt * VV); sj.put(Bt * VV); sj.put(-2.0 * gs * Va - A * Vb); sj.put(-A * Va);
-        sj.put(-A * VV); sj.put(A * VV); sj.put(2.0 * bs * Va + Bt * Vb); sj.put(Bt * Va);
-        // H clique order over [th_a, th_b, V_a, V_b]: aa bb VaVa VbVb ab aVa aVb bVa bVb VaVb
-        sh.put(muP * A * VV); sh.put(muP * A * VV); sh.put(muP * -2.0 * gs); sh.put(0.0); sh.put(-muP * A * VV);
-        sh.put(-muP * Bt * Vb); sh.put(-muP * Bt * Va); sh.put(muP * Bt * Vb); sh.put(muP * Bt * Va); sh.put(-muP * A);
-        sh.put(-muQ * Bt * VV); sh.put(-muQ * Bt * VV); sh.put(muQ * 2.0 * bs); sh.put(0.0); sh.put(muQ * Bt * VV);
-        sh.put(-muQ * A * Vb); sh.put(-muQ * A * Va); sh.put(muQ * A * Vb); sh.put(muQ * A * Va); sh.put(muQ * Bt);
-      } else if constexpr (FORM == PNRARV) {                   // :235-243  T3
-        const int b = side ? P.f[k] : P.t[k];
-        const double gs = st * (side ? P.gt[k] : P.gf[k]), bs = st * (side ? P.bt[k] : P.bf[k]);
-        const double G = st * (side ? P.Gt[k] : P.Gf[k]), B = st * (side ? P.Bt[k] : P.Bf[k]);
-        const double ra = vb0, ia = va0, rb = x[P.o_b + b], ib = x[P.o_a + b];
-        const double A2 = ra * ra + ia * ia, C = ra * rb + ia * ib, S = ra * ib - ia * rb;
-        accP = ((accP - gs * A2) - G * C) + B * S;
-        accQ = ((accQ + bs * A2) + B * C) + G * S;
-        // J: d/d(ra, ia, rb, ib)
-        sj.put(-2.0 * gs * ra - G * rb + B * ib); sj.put(-2.0 * gs * ia - G * ib - B * rb);
-        sj.put(-G * ra - B * ia); sj.put(-G * ia + B * ra);
-        sj.put(2.0 * bs * ra + B * rb + G * ib); sj.put(2.0 * bs * ia + B * ib - G * rb);
-        sj.put(B * ra - G * ia); sj.put(B * ia + G * ra);
-        // H: (ra,ra)(ia,ia)(rb,rb)(ib,ib)(ra,rb)(ia,ib)(ra,ib)(ia,rb)
-        sh.put(muP * -2.0 * gs); sh.put(muP * -2.0 * gs); sh.put(0.0); sh.put(0.0);
-        sh.put(-muP * G); sh.put(-muP * G); sh.put(muP * B); sh.put(-muP * B);
-        sh.put(muQ * 2.0 * bs); sh.put(muQ * 2.0 * bs); sh.put(0.0); sh.put(0.0);
-        sh.put(muQ * B); sh.put(muQ * B); sh.put(muQ * G); sh.put(-muQ * G);
+  for (int q = P.he_ptr[i] - T.hp0, q1 = P.he_ptr[i + 1] - T.hp0; q < q1; q++) {     // Sij ascending, then Sji ascending
+    const int side = T.heks[q] & 1;
+    const double st = has_status ? (double)T.sst[q] : 1.0;
+    const double v0 = xs[T.xh + 2 * q], v1 = xs[T.xh + 2 * q + 1];
+    if constexpr (FORM == PBRAPV || FORM == PBRARV) {          // :188-196  v0/v1 = P / Q flow variable
+      accP = accP + st * v0;
+      accQ = accQ + st * v1;
+      sj.put(st);
+      sj.put(st);
+    } else if constexpr (FORM == CBRARV || FORM == CBRAWV) {   // :206-214  T4, v0/v1 = Ir / Ii
+      const double Ir = v0, Ii = v1, ra = vb0, ia = va0;
+      accP = (accP + st * (ra * Ir)) + st * (ia * Ii);
+      accQ = (accQ + st * (ia * Ir)) - st * (ra * Ii);
+      sj.put(st * Ir); sj.put(st * Ii); sj.put(st * ra); sj.put(st * ia);          // P: d/d(ra, ia, Ir, Ii)
+      sj.put(-st * Ii); sj.put(st * Ir); sj.put(st * ia); sj.put(-st * ra);        // Q
+      sh.put(0.0); sh.put(0.0); sh.put(st * muP); sh.put(0.0); sh.put(0.0); sh.put(st * muP);
+      sh.put(0.0); sh.put(0.0); sh.put(st * muQ); sh.put(0.0); sh.put(0.0); sh.put(-st * muQ);
+    } else if constexpr (FORM == PNPAPV || FORM == PNRAPV) {   // :215-234  T2 / T1, v0/v1 = theta_b / V_b
+      const double gs = st * T.hc[q], bs = st * T.hc[T.nhe + q];
+      const double thb = v0, Vb = v1, Va = vb0, dl = va0 - thb;
+      double A, Bt;
+      if constexpr (FORM == PNPAPV) {
+        const double Y = st * T.hc[2 * T.nhe + q], phi = T.hc[3 * T.nhe + q];
+        double s, c;
+        sincos(dl - phi, &s, &c);
+        A = Y * c; Bt = -(Y * s);
+      } else {
+        const double G = st * T.hc[2 * T.nhe + q], B = st * T.hc[3 * T.nhe + q];
+        double s, c;
+        sincos(dl, &s, &c);
+        A = G * c + B * s; Bt = B * c - G * s;
       }
+      const double Vf = side ? Vb : Va, Vt = side ? Va : Vb;  // source order V[f]*V[t]
+      const double VV = Va * Vb;
+      accP = (accP - gs * (Va * Va)) - A * Vf * Vt;
+      accQ = (accQ + bs * (Va * Va)) + Bt * Vf * Vt;
+      // J: d/d(th_a, th_b, V_a, V_b)
+      sj.put(-Bt * VV); sj.put(Bt * VV); sj.put(-2.0 * gs * Va - A * Vb); sj.put(-A * Va);
+      sj.put(-A * VV); sj.put(A * VV); sj.put(2.0 * bs * Va + Bt * Vb); sj.put(Bt * Va);
+      // H clique order over [th_a, th_b, V_a, V_b]: aa bb VaVa VbVb ab aVa aVb bVa bVb VaVb
+      sh.put(muP * A * VV); sh.put(muP * A * VV); sh.put(muP * -2.0 * gs); sh.put(0.0); sh.put(-muP * A * VV);
+      sh.put(-muP * Bt * Vb); sh.put(-muP * Bt * Va); sh.put(muP * Bt * Vb); sh.put(muP * Bt * Va); sh.put(-muP * A);
+      sh.put(-muQ * Bt * VV); sh.put(-muQ * Bt * VV); sh.put(muQ * 2.0 * bs); sh.put(0.0); sh.put(muQ * Bt * VV);
+      sh.put(-muQ * A * Vb); sh.put(-muQ * A * Va); sh.put(muQ * A * Vb); sh.put(muQ * A * Va); sh.put(muQ * Bt);
+    } else if constexpr (FORM == PNRARV) {                     // :235-243  T3, v0/v1 = vi_b / vr_b
+      const double gs = st * T.hc[q], bs = st * T.hc[T.nhe + q];
+      const double G = st * T.hc[2 * T.nhe + q], B = st * T.hc[3 * T.nhe + q];
+      const double ra = vb0, ia = va0, rb = v1, ib = v0;
+      const double A2 = ra * ra + ia * ia, C = ra * rb + ia * ib, S = ra * ib - ia * rb;
+      accP = ((accP - gs * A2) - G * C) + B * S;
+      accQ = ((accQ + bs * A2) + B * C) + G * S;
+      // J: d/d(ra, ia, rb, ib)
+      sj.put(-2.0 * gs * ra - G * rb + B * ib); sj.put(-2.0 * gs * ia - G * ib - B * rb);
+      sj.put(-G * ra - B * ia); sj.put(-G * ia + B * ra);
+      sj.put(2.0 * bs * ra + B * rb + G * ib); sj.put(2.0 * bs * ia + B * ib - G * rb);
+      sj.put(B * ra - G * ia); sj.put(B * ia + G * ra);
+      // H: (ra,ra)(ia,ia)(rb,rb)(ib,ib)(ra,rb)(ia,ib)(ra,ib)(ia,rb)
+      sh.put(muP * -2.0 * gs); sh.put(muP * -2.0 * gs); sh.put(0.0); sh.put(0.0);
+      sh.put(-muP * G); sh.put(-muP * G); sh.put(muP * B); sh.put(-muP * B);
+      sh.put(muQ * 2.0 * bs); sh.put(muQ * 2.0 * bs); sh.put(0.0); sh.put(0.0);
+      sh.put(muQ * B); sh.put(muQ * B); sh.put(muQ * G); sh.put(-muQ * G);
     }
   }
   // shunt terms :256-279
   const double Gl = P.Gl[i], Bl = P.Bl[i];
   const bool facts = (P.flags & FLAG_FACTS) != 0;
+  const int f0 = P.sh_ptr[i] - T.sp0, f1 = facts ? P.sh_ptr[i + 1] - T.sp0 : f0;
   if constexpr (is_polar(FORM)) {
     const double V = vb0, V2 = V * V;
     accP = accP - Gl * V2;
     accQ = accQ + Bl * V2;
     sj.put(-2.0 * Gl * V); sj.put(2.0 * Bl * V);
     sh.put(-2.0 * Gl * muP); sh.put(2.0 * Bl * muQ);
-    if (facts) for (int q = P.sh_ptr[i]; q < P.sh_ptr[i + 1]; q++) {
-      const double bss = x[P.o_bss + P.sh_idx[q]];
+    for (int q = f0; q < f1; q++) {
+      const double bss = xs[T.xs_ + q];
       accQ = accQ + bss * V2;
       sj.put(V2); sj.put(2.0 * bss * V);
       sh.put(0.0); sh.put(2.0 * bss * muQ); sh.put(2.0 * V * muQ);
@@ -537,27 +550,64 @@ __device__ __forceinline__ void bus_rows(const DevPlan& P, BusOut& o, Stream& sj
     accQ = accQ + Bl * A2;
     sj.put(-2.0 * Gl * r); sj.put(-2.0 * Gl * im); sj.put(2.0 * Bl * r); sj.put(2.0 * Bl * im);
     sh.put(-2.0 * Gl * muP); sh.put(-2.0 * Gl * muP); sh.put(2.0 * Bl * muQ); sh.put(2.0 * Bl * muQ);
-    if (facts) for (int q = P.sh_ptr[i]; q < P.sh_ptr[i + 1]; q++) {
-      const double bss = x[P.o_bss + P.sh_idx[q]];
+    for (int q = f0; q < f1; q++) {
+      const double bss = xs[T.xs_ + q];
       accQ = accQ + bss * A2;
       sj.put(A2); sj.put(2.0 * bss * r); sj.put(2.0 * bss * im);
       sh.put(0.0); sh.put(2.0 * bss * muQ); sh.put(2.0 * bss * muQ);
       sh.put(2.0 * r * muQ); sh.put(2.0 * im * muQ); sh.put(0.0);
     }
   } else if constexpr (FORM == CBRAWV) {
-    const double W = x[P.o_Wd + i];
+    const double W = xs[T.xw + lu];
     accP = accP - Gl * W;
     accQ = accQ + Bl * W;
     sj.put(-Gl); sj.put(Bl);
-    if (facts) for (int q = P.sh_ptr[i]; q < P.sh_ptr[i + 1]; q++) {
-      const double bss = x[P.o_bss + P.sh_idx[q]];
+    for (int q = f0; q < f1; q++) {
+      const double bss = xs[T.xs_ + q];
       accQ = accQ + bss * W;
       sj.put(W); sj.put(bss);
       sh.put(0.0); sh.put(0.0); sh.put(muQ);
     }
   }
-  o.G(0, accP - Pd[i]);                                        // :291
-  o.G(1, accQ - Qd[i]);                                        // :292
+  o.G(0, accP - xs[T.xl + lu]);                                // :291
+  o.G(1, accQ - xs[T.xl + T.nbt + lu]);                        // :292
+}
+
+// issue the cp.async gather of one scenario's inputs of a bus tile
+template <int FORM>
+__device__ __forceinline__ void bus_gather(const DevPlan& P, const EvalArgs& A, const BusTile& T, const Tile& tl, int s, double* xs) {
+  const double* __restrict__ x = A.x + (long long)s * A.ldx;
+  const int tid = threadIdx.x;
+  for (int q = tid; q < T.nbt; q += TPB) {
+    cp_async8(xs + q, x + P.o_a + tl.u0 + q);
+    cp_async8(xs + T.nbt + q, x + P.o_b + tl.u0 + q);
+    if constexpr (FORM == CBRAWV) cp_async8(xs + T.xw + q, x + P.o_Wd + tl.u0 + q);
+    const double* pd = A.Pd ? A.Pd + (long long)s * A.ldl : P.Pd0;
+    const double* qd = A.Qd ? A.Qd + (long long)s * A.ldl : P.Qd0;
+    cp_async8(xs + T.xl + q, pd + tl.u0 + q);
+    cp_async8(xs + T.xl + T.nbt + q, qd + tl.u0 + q);
+  }
+  if (A.what & EV_H) {
+    const double* __restrict__ mu = A.mu + (long long)s * A.ldmu + 2 * tl.u0;
+    for (int q = tid; q < 2 * T.nbt; q += TPB) cp_async8(xs + T.xm + q, mu + q);
+  }
+  for (int q = tid; q < T.nhe; q += TPB) {
+    const int ks = T.heks[q], k = ks >> 1, side = ks & 1;
+    if constexpr (is_PN(FORM)) {
+      const int b = T.hoth[q];
+      cp_async8(xs + T.xh + 2 * q, x + P.o_a + b);
+      cp_async8(xs + T.xh + 2 * q + 1, x + P.o_b + b);
+    } else {
+      cp_async8(xs + T.xh + 2 * q, x + P.o_f[0 + 2 * side] + k);
+      cp_async8(xs + T.xh + 2 * q + 1, x + P.o_f[1 + 2 * side] + k);
+    }
+  }
+  for (int q = tid; q < T.ngt; q += TPB) {
+    const int g = T.sgen[q];
+    cp_async8(xs + T.xg + 2 * q, x + P.o_pg + g);
+    cp_async8(xs + T.xg + 2 * q + 1, x + P.o_qg + g);
+  }
+  for (int q = tid; q < T.nsh; q += TPB) cp_async8(xs + T.xs_ + q, x + P.o_bss + T.ssh[q]);
 }
 
 // ------------------------------------------------------------------------------- helpers
@@ -657,25 +707,67 @@ __global__ void __launch_bounds__(TPB) eval_kernel(const __grid_constant__ DevPl
     }
   } else if (tl.kind == 0) {
     if constexpr (has_bus_rows(FORM)) {
-      double* sG = smem;
-      double* sJ = sG + tl.gn;
-      double* sH = sJ + tl.jn;
+      const bool facts = (P.flags & FLAG_FACTS) != 0;
+      BusTile T;
+      T.nbt = tl.u1 - tl.u0;
+      T.hp0 = P.he_ptr[tl.u0]; T.nhe = P.he_ptr[tl.u1] - T.hp0;
+      T.gp0 = P.gen_ptr[tl.u0]; T.ngt = P.gen_ptr[tl.u1] - T.gp0;
+      T.sp0 = P.sh_ptr[tl.u0]; T.nsh = facts ? P.sh_ptr[tl.u1] - T.sp0 : 0;
+      T.cj0 = P.bus_jpp[tl.u0]; T.ch0 = P.bus_hpp[tl.u0];
+      const int ncj = P.bus_jpp[tl.u1] - T.cj0, nch = P.bus_hpp[tl.u1] - T.ch0;
+      // gathered-input layout: own a | own b | half-edge pairs | generator pairs | Wd | bss | mu (P,Q) | Pd | Qd
+      T.xh = 2 * T.nbt; T.xg = T.xh + 2 * T.nhe; T.xw = T.xg + 2 * T.ngt;
+      T.xs_ = T.xw + (FORM == CBRAWV ? T.nbt : 0); T.xm = T.xs_ + T.nsh; T.xl = T.xm + 2 * T.nbt; T.nx = T.xl + 2 * T.nbt;
+      T.sG = smem; T.sJ = T.sG + tl.gn; T.sH = T.sJ + tl.jn;
+      T.xb[0] = T.sH + tl.hn; T.xb[1] = T.xb[0] + T.nx;
+      T.hc = T.xb[1] + T.nx;
+      T.heks = (int*)(T.hc + (is_PN(FORM) ? 4 * T.nhe : 0));
+      T.hoth = T.heks + T.nhe;
+      T.sgen = T.hoth + (is_PN(FORM) ? T.nhe : 0);
+      T.ssh = T.sgen + T.ngt;
+      T.jpos = (uint16_t*)(T.ssh + T.nsh);
+      T.hpos = T.jpos + ncj;
+      T.sst = (uint8_t*)(T.hpos + nch);
+      // ---- scenario-independent staging (once per CTA)
+      for (int q = threadIdx.x; q < T.nhe; q += TPB) {
+        T.heks[q] = P.he_ks[T.hp0 + q];
+        if constexpr (is_PN(FORM)) {
+          T.hoth[q] = P.he_other[T.hp0 + q];
+#pragma unroll
+          for (int c = 0; c < 4; c++) T.hc[c * T.nhe + q] = P.he_c[(long long)c * P.nhe + T.hp0 + q];
+        }
+      }
+      for (int q = threadIdx.x; q < T.ngt; q += TPB) T.sgen[q] = P.gen_idx[T.gp0 + q];
+      for (int q = threadIdx.x; q < T.nsh; q += TPB) T.ssh[q] = P.sh_idx[T.sp0 + q];
+      for (int q = threadIdx.x; q < ncj; q += TPB) T.jpos[q] = P.bus_jpos[T.cj0 + q];
+      for (int q = threadIdx.x; q < nch; q += TPB) T.hpos[q] = P.bus_hpos[T.ch0 + q];
       const int jbase = act ? P.jptr[2 * u] - tl.j0 : 0, hbase = act ? P.hptr[2 * u] - tl.h0 : 0;
-      const int cj0 = act ? P.bus_jpp[u] : 0, ch0 = act ? P.bus_hpp[u] : 0;
+      const int cjo = act ? P.bus_jpp[u] - T.cj0 : 0, cho = act ? P.bus_hpp[u] - T.ch0 : 0;
+      const bool has_status = A.status != nullptr;
       BusOut o;
-      o.g = sG + 2 * threadIdx.x; o.wg = wg; o.tol = A.viol_tol;
+      o.g = T.sG + 2 * threadIdx.x; o.wg = wg; o.tol = A.viol_tol;
+      __syncthreads();
+      bus_gather<FORM>(P, A, T, tl, s0, T.xb[0]);
+      cp_async_commit();
       for (int s = s0; s < s1; s++) {
+        const int cur = (s - s0) & 1;
+        if (s + 1 < s1) bus_gather<FORM>(P, A, T, tl, s + 1, T.xb[cur ^ 1]);    // one scenario ahead
+        cp_async_commit();
+        if (has_status) {
+          const uint8_t* __restrict__ stp = A.status + (long long)s * A.ldst;
+          for (int q = threadIdx.x; q < T.nhe; q += TPB) T.sst[q] = stp[T.heks[q] >> 1];
+        }
+        cp_async_wait<1>();                                                    // this scenario's gather has landed
+        __syncthreads();
         o.vmax = 0.0; o.nviol = 0;
         if (act) {
-          Stream sj{sJ + jbase, P.bus_jpos + cj0, wj}, sh{sH + hbase, P.bus_hpos + ch0, wh};
-          bus_rows<FORM>(P, o, sj, sh, u, A.x + (long long)s * A.ldx, wh ? A.mu + (long long)s * A.ldmu : nullptr,
-                         A.Pd ? A.Pd + (long long)s * A.ldl : P.Pd0, A.Qd ? A.Qd + (long long)s * A.ldl : P.Qd0,
-                         A.status ? A.status + (long long)s * A.ldst : nullptr);
+          Stream sj{T.sJ + jbase, T.jpos + cjo, wj}, sh{T.sH + hbase, T.hpos + cho, wh};
+          bus_rows<FORM>(P, T, T.xb[cur], o, sj, sh, u, threadIdx.x, has_status);
         }
         __syncthreads();
-        if (wg) copy_out(A.g + (long long)s * A.ldg + tl.g0, sG, tl.gn);
-        if (wj) copy_out(A.J + (long long)s * A.ldJ + tl.j0, sJ, tl.jn);
-        if (wh) copy_out(A.H + (long long)s * A.ldH + tl.h0, sH, tl.hn);
+        if (wg) copy_out(A.g + (long long)s * A.ldg + tl.g0, T.sG, tl.gn);
+        if (wj) copy_out(A.J + (long long)s * A.ldJ + tl.j0, T.sJ, tl.jn);
+        if (wh) copy_out(A.H + (long long)s * A.ldH + tl.h0, T.sH, tl.hn);
         reduce_scalars(A.scal ? A.scal + (long long)s * NSCAL : nullptr, o.vmax, o.nviol);
         __syncthreads();
       }
@@ -714,8 +806,8 @@ __global__ void __launch_bounds__(256) csc_assemble_kernel(const int32_t* __rest
 
 }  // namespace
 
-cudaError_t configure_eval(int form, int src, int64_t smem_doubles) {
-  const size_t smem = (size_t)smem_doubles * sizeof(double);
+cudaError_t configure_eval(int form, int src, int64_t smem_bytes) {
+  const size_t smem = (size_t)smem_bytes;
   switch (form) {
     case PBRAPV: return configure_form<PBRAPV>(src, smem);
     case PBRARV: return configure_form<PBRARV>(src, smem);
@@ -730,9 +822,9 @@ cudaError_t configure_eval(int form, int src, int64_t smem_doubles) {
   return cudaErrorInvalidValue;
 }
 
-cudaError_t launch_eval(const DevPlan& P, const EvalArgs& A, int64_t smem_doubles, cudaStream_t stream) {
+cudaError_t launch_eval(const DevPlan& P, const EvalArgs& A, int64_t smem_bytes, cudaStream_t stream) {
   if (A.S <= 0) return cudaSuccess;
-  const size_t smem = (size_t)smem_doubles * sizeof(double);
+  const size_t smem = (size_t)smem_bytes;
   const int nchunks = (A.S + A.chunk - 1) / A.chunk;
   if (nchunks > 65535) return cudaErrorInvalidConfiguration;
   const dim3 grid((unsigned)P.ntiles, (unsigned)nchunks);

@@ -8,7 +8,10 @@
 
 namespace ps {
 
-constexpr int TPB = 128;            // threads per CTA == units (branches / buses) per tile
+#ifndef PS_TPB
+#define PS_TPB 128
+#endif
+constexpr int TPB = PS_TPB;         // threads per CTA == units (branches / buses) per tile
 constexpr int NSCAL = 4;            // PS_NSCALARS
 
 struct DevPlan {                    // passed to kernels by value (constant bank)
@@ -26,6 +29,9 @@ struct DevPlan {                    // passed to kernels by value (constant bank
   const int32_t *jptr, *hptr;
   const uint16_t *bus_jpos, *bus_hpos;
   const int32_t *bus_jpp, *bus_hpp;
+  const int32_t *he_ptr, *he_ks, *he_other;         // half-edges in bus order (Sij then Sji per bus)
+  const double* he_c;                               // [4][nhe] PN* admittance entries staged per tile
+  int nhe;
   const Tile* tiles;
 };
 
@@ -43,9 +49,9 @@ struct EvalArgs {
 };
 
 // launches the fused g/J/H kernel for all tiles x scenarios on `stream`
-cudaError_t launch_eval(const DevPlan& P, const EvalArgs& A, int64_t smem_doubles, cudaStream_t stream);
+cudaError_t launch_eval(const DevPlan& P, const EvalArgs& A, int64_t smem_bytes, cudaStream_t stream);
 // opt the kernels of one formulation into the needed dynamic shared memory (once per device)
-cudaError_t configure_eval(int form, int src, int64_t smem_doubles);
+cudaError_t configure_eval(int form, int src, int64_t smem_bytes);
 
 // COO -> CSC assembly (replaces src/opt/algorithms/common.jl:12-20): nz[j] = sum_{q in seg j} dE[perm[q]]
 cudaError_t launch_csc_assemble(const int32_t* segptr, const int32_t* perm, int nnz_csc, int64_t S,

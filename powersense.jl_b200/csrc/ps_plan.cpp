@@ -290,27 +290,65 @@ std::string build_plan(const HostNet& net, int form, int src, int flags, int tpb
 
   // ---- tiles
   P.tile_units_br = tpb;
-  // bus tiles: greedy, at most tpb buses and at most `budget` staged doubles per tile
-  const int64_t budget = 8800, hard = 27000;     // doubles of staged output per CTA (~70 KB / 216 KB)
+  // half-edge tables (bus kernel order) and the PN* constants staged in shared memory per tile
+  P.he_ptr.assign(nb + 1, 0);
+  for (int64_t i = 0; i < nb; i++) {
+    for (int side = 0; side < 2; side++) {
+      const std::vector<int32_t>& ptr = side ? net.sji_ptr : net.sij_ptr;
+      const std::vector<int32_t>& idx = side ? net.sji_idx : net.sij_idx;
+      for (int32_t q = ptr[i]; q < ptr[i + 1]; q++) {
+        const int32_t k = idx[q];
+        P.he_ks.push_back(2 * k + side);
+        P.he_other.push_back(side ? net.f[k] : net.t[k]);
+      }
+    }
+    P.he_ptr[i + 1] = (int32_t)P.he_ks.size();
+  }
+  const int64_t nhe = (int64_t)P.he_ks.size();
+  if (is_PN(form)) {
+    P.he_c.assign(4 * nhe, 0.0);
+    for (int64_t q = 0; q < nhe; q++) {
+      const int64_t k = P.he_ks[q] >> 1;
+      const int side = P.he_ks[q] & 1;
+      P.he_c[0 * nhe + q] = side ? net.gt[k] : net.gf[k];
+      P.he_c[1 * nhe + q] = side ? net.bt[k] : net.bf[k];
+      if (form == PNPAPV) {                       // |G+jB|, angle(G+jB)  (:217, :222)
+        P.he_c[2 * nhe + q] = P.c0[side * nr + k];
+        P.he_c[3 * nhe + q] = P.c1[side * nr + k];
+      } else {
+        P.he_c[2 * nhe + q] = side ? net.Gt[k] : net.Gf[k];
+        P.he_c[3 * nhe + q] = side ? net.Bt[k] : net.Bf[k];
+      }
+    }
+  }
+  // bus tiles: greedy, at most tpb buses and at most `budget` bytes of shared memory per tile
+  auto bus_tile_bytes = [&](int64_t u0, int64_t u1) -> int64_t {
+    const int64_t nbt = u1 - u0, nh = P.he_ptr[u1] - P.he_ptr[u0], ngt = net.gen_ptr[u1] - net.gen_ptr[u0];
+    const int64_t nsh = facts ? net.sh_ptr[u1] - net.sh_ptr[u0] : 0;
+    const int64_t outs = 2 * nbt + (P.jptr[2 * u1] - P.jptr[2 * u0]) + (P.hptr[2 * u1] - P.hptr[2 * u0]);
+    const int64_t nx = 2 * nbt + 2 * nh + 2 * ngt + (form == CBRAWV ? nbt : 0) + nsh + 4 * nbt;
+    const int64_t ncj = P.bus_jpp[u1] - P.bus_jpp[u0], nch = P.bus_hpp[u1] - P.bus_hpp[u0];
+    int64_t b = 8 * (outs + 2 * nx + (is_PN(form) ? 4 * nh : 0));
+    b += 4 * (nh + (is_PN(form) ? nh : 0) + ngt + nsh);
+    b += 2 * (ncj + nch + 4);
+    b += nh + 64;                                  // status bytes + alignment slack
+    return b;
+  };
+  const int64_t budget = 71 * 1024, hard = 220 * 1024;
   int64_t mx = 0;
   P.tiles.clear();
   if (has_bus_rows(form)) {
     int64_t u0 = 0;
     while (u0 < nb) {
-      int64_t u1 = u0, tot = 0;
-      while (u1 < nb && u1 - u0 < tpb) {
-        const int64_t need = 2 + (P.jptr[2 * u1 + 2] - P.jptr[2 * u1]) + (P.hptr[2 * u1 + 2] - P.hptr[2 * u1]);
-        if (need > hard) return "a bus does not fit in shared memory (bus degree too large)";
-        if (u1 > u0 && tot + need > budget) break;
-        tot += need;
-        u1++;
-      }
+      int64_t u1 = u0 + 1;
+      if (bus_tile_bytes(u0, u1) > hard) return "a bus does not fit in shared memory (bus degree too large)";
+      while (u1 < nb && u1 - u0 < tpb && bus_tile_bytes(u0, u1 + 1) <= budget) u1++;
       Tile t{};
       t.kind = 0; t.u0 = (int32_t)u0; t.u1 = (int32_t)u1;
       t.g0 = (int32_t)(2 * u0); t.gn = (int32_t)(2 * (u1 - u0));
       t.j0 = P.jptr[2 * u0]; t.jn = P.jptr[2 * u1] - t.j0;
       t.h0 = P.hptr[2 * u0]; t.hn = P.hptr[2 * u1] - t.h0;
-      mx = std::max<int64_t>(mx, (int64_t)t.gn + t.jn + t.hn);
+      mx = std::max<int64_t>(mx, bus_tile_bytes(u0, u1));
       P.tiles.push_back(t);
       u0 = u1;
     }
@@ -318,7 +356,7 @@ std::string build_plan(const HostNet& net, int form, int src, int flags, int tpb
   P.tile_units_bus = tpb;
   P.n_bus_tiles = (int)P.tiles.size();
   P.NRP = pat.nrows | 1; P.RJP = P.RJ | 1; P.RHP = P.RH | 1;
-  int64_t mxb = nr > 0 ? (int64_t)tpb * (P.NRP + P.RJP + P.RHP) : 0;
+  const int64_t mxb = nr > 0 ? (int64_t)8 * tpb * (P.NRP + P.RJP + P.RHP) : 0;
   for (int64_t u0 = 0; u0 < nr; u0 += tpb) {
     const int64_t u1 = std::min<int64_t>(nr, u0 + tpb);
     Tile t;
@@ -333,7 +371,8 @@ std::string build_plan(const HostNet& net, int form, int src, int flags, int tpb
     t.kind = 2; t.u0 = 0; t.u1 = (int32_t)ng;
     P.tiles.push_back(t);
   }
-  P.smem_doubles = std::max<int64_t>(std::max(mx, mxb), 64);
+  P.smem_bytes = std::max<int64_t>(std::max(mx, mxb), 1024);
+  P.smem_doubles = (P.smem_bytes + 7) / 8;
   return "";
 }
 

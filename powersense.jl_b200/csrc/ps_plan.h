@@ -44,6 +44,12 @@ struct Plan {
   // bus position streams (emission order of the bus kernel); bit 15 = accumulate into the slot
   std::vector<uint16_t> bus_jpos, bus_hpos;
   std::vector<int32_t> bus_jpp, bus_hpp;            // per-bus start in the streams (size nbus+1)
+  // half-edges in the bus kernel's order: for bus i, Sij(i) ascending then Sji(i) ascending
+  std::vector<int32_t> he_ptr;                      // [nbus+1]
+  std::vector<int32_t> he_ks;                       // branch * 2 + side (side 0: bus is the from end)
+  std::vector<int32_t> he_other;                    // the bus at the other end
+  std::vector<double> he_c;                         // [4][nhe] staged constants of the PN* balances (g_s, b_s, c, d)
+  int64_t smem_bytes = 0;                           // dynamic shared memory of the kernel (max over tile kinds)
   // derived per-side constants (side 0 = from, 1 = to), each [2*nbr]
   std::vector<double> c0, c1, c2, c3;
   std::vector<Tile> tiles;

@@ -23,7 +23,7 @@ NAMED_CASES = {            # published MATPOWER dimensions: (nbus, nbranch, ngen
 
 
 def synth_network(nb: int, nr: int, ng: int, seed: int = 0, source_type: str = "matpower",
-                  frac_out: float = 0.0, nbss: int = 0, frac_parallel: float = 0.015) -> Network:
+                  frac_out: float = 0.0, nbss: int = 0, frac_parallel: float = 0.015, x_min: float = 1e-4) -> Network:
     rng = np.random.default_rng(seed)
     assert nr >= nb - 1
     # spanning tree, parent close in index with a heavy (log-uniform) tail
@@ -51,7 +51,7 @@ def synth_network(nb: int, nr: int, ng: int, seed: int = 0, source_type: str = "
     f, t = np.where(flip, t, f), np.where(flip, f, t)
     perm = rng.permutation(nr)
     f, t = f[perm] + 1, t[perm] + 1
-    x = np.exp(rng.uniform(np.log(1e-4), np.log(0.5), nr))
+    x = np.exp(rng.uniform(np.log(x_min), np.log(0.5), nr))
     r = x * rng.uniform(0.05, 0.5, nr)
     is_tr = rng.random(nr) < 0.12
     tap = np.where(is_tr, rng.uniform(0.9, 1.1, nr), 1.0)

@@ -45,6 +45,10 @@ def synthetic(name: str) -> PowersenseData:
         return ps.create_PowersenseData(synth.synth_network(30, 45, 8, seed=3, source_type="arpae", nbss=4, frac_out=0.1))
     if name == "mp40_out":
         return ps.create_PowersenseData(synth.synth_network(40, 70, 9, seed=11, frac_out=0.15, frac_parallel=0.1))
+    if name == "wellcond":                 # |y| <= ~50: no catastrophic cancellation in the L4 / L5 rows
+        return ps.create_PowersenseData(synth.synth_network(60, 95, 12, seed=17, x_min=0.02))
+    if name == "wellcond_arpae":
+        return ps.create_PowersenseData(synth.synth_network(60, 95, 12, seed=18, x_min=0.02, source_type="arpae", nbss=3))
     if name == "hub":                      # one bus of degree ~60: uneven bus tiles
         net = synth.synth_network(200, 330, 20, seed=5)
         net.f[:60] = 1
@@ -59,3 +63,12 @@ def tol_err(a, ref):
     if a.size == 0:
         return 0.0
     return float(np.max(np.abs(a - ref) / (1e-10 + 1e-12 * np.abs(ref))))
+
+
+def tol_err_scaled(a, ref, scale):
+    """Same, with the relative part taken against max(|ref|, scale): scale is the oracle's condition scale
+    (COracle.condition_scale), the magnitude of the terms the reference formula sums for that output."""
+    a, ref, scale = np.asarray(a), np.asarray(ref), np.asarray(scale)
+    if a.size == 0:
+        return 0.0
+    return float(np.max(np.abs(a - ref) / (1e-10 + 1e-12 * np.maximum(np.abs(ref), scale))))

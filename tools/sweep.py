@@ -13,7 +13,7 @@ import powersense_b200 as ps  # noqa: E402
 from powersense_b200 import capi, synth  # noqa: E402
 
 
-def run(case, Fname, S, chunks, what=7, steps=5):
+def run(case, Fname, S, chunks, what=7, steps=5, scal=True):
     d = synth.named_case(case)
     F = ps.BY_NAME[Fname]
     h = capi.Handle(d, F.code, device=0)
@@ -26,7 +26,7 @@ def run(case, Fname, S, chunks, what=7, steps=5):
     g = torch.empty(S, h.m_nl, dtype=torch.float64, device=dev)
     J = torch.empty(S, h.nnzJ, dtype=torch.float64, device=dev)
     H = torch.empty(S, h.nnzH, dtype=torch.float64, device=dev)
-    sc = torch.empty(S, 4, dtype=torch.float64, device=dev)
+    sc = torch.empty(S, 4, dtype=torch.float64, device=dev) if scal else None
     ab = h.algorithmic_bytes(what)
     for c in chunks:
         os.environ["PS_CHUNK"] = str(c)
@@ -40,7 +40,7 @@ def run(case, Fname, S, chunks, what=7, steps=5):
         e1.record()
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1) / steps
-        print(f"{case} {Fname} S={S} what={what} chunk={c}: {ms:.3f} ms  {S / ms * 1e3:.0f} evals/s  {ab * S / ms / 1e6:.0f} GB/s", flush=True)
+        print(f"{case} {Fname} S={S} what={what} scal={scal} chunk={c}: {ms:.3f} ms  {S / ms * 1e3:.0f} evals/s  {ab * S / ms / 1e6:.0f} GB/s", flush=True)
     b.close()
     h.close()
 
@@ -52,6 +52,13 @@ if __name__ == "__main__":
         run("case13659pegase", "PBRARVmodel", 1024, [8], what=1)
         run("case13659pegase", "PBRARVmodel", 1024, [8], what=2)
         run("case13659pegase", "PBRARVmodel", 1024, [8], what=4)
+    if sel == "noscal":
+        run("case13659pegase", "PBRARVmodel", 1024, [2, 4, 8], scal=False)
+        run("case13659pegase", "PBRARVmodel", 1024, [4], what=1, scal=False)
+        run("case13659pegase", "PBRARVmodel", 1024, [4], what=2, scal=False)
+        run("case13659pegase", "PBRARVmodel", 1024, [4], what=4, scal=False)
+    if sel == "ncu":
+        run("case13659pegase", "PBRARVmodel", 256, [4], steps=1)
     if sel in ("all", "others"):
         run("case13659pegase", "CBRARVmodel", 1024, [4, 16])
         run("case2869pegase", "PNPAPVmodel", 1024, [4, 16])

@@ -110,6 +110,17 @@ int ps_hessian_structure(const ps_handle* h, int64_t* row, int64_t* col);
  * a(theta|vi), b(V|vr), Wd, Wr, Wi, pg, qg, F0, F1, F2, F3, cg, bss, tgh, n_var, nx_nl ; -1 = absent */
 int ps_variable_offsets(const ps_handle* h, int64_t out[16]);
 
+/* Execution plan facts for reports and tests: out[0..7] = number of bus tiles, number of branch tiles, dynamic shared
+ * memory of the bus kernel (bytes), of the staged branch kernel (bytes), 1 if the branch rows can take the direct
+ * (register -> 32-byte sector) store path, 1 if the PB* bus rows use the implicit slot order, J / H slot where the
+ * branch rows start (0-based; the direct path needs these on a 32-byte sector: see ps_preferred_layout). */
+int ps_plan_info(const ps_handle* h, int64_t out[8]);
+/* Leading dimension (doubles, multiple of 4) and leading pad (doubles, 0..3) for the batched g / J / H arrays
+ * (index 0, 1, 2) such that, on a 32-byte aligned allocation, row s starts at base + pad + s*ld and the branch block
+ * of every row starts on a 32-byte sector -- the condition for the direct store path of ps_batch_eval.  Other
+ * layouts are accepted and take the staged path. */
+int ps_preferred_layout(const ps_handle* h, int64_t ld[3], int64_t pad[3]);
+
 /* ---- single-scenario callbacks: host pointers, synchronous -------------------------------- */
 /* MOI.eval_constraint(d, g, x) (call site src/opt/MOI_wrapper.jl:969).  `g` may point into a larger
  * array (the wrapper passes view(g, row:length(g)), :967). */

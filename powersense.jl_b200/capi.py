@@ -49,6 +49,8 @@ _SIGS = {
     "ps_jacobian_structure": (C.c_int, [_VP, _P64, _P64]),
     "ps_hessian_structure": (C.c_int, [_VP, _P64, _P64]),
     "ps_variable_offsets": (C.c_int, [_VP, _P64]),
+    "ps_plan_info": (C.c_int, [_VP, _P64]),
+    "ps_preferred_layout": (C.c_int, [_VP, _P64, _P64]),
     "ps_eval_constraint": (C.c_int, [_VP, _PD, _PD]),
     "ps_eval_jacobian": (C.c_int, [_VP, _PD, _PD]),
     "ps_eval_hessian": (C.c_int, [_VP, _PD, C.c_double, _PD, _PD]),
@@ -181,6 +183,18 @@ class Handle:
         self._check(lib().ps_variable_offsets(self.h, _p64(out)))
         names = ("a", "b", "Wd", "Wr", "Wi", "pg", "qg", "F0", "F1", "F2", "F3", "cg", "bss", "tgh", "n_var", "nx_nl")
         return dict(zip(names, out.tolist()))
+
+    def plan_info(self):
+        out = np.zeros(8, np.int64)
+        self._check(lib().ps_plan_info(self.h, _p64(out)))
+        names = ("bus_tiles", "branch_tiles", "smem_bus_bytes", "smem_branch_bytes", "direct_ok", "pb_implicit", "j_br0", "h_br0")
+        return dict(zip(names, out.tolist()))
+
+    def preferred_layout(self):
+        """((ld_g, ld_J, ld_H), (pad_g, pad_J, pad_H)) in doubles: see ps_preferred_layout."""
+        ld, pad = np.zeros(3, np.int64), np.zeros(3, np.int64)
+        self._check(lib().ps_preferred_layout(self.h, _p64(ld), _p64(pad)))
+        return tuple(ld.tolist()), tuple(pad.tolist())
 
     def algorithmic_bytes(self, what=7):
         return int(lib().ps_algorithmic_bytes(self.h, what))

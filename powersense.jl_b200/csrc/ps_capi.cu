@@ -153,9 +153,9 @@ int do_eval(ps_batch* b, int what, int64_t s_begin, int64_t s_count, const doubl
   A.ldst = P.net.nbr;
   A.g = g; A.ldg = ldg; A.J = J; A.ldJ = ldJ; A.H = H; A.ldH = ldH;
   A.scal = scalars; A.viol_tol = b->viol_tol;
-  e = launch_eval(h->dev, A, P.smem_bytes, stream);
+  e = launch_eval(h->dev, A, P.smem_branch_bytes, P.smem_bus_bytes, stream, &b->launches);
   if (e != cudaSuccess) return cuda_fail(h, e, "eval_kernel launch");
-  b->launches += 1 + (scalars ? 1 : 0);
+  b->launches += (scalars ? 1 : 0);                  // the memset node
   return PS_OK;
 }
 
@@ -246,6 +246,11 @@ int ps_create(const ps_network* net, int formulation, int source_type, int flags
   D.o_cg = (int)P.o_cg; D.o_bss = (int)P.o_bss;
   D.bus_rows = (int)P.bus_rows;
   D.ntiles = (int)P.tiles.size();
+  D.n_bus_tiles = P.n_bus_tiles;
+  D.j_br0 = P.jptr[P.bus_rows]; D.h_br0 = P.hptr[P.bus_rows];
+  D.pb_implicit = P.pb_implicit ? 1 : 0;
+  D.pb_slots = P.pb_slots ? 1 : 0;
+  D.pb_jcode = M.upload(P.pb_jcode); D.pb_hcode = M.upload(P.pb_hcode);
   D.cost_order = P.net.cost_order;
   D.f = M.upload(P.net.f); D.t = M.upload(P.net.t);
   D.Gf = M.upload(P.net.Gf); D.Bf = M.upload(P.net.Bf); D.Gt = M.upload(P.net.Gt); D.Bt = M.upload(P.net.Bt);
@@ -275,7 +280,7 @@ int ps_create(const ps_network* net, int formulation, int source_type, int flags
   if ((e = cudaHostAlloc((void**)&h->h_in, std::max<int64_t>(n_in, 1) * sizeof(double), cudaHostAllocDefault)) != cudaSuccess ||
       (e = cudaHostAlloc((void**)&h->h_out, std::max<int64_t>(n_out, 1) * sizeof(double), cudaHostAllocDefault)) != cudaSuccess ||
       (e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking)) != cudaSuccess ||
-      (e = configure_eval(P.form, P.src, P.smem_bytes)) != cudaSuccess) {
+      (e = configure_eval(P.form, P.src, P.smem_branch_bytes, P.smem_bus_bytes)) != cudaSuccess) {
     ps_destroy(h);
     return cuda_fail(nullptr, e, "handle setup");
   }
@@ -333,6 +338,32 @@ int ps_variable_offsets(const ps_handle* h, int64_t out[16]) {
   const int64_t v[16] = {P.o_a, P.o_b, P.o_Wd, P.o_Wr, P.o_Wi, P.o_pg, P.o_qg, P.o_f[0], P.o_f[1], P.o_f[2], P.o_f[3],
                          P.o_cg, P.o_bss, P.o_tgh, P.n_var, P.nx_nl};
   std::copy(v, v + 16, out);
+  return PS_OK;
+}
+
+int ps_plan_info(const ps_handle* h, int64_t out[8]) {
+  if (!h || !out) return PS_ERR_ARG;
+  const Plan& P = h->plan;
+  out[0] = P.n_bus_tiles;
+  out[1] = (int64_t)P.tiles.size() - P.n_bus_tiles - 1;
+  out[2] = P.smem_bus_bytes;
+  out[3] = P.smem_branch_bytes;
+  out[4] = direct_ok(P.form, P.src) ? 1 : 0;
+  out[5] = (P.pb_implicit ? 1 : 0) | (P.pb_slots ? 2 : 0);
+  out[6] = P.jptr[P.bus_rows];
+  out[7] = P.hptr[P.bus_rows];
+  return PS_OK;
+}
+
+int ps_preferred_layout(const ps_handle* h, int64_t ld[3], int64_t pad[3]) {
+  if (!h || !ld || !pad) return PS_ERR_ARG;
+  const Plan& P = h->plan;
+  const int64_t n[3] = {P.m_nl, P.nnzJ, P.nnzH};
+  const int64_t first[3] = {P.bus_rows, P.jptr[P.bus_rows], P.hptr[P.bus_rows]};
+  for (int q = 0; q < 3; q++) {
+    ld[q] = (n[q] + 3) / 4 * 4;
+    pad[q] = (4 - first[q] % 4) % 4;
+  }
   return PS_OK;
 }
 

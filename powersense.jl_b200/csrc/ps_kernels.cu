@@ -11,11 +11,20 @@
 // with fully coalesced stores.  HBM traffic per scenario = reads of x / mu / loads + exactly one
 // write of every output slot.  The path is sparse FP64 and HBM-bound: no tensor cores.
 #include <cstdio>
+#include <cstdlib>
+#include <utility>
 
 #include "ps_kernels.cuh"
 
 namespace ps {
 namespace {
+
+// one full 32-byte sector per thread: the store shape that keeps HBM writes at copy bandwidth when every
+// thread owns a contiguous run of the output (8- and 16-byte stores of such runs are partial-sector writes and
+// run ~6x slower: profiles/r01_store_patterns.txt).  Streaming (evict-first): outputs are never re-read.
+__device__ __forceinline__ void st_v4(double* p, double a, double b, double c, double d) {
+  asm volatile("st.global.cs.v4.f64 [%0], {%1, %2, %3, %4};" ::"l"(p), "d"(a), "d"(b), "d"(c), "d"(d) : "memory");
+}
 
 // ------------------------------------------------------------------------------- branch rows
 // Thread lu of a branch tile stages its rows at sG[lu*NRP + r], sJ[lu*RJP + p], sH[lu*RHP + p];
@@ -45,6 +54,46 @@ struct Branch {
     template <int T> __device__ __forceinline__ void J(double v) { j[sw ? JP<T>::p1 : JP<T>::p0] = v; }
     template <int T> __device__ __forceinline__ void H(double v) { h[sw ? HP<T>::p1 : HP<T>::p0] = v; }
   };
+
+  // Register writer of the direct path: values are kept by *tag* in registers (all indices are compile-time
+  // constants) and emitted in slot order as full 32-byte sectors, st.global.v4.f64, by the owning thread.
+  template <int P> struct JI { static constexpr int t0 = SL.jinv[0][P], t1 = SL.jinv[1][P]; };
+  template <int P> struct HI { static constexpr int t0 = SL.hinv[0][P], t1 = SL.hinv[1][P]; };
+  template <bool WJ, bool WH>
+  struct OutR {                      // WJ / WH are compile-time: a J pass and an H pass keep register pressure low
+    static constexpr bool wj = WJ, wh = WH;
+    double gt[NR > 0 ? NR : 1], jt[WJ && RJ > 0 ? RJ : 1], ht[WH && RH > 0 ? RH : 1];
+    bool sw, track;
+    double vmax, tol;
+    int nviol;
+    template <int R> __device__ __forceinline__ void G(double v, bool eq) {
+      if constexpr (WJ) {            // g and the violation scalars belong to the J pass
+        gt[R] = v;
+        const double vv = eq ? fabs(v) : v;
+        vmax = fmax(vmax, vv);
+        nviol += (vv > tol) ? 1 : 0;
+      }
+    }
+    template <int T> __device__ __forceinline__ void J(double v) { if constexpr (WJ) jt[T] = v; }
+    template <int T> __device__ __forceinline__ void H(double v) { if constexpr (WH) ht[T] = v; }
+    template <int P> __device__ __forceinline__ double jsel() const {
+      if constexpr (JI<P>::t0 == JI<P>::t1) return jt[JI<P>::t0];
+      else return sw ? jt[JI<P>::t1] : jt[JI<P>::t0];
+    }
+    template <int P> __device__ __forceinline__ double hsel() const {
+      if constexpr (HI<P>::t0 == HI<P>::t1) return ht[HI<P>::t0];
+      else return sw ? ht[HI<P>::t1] : ht[HI<P>::t0];
+    }
+    template <int P0> __device__ __forceinline__ void storeJ4(double* p) const {
+      st_v4(p + P0, jsel<P0>(), jsel<P0 + 1>(), jsel<P0 + 2>(), jsel<P0 + 3>());
+    }
+    template <int P0> __device__ __forceinline__ void storeH4(double* p) const {
+      st_v4(p + P0, hsel<P0>(), hsel<P0 + 1>(), hsel<P0 + 2>(), hsel<P0 + 3>());
+    }
+    template <int... Q> __device__ __forceinline__ void storeJ(double* p, std::integer_sequence<int, Q...>) const { (storeJ4<4 * Q>(p), ...); }
+    template <int... Q> __device__ __forceinline__ void storeH(double* p, std::integer_sequence<int, Q...>) const { (storeH4<4 * Q>(p), ...); }
+  };
+  static constexpr bool DIRECT_OK = (RJ % 4 == 0) && (RH % 4 == 0) && RJ > 0 && RH > 0;
 
   struct Cst { double gf, bf, Gf, Bf, gt, bt, Gt, Bt, Imax; double d[8]; };   // d: c0..c3 per side
   struct In { double af, at, bf, bt, wf, wt, wr, wi, F0, F1, F2, F3, st; double mu[NR > 0 ? NR : 1]; };
@@ -90,8 +139,8 @@ struct Branch {
 
   // polar flow-definition row (PBRAPV :302-305 | :366-369): row = flow - T,  T from SURVEY F.1
   // SIDE 0: a = f ; SIDE 1: a = t.  PQ 0: P row, 1: Q row.  cs/sn = cos/sin(th_f - th_t)
-  template <int R, int SIDE, int PQ>
-  static __device__ __forceinline__ void polar_flow(Out& o, double flow, double Vf, double Vt, double cs, double sn,
+  template <int R, int SIDE, int PQ, class O>
+  static __device__ __forceinline__ void polar_flow(O& o, double flow, double Vf, double Vt, double cs, double sn,
                                                     double gs, double bs, double G, double B, double mu) {
     constexpr int J0 = Row<R>::J0, H0 = Row<R>::H0;
     const double Va = SIDE ? Vt : Vf, Vb = SIDE ? Vf : Vt;
@@ -137,8 +186,8 @@ struct Branch {
   }
 
   // rectangular flow-definition row (PBRARV :309-312 | :373-376), T from SURVEY F.2
-  template <int R, int SIDE, int PQ>
-  static __device__ __forceinline__ void rect_flow(Out& o, double flow, double ra, double ia, double rb, double ib,
+  template <int R, int SIDE, int PQ, class O>
+  static __device__ __forceinline__ void rect_flow(O& o, double flow, double ra, double ia, double rb, double ib,
                                                    double gs, double bs, double G, double B, double mu) {
     constexpr int J0 = Row<R>::J0, H0 = Row<R>::H0;
     const double A2 = ra * ra + ia * ia, C = ra * rb + ia * ib, S = ra * ib - ia * rb;
@@ -179,8 +228,8 @@ struct Branch {
 
   // L1: P^2 + Q^2 - Imax^2 [* |V_a|^2]   (:306-307,:313-314,:321-322 | :370-371,:377-378,:385-386)
   // va, vb: V_a (polar) | (vr_a, vi_a) (rect) | Wd_a (W)
-  template <int R>
-  static __device__ __forceinline__ void limit_L1(Out& o, double Pf, double Qf, double va, double vb, double Im2, double mu) {
+  template <int R, class O>
+  static __device__ __forceinline__ void limit_L1(O& o, double Pf, double Qf, double va, double vb, double Im2, double mu) {
     constexpr int J0 = Row<R>::J0, H0 = Row<R>::H0;
     const double lhs = Pf * Pf + Qf * Qf;
     double rhs = Im2;
@@ -210,8 +259,8 @@ struct Branch {
   }
 
   // L2 / L3 (CBRARV :328-329 | :392-393 ; CBRAWV :335-336 | :399-400).  a1 = vr_a | Wd_a, a0 = vi_a
-  template <int R>
-  static __device__ __forceinline__ void limit_CB(Out& o, double Ir, double Ii, double a1, double a0, double Im2, double mm) {
+  template <int R, class O>
+  static __device__ __forceinline__ void limit_CB(O& o, double Ir, double Ii, double a1, double a0, double Im2, double mm) {
     constexpr int J0 = Row<R>::J0, H0 = Row<R>::H0;
     const double I2 = Ir * Ir + Ii * Ii;
     if constexpr (!MP) {
@@ -238,8 +287,8 @@ struct Branch {
   }
 
   // L4 (PNPAPV / PNRAPV :337-343 | :401-407), SURVEY F.5
-  template <int SIDE>
-  static __device__ __forceinline__ void limit_L4(Out& o, double thf, double tht, double Vf, double Vt, double gs, double bs,
+  template <int SIDE, class O>
+  static __device__ __forceinline__ void limit_L4(O& o, double thf, double tht, double Vf, double Vt, double gs, double bs,
                                                   double G, double B, double y3, double th1, double th2, double Im2, double mm) {
     constexpr int R = SIDE;
     constexpr int J0 = Row<R>::J0, H0 = Row<R>::H0;
@@ -290,8 +339,8 @@ struct Branch {
   }
 
   // L5 (PNRARV :344-352 | :408-414), SURVEY F.5
-  template <int SIDE>
-  static __device__ __forceinline__ void limit_L5(Out& o, double ra, double ia, double rb, double ib, double y, double Y,
+  template <int SIDE, class O>
+  static __device__ __forceinline__ void limit_L5(O& o, double ra, double ia, double rb, double ib, double y, double Y,
                                                   double y1, double y2, double Im2, double mm) {
     constexpr int R = SIDE;
     constexpr int J0 = Row<R>::J0, H0 = Row<R>::H0;
@@ -337,7 +386,8 @@ struct Branch {
     }
   }
 
-  static __device__ __forceinline__ void run(Out& o, const Cst& c, const In& in) {
+  template <class O>
+  static __device__ __forceinline__ void run(O& o, const Cst& c, const In& in) {
     const double st = in.st;
     double Imax = c.Imax * st;
     if (Imax == 0.0) Imax = 10000.0;                          // PowersenseData.jl:206-207
@@ -408,8 +458,8 @@ struct Branch {
 // diagonal block of the nodal balances, parallel branches).  A bus's slots are private to its thread, so
 // there are no races and the accumulation order is the reference's term order.
 struct Stream {
-  double* base;
-  const uint16_t* pos;
+  double* __restrict__ base;
+  const uint16_t* __restrict__ pos;
   bool on;
   __device__ __forceinline__ void put(double v) {
     if (on) {
@@ -441,23 +491,30 @@ __device__ __forceinline__ void cp_async8(void* smem_dst, const void* gsrc) {
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
 template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
 
+// per-bus invariants, loaded once per CTA and kept in registers across the scenario loop
+struct BusInv {
+  int g0, g1, h0, h1, f0, f1;        // tile-local ranges of the bus's generators / half-edges / switched shunts
+  int jbase, hbase, cjo, cho;        // first J / H slot in the tile, first entry of the position streams
+  double Gl, Bl;
+};
+
 // shared-memory view of one bus tile
 struct BusTile {
   int nbt, nhe, ngt, nsh;            // buses, half-edges, generators, switched shunts in the tile
   int hp0, gp0, sp0, cj0, ch0;       // first global index of each list
   int xh, xg, xw, xs_, xm, xl, nx;   // offsets inside the gathered-input array
-  double *sG, *sJ, *sH, *xb[2], *hc;
+  double *sG, *sJ, *sH, *xb0, *xb1, *hc;
   int *heks, *hoth, *sgen, *ssh;
   uint16_t *jpos, *hpos;
   uint8_t* sst;
 };
 
 template <int FORM>
-__device__ __forceinline__ void bus_rows(const DevPlan& P, const BusTile& T, const double* xs, BusOut& o, Stream& sj,
-                                         Stream& sh, int i, int lu, bool has_status) {
+__device__ __forceinline__ void bus_rows(const DevPlan& P, const BusTile& T, const BusInv& B, const double* xs, BusOut& o,
+                                         Stream& sj, Stream& sh, int lu, bool has_status) {
   const double muP = sh.on ? xs[T.xm + 2 * lu] : 0.0, muQ = sh.on ? xs[T.xm + 2 * lu + 1] : 0.0;
   double accP = 0.0, accQ = 0.0;                               // formulations.jl:171-172
-  for (int q = P.gen_ptr[i] - T.gp0, q1 = P.gen_ptr[i + 1] - T.gp0; q < q1; q++) {   // :177-180
+  for (int q = B.g0; q < B.g1; q++) {                           // :177-180
     accP = accP + xs[T.xg + 2 * q];
     accQ = accQ + xs[T.xg + 2 * q + 1];
     sj.put(1.0);
@@ -465,7 +522,7 @@ __device__ __forceinline__ void bus_rows(const DevPlan& P, const BusTile& T, con
   }
   const double va0 = xs[lu], vb0 = xs[T.nbt + lu];             // own voltage: (theta_i, V_i) | (vi_i, vr_i)
 #pragma unroll 1
-  for (int q = P.he_ptr[i] - T.hp0, q1 = P.he_ptr[i + 1] - T.hp0; q < q1; q++) {     // Sij ascending, then Sji ascending
+  for (int q = B.h0; q < B.h1; q++) {                           // Sij ascending, then Sji ascending
     const int side = T.heks[q] & 1;
     const double st = has_status ? (double)T.sst[q] : 1.0;
     const double v0 = xs[T.xh + 2 * q], v1 = xs[T.xh + 2 * q + 1];
@@ -529,9 +586,8 @@ __device__ __forceinline__ void bus_rows(const DevPlan& P, const BusTile& T, con
     }
   }
   // shunt terms :256-279
-  const double Gl = P.Gl[i], Bl = P.Bl[i];
-  const bool facts = (P.flags & FLAG_FACTS) != 0;
-  const int f0 = P.sh_ptr[i] - T.sp0, f1 = facts ? P.sh_ptr[i + 1] - T.sp0 : f0;
+  const double Gl = B.Gl, Bl = B.Bl;
+  const int f0 = B.f0, f1 = B.f1;
   if constexpr (is_polar(FORM)) {
     const double V = vb0, V2 = V * V;
     accP = accP - Gl * V2;
@@ -568,6 +624,50 @@ __device__ __forceinline__ void bus_rows(const DevPlan& P, const BusTile& T, con
       sj.put(W); sj.put(bss);
       sh.put(0.0); sh.put(0.0); sh.put(muQ);
     }
+  }
+  o.G(0, accP - xs[T.xl + lu]);                                // :291
+  o.G(1, accQ - xs[T.xl + T.nbt + lu]);                        // :292
+}
+
+// Power-branch-flow balances (PBRAPV / PBRARV, formulations.jl:188-196): the row is linear in the generator and
+// flow variables, so its Jacobian slots are, in JuMP's sorted-column order, [own voltage slots][pg | qg of the
+// bus's generators][Pij | Qij of Sij][Pji | Qji of Sji] -- the emission order -- and every entry but the voltage
+// ones is the constant 1 (times the branch status).  The constant slots are written once per CTA and stay in the
+// staging tile; per scenario a bus thread sums its injections and rewrites the 2-4 voltage-dependent slots.
+template <int FORM>
+__device__ __forceinline__ void bus_rows_pb(const BusTile& T, const BusInv& B, const double* __restrict__ xs, BusOut& o,
+                                            bool wj, bool wh, int lu, bool has_status, bool fill_const) {
+  constexpr int NV = (FORM == PBRARV) ? 2 : 1;                 // (vi_i, vr_i) | V_i
+  const int len = NV + (B.g1 - B.g0) + (B.h1 - B.h0);          // slots of the P row == slots of the Q row
+  double* __restrict__ jP = T.sJ + B.jbase;
+  double* __restrict__ jQ = jP + len;
+  double accP = 0.0, accQ = 0.0;                               // formulations.jl:171-172
+  int c = NV;
+  for (int q = B.g0; q < B.g1; q++, c++) {                     // :177-180
+    accP = accP + xs[T.xg + 2 * q];
+    accQ = accQ + xs[T.xg + 2 * q + 1];
+    if (fill_const) { jP[c] = 1.0; jQ[c] = 1.0; }
+  }
+  for (int q = B.h0; q < B.h1; q++, c++) {                     // :188-196, Sij ascending then Sji ascending
+    const double st = has_status ? (double)T.sst[q] : 1.0;
+    accP = accP + st * xs[T.xh + 2 * q];
+    accQ = accQ + st * xs[T.xh + 2 * q + 1];
+    if (fill_const || (has_status && wj)) { jP[c] = st; jQ[c] = st; }
+  }
+  const double muP = wh ? xs[T.xm + 2 * lu] : 0.0, muQ = wh ? xs[T.xm + 2 * lu + 1] : 0.0;
+  double* __restrict__ hP = T.sH + B.hbase;
+  if constexpr (FORM == PBRARV) {                              // :264-266
+    const double im = xs[lu], r = xs[T.nbt + lu], A2 = r * r + im * im;
+    accP = accP - B.Gl * A2;
+    accQ = accQ + B.Bl * A2;
+    if (wj) { jP[0] = -2.0 * B.Gl * im; jP[1] = -2.0 * B.Gl * r; jQ[0] = 2.0 * B.Bl * im; jQ[1] = 2.0 * B.Bl * r; }
+    if (wh) { hP[0] = -2.0 * B.Gl * muP; hP[1] = -2.0 * B.Gl * muP; hP[2] = 2.0 * B.Bl * muQ; hP[3] = 2.0 * B.Bl * muQ; }
+  } else {                                                     // :256-258
+    const double V = xs[T.nbt + lu], V2 = V * V;
+    accP = accP - B.Gl * V2;
+    accQ = accQ + B.Bl * V2;
+    if (wj) { jP[0] = -2.0 * B.Gl * V; jQ[0] = 2.0 * B.Bl * V; }
+    if (wh) { hP[0] = -2.0 * B.Gl * muP; hP[1] = 2.0 * B.Bl * muQ; }
   }
   o.G(0, accP - xs[T.xl + lu]);                                // :291
   o.G(1, accQ - xs[T.xl + T.nbt + lu]);                        // :292
@@ -611,16 +711,21 @@ __device__ __forceinline__ void bus_gather(const DevPlan& P, const EvalArgs& A, 
 }
 
 // ------------------------------------------------------------------------------- helpers
-// stream a staged tile to HBM: consecutive threads write consecutive doubles (full 32-byte sectors)
+// Stream a staged tile to HBM.  Consecutive threads write consecutive doubles, and the thread -> element map is
+// shifted so that every warp-wide store covers whole 32-byte sectors of the destination (partial-sector writes
+// are several times slower); only the few elements before the first sector boundary are written separately.
+template <int NTHR, class F>
+__device__ __forceinline__ void copy_aligned(double* __restrict__ dst, int n, int tid, F get) {
+  const int a = min(n, (int)((4 - ((reinterpret_cast<unsigned long long>(dst) >> 3) & 3)) & 3));
+  if (tid < a) dst[tid] = get(tid);
+  for (int e = a + tid; e < n; e += NTHR) dst[e] = get(e);
+}
 template <int N, int NP>
 __device__ __forceinline__ void copy_out_padded(double* __restrict__ dst, const double* tile, int n) {
-  for (int e = threadIdx.x; e < n; e += TPB) {
-    const int lu = e / N;                                      // N is a compile-time constant
-    dst[e] = tile[e + lu * (NP - N)];
-  }
+  copy_aligned<TPB>(dst, n, threadIdx.x, [&](int e) { return tile[e + (e / N) * (NP - N)]; });   // N: compile-time
 }
 __device__ __forceinline__ void copy_out(double* __restrict__ dst, const double* tile, int n) {
-  for (int e = threadIdx.x; e < n; e += TPB) dst[e] = tile[e];
+  copy_aligned<TPB>(dst, n, threadIdx.x, [&](int e) { return tile[e]; });
 }
 
 __device__ __forceinline__ void reduce_scalars(double* scal, double vmax, int nviol) {
@@ -666,23 +771,274 @@ __device__ __forceinline__ void objective_tile(const DevPlan& P, const EvalArgs&
   }
 }
 
+// Staged path of the branch rows (any row size, any alignment): every thread evaluates its branch into a
+// shared-memory tile laid out like the output (odd per-thread strides: conflict-free), then the CTA streams the
+// tile to HBM with warp-contiguous, sector-aligned stores.
 template <int FORM, int SRC>
-__global__ void __launch_bounds__(TPB) eval_kernel(const __grid_constant__ DevPlan P, const __grid_constant__ EvalArgs A) {
+__global__ void __launch_bounds__(TPB) branch_staged_kernel(const __grid_constant__ DevPlan P, const __grid_constant__ EvalArgs A) {
   extern __shared__ double smem[];
-  const Tile tl = P.tiles[blockIdx.x];
+  using BR = Branch<FORM, SRC>;
+  const Tile tl = P.tiles[P.n_bus_tiles + blockIdx.x];
   const int s0 = blockIdx.y * A.chunk, s1 = min(A.S, s0 + A.chunk);
   const bool wg = (A.what & EV_G) != 0, wj = (A.what & EV_J) != 0, wh = (A.what & EV_H) != 0;
   const int u = tl.u0 + threadIdx.x;
   const bool act = u < tl.u1;
+  double* sG = smem;
+  double* sJ = sG + TPB * BR::NRP;
+  double* sH = sJ + TPB * BR::RJP;
+  typename BR::Out o;
+  o.g = sG + threadIdx.x * BR::NRP; o.j = sJ + threadIdx.x * BR::RJP; o.h = sH + threadIdx.x * BR::RHP;
+  o.wg = wg; o.wj = wj; o.wh = wh; o.tol = A.viol_tol;
+  typename BR::Cst cst{};
+  typename BR::In cur{};
+  int f = 0, t = 1;
+  if (act) {
+    f = P.f[u]; t = P.t[u];
+    cst = BR::load_cst(P, u);
+    cur = BR::load_in(P, A, s0, u, f, t);
+  }
+  o.sw = f > t;
+  for (int s = s0; s < s1; s++) {
+    typename BR::In nxt{};
+    if (act && s + 1 < s1) nxt = BR::load_in(P, A, s + 1, u, f, t);   // prefetch the next scenario's inputs
+    o.vmax = 0.0; o.nviol = 0;
+    if (act) BR::run(o, cst, cur);
+    __syncthreads();
+    if (wg) copy_out_padded<BR::NR, BR::NRP>(A.g + (long long)s * A.ldg + tl.g0, sG, tl.gn);
+    if (wj) copy_out_padded<BR::RJ, BR::RJP>(A.J + (long long)s * A.ldJ + tl.j0, sJ, tl.jn);
+    if (wh) copy_out_padded<BR::RH, BR::RHP>(A.H + (long long)s * A.ldH + tl.h0, sH, tl.hn);
+    reduce_scalars(A.scal ? A.scal + (long long)s * NSCAL : nullptr, o.vmax, o.nviol);
+    __syncthreads();
+    if (s + 1 < s1) cur = nxt;
+  }
+}
 
-  if (tl.kind == 1) {
-    using BR = Branch<FORM, SRC>;
-    double* sG = smem;
-    double* sJ = sG + TPB * BR::NRP;
-    double* sH = sJ + TPB * BR::RJP;
-    typename BR::Out o;
-    o.g = sG + threadIdx.x * BR::NRP; o.j = sJ + threadIdx.x * BR::RJP; o.h = sH + threadIdx.x * BR::RHP;
-    o.wg = wg; o.wj = wj; o.wh = wh; o.tol = A.viol_tol;
+// Bus rows (nodal balances, formulations.jl:170-297) plus, in the last CTA column, the objective scalar.
+template <int FORM>
+__global__ void __launch_bounds__(TPB) bus_kernel(const __grid_constant__ DevPlan P, const __grid_constant__ EvalArgs A) {
+  extern __shared__ double smem[];
+  const int s0 = blockIdx.y * A.chunk, s1 = min(A.S, s0 + A.chunk);
+  if ((int)blockIdx.x >= P.n_bus_tiles) {
+    if (A.scal) objective_tile(P, A, s0, s1, smem);
+    return;
+  }
+  if constexpr (has_bus_rows(FORM)) {
+    const Tile tl = P.tiles[blockIdx.x];
+    const bool wg = (A.what & EV_G) != 0, wj = (A.what & EV_J) != 0, wh = (A.what & EV_H) != 0;
+    const int u = tl.u0 + threadIdx.x;
+    const bool act = u < tl.u1;
+    const bool facts = (P.flags & FLAG_FACTS) != 0;
+    BusTile T;
+    T.nbt = tl.u1 - tl.u0;
+    T.hp0 = P.he_ptr[tl.u0]; T.nhe = P.he_ptr[tl.u1] - T.hp0;
+    T.gp0 = P.gen_ptr[tl.u0]; T.ngt = P.gen_ptr[tl.u1] - T.gp0;
+    T.sp0 = P.sh_ptr[tl.u0]; T.nsh = facts ? P.sh_ptr[tl.u1] - T.sp0 : 0;
+    T.cj0 = P.bus_jpp[tl.u0]; T.ch0 = P.bus_hpp[tl.u0];
+    const int ncj = P.bus_jpp[tl.u1] - T.cj0, nch = P.bus_hpp[tl.u1] - T.ch0;
+    // gathered-input layout: own a | own b | half-edge pairs | generator pairs | Wd | bss | mu (P,Q) | Pd | Qd
+    T.xh = 2 * T.nbt; T.xg = T.xh + 2 * T.nhe; T.xw = T.xg + 2 * T.ngt;
+    T.xs_ = T.xw + (FORM == CBRAWV ? T.nbt : 0); T.xm = T.xs_ + T.nsh; T.xl = T.xm + 2 * T.nbt; T.nx = T.xl + 2 * T.nbt;
+    T.sG = smem; T.sJ = T.sG + tl.gn; T.sH = T.sJ + tl.jn;
+    T.xb0 = T.sH + tl.hn; T.xb1 = T.xb0 + T.nx;
+    T.hc = T.xb1 + T.nx;
+    T.heks = (int*)(T.hc + (is_PN(FORM) ? 4 * T.nhe : 0));
+    T.hoth = T.heks + T.nhe;
+    T.sgen = T.hoth + (is_PN(FORM) ? T.nhe : 0);
+    T.ssh = T.sgen + T.ngt;
+    T.jpos = (uint16_t*)(T.ssh + T.nsh);
+    T.hpos = T.jpos + ncj;
+    T.sst = (uint8_t*)(T.hpos + nch);
+    // ---- scenario-independent staging (once per CTA)
+    for (int q = threadIdx.x; q < T.nhe; q += TPB) {
+      T.heks[q] = P.he_ks[T.hp0 + q];
+      if constexpr (is_PN(FORM)) {
+        T.hoth[q] = P.he_other[T.hp0 + q];
+#pragma unroll
+        for (int c = 0; c < 4; c++) T.hc[c * T.nhe + q] = P.he_c[(long long)c * P.nhe + T.hp0 + q];
+      }
+    }
+    for (int q = threadIdx.x; q < T.ngt; q += TPB) T.sgen[q] = P.gen_idx[T.gp0 + q];
+    for (int q = threadIdx.x; q < T.nsh; q += TPB) T.ssh[q] = P.sh_idx[T.sp0 + q];
+    for (int q = threadIdx.x; q < ncj; q += TPB) T.jpos[q] = P.bus_jpos[T.cj0 + q];
+    for (int q = threadIdx.x; q < nch; q += TPB) T.hpos[q] = P.bus_hpos[T.ch0 + q];
+    BusInv B{};
+    if (act) {
+      B.g0 = P.gen_ptr[u] - T.gp0; B.g1 = P.gen_ptr[u + 1] - T.gp0;
+      B.h0 = P.he_ptr[u] - T.hp0; B.h1 = P.he_ptr[u + 1] - T.hp0;
+      B.f0 = P.sh_ptr[u] - T.sp0; B.f1 = facts ? P.sh_ptr[u + 1] - T.sp0 : B.f0;
+      B.jbase = P.jptr[2 * u] - tl.j0; B.hbase = P.hptr[2 * u] - tl.h0;
+      B.cjo = P.bus_jpp[u] - T.cj0; B.cho = P.bus_hpp[u] - T.ch0;
+      B.Gl = P.Gl[u]; B.Bl = P.Bl[u];
+    }
+    const bool has_status = A.status != nullptr;
+    const bool pb_fast = P.pb_implicit && T.nsh == 0;          // implicit slot order verified by the plan builder
+    BusOut o;
+    o.g = T.sG + 2 * threadIdx.x; o.wg = wg; o.tol = A.viol_tol;
+    __syncthreads();
+    bus_gather<FORM>(P, A, T, tl, s0, T.xb0);
+    cp_async_commit();
+    for (int s = s0; s < s1; s++) {
+      const bool odd = ((s - s0) & 1) != 0;
+      double* const xcur = odd ? T.xb1 : T.xb0;
+      if (s + 1 < s1) bus_gather<FORM>(P, A, T, tl, s + 1, odd ? T.xb0 : T.xb1);   // one scenario ahead
+      cp_async_commit();
+      if (has_status) {
+        const uint8_t* __restrict__ stp = A.status + (long long)s * A.ldst;
+        for (int q = threadIdx.x; q < T.nhe; q += TPB) T.sst[q] = stp[T.heks[q] >> 1];
+      }
+      cp_async_wait<1>();                                                    // this scenario's gather has landed
+      __syncthreads();
+      o.vmax = 0.0; o.nviol = 0;
+      if (act) {
+        bool done = false;
+        if constexpr (FORM == PBRAPV || FORM == PBRARV) {
+          if (pb_fast) {
+            bus_rows_pb<FORM>(T, B, xcur, o, wj, wh, threadIdx.x, has_status, wj && s == s0);
+            done = true;
+          }
+        }
+        if (!done) {
+          Stream sj{T.sJ + B.jbase, T.jpos + B.cjo, wj}, sh{T.sH + B.hbase, T.hpos + B.cho, wh};
+          bus_rows<FORM>(P, T, B, xcur, o, sj, sh, threadIdx.x, has_status);
+        }
+      }
+      __syncthreads();
+      if (wg) copy_out(A.g + (long long)s * A.ldg + tl.g0, T.sG, tl.gn);
+      if (wj) copy_out(A.J + (long long)s * A.ldJ + tl.j0, T.sJ, tl.jn);
+      if (wh) copy_out(A.H + (long long)s * A.ldH + tl.h0, T.sH, tl.hn);
+      reduce_scalars(A.scal ? A.scal + (long long)s * NSCAL : nullptr, o.vmax, o.nviol);
+      __syncthreads();
+    }
+  }
+}
+
+// ---- PB* balances, fast path (PBRAPV / PBRARV without switched shunts) ------------------------------------------
+// The nodal balance of a power-branch-flow model is linear in the generator and flow variables
+// (formulations.jl:188-196): its Jacobian entries are the constant 1 (times the branch status) except the 1-2
+// own-voltage slots, and its Hessian block is (-2 Gl mu_P | 2 Bl mu_Q).  So the bus block of J and H is produced
+// slot-parallel from per-slot codes -- one 32-byte sector per thread, no staging, no barrier -- and the two
+// residuals of a bus by one thread that walks the bus's generator / Sij / Sji lists in the reference's order.
+constexpr int PBT = 256;
+
+template <int FORM>
+__device__ __forceinline__ double pb_jval(const DevPlan& P, int code, const double* __restrict__ x, const uint8_t* __restrict__ st) {
+  if (code == -1) return 1.0;
+  if (code >= 0) return st ? (double)st[code] : 1.0;
+  const int v = -2 - code, i = v >> 2, w = v & 3;
+  const double coef = (w < 2) ? -2.0 * P.Gl[i] : 2.0 * P.Bl[i];
+  return coef * x[((w & 1) ? P.o_b : P.o_a) + i];
+}
+__device__ __forceinline__ double pb_hval(const DevPlan& P, int code, const double* __restrict__ mu) {
+  const int i = code >> 1;
+  return (code & 1) ? 2.0 * P.Bl[i] * mu[code] : -2.0 * P.Gl[i] * mu[code];
+}
+
+// writes dst[0..n) = f(e): the few elements before the first 32-byte boundary and after the last one with scalar
+// stores, everything else as whole sectors
+template <class F>
+__device__ __forceinline__ void emit_sectors(double* __restrict__ dst, int n, int t, int nt, F f) {
+  const int a = min(n, (int)((4 - ((reinterpret_cast<unsigned long long>(dst) >> 3) & 3)) & 3));
+  const int nfull = (n - a) >> 2;
+  for (int q = t; q < nfull; q += nt) {
+    const int e = a + 4 * q;
+    st_v4(dst + e, f(e), f(e + 1), f(e + 2), f(e + 3));
+  }
+  if (t < a) dst[t] = f(t);
+  const int tail = a + 4 * nfull;
+  if (t < n - tail) dst[tail + t] = f(tail + t);
+}
+
+template <int FORM>
+__global__ void __launch_bounds__(PBT) pb_bus_jh_kernel(const __grid_constant__ DevPlan P, const __grid_constant__ EvalArgs A) {
+  const int s0 = blockIdx.y * A.chunk, s1 = min(A.S, s0 + A.chunk);
+  const int t = blockIdx.x * PBT + threadIdx.x, nt = gridDim.x * PBT;
+  for (int s = s0; s < s1; s++) {
+    const double* __restrict__ x = A.x + (long long)s * A.ldx;
+    const uint8_t* __restrict__ st = A.status ? A.status + (long long)s * A.ldst : nullptr;
+    if (A.what & EV_J)
+      emit_sectors(A.J + (long long)s * A.ldJ, P.j_br0, t, nt, [&](int e) { return pb_jval<FORM>(P, P.pb_jcode[e], x, st); });
+    if (A.what & EV_H) {
+      const double* __restrict__ mu = A.mu + (long long)s * A.ldmu;
+      emit_sectors(A.H + (long long)s * A.ldH, P.h_br0, t, nt, [&](int e) { return pb_hval(P, P.pb_hcode[e], mu); });
+    }
+  }
+}
+
+template <int FORM>
+__global__ void __launch_bounds__(PBT) pb_bus_g_kernel(const __grid_constant__ DevPlan P, const __grid_constant__ EvalArgs A) {
+  const int s0 = blockIdx.y * A.chunk, s1 = min(A.S, s0 + A.chunk);
+  const int i = blockIdx.x * PBT + threadIdx.x;
+  const bool act = i < P.nb;
+  int g0 = 0, g1 = 0, h0 = 0, h1 = 0;
+  double Gl = 0.0, Bl = 0.0;
+  if (act) { g0 = P.gen_ptr[i]; g1 = P.gen_ptr[i + 1]; h0 = P.he_ptr[i]; h1 = P.he_ptr[i + 1]; Gl = P.Gl[i]; Bl = P.Bl[i]; }
+  const bool wg = (A.what & EV_G) != 0;
+  for (int s = s0; s < s1; s++) {
+    double vmax = 0.0;
+    int nviol = 0;
+    if (act) {
+      const double* __restrict__ x = A.x + (long long)s * A.ldx;
+      const uint8_t* __restrict__ stp = A.status ? A.status + (long long)s * A.ldst : nullptr;
+      double accP = 0.0, accQ = 0.0;                           // formulations.jl:171-172
+      for (int q = g0; q < g1; q++) {                          // :177-180
+        const int g = P.gen_idx[q];
+        accP = accP + x[P.o_pg + g];
+        accQ = accQ + x[P.o_qg + g];
+      }
+      for (int q = h0; q < h1; q++) {                          // :188-196, Sij ascending then Sji ascending
+        const int ks = P.he_ks[q], k = ks >> 1, side = ks & 1;
+        const double stv = stp ? (double)stp[k] : 1.0;
+        accP = accP + stv * x[P.o_f[0 + 2 * side] + k];
+        accQ = accQ + stv * x[P.o_f[1 + 2 * side] + k];
+      }
+      if constexpr (FORM == PBRARV) {                          // :264-266
+        const double im = x[P.o_a + i], r = x[P.o_b + i], A2 = r * r + im * im;
+        accP = accP - Gl * A2;
+        accQ = accQ + Bl * A2;
+      } else {                                                 // :256-258
+        const double V = x[P.o_b + i], V2 = V * V;
+        accP = accP - Gl * V2;
+        accQ = accQ + Bl * V2;
+      }
+      const double* pd = A.Pd ? A.Pd + (long long)s * A.ldl : P.Pd0;
+      const double* qd = A.Qd ? A.Qd + (long long)s * A.ldl : P.Qd0;
+      const double gP = accP - pd[i], gQ = accQ - qd[i];       // :291-292
+      if (wg) {
+        double* gd = A.g + (long long)s * A.ldg + 2 * i;
+        if ((reinterpret_cast<unsigned long long>(gd) & 15) == 0) *reinterpret_cast<double2*>(gd) = make_double2(gP, gQ);
+        else { gd[0] = gP; gd[1] = gQ; }
+      }
+      vmax = fmax(fabs(gP), fabs(gQ));
+      nviol = (fabs(gP) > A.viol_tol ? 1 : 0) + (fabs(gQ) > A.viol_tol ? 1 : 0);
+    }
+    reduce_scalars(A.scal ? A.scal + (long long)s * NSCAL : nullptr, vmax, nviol);
+  }
+}
+
+// objective scalar only (used with the PB* fast path, where no bus_kernel runs)
+__global__ void __launch_bounds__(TPB) objective_kernel(const __grid_constant__ DevPlan P, const __grid_constant__ EvalArgs A) {
+  __shared__ double red[TPB / 32];
+  const int s0 = blockIdx.x * A.chunk, s1 = min(A.S, s0 + A.chunk);
+  objective_tile(P, A, s0, s1, red);
+}
+
+// Direct path of the branch rows: thread per branch, no shared-memory staging of J / H and no CTA barrier.
+// Inputs of the next scenario are prefetched into registers while the current one is evaluated; the branch's
+// J and H blocks (whole 32-byte sectors) go straight from registers to HBM; g goes through a per-warp staging
+// row so that it is written with warp-contiguous stores.
+template <int FORM, int SRC>
+__global__ void __launch_bounds__(TPB) branch_direct_kernel(const __grid_constant__ DevPlan P, const __grid_constant__ EvalArgs A) {
+  using BR = Branch<FORM, SRC>;
+  if constexpr (BR::DIRECT_OK) {
+    __shared__ double sG[TPB / 32][32 * BR::NR];
+    const int u = blockIdx.x * TPB + threadIdx.x;
+    const bool act = u < P.nr;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int s0 = blockIdx.y * A.chunk, s1 = min(A.S, s0 + A.chunk);
+    const bool wg = (A.what & EV_G) != 0, wj = (A.what & EV_J) != 0, wh = (A.what & EV_H) != 0;
+    typename BR::template OutR<true, false> oj;
+    typename BR::template OutR<false, true> oh;
+    oj.tol = A.viol_tol; oh.tol = A.viol_tol;
     typename BR::Cst cst{};
     typename BR::In cur{};
     int f = 0, t = 1;
@@ -691,104 +1047,68 @@ __global__ void __launch_bounds__(TPB) eval_kernel(const __grid_constant__ DevPl
       cst = BR::load_cst(P, u);
       cur = BR::load_in(P, A, s0, u, f, t);
     }
-    o.sw = f > t;
+    oj.sw = oh.sw = f > t;
+    const long long jb = P.j_br0 + (long long)u * BR::RJ, hb = P.h_br0 + (long long)u * BR::RH;
+    const int ubase = blockIdx.x * TPB + w * 32;
+    const int ng = max(0, min(32, P.nr - ubase)) * BR::NR;
+    const long long gb = P.bus_rows + (long long)ubase * BR::NR;
     for (int s = s0; s < s1; s++) {
       typename BR::In nxt{};
-      if (act && s + 1 < s1) nxt = BR::load_in(P, A, s + 1, u, f, t);   // prefetch the next scenario's inputs
-      o.vmax = 0.0; o.nviol = 0;
-      if (act) BR::run(o, cst, cur);
-      __syncthreads();
-      if (wg) copy_out_padded<BR::NR, BR::NRP>(A.g + (long long)s * A.ldg + tl.g0, sG, tl.gn);
-      if (wj) copy_out_padded<BR::RJ, BR::RJP>(A.J + (long long)s * A.ldJ + tl.j0, sJ, tl.jn);
-      if (wh) copy_out_padded<BR::RH, BR::RHP>(A.H + (long long)s * A.ldH + tl.h0, sH, tl.hn);
-      reduce_scalars(A.scal ? A.scal + (long long)s * NSCAL : nullptr, o.vmax, o.nviol);
-      __syncthreads();
+      if (act && s + 1 < s1) nxt = BR::load_in(P, A, s + 1, u, f, t);
+      oj.vmax = 0.0; oj.nviol = 0;
+      if (act) {
+        if (wj || wg || A.scal) {
+          BR::run(oj, cst, cur);                                   // pass 1: g + Jacobian tags
+          if (wj) oj.storeJ(A.J + (long long)s * A.ldJ + jb, std::make_integer_sequence<int, BR::RJ / 4>{});
+        }
+        if (wh) {
+          BR::run(oh, cst, cur);                                   // pass 2: Hessian tags
+          oh.storeH(A.H + (long long)s * A.ldH + hb, std::make_integer_sequence<int, BR::RH / 4>{});
+        }
+      }
+      if (wg) {
+        double* sg = sG[w];
+        if (act) {
+#pragma unroll
+          for (int r = 0; r < BR::NR; r++) sg[lane * BR::NR + r] = oj.gt[r];
+        }
+        __syncwarp();
+        copy_aligned<32>(A.g + (long long)s * A.ldg + gb, ng, lane, [&](int e) { return sg[e]; });
+        __syncwarp();
+      }
+      reduce_scalars(A.scal ? A.scal + (long long)s * NSCAL : nullptr, oj.vmax, oj.nviol);
       if (s + 1 < s1) cur = nxt;
     }
-  } else if (tl.kind == 0) {
-    if constexpr (has_bus_rows(FORM)) {
-      const bool facts = (P.flags & FLAG_FACTS) != 0;
-      BusTile T;
-      T.nbt = tl.u1 - tl.u0;
-      T.hp0 = P.he_ptr[tl.u0]; T.nhe = P.he_ptr[tl.u1] - T.hp0;
-      T.gp0 = P.gen_ptr[tl.u0]; T.ngt = P.gen_ptr[tl.u1] - T.gp0;
-      T.sp0 = P.sh_ptr[tl.u0]; T.nsh = facts ? P.sh_ptr[tl.u1] - T.sp0 : 0;
-      T.cj0 = P.bus_jpp[tl.u0]; T.ch0 = P.bus_hpp[tl.u0];
-      const int ncj = P.bus_jpp[tl.u1] - T.cj0, nch = P.bus_hpp[tl.u1] - T.ch0;
-      // gathered-input layout: own a | own b | half-edge pairs | generator pairs | Wd | bss | mu (P,Q) | Pd | Qd
-      T.xh = 2 * T.nbt; T.xg = T.xh + 2 * T.nhe; T.xw = T.xg + 2 * T.ngt;
-      T.xs_ = T.xw + (FORM == CBRAWV ? T.nbt : 0); T.xm = T.xs_ + T.nsh; T.xl = T.xm + 2 * T.nbt; T.nx = T.xl + 2 * T.nbt;
-      T.sG = smem; T.sJ = T.sG + tl.gn; T.sH = T.sJ + tl.jn;
-      T.xb[0] = T.sH + tl.hn; T.xb[1] = T.xb[0] + T.nx;
-      T.hc = T.xb[1] + T.nx;
-      T.heks = (int*)(T.hc + (is_PN(FORM) ? 4 * T.nhe : 0));
-      T.hoth = T.heks + T.nhe;
-      T.sgen = T.hoth + (is_PN(FORM) ? T.nhe : 0);
-      T.ssh = T.sgen + T.ngt;
-      T.jpos = (uint16_t*)(T.ssh + T.nsh);
-      T.hpos = T.jpos + ncj;
-      T.sst = (uint8_t*)(T.hpos + nch);
-      // ---- scenario-independent staging (once per CTA)
-      for (int q = threadIdx.x; q < T.nhe; q += TPB) {
-        T.heks[q] = P.he_ks[T.hp0 + q];
-        if constexpr (is_PN(FORM)) {
-          T.hoth[q] = P.he_other[T.hp0 + q];
-#pragma unroll
-          for (int c = 0; c < 4; c++) T.hc[c * T.nhe + q] = P.he_c[(long long)c * P.nhe + T.hp0 + q];
-        }
-      }
-      for (int q = threadIdx.x; q < T.ngt; q += TPB) T.sgen[q] = P.gen_idx[T.gp0 + q];
-      for (int q = threadIdx.x; q < T.nsh; q += TPB) T.ssh[q] = P.sh_idx[T.sp0 + q];
-      for (int q = threadIdx.x; q < ncj; q += TPB) T.jpos[q] = P.bus_jpos[T.cj0 + q];
-      for (int q = threadIdx.x; q < nch; q += TPB) T.hpos[q] = P.bus_hpos[T.ch0 + q];
-      const int jbase = act ? P.jptr[2 * u] - tl.j0 : 0, hbase = act ? P.hptr[2 * u] - tl.h0 : 0;
-      const int cjo = act ? P.bus_jpp[u] - T.cj0 : 0, cho = act ? P.bus_hpp[u] - T.ch0 : 0;
-      const bool has_status = A.status != nullptr;
-      BusOut o;
-      o.g = T.sG + 2 * threadIdx.x; o.wg = wg; o.tol = A.viol_tol;
-      __syncthreads();
-      bus_gather<FORM>(P, A, T, tl, s0, T.xb[0]);
-      cp_async_commit();
-      for (int s = s0; s < s1; s++) {
-        const int cur = (s - s0) & 1;
-        if (s + 1 < s1) bus_gather<FORM>(P, A, T, tl, s + 1, T.xb[cur ^ 1]);    // one scenario ahead
-        cp_async_commit();
-        if (has_status) {
-          const uint8_t* __restrict__ stp = A.status + (long long)s * A.ldst;
-          for (int q = threadIdx.x; q < T.nhe; q += TPB) T.sst[q] = stp[T.heks[q] >> 1];
-        }
-        cp_async_wait<1>();                                                    // this scenario's gather has landed
-        __syncthreads();
-        o.vmax = 0.0; o.nviol = 0;
-        if (act) {
-          Stream sj{T.sJ + jbase, T.jpos + cjo, wj}, sh{T.sH + hbase, T.hpos + cho, wh};
-          bus_rows<FORM>(P, T, T.xb[cur], o, sj, sh, u, threadIdx.x, has_status);
-        }
-        __syncthreads();
-        if (wg) copy_out(A.g + (long long)s * A.ldg + tl.g0, T.sG, tl.gn);
-        if (wj) copy_out(A.J + (long long)s * A.ldJ + tl.j0, T.sJ, tl.jn);
-        if (wh) copy_out(A.H + (long long)s * A.ldH + tl.h0, T.sH, tl.hn);
-        reduce_scalars(A.scal ? A.scal + (long long)s * NSCAL : nullptr, o.vmax, o.nviol);
-        __syncthreads();
-      }
-    }
-  } else {
-    if (A.scal) objective_tile(P, A, s0, s1, smem);
   }
 }
 
 template <int FORM>
-cudaError_t launch_form(const DevPlan& P, const EvalArgs& A, size_t smem, cudaStream_t st, dim3 grid) {
-  if (P.src == SRC_MATPOWER) eval_kernel<FORM, SRC_MATPOWER><<<grid, TPB, smem, st>>>(P, A);
-  else eval_kernel<FORM, SRC_ARPAE><<<grid, TPB, smem, st>>>(P, A);
+cudaError_t launch_direct(const DevPlan& P, const EvalArgs& A, cudaStream_t st, dim3 grid) {
+  if (P.src == SRC_MATPOWER) branch_direct_kernel<FORM, SRC_MATPOWER><<<grid, TPB, 0, st>>>(P, A);
+  else branch_direct_kernel<FORM, SRC_ARPAE><<<grid, TPB, 0, st>>>(P, A);
   return cudaGetLastError();
 }
 
 template <int FORM>
-cudaError_t configure_form(int src, size_t smem) {
+cudaError_t launch_form(const DevPlan& P, const EvalArgs& A, size_t smem, cudaStream_t st, dim3 grid) {
+  if (P.src == SRC_MATPOWER) branch_staged_kernel<FORM, SRC_MATPOWER><<<grid, TPB, smem, st>>>(P, A);
+  else branch_staged_kernel<FORM, SRC_ARPAE><<<grid, TPB, smem, st>>>(P, A);
+  return cudaGetLastError();
+}
+
+template <int FORM>
+cudaError_t launch_bus_form(const DevPlan& P, const EvalArgs& A, size_t smem, cudaStream_t st, dim3 grid) {
+  bus_kernel<FORM><<<grid, TPB, smem, st>>>(P, A);
+  return cudaGetLastError();
+}
+
+template <int FORM>
+cudaError_t configure_form(int src, size_t smem_branch, size_t smem_bus) {
+  cudaError_t e = cudaFuncSetAttribute(bus_kernel<FORM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bus);
+  if (e != cudaSuccess) return e;
   if (src == SRC_MATPOWER)
-    return cudaFuncSetAttribute(eval_kernel<FORM, SRC_MATPOWER>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  return cudaFuncSetAttribute(eval_kernel<FORM, SRC_ARPAE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    return cudaFuncSetAttribute(branch_staged_kernel<FORM, SRC_MATPOWER>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_branch);
+  return cudaFuncSetAttribute(branch_staged_kernel<FORM, SRC_ARPAE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_branch);
 }
 
 __global__ void __launch_bounds__(256) csc_assemble_kernel(const int32_t* __restrict__ segptr, const int32_t* __restrict__ perm,
@@ -806,40 +1126,127 @@ __global__ void __launch_bounds__(256) csc_assemble_kernel(const int32_t* __rest
 
 }  // namespace
 
-cudaError_t configure_eval(int form, int src, int64_t smem_bytes) {
-  const size_t smem = (size_t)smem_bytes;
+cudaError_t configure_eval(int form, int src, int64_t smem_branch_bytes, int64_t smem_bus_bytes) {
+  const size_t sb = (size_t)smem_branch_bytes, su = (size_t)smem_bus_bytes;
   switch (form) {
-    case PBRAPV: return configure_form<PBRAPV>(src, smem);
-    case PBRARV: return configure_form<PBRARV>(src, smem);
-    case PBRAWV: return configure_form<PBRAWV>(src, smem);
-    case CBRARV: return configure_form<CBRARV>(src, smem);
-    case CBRAWV: return configure_form<CBRAWV>(src, smem);
-    case PNPAPV: return configure_form<PNPAPV>(src, smem);
-    case PNRAPV: return configure_form<PNRAPV>(src, smem);
-    case PNRARV: return configure_form<PNRARV>(src, smem);
-    case PNRAWV: return configure_form<PNRAWV>(src, smem);
+    case PBRAPV: return configure_form<PBRAPV>(src, sb, su);
+    case PBRARV: return configure_form<PBRARV>(src, sb, su);
+    case PBRAWV: return configure_form<PBRAWV>(src, sb, su);
+    case CBRARV: return configure_form<CBRARV>(src, sb, su);
+    case CBRAWV: return configure_form<CBRAWV>(src, sb, su);
+    case PNPAPV: return configure_form<PNPAPV>(src, sb, su);
+    case PNRAPV: return configure_form<PNRAPV>(src, sb, su);
+    case PNRARV: return configure_form<PNRARV>(src, sb, su);
+    case PNRAWV: return configure_form<PNRAWV>(src, sb, su);
   }
   return cudaErrorInvalidValue;
 }
 
-cudaError_t launch_eval(const DevPlan& P, const EvalArgs& A, int64_t smem_bytes, cudaStream_t stream) {
-  if (A.S <= 0) return cudaSuccess;
-  const size_t smem = (size_t)smem_bytes;
+#define PS_FORM_SWITCH(CALL)                                   \
+  switch (P.form) {                                            \
+    case PBRAPV: return CALL(PBRAPV);                          \
+    case PBRARV: return CALL(PBRARV);                          \
+    case PBRAWV: return CALL(PBRAWV);                          \
+    case CBRARV: return CALL(CBRARV);                          \
+    case CBRAWV: return CALL(CBRAWV);                          \
+    case PNPAPV: return CALL(PNPAPV);                          \
+    case PNRAPV: return CALL(PNRAPV);                          \
+    case PNRARV: return CALL(PNRARV);                          \
+    case PNRAWV: return CALL(PNRAWV);                          \
+  }                                                            \
+  return cudaErrorInvalidValue;
+
+static cudaError_t launch_staged(const DevPlan& P, const EvalArgs& A, size_t smem, cudaStream_t stream, dim3 grid) {
+#define PS_CALL(F) launch_form<F>(P, A, smem, stream, grid)
+  PS_FORM_SWITCH(PS_CALL)
+#undef PS_CALL
+}
+static cudaError_t launch_bus(const DevPlan& P, const EvalArgs& A, size_t smem, cudaStream_t stream, dim3 grid) {
+#define PS_CALL(F) launch_bus_form<F>(P, A, smem, stream, grid)
+  PS_FORM_SWITCH(PS_CALL)
+#undef PS_CALL
+}
+template <int FORM>
+cudaError_t launch_pb_form(const DevPlan& P, const EvalArgs& A, cudaStream_t st, int nchunks, int64_t* launches) {
+  if constexpr (FORM == PBRAPV || FORM == PBRARV) {
+    if ((A.what & EV_G) || A.scal) {
+      pb_bus_g_kernel<FORM><<<dim3((unsigned)((P.nb + PBT - 1) / PBT), (unsigned)nchunks), PBT, 0, st>>>(P, A);
+      if (launches) *launches += 1;
+    }
+    if (A.what & (EV_J | EV_H)) {
+      const int n = (P.j_br0 > P.h_br0 ? P.j_br0 : P.h_br0) / 4 + 1;
+      pb_bus_jh_kernel<FORM><<<dim3((unsigned)((n + PBT - 1) / PBT), (unsigned)nchunks), PBT, 0, st>>>(P, A);
+      if (launches) *launches += 1;
+    }
+    if (A.scal) {
+      objective_kernel<<<dim3((unsigned)nchunks), TPB, 0, st>>>(P, A);
+      if (launches) *launches += 1;
+    }
+    return cudaGetLastError();
+  } else {
+    return cudaErrorInvalidValue;
+  }
+}
+static cudaError_t launch_pb(const DevPlan& P, const EvalArgs& A, cudaStream_t stream, int nchunks, int64_t* launches) {
+#define PS_CALL(F) launch_pb_form<F>(P, A, stream, nchunks, launches)
+  PS_FORM_SWITCH(PS_CALL)
+#undef PS_CALL
+}
+static cudaError_t launch_branch_direct(const DevPlan& P, const EvalArgs& A, cudaStream_t stream, dim3 grid) {
+#define PS_CALL(F) launch_direct<F>(P, A, stream, grid)
+  PS_FORM_SWITCH(PS_CALL)
+#undef PS_CALL
+}
+
+static bool sector_aligned(const double* p, long long first, long long ld) {
+  return ((reinterpret_cast<unsigned long long>(p) >> 3) + (unsigned long long)first) % 4 == 0 && ld % 4 == 0;
+}
+
+static int env_int(const char* name, int dflt) {
+  const char* e = getenv(name);
+  const int v = e ? atoi(e) : 0;
+  return v > 0 ? v : dflt;
+}
+
+// One evaluation = two launches on `stream`: the bus kernel (nodal balances + objective scalar) and the branch
+// kernel (flow definitions / limits / cones) -- direct when the branch blocks of J and H start on 32-byte
+// sectors in every scenario row, staged otherwise.
+cudaError_t launch_eval(const DevPlan& P, const EvalArgs& A0, int64_t smem_branch_bytes, int64_t smem_bus_bytes,
+                        cudaStream_t stream, int64_t* launches) {
+  if (A0.S <= 0) return cudaSuccess;
+  EvalArgs A = A0;
+  cudaError_t e = cudaSuccess;
+  const bool pb_fast = P.pb_slots && !getenv("PS_NO_PBFAST");
+  if (pb_fast) {
+    A.chunk = env_int("PS_CHUNK_PB", 4);
+    const int nchunks = (A.S + A.chunk - 1) / A.chunk;
+    if (nchunks > 65535) return cudaErrorInvalidConfiguration;
+    e = launch_pb(P, A, stream, nchunks, launches);
+    if (e != cudaSuccess) return e;
+  } else if (P.n_bus_tiles > 0 || A.scal) {
+    // bus tiles are few and pay a per-CTA staging cost: longer scenario chunks than the branch kernel
+    const long long want = 148LL * 4 * 6;
+    long long c = ((long long)A.S * (P.n_bus_tiles + 1)) / want;
+    A.chunk = env_int("PS_CHUNK_BUS", (int)(c < 1 ? 1 : (c > 32 ? 32 : c)));
+    const int nchunks = (A.S + A.chunk - 1) / A.chunk;
+    if (nchunks > 65535) return cudaErrorInvalidConfiguration;
+    if (launches) *launches += 1;
+    e = launch_bus(P, A, (size_t)smem_bus_bytes, stream, dim3((unsigned)P.n_bus_tiles + 1, (unsigned)nchunks));
+    if (e != cudaSuccess) return e;
+  }
+  if (P.nr == 0 || !(A.what & (EV_G | EV_J | EV_H)) ) {
+    if (P.nr == 0 || !A.scal) return e;
+  }
+  A.chunk = A0.chunk;
   const int nchunks = (A.S + A.chunk - 1) / A.chunk;
   if (nchunks > 65535) return cudaErrorInvalidConfiguration;
-  const dim3 grid((unsigned)P.ntiles, (unsigned)nchunks);
-  switch (P.form) {
-    case PBRAPV: return launch_form<PBRAPV>(P, A, smem, stream, grid);
-    case PBRARV: return launch_form<PBRARV>(P, A, smem, stream, grid);
-    case PBRAWV: return launch_form<PBRAWV>(P, A, smem, stream, grid);
-    case CBRARV: return launch_form<CBRARV>(P, A, smem, stream, grid);
-    case CBRAWV: return launch_form<CBRAWV>(P, A, smem, stream, grid);
-    case PNPAPV: return launch_form<PNPAPV>(P, A, smem, stream, grid);
-    case PNRAPV: return launch_form<PNRAPV>(P, A, smem, stream, grid);
-    case PNRARV: return launch_form<PNRARV>(P, A, smem, stream, grid);
-    case PNRAWV: return launch_form<PNRAWV>(P, A, smem, stream, grid);
-  }
-  return cudaErrorInvalidValue;
+  const unsigned nbt = (unsigned)((P.nr + TPB - 1) / TPB);
+  bool direct = direct_ok(P.form, P.src) && !getenv("PS_NO_DIRECT");
+  if (direct && (A.what & EV_J)) direct = sector_aligned(A.J, P.j_br0, A.ldJ);
+  if (direct && (A.what & EV_H)) direct = sector_aligned(A.H, P.h_br0, A.ldH);
+  if (launches) *launches += 1;
+  if (direct) return launch_branch_direct(P, A, stream, dim3(nbt, (unsigned)nchunks));
+  return launch_staged(P, A, (size_t)smem_branch_bytes, stream, dim3(nbt, (unsigned)nchunks));
 }
 
 cudaError_t launch_csc_assemble(const int32_t* segptr, const int32_t* perm, int nnz_csc, int64_t S, const double* dE,

@@ -19,7 +19,11 @@ struct DevPlan {                    // passed to kernels by value (constant bank
   int nb, nr, ng;
   int o_a, o_b, o_Wd, o_Wr, o_Wi, o_pg, o_qg, o_f[4], o_cg, o_bss;
   int bus_rows;
-  int ntiles;
+  int ntiles, n_bus_tiles;
+  int j_br0, h_br0;                                 // first J / H slot of the branch rows
+  int pb_slots;                                     // PB* bus block: slot-parallel fast path available
+  const int32_t *pb_jcode, *pb_hcode;               // per-slot codes of the bus block (see ps_plan.h)
+  int pb_implicit;                                  // PB* bus rows: slot order == emission order (see bus_rows_pb)
   int cost_order;
   const int32_t *f, *t;
   const double *Gf, *Bf, *Gt, *Bt, *gf, *bf, *gt, *bt, *Imax, *Gl, *Bl, *Pd0, *Qd0;
@@ -48,10 +52,11 @@ struct EvalArgs {
   double viol_tol;
 };
 
-// launches the fused g/J/H kernel for all tiles x scenarios on `stream`
-cudaError_t launch_eval(const DevPlan& P, const EvalArgs& A, int64_t smem_bytes, cudaStream_t stream);
+// Launches one evaluation (bus kernel + branch kernel) on `stream`; *launches is incremented per kernel.
+cudaError_t launch_eval(const DevPlan& P, const EvalArgs& A, int64_t smem_branch_bytes, int64_t smem_bus_bytes,
+                        cudaStream_t stream, int64_t* launches);
 // opt the kernels of one formulation into the needed dynamic shared memory (once per device)
-cudaError_t configure_eval(int form, int src, int64_t smem_bytes);
+cudaError_t configure_eval(int form, int src, int64_t smem_branch_bytes, int64_t smem_bus_bytes);
 
 // COO -> CSC assembly (replaces src/opt/algorithms/common.jl:12-20): nz[j] = sum_{q in seg j} dE[perm[q]]
 cudaError_t launch_csc_assemble(const int32_t* segptr, const int32_t* perm, int nnz_csc, int64_t S,

@@ -136,6 +136,7 @@ PS_HD constexpr BranchPat branch_pattern(int form, int src) {
 
 constexpr int MAX_BR_JTAGS = 32;
 constexpr int MAX_BR_HTAGS = 48;
+constexpr int MAX_BR_ROWS = 6;
 
 // ---------------------------------------------------------------------------------------------
 // Slot positions of every tag inside its branch's block, as compile-time tables.
@@ -162,6 +163,8 @@ PS_HD constexpr int role_key(int role, int swap) {
 struct BranchSlots {
   uint8_t jpos[2][MAX_BR_JTAGS];   // [swap][tag] -> position inside the branch's J block
   uint8_t hpos[2][MAX_BR_HTAGS];   // [swap][tag] -> position inside the branch's H block
+  uint8_t jinv[2][MAX_BR_JTAGS];   // [swap][position] -> tag (inverse of jpos)
+  uint8_t hinv[2][MAX_BR_HTAGS];
   int nrows, nj, nh;
 };
 
@@ -198,8 +201,16 @@ PS_HD constexpr BranchSlots branch_slots(int form, int src) {
       jb += rp.nj;
       hb += rp.nh;
     }
+    for (int t = 0; t < s.nj; t++) s.jinv[swap][s.jpos[swap][t]] = (uint8_t)t;
+    for (int t = 0; t < s.nh; t++) s.hinv[swap][s.hpos[swap][t]] = (uint8_t)t;
   }
   return s;
+}
+
+// the direct (register -> 32-byte sector) store path needs whole sectors per branch
+PS_HD constexpr bool direct_ok(int form, int src) {
+  const BranchSlots s = branch_slots(form, src);
+  return s.nj > 0 && s.nh > 0 && s.nj % 4 == 0 && s.nh % 4 == 0;
 }
 
 }  // namespace ps

@@ -321,6 +321,50 @@ std::string build_plan(const HostNet& net, int form, int src, int flags, int tpb
       }
     }
   }
+  // PB* balances: check that the canonical slot order equals the emission order the specialised bus rows
+  // assume ([voltage slots][gens][Sij][Sji], no accumulation); true whenever the adjacency lists are ascending
+  if (form == PBRAPV || form == PBRARV) {
+    const int nv = form == PBRARV ? 2 : 1;
+    bool ok = true;
+    for (int64_t i = 0; i < nb && ok; i++) {
+      const int64_t ngi = net.gen_ptr[i + 1] - net.gen_ptr[i], nhi = P.he_ptr[i + 1] - P.he_ptr[i];
+      const int64_t nshi = facts ? net.sh_ptr[i + 1] - net.sh_ptr[i] : 0;
+      if (nshi) continue;                          // such tiles take the generic path
+      const int64_t len = nv + ngi + nhi;
+      const uint16_t* jp = P.bus_jpos.data() + P.bus_jpp[i];
+      if (P.bus_jpp[i + 1] - P.bus_jpp[i] != 2 * len) { ok = false; break; }
+      // emission: (P,Q) per gen, (P,Q) per half-edge, then the voltage terms: rect J(0,vr) J(0,vi) J(1,vr) J(1,vi)
+      int64_t e = 0;
+      for (int64_t c = 0; c < ngi + nhi && ok; c++) {
+        ok = jp[e] == (uint16_t)(nv + c) && jp[e + 1] == (uint16_t)(len + nv + c);
+        e += 2;
+      }
+      if (!ok) break;
+      if (nv == 2) ok = jp[e] == 1 && jp[e + 1] == 0 && jp[e + 2] == len + 1 && jp[e + 3] == len;
+      else ok = jp[e] == 0 && jp[e + 1] == len;
+      if (P.hptr[2 * i + 2] - P.hptr[2 * i] != 2 * nv) ok = false;
+    }
+    P.pb_implicit = ok;
+    // slot codes of the whole bus block (only when no bus carries a switched shunt term)
+    bool any_sh = false;
+    if (facts) for (int64_t i = 0; i < nb; i++) any_sh = any_sh || net.sh_ptr[i + 1] > net.sh_ptr[i];
+    if (ok && !any_sh && nb > 0) {
+      P.pb_jcode.assign(P.jptr[P.bus_rows], -1);
+      P.pb_hcode.assign(P.hptr[P.bus_rows], 0);
+      for (int64_t i = 0; i < nb; i++) {
+        const int64_t ngi = net.gen_ptr[i + 1] - net.gen_ptr[i], nhi = P.he_ptr[i + 1] - P.he_ptr[i];
+        for (int pq = 0; pq < 2; pq++) {
+          int32_t* jc = P.pb_jcode.data() + P.jptr[2 * i + pq];
+          if (nv == 2) { jc[0] = -2 - (int32_t)(4 * i + 2 * pq + 0); jc[1] = -2 - (int32_t)(4 * i + 2 * pq + 1); }
+          else jc[0] = -2 - (int32_t)(4 * i + 2 * pq + 1);
+          for (int64_t c = 0; c < nhi; c++) jc[nv + ngi + c] = P.he_ks[P.he_ptr[i] + c] >> 1;
+          int32_t* hc = P.pb_hcode.data() + P.hptr[2 * i + pq];
+          for (int q = 0; q < nv; q++) hc[q] = (int32_t)(2 * i + pq);
+        }
+      }
+      P.pb_slots = true;
+    }
+  }
   // bus tiles: greedy, at most tpb buses and at most `budget` bytes of shared memory per tile
   auto bus_tile_bytes = [&](int64_t u0, int64_t u1) -> int64_t {
     const int64_t nbt = u1 - u0, nh = P.he_ptr[u1] - P.he_ptr[u0], ngt = net.gen_ptr[u1] - net.gen_ptr[u0];
@@ -372,6 +416,8 @@ std::string build_plan(const HostNet& net, int form, int src, int flags, int tpb
     P.tiles.push_back(t);
   }
   P.smem_bytes = std::max<int64_t>(std::max(mx, mxb), 1024);
+  P.smem_bus_bytes = std::max<int64_t>(mx, 1024);
+  P.smem_branch_bytes = std::max<int64_t>(mxb, 1024);
   P.smem_doubles = (P.smem_bytes + 7) / 8;
   return "";
 }

@@ -49,7 +49,14 @@ struct Plan {
   std::vector<int32_t> he_ks;                       // branch * 2 + side (side 0: bus is the from end)
   std::vector<int32_t> he_other;                    // the bus at the other end
   std::vector<double> he_c;                         // [4][nhe] staged constants of the PN* balances (g_s, b_s, c, d)
+  // PB* balances without switched shunts: per-slot codes of the bus block for the slot-parallel fast path
+  //   J: -1 -> 1.0 ; k >= 0 -> status of branch k ; -2 - (4*bus + w) -> voltage slot w (see pb_bus_jh_kernel)
+  //   H: 2*bus + (0: P row, 1: Q row)
+  std::vector<int32_t> pb_jcode, pb_hcode;
+  bool pb_slots = false;
+  bool pb_implicit = false;                         // PB* bus rows: J slots follow [voltage][gens][Sij][Sji]
   int64_t smem_bytes = 0;                           // dynamic shared memory of the kernel (max over tile kinds)
+  int64_t smem_bus_bytes = 0, smem_branch_bytes = 0; // bus kernel / staged branch kernel
   // derived per-side constants (side 0 = from, 1 = to), each [2*nbr]
   std::vector<double> c0, c1, c2, c3;
   std::vector<Tile> tiles;

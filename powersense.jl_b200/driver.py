@@ -55,9 +55,16 @@ class ScenarioDriver:
         n = max(self.S, 1)
         self.x = torch.zeros(n, h.n_var, dtype=f64, device=self.device)
         self.mu = torch.zeros(n, h.m_nl, dtype=f64, device=self.device) if what & EVAL_H else None
-        self.g = torch.empty(n, h.m_nl, dtype=f64, device=self.device) if what & EVAL_G else None
-        self.J = torch.empty(n, h.nnzJ, dtype=f64, device=self.device) if what & EVAL_J else None
-        self.H = torch.empty(n, h.nnzH, dtype=f64, device=self.device) if what & EVAL_H else None
+        # outputs in the layout ps_preferred_layout asks for: rows of ld doubles starting `pad` doubles into a
+        # 32-byte aligned allocation, so that the branch block of every row starts on a 32-byte sector
+        (ldg, ldJ, ldH), (pg, pJ, pH) = h.preferred_layout()
+
+        def rows(width, ld, pad):
+            flat = torch.empty(pad + n * ld, dtype=f64, device=self.device)
+            return flat[pad:].view(n, ld)[:, :width]
+        self.g = rows(h.m_nl, ldg, pg) if what & EVAL_G else None
+        self.J = rows(h.nnzJ, ldJ, pJ) if what & EVAL_J else None
+        self.H = rows(h.nnzH, ldH, pH) if what & EVAL_H else None
         self.scalars = torch.zeros(n, capi.PS_NSCALARS, dtype=f64, device=self.device)
 
     def set_loads(self, Pd: np.ndarray, Qd: np.ndarray):

@@ -23,9 +23,14 @@ def run(case, Fname, S, chunks, what=7, steps=5, scal=True):
     x = torch.from_numpy(xb).to(dev).repeat(-(-S // 8), 1)[:S].contiguous()
     x *= 1.0 + 1e-3 * (torch.rand_like(x) - 0.5)
     mu = torch.randn(S, h.m_nl, dtype=torch.float64, device=dev)
-    g = torch.empty(S, h.m_nl, dtype=torch.float64, device=dev)
-    J = torch.empty(S, h.nnzJ, dtype=torch.float64, device=dev)
-    H = torch.empty(S, h.nnzH, dtype=torch.float64, device=dev)
+    (ldg, ldJ, ldH), (pg, pJ, pH) = h.preferred_layout()
+
+    def rows(width, ld, pad):
+        if os.environ.get("PS_PLAIN_LAYOUT"):
+            return torch.empty(S, width, dtype=torch.float64, device=dev)
+        flat = torch.empty(pad + S * ld, dtype=torch.float64, device=dev)
+        return flat[pad:].view(S, ld)[:, :width]
+    g, J, H = rows(h.m_nl, ldg, pg), rows(h.nnzJ, ldJ, pJ), rows(h.nnzH, ldH, pH)
     sc = torch.empty(S, 4, dtype=torch.float64, device=dev) if scal else None
     ab = h.algorithmic_bytes(what)
     for c in chunks:

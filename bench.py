@@ -260,9 +260,11 @@ def main():
     if world > 1:
         dist.barrier()
     launches0 = drv.batch.launch_count
+    drv.batch.enable_timing(True)          # CUDA events around every kernel, recorded on the launching stream
     sampler.start()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ktimes = []
     torch.cuda.synchronize()
     t0 = time.time()
     e0.record()
@@ -272,6 +274,7 @@ def main():
         ev[k][1].record()
         if world > 1:
             drv.gather_scalars()
+        ktimes.append(drv.batch.kernel_times())      # waits for this step's kernels (event sync, no device idle of note)
     e1.record()
     torch.cuda.synchronize()
     t1 = time.time()
@@ -279,6 +282,7 @@ def main():
         dist.barrier()
     ms_total = e0.elapsed_time(e1)
     kernel_ms = float(np.mean([a.elapsed_time(b) for a, b in ev]))
+    kavg = {k: float(np.mean([t[k] for t in ktimes])) for k in ktimes[0]}
     launches = drv.batch.launch_count - launches0
     if world > 1:
         t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
@@ -288,11 +292,25 @@ def main():
     ms_per_step = ms_total / args.steps
     value = S * world / (ms_per_step * 1e-3)
     alg_bytes = h.algorithmic_bytes(args.what)
+    alg_branch = h.algorithmic_bytes_branch(args.what)
     peak, peak_src = measured_peak()
-    achieved = alg_bytes * S / (kernel_ms * 1e-3) / 1e9
+    achieved_step = alg_bytes * S / (kernel_ms * 1e-3) / 1e9
+    achieved = alg_branch * S / (kavg["branch"] * 1e-3) / 1e9      # the dominant kernel: branch rows
+    info = h.plan_info()
+    kname = ("branch_direct_kernel" if info["direct_ok"] else "branch_staged_kernel") + f"<{args.formulation[:6]}>"
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "traffic.json")             # dram bytes/launch from the committed ncu capture
+    if os.path.exists(tp):
+        try:
+            tj = json.load(open(tp))
+            key = f"{args.case}:{args.formulation}:{S}:{args.what}"
+            traffic = tj.get(key, {}).get("dram_bytes_per_launch")
+        except Exception:
+            traffic = None
     # one scenario's scalars make a quick sanity line for the log (stderr)
     sc = drv.scalars[:2].cpu().numpy()
-    print(f"[rank {rank}] S={S} kernel {kernel_ms:.3f} ms/step, {achieved:.0f} GB/s algorithmic, scalars[0]={sc[0].tolist()}",
+    print(f"[rank {rank}] S={S} step {kernel_ms:.3f} ms ({achieved_step:.0f} GB/s algorithmic); kernels {kavg}; branch kernel "
+          f"{achieved:.0f} GB/s; scalars[0]={sc[0].tolist()}",
           file=sys.stderr, flush=True)
 
     # ---- e2e: host buffers through ps_batch_eval_host
@@ -341,8 +359,12 @@ def main():
                 "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
                 "data": "synthetic", "config": cfg, "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                             "traffic": None, "peak_source": peak_src, "kernel": "eval_kernel<PBRARV,MATPOWER>" if args.formulation == "PBRARVmodel" else "eval_kernel",
-                             "kernel_ms_per_launch": kernel_ms, "units_per_launch": S},
+                             "traffic": traffic, "peak_source": peak_src, "kernel": kname,
+                             "kernel_ms_per_launch": kavg["branch"], "units_per_launch": S,
+                             "algorithmic_bytes_per_unit": alg_branch,
+                             "step": {"achieved": achieved_step, "frac": achieved_step / peak, "ms": kernel_ms,
+                                      "algorithmic_bytes_per_unit": alg_bytes, "kernels_ms": kavg,
+                                      "note": "all kernels of one evaluation (bus rows, bus J/H slots, objective, branch rows)"}},
                 "cpu_baseline": cpu}
         print(json.dumps(line), flush=True)
     drv.close()

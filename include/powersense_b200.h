@@ -166,6 +166,14 @@ int ps_batch_eval_host(ps_batch* b, int what, int64_t s_begin, int64_t s_count,
 int64_t ps_batch_launch_count(const ps_batch* b);
 /* algorithmic HBM bytes of one scenario evaluation for `what` */
 int64_t ps_algorithmic_bytes(const ps_handle* h, int what);
+/* the share of it that belongs to the branch-row kernel (flow definitions, limits, cones): the x entries and
+ * multipliers those rows read plus their g / J / H slots */
+int64_t ps_algorithmic_bytes_branch(const ps_handle* h, int what);
+/* Optional per-kernel timing: when enabled, ps_batch_eval records CUDA events around each kernel it launches;
+ * ps_batch_kernel_times waits for the last evaluation and returns ms[0..3] = bus rows (g, or the whole bus
+ * kernel), bus J/H slots (PB* fast path), objective scalar, branch rows (0 when a kernel did not run). */
+int ps_batch_enable_timing(ps_batch* b, int on);
+int ps_batch_kernel_times(ps_batch* b, float ms[4]);
 
 /* pinned host memory for the *_host entry points */
 int ps_host_alloc(void** p, int64_t bytes);

@@ -67,6 +67,9 @@ _SIGS = {
                                      _VP, C.c_int64, _VP, C.c_int64, _VP]),
     "ps_batch_launch_count": (C.c_int64, [_VP]),
     "ps_algorithmic_bytes": (C.c_int64, [_VP, C.c_int]),
+    "ps_algorithmic_bytes_branch": (C.c_int64, [_VP, C.c_int]),
+    "ps_batch_enable_timing": (C.c_int, [_VP, C.c_int]),
+    "ps_batch_kernel_times": (C.c_int, [_VP, C.POINTER(C.c_float)]),
     "ps_host_alloc": (C.c_int, [C.POINTER(_VP), C.c_int64]),
     "ps_host_free": (None, [_VP]),
     "ps_csc_create": (C.c_int, [C.c_int64, C.c_int64, C.c_int64, _P64, _P64, C.c_int, C.POINTER(_VP)]),
@@ -199,6 +202,9 @@ class Handle:
     def algorithmic_bytes(self, what=7):
         return int(lib().ps_algorithmic_bytes(self.h, what))
 
+    def algorithmic_bytes_branch(self, what=7):
+        return int(lib().ps_algorithmic_bytes_branch(self.h, what))
+
     # single-scenario callbacks (outputs may be views into larger arrays, like the MOI wrapper's)
     def eval_constraint(self, x, g=None):
         x = _f64(x, self.n_var)
@@ -270,6 +276,15 @@ class Batch:
 
     def set_viol_tol(self, tol):
         self.handle._check(lib().ps_batch_set_viol_tol(self.b, float(tol)))
+
+    def enable_timing(self, on=True):
+        self.handle._check(lib().ps_batch_enable_timing(self.b, 1 if on else 0))
+
+    def kernel_times(self):
+        """ms of the last evaluation per kernel: {'bus', 'bus_jh', 'objective', 'branch'} (waits for it)."""
+        ms = (C.c_float * 4)()
+        self.handle._check(lib().ps_batch_kernel_times(self.b, ms))
+        return dict(zip(("bus", "bus_jh", "objective", "branch"), [float(v) for v in ms]))
 
     @property
     def launch_count(self):

@@ -65,6 +65,9 @@ struct ps_batch {
   double viol_tol = 1e-6;
   int64_t launches = 0;
   int chunk_override = 0;
+  bool timing = false;               // per-kernel CUDA events (ps_batch_enable_timing)
+  cudaEvent_t tev[2 * K_COUNT] = {};
+  unsigned tmask = 0;
   // host-streaming state (ps_batch_eval_host)
   int64_t stage_S = 0;
   double *sx[2] = {nullptr, nullptr}, *smu[2] = {nullptr, nullptr}, *sg[2] = {nullptr, nullptr},
@@ -153,7 +156,8 @@ int do_eval(ps_batch* b, int what, int64_t s_begin, int64_t s_count, const doubl
   A.ldst = P.net.nbr;
   A.g = g; A.ldg = ldg; A.J = J; A.ldJ = ldJ; A.H = H; A.ldH = ldH;
   A.scal = scalars; A.viol_tol = b->viol_tol;
-  e = launch_eval(h->dev, A, P.smem_branch_bytes, P.smem_bus_bytes, stream, &b->launches);
+  b->tmask = 0;
+  e = launch_eval(h->dev, A, P.smem_branch_bytes, P.smem_bus_bytes, stream, &b->launches, b->timing ? b->tev : nullptr, &b->tmask);
   if (e != cudaSuccess) return cuda_fail(h, e, "eval_kernel launch");
   b->launches += (scalars ? 1 : 0);                  // the memset node
   return PS_OK;
@@ -379,6 +383,17 @@ int64_t ps_algorithmic_bytes(const ps_handle* h, int what) {
   return 8 * n;
 }
 
+int64_t ps_algorithmic_bytes_branch(const ps_handle* h, int what) {
+  if (!h) return 0;
+  const Plan& P = h->plan;
+  const int64_t nr = P.net.nbr, NR = P.rows_per_branch;
+  int64_t n = P.nx_branch;
+  if (what & EV_G) n += NR * nr;
+  if (what & EV_J) n += (int64_t)P.RJ * nr;
+  if (what & EV_H) n += (int64_t)P.RH * nr + NR * nr;
+  return 8 * n;
+}
+
 // ---- single-scenario callbacks ------------------------------------------------------------
 static int eval_single(ps_handle* h, int what, const double* x, const double* mu, double* g, double* J, double* H,
                        double* f) {
@@ -461,6 +476,7 @@ void ps_batch_destroy(ps_batch* b) {
     if (b->ev_k[q]) cudaEventDestroy(b->ev_k[q]);
     if (b->ev_out[q]) cudaEventDestroy(b->ev_out[q]);
   }
+  for (int q = 0; q < 2 * K_COUNT; q++) if (b->tev[q]) cudaEventDestroy(b->tev[q]);
   if (b->st_in) cudaStreamDestroy(b->st_in);
   if (b->st_k) cudaStreamDestroy(b->st_k);
   if (b->st_out) cudaStreamDestroy(b->st_out);
@@ -508,6 +524,31 @@ int ps_batch_set_viol_tol(ps_batch* b, double tol) {
 }
 
 int64_t ps_batch_launch_count(const ps_batch* b) { return b ? b->launches : 0; }
+
+int ps_batch_enable_timing(ps_batch* b, int on) {
+  if (!b) return PS_ERR_ARG;
+  cudaError_t e = cudaSetDevice(b->h->device);
+  if (e != cudaSuccess) return cuda_fail(b->h, e, "cudaSetDevice");
+  if (on && !b->tev[0])
+    for (int q = 0; q < 2 * K_COUNT; q++)
+      if ((e = cudaEventCreate(&b->tev[q])) != cudaSuccess) return cuda_fail(b->h, e, "cudaEventCreate");
+  b->timing = on != 0;
+  return PS_OK;
+}
+
+int ps_batch_kernel_times(ps_batch* b, float ms[4]) {
+  if (!b || !ms) return PS_ERR_ARG;
+  if (!b->timing) return fail(b->h, PS_ERR_STATE, "timing is not enabled on this batch");
+  for (int id = 0; id < K_COUNT; id++) {
+    ms[id] = 0.0f;
+    if (b->tmask & (1u << id)) {
+      cudaError_t e = cudaEventSynchronize(b->tev[2 * id + 1]);
+      if (e == cudaSuccess) e = cudaEventElapsedTime(&ms[id], b->tev[2 * id], b->tev[2 * id + 1]);
+      if (e != cudaSuccess) return cuda_fail(b->h, e, "cudaEventElapsedTime");
+    }
+  }
+  return PS_OK;
+}
 
 int ps_batch_eval(ps_batch* b, int what, int64_t s_begin, int64_t s_count, const double* x, int64_t ldx, const double* mu,
                   int64_t ldmu, double* g, int64_t ldg, double* J, int64_t ldJ, double* H, int64_t ldH, double* scalars,

@@ -53,8 +53,10 @@ struct EvalArgs {
 };
 
 // Launches one evaluation (bus kernel + branch kernel) on `stream`; *launches is incremented per kernel.
+// kernel ids for the optional per-kernel timing: events ev[2*id], ev[2*id+1] are recorded around kernel `id`
+enum KernelId : int { K_BUS = 0, K_BUS_JH = 1, K_OBJ = 2, K_BRANCH = 3, K_COUNT = 4 };
 cudaError_t launch_eval(const DevPlan& P, const EvalArgs& A, int64_t smem_branch_bytes, int64_t smem_bus_bytes,
-                        cudaStream_t stream, int64_t* launches);
+                        cudaStream_t stream, int64_t* launches, cudaEvent_t* ev = nullptr, unsigned* ev_mask = nullptr);
 // opt the kernels of one formulation into the needed dynamic shared memory (once per device)
 cudaError_t configure_eval(int form, int src, int64_t smem_branch_bytes, int64_t smem_bus_bytes);
 

@@ -264,6 +264,9 @@ std::string build_plan(const HostNet& net, int form, int src, int flags, int tpb
     std::vector<int64_t> u(P.jcol);
     std::sort(u.begin(), u.end());
     P.nx_nl = (int64_t)(std::unique(u.begin(), u.end()) - u.begin());
+    std::vector<int64_t> ub(P.jcol.begin() + P.jptr[P.bus_rows], P.jcol.end());
+    std::sort(ub.begin(), ub.end());
+    P.nx_branch = (int64_t)(std::unique(ub.begin(), ub.end()) - ub.begin());
   }
 
   // ---- derived per-side constants (host-precomputed like formulations.jl:217,222,338-350)

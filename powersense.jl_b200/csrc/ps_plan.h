@@ -64,6 +64,7 @@ struct Plan {
   int tile_units_bus = 0, tile_units_br = 0;
   int64_t smem_doubles = 0;                         // max over tiles of staged outputs (padded)
   int NRP = 0, RJP = 0, RHP = 0;                    // per-thread staging strides of a branch tile (odd)
+  int64_t nx_branch = 0;                            // variables the branch rows touch
   int64_t nx_nl = 0;                                // variables the NL rows touch (roofline accounting)
 };
 

@@ -62,6 +62,10 @@ if __name__ == "__main__":
         run("case13659pegase", "PBRARVmodel", 1024, [4], what=1, scal=False)
         run("case13659pegase", "PBRARVmodel", 1024, [4], what=2, scal=False)
         run("case13659pegase", "PBRARVmodel", 1024, [4], what=4, scal=False)
+    if sel == "tune":
+        for cpb in (2, 4, 8, 16):
+            os.environ["PS_CHUNK_PB"] = str(cpb)
+            run("case13659pegase", "PBRARVmodel", 2048, [4, 8, 16])
     if sel == "ncu":
         run("case13659pegase", "PBRARVmodel", 256, [4], steps=1)
     if sel in ("all", "others"):

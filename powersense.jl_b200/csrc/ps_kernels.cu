@@ -1297,407 +1297,6 @@ cudaError_t launch_eval(const DevPlan& P, const EvalArgs& A0, int64_t smem_branc
   cudaError_t e = cudaSuccess;
   const bool pb_fast = P.pb_slots && !getenv("PS_NO_PBFAST");
   if (pb_fast) {
-            bus_rows_pb<FORM>(T, B, xcur, o, wj, wh, threadIdx.x, has_status, wj && s == s0);
-            done = true;
-          }
-        }
-        if (!done) {
-          Stream sj{T.sJ + B.jbase, T.jpos + B.cjo, wj}, sh{T.sH + B.hbase, T.hpos + B.cho, wh};
-          bus_rows<FORM>(P, T, B, xcur, o, sj, sh, threadIdx.x, has_status);
-        }
-      }
-      __syncthreads();
-      if (wg) copy_out(A.g + (long long)s * A.ldg + tl.g0, T.sG, tl.gn);
-      if (wj) copy_out(A.J + (long long)s * A.ldJ + tl.j0, T.sJ, tl.jn);
-      if (wh) copy_out(A.H + (long long)s * A.ldH + tl.h0, T.sH, tl.hn);
-      reduce_scalars(A.scal ? A.scal + (long long)s * NSCAL : nullptr, o.vmax, o.nviol);
-      __syncthreads();
-    }
-  }
-}
-
-// ---- PB* balances, fast path (PBRAPV / PBRARV without switched shunts) ------------------------------------------
-// The nodal balance of a power-branch-flow model is linear in the generator and flow variables
-// (formulations.jl:188-196): its Jacobian entries are the constant 1 (times the branch status) except the 1-2
-// own-voltage slots, and its Hessian block is (-2 Gl mu_P | 2 Bl mu_Q).  So the bus block of J and H is produced
-// slot-parallel from per-slot codes -- one 32-byte sector per thread, no staging, no barrier -- and the two
-// residuals of a bus by one thread that walks the bus's generator / Sij / Sji lists in the reference's order.
-constexpr int PBT = TPB;
-
-template <int FORM>
-__device__ __forceinline__ double pb_jval(const DevPlan& P, int code, const double* __restrict__ x, const uint8_t* __restrict__ st) {
-  if (code == -1) return 1.0;
-  if (code >= 0) return st ? (double)st[code] : 1.0;
-  const int v = -2 - code, i = v >> 2, w = v & 3;
-  const double coef = (w < 2) ? -2.0 * P.Gl[i] : 2.0 * P.Bl[i];
-  return coef * x[((w & 1) ? P.o_b : P.o_a) + i];
-}
-__device__ __forceinline__ double pb_hval(const DevPlan& P, int code, const double* __restrict__ mu) {
-  const int i = code >> 1;
-  return (code & 1) ? 2.0 * P.Bl[i] * mu[code] : -2.0 * P.Gl[i] * mu[code];
-}
-
-// writes dst[0..n) = f(e): the few elements before the first 32-byte boundary and after the last one with scalar
-// stores, everything else as whole sectors
-template <class F>
-__device__ __forceinline__ void emit_sectors(double* __restrict__ dst, int n, int t, int nt, F f) {
-  const int a = min(n, (int)((4 - ((reinterpret_cast<unsigned long long>(dst) >> 3) & 3)) & 3));
-  const int nfull = (n - a) >> 2;
-  for (int q = t; q < nfull; q += nt) {
-    const int e = a + 4 * q;
-    st_v4(dst + e, f(e), f(e + 1), f(e + 2), f(e + 3));
-  }
-  if (t < a) dst[t] = f(t);
-  const int tail = a + 4 * nfull;
-  if (t < n - tail) dst[tail + t] = f(tail + t);
-}
-
-template <int FORM>
-__device__ __forceinline__ void pb_bus_jh_body(const DevPlan& P, const EvalArgs& A, int bx, int nbx) {
-  const int s0 = blockIdx.y * A.chunk, s1 = min(A.S, s0 + A.chunk);
-  const int t = bx * PBT + threadIdx.x, nt = nbx * PBT;
-  for (int s = s0; s < s1; s++) {
-    const double* __restrict__ x = A.x + (long long)s * A.ldx;
-    const uint8_t* __restrict__ st = A.status ? A.status + (long long)s * A.ldst : nullptr;
-    if (A.what & EV_J)
-      emit_sectors(A.J + (long long)s * A.ldJ, P.j_br0, t, nt, [&](int e) { return pb_jval<FORM>(P, P.pb_jcode[e], x, st); });
-    if (A.what & EV_H) {
-      const double* __restrict__ mu = A.mu + (long long)s * A.ldmu;
-      emit_sectors(A.H + (long long)s * A.ldH, P.h_br0, t, nt, [&](int e) { return pb_hval(P, P.pb_hcode[e], mu); });
-    }
-  }
-}
-
-template <int FORM>
-__global__ void __launch_bounds__(PBT) pb_bus_jh_kernel(const __grid_constant__ DevPlan P, const __grid_constant__ EvalArgs A) {
-  pb_bus_jh_body<FORM>(P, A, blockIdx.x, gridDim.x);
-}
-
-template <int FORM>
-__device__ __forceinline__ void pb_bus_g_body(const DevPlan& P, const EvalArgs& A, int bx) {
-  const int s0 = blockIdx.y * A.chunk, s1 = min(A.S, s0 + A.chunk);
-  const int i = bx * PBT + threadIdx.x;
-  const bool act = i < P.nb;
-  int g0 = 0, g1 = 0, h0 = 0, h1 = 0;
-  double Gl = 0.0, Bl = 0.0;
-  if (act) { g0 = P.gen_ptr[i]; g1 = P.gen_ptr[i + 1]; h0 = P.he_ptr[i]; h1 = P.he_ptr[i + 1]; Gl = P.Gl[i]; Bl = P.Bl[i]; }
-  const bool wg = (A.what & EV_G) != 0;
-  for (int s = s0; s < s1; s++) {
-    double vmax = 0.0;
-    int nviol = 0;
-    if (act) {
-      const double* __restrict__ x = A.x + (long long)s * A.ldx;
-      const uint8_t* __restrict__ stp = A.status ? A.status + (long long)s * A.ldst : nullptr;
-      double accP = 0.0, accQ = 0.0;                           // formulations.jl:171-172
-      for (int q = g0; q < g1; q++) {                          // :177-180
-        const int g = P.gen_idx[q];
-        accP = accP + x[P.o_pg + g];
-        accQ = accQ + x[P.o_qg + g];
-      }
-      for (int q = h0; q < h1; q++) {                          // :188-196, Sij ascending then Sji ascending
-        const int ks = P.he_ks[q], k = ks >> 1, side = ks & 1;
-        const double stv = stp ? (double)stp[k] : 1.0;
-        accP = accP + stv * x[P.o_f[0 + 2 * side] + k];
-        accQ = accQ + stv * x[P.o_f[1 + 2 * side] + k];
-      }
-      if constexpr (FORM == PBRARV) {                          // :264-266
-        const double im = x[P.o_a + i], r = x[P.o_b + i], A2 = r * r + im * im;
-        accP = accP - Gl * A2;
-        accQ = accQ + Bl * A2;
-      } else {                                                 // :256-258
-        const double V = x[P.o_b + i], V2 = V * V;
-        accP = accP - Gl * V2;
-        accQ = accQ + Bl * V2;
-      }
-      const double* pd = A.Pd ? A.Pd + (long long)s * A.ldl : P.Pd0;
-      const double* qd = A.Qd ? A.Qd + (long long)s * A.ldl : P.Qd0;
-      const double gP = accP - pd[i], gQ = accQ - qd[i];       // :291-292
-      if (wg) {
-        double* gd = A.g + (long long)s * A.ldg + 2 * i;
-        if ((reinterpret_cast<unsigned long long>(gd) & 15) == 0) *reinterpret_cast<double2*>(gd) = make_double2(gP, gQ);
-        else { gd[0] = gP; gd[1] = gQ; }
-      }
-      vmax = fmax(fabs(gP), fabs(gQ));
-      nviol = (fabs(gP) > A.viol_tol ? 1 : 0) + (fabs(gQ) > A.viol_tol ? 1 : 0);
-    }
-    reduce_scalars(A.scal ? A.scal + (long long)s * NSCAL : nullptr, vmax, nviol);
-  }
-}
-
-template <int FORM>
-__global__ void __launch_bounds__(PBT) pb_bus_g_kernel(const __grid_constant__ DevPlan P, const __grid_constant__ EvalArgs A) {
-  pb_bus_g_body<FORM>(P, A, blockIdx.x);
-}
-
-// objective scalar only (used with the PB* fast path, where no bus_kernel runs)
-__global__ void __launch_bounds__(TPB) objective_kernel(const __grid_constant__ DevPlan P, const __grid_constant__ EvalArgs A) {
-  __shared__ double red[TPB / 32];
-  const int s0 = blockIdx.x * A.chunk, s1 = min(A.S, s0 + A.chunk);
-  objective_tile(P, A, s0, s1, red);
-}
-
-// Direct path of the branch rows: thread per branch, no shared-memory staging of J / H and no CTA barrier.
-// Inputs of the next scenario are prefetched into registers while the current one is evaluated; the branch's
-// J and H blocks (whole 32-byte sectors) go straight from registers to HBM; g goes through a per-warp staging
-// row so that it is written with warp-contiguous stores.
-// write the first `nsec` 32-byte sectors of a per-warp staging buffer to `dst` (sector q by lane q % 32)
-template <int R>
-__device__ __forceinline__ void warp_flush(const double* sw, double* __restrict__ dst, int nsec, int lane) {
-#pragma unroll
-  for (int i = 0; i < R / 4; i++) {
-    const int q = i * 32 + lane;
-    if (q < nsec) {
-      const double2 a = *reinterpret_cast<const double2*>(sw + 4 * q), b = *reinterpret_cast<const double2*>(sw + 4 * q + 2);
-      st_v4(dst + 4 * q, a.x, a.y, b.x, b.y);
-    }
-  }
-}
-
-#ifndef PS_DIRECT_MINB
-#define PS_DIRECT_MINB 1
-#endif
-template <int FORM, int SRC>
-__device__ __forceinline__ void branch_direct_body(const DevPlan& P, const EvalArgs& A, int bx) {
-  using BR = Branch<FORM, SRC>;
-  if constexpr (BR::DIRECT_OK) {
-    __shared__ __align__(16) double sW[TPB / 32][BR::WBUF_ALL];   // per-warp staging: transposed J / H blocks, then g
-    const int u = bx * TPB + threadIdx.x;
-    const bool act = u < P.nr;
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    const int s0 = blockIdx.y * A.chunk, s1 = min(A.S, s0 + A.chunk);
-    const bool wg = (A.what & EV_G) != 0, wj = (A.what & EV_J) != 0, wh = (A.what & EV_H) != 0;
-    typename BR::template OutR<true, false> oj;
-    typename BR::template OutR<false, true> oh;
-    oj.tol = A.viol_tol; oh.tol = A.viol_tol;
-    typename BR::Cst cst{};
-    typename BR::In cur{};
-    int f = 0, t = 1;
-    if (act) {
-      f = P.f[u]; t = P.t[u];
-      cst = BR::load_cst(P, u);
-      cur = BR::load_in(P, A, s0, u, f, t);
-    }
-    oj.sw = oh.sw = f > t;
-    const long long jb = P.j_br0 + (long long)u * BR::RJ, hb = P.h_br0 + (long long)u * BR::RH;
-    const int ubase = bx * TPB + w * 32;
-    const int nact = max(0, min(32, P.nr - ubase));               // active lanes of this warp
-    const int ng = nact * BR::NR;
-    const long long gb = P.bus_rows + (long long)ubase * BR::NR;
-    for (int s = s0; s < s1; s++) {
-      typename BR::In nxt{};
-      if (act && s + 1 < s1) nxt = BR::load_in(P, A, s + 1, u, f, t);
-      oj.vmax = 0.0; oj.nviol = 0;
-      double* sw = sW[w];
-      if (wj || wg || A.scal) {
-        if (act) BR::run(oj, cst, cur);                            // pass 1: g + Jacobian tags
-        if (wj) {
-          if constexpr (BR::TJ) {
-            if (act) oj.stageJ(sw + lane * BR::RJ, std::make_integer_sequence<int, BR::RJ / 2>{});
-            __syncwarp();
-            warp_flush<BR::RJ>(sw, A.J + (long long)s * A.ldJ + P.j_br0 + (long long)ubase * BR::RJ, nact * (BR::RJ / 4), lane);
-            __syncwarp();
-          } else if (act) {
-            oj.storeJ(A.J + (long long)s * A.ldJ + jb, std::make_integer_sequence<int, BR::RJ / 4>{});
-          }
-        }
-      }
-      if (wh) {
-        if (act) BR::run(oh, cst, cur);                            // pass 2: Hessian tags
-        if constexpr (BR::TH) {
-          if (act) oh.stageH(sw + lane * BR::RH, std::make_integer_sequence<int, BR::RH / 2>{});
-          __syncwarp();
-          warp_flush<BR::RH>(sw, A.H + (long long)s * A.ldH + P.h_br0 + (long long)ubase * BR::RH, nact * (BR::RH / 4), lane);
-          __syncwarp();
-        } else if (act) {
-          oh.storeH(A.H + (long long)s * A.ldH + hb, std::make_integer_sequence<int, BR::RH / 4>{});
-        }
-      }
-      if (wg) {
-        double* sg = sw;
-        if (act) {
-#pragma unroll
-          for (int r = 0; r < BR::NR; r++) sg[lane * BR::NR + r] = oj.gt[r];
-        }
-        __syncwarp();
-        copy_aligned<32>(A.g + (long long)s * A.ldg + gb, ng, lane, [&](int e) { return sg[e]; });
-        __syncwarp();
-      }
-      reduce_scalars(A.scal ? A.scal + (long long)s * NSCAL : nullptr, oj.vmax, oj.nviol);
-      if (s + 1 < s1) cur = nxt;
-    }
-  }
-}
-
-template <int FORM, int SRC>
-__global__ void __launch_bounds__(TPB, PS_DIRECT_MINB) branch_direct_kernel(const __grid_constant__ DevPlan P, const __grid_constant__ EvalArgs A) {
-  branch_direct_body<FORM, SRC>(P, A, blockIdx.x);
-}
-
-template <int FORM>
-cudaError_t launch_direct(const DevPlan& P, const EvalArgs& A, cudaStream_t st, dim3 grid) {
-  if (P.src == SRC_MATPOWER) branch_direct_kernel<FORM, SRC_MATPOWER><<<grid, TPB, 0, st>>>(P, A);
-  else branch_direct_kernel<FORM, SRC_ARPAE><<<grid, TPB, 0, st>>>(P, A);
-  return cudaGetLastError();
-}
-
-template <int FORM>
-cudaError_t launch_form(const DevPlan& P, const EvalArgs& A, size_t smem, cudaStream_t st, dim3 grid) {
-  if (P.src == SRC_MATPOWER) branch_staged_kernel<FORM, SRC_MATPOWER><<<grid, TPB, smem, st>>>(P, A);
-  else branch_staged_kernel<FORM, SRC_ARPAE><<<grid, TPB, smem, st>>>(P, A);
-  return cudaGetLastError();
-}
-
-template <int FORM>
-cudaError_t launch_bus_form(const DevPlan& P, const EvalArgs& A, size_t smem, cudaStream_t st, dim3 grid) {
-  bus_kernel<FORM><<<grid, TPB, smem, st>>>(P, A);
-  return cudaGetLastError();
-}
-
-template <int FORM>
-cudaError_t configure_form(int src, size_t smem_branch, size_t smem_bus) {
-  cudaError_t e = cudaFuncSetAttribute(bus_kernel<FORM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bus);
-  if (e != cudaSuccess) return e;
-  if (src == SRC_MATPOWER)
-    return cudaFuncSetAttribute(branch_staged_kernel<FORM, SRC_MATPOWER>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_branch);
-  return cudaFuncSetAttribute(branch_staged_kernel<FORM, SRC_ARPAE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_branch);
-}
-
-__global__ void __launch_bounds__(256) csc_assemble_kernel(const int32_t* __restrict__ segptr, const int32_t* __restrict__ perm,
-                                                           int nnz, const double* __restrict__ dE, long long ldE,
-                                                           double* __restrict__ nz, long long ldnz) {
-  const int j = blockIdx.x * 256 + threadIdx.x;
-  if (j >= nnz) return;
-  const int q0 = segptr[j], q1 = segptr[j + 1];
-  const long long s = blockIdx.y + (long long)blockIdx.z * gridDim.y;
-  const double* __restrict__ e = dE + s * ldE;
-  double acc = 0.0;                                           // common.jl:16-18: J[r,c] += dE[i], in COO order
-  for (int q = q0; q < q1; q++) acc += e[perm[q]];
-  nz[s * ldnz + j] = acc;
-}
-
-}  // namespace
-
-cudaError_t configure_eval(int form, int src, int64_t smem_branch_bytes, int64_t smem_bus_bytes) {
-  const size_t sb = (size_t)smem_branch_bytes, su = (size_t)smem_bus_bytes;
-  switch (form) {
-    case PBRAPV: return configure_form<PBRAPV>(src, sb, su);
-    case PBRARV: return configure_form<PBRARV>(src, sb, su);
-    case PBRAWV: return configure_form<PBRAWV>(src, sb, su);
-    case CBRARV: return configure_form<CBRARV>(src, sb, su);
-    case CBRAWV: return configure_form<CBRAWV>(src, sb, su);
-    case PNPAPV: return configure_form<PNPAPV>(src, sb, su);
-    case PNRAPV: return configure_form<PNRAPV>(src, sb, su);
-    case PNRARV: return configure_form<PNRARV>(src, sb, su);
-    case PNRAWV: return configure_form<PNRAWV>(src, sb, su);
-  }
-  return cudaErrorInvalidValue;
-}
-
-#define PS_FORM_SWITCH(CALL)                                   \
-  switch (P.form) {                                            \
-    case PBRAPV: return CALL(PBRAPV);                          \
-    case PBRARV: return CALL(PBRARV);                          \
-    case PBRAWV: return CALL(PBRAWV);                          \
-    case CBRARV: return CALL(CBRARV);                          \
-    case CBRAWV: return CALL(CBRAWV);                          \
-    case PNPAPV: return CALL(PNPAPV);                          \
-    case PNRAPV: return CALL(PNRAPV);                          \
-    case PNRARV: return CALL(PNRARV);                          \
-    case PNRAWV: return CALL(PNRAWV);                          \
-  }                                                            \
-  return cudaErrorInvalidValue;
-
-static cudaError_t launch_staged(const DevPlan& P, const EvalArgs& A, size_t smem, cudaStream_t stream, dim3 grid) {
-#define PS_CALL(F) launch_form<F>(P, A, smem, stream, grid)
-  PS_FORM_SWITCH(PS_CALL)
-#undef PS_CALL
-}
-static cudaError_t launch_bus(const DevPlan& P, const EvalArgs& A, size_t smem, cudaStream_t stream, dim3 grid) {
-#define PS_CALL(F) launch_bus_form<F>(P, A, smem, stream, grid)
-  PS_FORM_SWITCH(PS_CALL)
-#undef PS_CALL
-}
-template <int FORM>
-cudaError_t launch_pb_form(const DevPlan& P, const EvalArgs& A, cudaStream_t st, int nchunks, int64_t* launches,
-                           cudaEvent_t* ev, unsigned* ev_mask) {
-  auto rec = [&](int id, int end) { if (ev) { cudaEventRecord(ev[2 * id + end], st); if (end && ev_mask) *ev_mask |= 1u << id; } };
-  if constexpr (FORM == PBRAPV || FORM == PBRARV) {
-    if ((A.what & EV_G) || A.scal) {
-      rec(K_BUS, 0);
-      pb_bus_g_kernel<FORM><<<dim3((unsigned)((P.nb + PBT - 1) / PBT), (unsigned)nchunks), PBT, 0, st>>>(P, A);
-      rec(K_BUS, 1);
-      if (launches) *launches += 1;
-    }
-    if (A.what & (EV_J | EV_H)) {
-      const int n = (P.j_br0 > P.h_br0 ? P.j_br0 : P.h_br0) / 4 + 1;
-      rec(K_BUS_JH, 0);
-      pb_bus_jh_kernel<FORM><<<dim3((unsigned)((n + PBT - 1) / PBT), (unsigned)nchunks), PBT, 0, st>>>(P, A);
-      rec(K_BUS_JH, 1);
-      if (launches) *launches += 1;
-    }
-    if (A.scal) {
-      rec(K_OBJ, 0);
-      objective_kernel<<<dim3((unsigned)nchunks), TPB, 0, st>>>(P, A);
-      rec(K_OBJ, 1);
-      if (launches) *launches += 1;
-    }
-    return cudaGetLastError();
-  } else {
-    return cudaErrorInvalidValue;
-  }
-}
-static cudaError_t launch_pb(const DevPlan& P, const EvalArgs& A, cudaStream_t stream, int nchunks, int64_t* launches,
-                             cudaEvent_t* ev, unsigned* ev_mask) {
-#define PS_CALL(F) launch_pb_form<F>(P, A, stream, nchunks, launches, ev, ev_mask)
-  PS_FORM_SWITCH(PS_CALL)
-#undef PS_CALL
-}
-static cudaError_t launch_branch_direct(const DevPlan& P, const EvalArgs& A, cudaStream_t stream, dim3 grid) {
-#define PS_CALL(F) launch_direct<F>(P, A, stream, grid)
-  PS_FORM_SWITCH(PS_CALL)
-#undef PS_CALL
-}
-
-static bool sector_aligned(const double* p, long long first, long long ld) {
-  return ((reinterpret_cast<unsigned long long>(p) >> 3) + (unsigned long long)first) % 4 == 0 && ld % 4 == 0;
-}
-
-struct KTimer {                        // records an event pair around one kernel when timing is enabled
-  cudaEvent_t* ev; unsigned* mask; cudaStream_t st; int id;
-  KTimer(cudaEvent_t* e, unsigned* m, cudaStream_t s, int i) : ev(e), mask(m), st(s), id(i) { if (ev) cudaEventRecord(ev[2 * id], st); }
-  ~KTimer() { if (ev) { cudaEventRecord(ev[2 * id + 1], st); if (mask) *mask |= 1u << id; } }
-};
-
-static int env_int(const char* name, int dflt) {
-  const char* e = getenv(name);
-  const int v = e ? atoi(e) : 0;
-  return v > 0 ? v : dflt;
-}
-
-// One evaluation = two launches on `stream`: the bus kernel (nodal balances + objective scalar) and the branch
-// kernel (flow definitions / limits / cones) -- direct when the branch blocks of J and H start on 32-byte
-// sectors in every scenario row, staged otherwise.
-cudaError_t launch_eval(const DevPlan& P, const EvalArgs& A0, int64_t smem_branch_bytes, int64_t smem_bus_bytes,
-                        cudaStream_t stream, int64_t* launches, cudaEvent_t* ev, unsigned* ev_mask) {
-  if (A0.S <= 0) return cudaSuccess;
-  EvalArgs A = A0;
-  cudaError_t e = cudaSuccess;
-  const bool pb_fast = P.pb_slots && !getenv("PS_NO_PBFAST");
-  {
-    bool direct = direct_ok(P.form, P.src) && !getenv("PS_NO_DIRECT") && P.nr > 0;
-    if (direct && (A.what & EV_J)) direct = sector_aligned(A.J, P.j_br0, A.ldJ);
-    if (direct && (A.what & EV_H)) direct = sector_aligned(A.H, P.h_br0, A.ldH);
-    if (pb_fast && direct && !getenv("PS_NO_FUSED")) {
-      const int nchunks = (A.S + A.chunk - 1) / A.chunk;
-      if (nchunks > 65535) return cudaErrorInvalidConfiguration;
-      if (launches) *launches += 1;
-      KTimer kt(ev, ev_mask, stream, K_BRANCH);
-#define PS_CALL(F) launch_fused_form<F>(P, A, stream, nchunks)
-      PS_FORM_SWITCH(PS_CALL)
-#undef PS_CALL
-    }
-  }
-  if (pb_fast) {
     A.chunk = env_int("PS_CHUNK_PB", 4);
     const int nchunks = (A.S + A.chunk - 1) / A.chunk;
     if (nchunks > 65535) return cudaErrorInvalidConfiguration;

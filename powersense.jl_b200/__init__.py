@@ -6,3 +6,5 @@ solvers consume.  All numeric work is done by the CUDA library behind include/po
 there is no CPU fallback (importing `.capi` raises if the library is missing)."""
 from .types import *  # noqa: F401,F403
 from .data import Network, PowersenseData, create_PowersenseData  # noqa: F401
+from .evaluator import GpuNLPEvaluator  # noqa: F401,E402
+from .opf import OPFModel, create_opf_model, run_opf  # noqa: F401,E402

@@ -80,22 +80,29 @@ class ScenarioDriver:
         self.batch.eval_torch(self.what if what is None else what, self.x, self.mu, self.g, self.J, self.H, self.scalars)
 
     def gather_scalars(self):
-        """[S_total, PS_NSCALARS] on every rank.  NCCL all_gather over NVLink when world_size > 1; shards may
-        differ by one scenario, so the gather is padded to the largest shard."""
-        torch = self.torch
+        """[S_total, PS_NSCALARS] on every rank: NCCL all_gather over NVLink when world_size > 1."""
         if self.world_size == 1:
             return self.scalars[:self.S]
-        import torch.distributed as dist
-        smax = -(-self.S_total // self.world_size)
-        pad = torch.zeros(smax, capi.PS_NSCALARS, dtype=torch.float64, device=self.scalars.device)
-        pad[:self.S] = self.scalars[:self.S]
-        out = torch.empty(self.world_size * smax, capi.PS_NSCALARS, dtype=torch.float64, device=self.scalars.device)
-        dist.all_gather_into_tensor(out, pad)
-        return gather_unpad(out, self.S_total, self.world_size)
+        return all_gather_rows(self.scalars[:self.S], self.S_total, self.world_size)
 
     def close(self):
         self.batch.close()
         self.handle.close()
+
+
+def all_gather_rows(local_rows, S_total: int, world_size: int):
+    """all_gather of per-rank row blocks whose sizes follow shard_range (they differ by at most one row, so the
+    collective is padded to the largest shard).  Works on any torch.distributed backend (NCCL on the GPUs, gloo in
+    the CPU tests); the only collective of the whole path."""
+    import torch
+    import torch.distributed as dist
+    smax = -(-S_total // world_size)
+    k = local_rows.shape[1]
+    pad = torch.zeros(smax, k, dtype=local_rows.dtype, device=local_rows.device)
+    pad[:local_rows.shape[0]] = local_rows
+    out = torch.empty(world_size * smax, k, dtype=local_rows.dtype, device=local_rows.device)
+    dist.all_gather_into_tensor(out, pad)
+    return gather_unpad(out, S_total, world_size)
 
 
 def gather_unpad(padded, S_total: int, world_size: int):

@@ -5,7 +5,8 @@ What stays on the host here is what the reference leaves to the *solver* side of
 quadratic `@constraint` rows (formulations.jl:123-127, 141-168, 324-334, 430-471), the variable bounds (tgh >= 0,
 :121) and the objective (:122-138).  The NL rows -- balances, flow definitions, limits -- are evaluated on the
 GPU through the C ABI.  The reference hands the model to an MOI solver (Ipopt, or its own SLP `OPT` with GLPK); neither
-exists in this image, so `run_opf` drives scipy's trust-constr with the same callbacks."""
+exists in this image, so `run_opf` drives scipy's SLSQP (default; dense, small cases) or trust-constr (sparse, exact
+Hessians) with the same callbacks."""
 from __future__ import annotations
 
 from dataclasses import dataclass
@@ -192,8 +193,8 @@ def create_opf_model(data: PowersenseData, **kw) -> OPFModel:
 
 
 def run_opf(data: PowersenseData, formulation: ACOPF_fromulation = PBRAPVmodel, create_model: bool = True,
-            solver: str = "trust-constr", initialize: bool = True, FACTS_bShunt: bool = True, box_constraints: bool = False,
-            solve: bool = True, obj_type: str = "linear", device: int = 0, maxiter: int = 600, verbose: int = 0):
+            solver: str = "SLSQP", initialize: bool = True, FACTS_bShunt: bool = True, box_constraints: bool = False,
+            solve: bool = True, obj_type: str = "linear", device: int = 0, maxiter: int = 1000, verbose: int = 0):
     """run_opf!(data; formulation, create_model, solver, initialize, FACTS_bShunt, box_constraints, solve, obj_type)
     (formulations.jl:584-653).  Writes the solution back into `data` exactly like the reference (:608-651)."""
     from scipy.optimize import Bounds, LinearConstraint, NonlinearConstraint, minimize
@@ -225,8 +226,19 @@ def run_opf(data: PowersenseData, formulation: ACOPF_fromulation = PBRAPVmodel, 
             return H
         cons.append(NonlinearConstraint(qv, M.rows.lo[idx], M.rows.hi[idx], jac=qj, hess=qh))
     cons.append(NonlinearConstraint(M.nl_value, M.nl_lo, M.nl_hi, jac=M.nl_jac, hess=M.nl_hess))
-    res = minimize(M.f, M.x0, jac=M.grad_f, hess=lambda x: sp.diags(M.qdiag), method=solver, bounds=Bounds(M.xl, M.xu),
-                   constraints=cons, options={"maxiter": maxiter, "verbose": verbose, "gtol": 1e-6, "xtol": 1e-9})
+    if solver.upper() == "SLSQP":
+        # dense SQP (small cases): same callbacks, Jacobians densified, no Hessian callbacks (BFGS inside SLSQP)
+        dense = []
+        for c in cons:
+            if isinstance(c, LinearConstraint):
+                dense.append(LinearConstraint(c.A.toarray(), c.lb, c.ub))
+            else:
+                dense.append(NonlinearConstraint(c.fun, c.lb, c.ub, jac=(lambda x, j=c.jac: j(x).toarray())))
+        res = minimize(M.f, M.x0, jac=M.grad_f, method="SLSQP", bounds=Bounds(M.xl, M.xu), constraints=dense,
+                       options={"maxiter": maxiter, "ftol": 1e-10, "disp": bool(verbose)})
+    else:
+        res = minimize(M.f, M.x0, jac=M.grad_f, hess=lambda x: sp.diags(M.qdiag), method=solver, bounds=Bounds(M.xl, M.xu),
+                       constraints=cons, options={"maxiter": maxiter, "verbose": verbose, "gtol": 1e-6, "xtol": 1e-9})
     x, lay, d = res.x, M.lay, data
     nb, nr, ng = d.nbus, d.nbr, d.ngen
     d.cost = float(res.fun)                                        # :609

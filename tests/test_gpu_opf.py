@@ -1,7 +1,7 @@
 """End-to-end known answer (the only numeric answer the reference's tests hold on this path): the 14-bus PSS/E case
 solved with obj_type = :linear gives cost ~ 146.7 at rtol 0.1 for PNPAPV, PBRARV + box and CBRARV +- box
 (test/opf/ACOPF_formulations.jl:7-9, examples/opf/ACOPF_formulations_example.jl:5-19).  The NL block is served by the
-GPU evaluator through the MOI-style callbacks; the NLP solver is scipy's trust-constr (no Ipopt / GLPK here)."""
+GPU evaluator through the MOI-style callbacks; the NLP solver is scipy's SLSQP (no Ipopt / GLPK here)."""
 import copy
 
 import numpy as np

@@ -141,7 +141,7 @@ def cpu_baseline(d, F, args, seconds, nthreads=0):
     from oracle import c_oracle
     from powersense_b200 import synth
     o = c_oracle.COracle(d, F.code)
-    cores = nthreads or c_oracle.lib().pso_max_threads()
+    cores = nthreads or os.cpu_count() or c_oracle.lib().pso_max_threads()    # torchrun sets OMP_NUM_THREADS=1: ask the OS
     n0 = max(cores, 4)
     x, Pd, Qd, _ = synth.scenario_batch(d, F, n0, seed=77)
     mu = np.random.default_rng(5).normal(size=(n0, o.m_nl))
@@ -170,7 +170,7 @@ def run_reference(args, rank):
     d = synth.named_case(args.case)
     F = ps.BY_NAME[args.formulation]
     o = c_oracle.COracle(d, F.code)
-    cores = c_oracle.lib().pso_max_threads()
+    cores = os.cpu_count() or c_oracle.lib().pso_max_threads()     # torchrun sets OMP_NUM_THREADS=1: ask the OS
     n = max(cores, 4)
     x, Pd, Qd, _ = synth.scenario_batch(d, F, n, seed=77)
     mu = np.random.default_rng(5).normal(size=(n, o.m_nl))

@@ -274,6 +274,8 @@ int ps_create(const ps_network* net, int formulation, int source_type, int flags
   D.bus_jpp = M.upload(P.bus_jpp); D.bus_hpp = M.upload(P.bus_hpp);
   D.he_ptr = M.upload(P.he_ptr); D.he_ks = M.upload(P.he_ks); D.he_other = M.upload(P.he_other);
   D.he_c = M.upload(P.he_c); D.nhe = (int)P.he_ks.size();
+  D.he_bus = M.upload(P.he_bus); D.jsrc = M.upload(P.jsrc); D.hsrc = M.upload(P.hsrc);
+  D.ms_dst = M.upload(P.ms_dst); D.ms_ptr = M.upload(P.ms_ptr); D.ms_list = M.upload(P.ms_list);
   D.tiles = M.upload(P.tiles);
   // single-scenario staging
   const int64_t n_in = P.n_var + P.m_nl, n_out = P.m_nl + P.nnzJ + P.nnzH + NSCAL;

@@ -463,42 +463,25 @@ struct Branch {
 };
 
 // --------------------------------------------------------------------------- bus rows
-// A bus tile stages, once per CTA, everything that does not depend on the scenario in shared memory: the
-// tile's half-edge list (branch, side, other bus), the admittance entries of the PN* balances, the generator /
-// shunt lists and the slot-position streams.  Per scenario the x entries the tile reads (own voltages, the
-// flow / current variables or the neighbour voltages of every half-edge, generator injections), its
-// multipliers and loads are gathered into a double-buffered shared array with cp.async one scenario ahead,
-// so a bus thread never waits on a dependent chain of global loads.
+// Nodal balances (formulations.jl:170-297).  A bus tile (a contiguous range of buses, i.e. of rows and of g / J / H
+// slots) stages, once per CTA, everything that does not depend on the scenario in shared memory: the tile's half-edge
+// list (branch, side, other bus, owning bus), the admittance entries of the PN* balances, the generator / shunt lists and
+// the slot -> contribution maps.  Per scenario the x entries the tile reads (own voltages, the flow / current variables
+// or the neighbour voltages of every half-edge, generator injections), its multipliers and loads are gathered into a
+// double-buffered shared array with cp.async one scenario ahead.
 //
-// Stream writer: slot positions (relative to the bus's first slot) come from the plan in emission order;
-// bit 15 = accumulate into a slot this thread has already written (duplicate variables of a row: the
-// diagonal block of the nodal balances, parallel branches).  A bus's slots are private to its thread, so
-// there are no races and the accumulation order is the reference's term order.
-struct Stream {
-  double* __restrict__ base;
-  const uint16_t* __restrict__ pos;
+// Evaluation is CONTRIBUTION-MAJOR and free of divergence on the bus degree:
+//   phase 1  half-edge-parallel: every half-edge writes its Jacobian (then Hessian) contributions and the pieces of
+//            its flow term to shared memory, in the fixed emission order of the reference's term order
+//            (generators, Sij ascending, Sji ascending, shunt terms);
+//   phase 2  slot-parallel: every output slot sums its contributions left to right in emission order (duplicate
+//            variables of a row: the diagonal block, parallel branches) and goes straight to HBM with warp-contiguous,
+//            sector-aligned stores; every bus row folds its pieces in the reference's association.
+// No atomics, bitwise reproducible, reference summation order.
+struct SeqW {                      // sequential writer of contributions
+  double* p;
   bool on;
-  __device__ __forceinline__ void put(double v) {
-    if (on) {
-      const unsigned p = *pos;
-      double* q = base + (p & 0x7fffu);
-      *q = (p & 0x8000u) ? *q + v : v;
-    }
-    pos++;
-  }
-};
-
-struct BusOut {
-  double* g;
-  bool wg;
-  double vmax, tol;
-  int nviol;
-  __device__ __forceinline__ void G(int r, double v) {
-    if (wg) g[r] = v;
-    const double vv = fabs(v);
-    vmax = fmax(vmax, vv);
-    nviol += (vv > tol) ? 1 : 0;
-  }
+  __device__ __forceinline__ void put(double v) { if (on) *p = v; p++; }
 };
 
 __device__ __forceinline__ void cp_async8(void* smem_dst, const void* gsrc) {
@@ -508,186 +491,188 @@ __device__ __forceinline__ void cp_async8(void* smem_dst, const void* gsrc) {
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
 template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
 
-// per-bus invariants, loaded once per CTA and kept in registers across the scenario loop
-struct BusInv {
-  int g0, g1, h0, h1, f0, f1;        // tile-local ranges of the bus's generators / half-edges / switched shunts
-  int jbase, hbase, cjo, cho;        // first J / H slot in the tile, first entry of the position streams
-  double Gl, Bl;
-};
+PS_HD constexpr int he_nj(int f) { return (f == PBRAPV || f == PBRARV) ? 2 : 8; }
+PS_HD constexpr int he_nh(int f) { return (f == PBRAPV || f == PBRARV) ? 0 : (is_CB(f) ? 12 : (f == PNRARV ? 16 : 20)); }
+PS_HD constexpr int he_np(int f) { return is_CB(f) ? 4 : (f == PNRARV ? 6 : (is_PN(f) ? 4 : 0)); }
 
 // shared-memory view of one bus tile
 struct BusTile {
   int nbt, nhe, ngt, nsh;            // buses, half-edges, generators, switched shunts in the tile
   int hp0, gp0, sp0, cj0, ch0;       // first global index of each list
   int xh, xg, xw, xs_, xm, xl, nx;   // offsets inside the gathered-input array
-  double *sG, *sJ, *sH, *xb0, *xb1, *hc;
+  double *cb, *gp, *xb0, *xb1, *hc;  // contributions, g pieces [np][nhe], gathered inputs (x2), PN* constants [4][nhe]
   int *heks, *hoth, *sgen, *ssh;
-  uint16_t *jpos, *hpos;
+  uint16_t *hbus, *jsrc, *hsrc, *mdst, *mptr, *mlist;   // multi-slot arrays: J part then H part
   uint8_t* sst;
 };
 
+// per-bus invariants, loaded once per CTA and kept in registers across the scenario loop
+struct BusInv {
+  int g0, g1, h0, h1, f0, f1;        // tile-local ranges of the bus's generators / half-edges / switched shunts
+  int cj, ch;                        // tile-local first J / H contribution of the bus
+  double Gl, Bl;
+};
+
+// One half-edge: contributions in the emission order of ps_plan.cpp (which is the reference's source order), and the
+// pieces of the flow term for the residual.  xs = gathered inputs of this scenario.
 template <int FORM>
-__device__ __forceinline__ void bus_rows(const DevPlan& P, const BusTile& T, const BusInv& B, const double* xs, BusOut& o,
-                                         Stream& sj, Stream& sh, int lu, bool has_status) {
-  const double muP = sh.on ? xs[T.xm + 2 * lu] : 0.0, muQ = sh.on ? xs[T.xm + 2 * lu + 1] : 0.0;
-  double accP = 0.0, accQ = 0.0;                               // formulations.jl:171-172
-  for (int q = B.g0; q < B.g1; q++) {                           // :177-180
-    accP = accP + xs[T.xg + 2 * q];
-    accQ = accQ + xs[T.xg + 2 * q + 1];
-    sj.put(1.0);
-    sj.put(1.0);
-  }
-  const double va0 = xs[lu], vb0 = xs[T.nbt + lu];             // own voltage: (theta_i, V_i) | (vi_i, vr_i)
-#pragma unroll 1
-  for (int q = B.h0; q < B.h1; q++) {                           // Sij ascending, then Sji ascending
-    const int side = T.heks[q] & 1;
-    const double st = has_status ? (double)T.sst[q] : 1.0;
-    const double v0 = xs[T.xh + 2 * q], v1 = xs[T.xh + 2 * q + 1];
-    if constexpr (FORM == PBRAPV || FORM == PBRARV) {          // :188-196  v0/v1 = P / Q flow variable
-      accP = accP + st * v0;
-      accQ = accQ + st * v1;
-      sj.put(st);
-      sj.put(st);
-    } else if constexpr (FORM == CBRARV || FORM == CBRAWV) {   // :206-214  T4, v0/v1 = Ir / Ii
-      const double Ir = v0, Ii = v1, ra = vb0, ia = va0;
-      accP = (accP + st * (ra * Ir)) + st * (ia * Ii);
-      accQ = (accQ + st * (ia * Ir)) - st * (ra * Ii);
-      sj.put(st * Ir); sj.put(st * Ii); sj.put(st * ra); sj.put(st * ia);          // P: d/d(ra, ia, Ir, Ii)
-      sj.put(-st * Ii); sj.put(st * Ir); sj.put(st * ia); sj.put(-st * ra);        // Q
-      sh.put(0.0); sh.put(0.0); sh.put(st * muP); sh.put(0.0); sh.put(0.0); sh.put(st * muP);
-      sh.put(0.0); sh.put(0.0); sh.put(st * muQ); sh.put(0.0); sh.put(0.0); sh.put(-st * muQ);
-    } else if constexpr (FORM == PNPAPV || FORM == PNRAPV) {   // :215-234  T2 / T1, v0/v1 = theta_b / V_b
-      const double gs = st * T.hc[q], bs = st * T.hc[T.nhe + q];
-      const double thb = v0, Vb = v1, Va = vb0, dl = va0 - thb;
-      double A, Bt;
-      if constexpr (FORM == PNPAPV) {
-        const double Y = st * T.hc[2 * T.nhe + q], phi = T.hc[3 * T.nhe + q];
-        double s, c;
-        sincos(dl - phi, &s, &c);
-        A = Y * c; Bt = -(Y * s);
-      } else {
-        const double G = st * T.hc[2 * T.nhe + q], B = st * T.hc[3 * T.nhe + q];
-        double s, c;
-        sincos(dl, &s, &c);
-        A = G * c + B * s; Bt = B * c - G * s;
-      }
-      const double Vf = side ? Vb : Va, Vt = side ? Va : Vb;  // source order V[f]*V[t]
-      const double VV = Va * Vb;
-      accP = (accP - gs * (Va * Va)) - A * Vf * Vt;
-      accQ = (accQ + bs * (Va * Va)) + Bt * Vf * Vt;
-      // J: d/d(th_a, th_b, V_a, V_b)
-      sj.put(-Bt * VV); sj.put(Bt * VV); sj.put(-2.0 * gs * Va - A * Vb); sj.put(-A * Va);
-      sj.put(-A * VV); sj.put(A * VV); sj.put(2.0 * bs * Va + Bt * Vb); sj.put(Bt * Va);
-      // H clique order over [th_a, th_b, V_a, V_b]: aa bb VaVa VbVb ab aVa aVb bVa bVb VaVb
-      sh.put(muP * A * VV); sh.put(muP * A * VV); sh.put(muP * -2.0 * gs); sh.put(0.0); sh.put(-muP * A * VV);
-      sh.put(-muP * Bt * Vb); sh.put(-muP * Bt * Va); sh.put(muP * Bt * Vb); sh.put(muP * Bt * Va); sh.put(-muP * A);
-      sh.put(-muQ * Bt * VV); sh.put(-muQ * Bt * VV); sh.put(muQ * 2.0 * bs); sh.put(0.0); sh.put(muQ * Bt * VV);
-      sh.put(-muQ * A * Vb); sh.put(-muQ * A * Va); sh.put(muQ * A * Vb); sh.put(muQ * A * Va); sh.put(muQ * Bt);
-    } else if constexpr (FORM == PNRARV) {                     // :235-243  T3, v0/v1 = vi_b / vr_b
-      const double gs = st * T.hc[q], bs = st * T.hc[T.nhe + q];
+__device__ __forceinline__ void he_terms(const BusTile& T, const double* __restrict__ xs, int q, SeqW& sj, SeqW& sh,
+                                         bool want_pieces, bool has_status) {
+  const int side = T.heks[q] & 1;
+  const int lb = T.hbus[q];
+  const double st = has_status ? (double)T.sst[q] : 1.0;
+  const double v0 = xs[T.xh + 2 * q], v1 = xs[T.xh + 2 * q + 1];
+  const double va0 = xs[lb], vb0 = xs[T.nbt + lb];             // own voltage: (theta_i, V_i) | (vi_i, vr_i)
+  const double muP = sh.on ? xs[T.xm + 2 * lb] : 0.0, muQ = sh.on ? xs[T.xm + 2 * lb + 1] : 0.0;
+  double* gpq = T.gp + q;
+  if constexpr (FORM == PBRAPV || FORM == PBRARV) {            // :188-196
+    sj.put(st);
+    sj.put(st);
+  } else if constexpr (FORM == CBRARV || FORM == CBRAWV) {     // :206-214  T4, v0/v1 = Ir / Ii
+    const double Ir = v0, Ii = v1, ra = vb0, ia = va0;
+    if (want_pieces) {
+      gpq[0] = st * (ra * Ir); gpq[T.nhe] = st * (ia * Ii);
+      gpq[2 * T.nhe] = st * (ia * Ir); gpq[3 * T.nhe] = st * (ra * Ii);
+    }
+    sj.put(st * Ir); sj.put(st * Ii); sj.put(st * ra); sj.put(st * ia);          // P: d/d(ra, ia, Ir, Ii)
+    sj.put(-st * Ii); sj.put(st * Ir); sj.put(st * ia); sj.put(-st * ra);        // Q
+    sh.put(0.0); sh.put(0.0); sh.put(st * muP); sh.put(0.0); sh.put(0.0); sh.put(st * muP);
+    sh.put(0.0); sh.put(0.0); sh.put(st * muQ); sh.put(0.0); sh.put(0.0); sh.put(-st * muQ);
+  } else if constexpr (FORM == PNPAPV || FORM == PNRAPV) {     // :215-234  T2 / T1, v0/v1 = theta_b / V_b
+    const double gs = st * T.hc[q], bs = st * T.hc[T.nhe + q];
+    const double thb = v0, Vb = v1, Va = vb0, dl = va0 - thb;
+    double A, Bt;
+    if constexpr (FORM == PNPAPV) {
+      const double Y = st * T.hc[2 * T.nhe + q], phi = T.hc[3 * T.nhe + q];
+      double s, c;
+      sincos(dl - phi, &s, &c);
+      A = Y * c; Bt = -(Y * s);
+    } else {
       const double G = st * T.hc[2 * T.nhe + q], B = st * T.hc[3 * T.nhe + q];
-      const double ra = vb0, ia = va0, rb = v1, ib = v0;
-      const double A2 = ra * ra + ia * ia, C = ra * rb + ia * ib, S = ra * ib - ia * rb;
-      accP = ((accP - gs * A2) - G * C) + B * S;
-      accQ = ((accQ + bs * A2) + B * C) + G * S;
-      // J: d/d(ra, ia, rb, ib)
-      sj.put(-2.0 * gs * ra - G * rb + B * ib); sj.put(-2.0 * gs * ia - G * ib - B * rb);
-      sj.put(-G * ra - B * ia); sj.put(-G * ia + B * ra);
-      sj.put(2.0 * bs * ra + B * rb + G * ib); sj.put(2.0 * bs * ia + B * ib - G * rb);
-      sj.put(B * ra - G * ia); sj.put(B * ia + G * ra);
-      // H: (ra,ra)(ia,ia)(rb,rb)(ib,ib)(ra,rb)(ia,ib)(ra,ib)(ia,rb)
-      sh.put(muP * -2.0 * gs); sh.put(muP * -2.0 * gs); sh.put(0.0); sh.put(0.0);
-      sh.put(-muP * G); sh.put(-muP * G); sh.put(muP * B); sh.put(-muP * B);
-      sh.put(muQ * 2.0 * bs); sh.put(muQ * 2.0 * bs); sh.put(0.0); sh.put(0.0);
-      sh.put(muQ * B); sh.put(muQ * B); sh.put(muQ * G); sh.put(-muQ * G);
+      double s, c;
+      sincos(dl, &s, &c);
+      A = G * c + B * s; Bt = B * c - G * s;
     }
+    const double Vf = side ? Vb : Va, Vt = side ? Va : Vb;    // source order V[f]*V[t]
+    const double VV = Va * Vb;
+    if (want_pieces) {                                         // acc = (acc -/+ p1) -/+ p2
+      gpq[0] = gs * (Va * Va); gpq[T.nhe] = A * Vf * Vt;
+      gpq[2 * T.nhe] = bs * (Va * Va); gpq[3 * T.nhe] = Bt * Vf * Vt;
+    }
+    // J: d/d(th_a, th_b, V_a, V_b)
+    sj.put(-Bt * VV); sj.put(Bt * VV); sj.put(-2.0 * gs * Va - A * Vb); sj.put(-A * Va);
+    sj.put(-A * VV); sj.put(A * VV); sj.put(2.0 * bs * Va + Bt * Vb); sj.put(Bt * Va);
+    // H clique order over [th_a, th_b, V_a, V_b]: aa bb VaVa VbVb ab aVa aVb bVa bVb VaVb
+    sh.put(muP * A * VV); sh.put(muP * A * VV); sh.put(muP * -2.0 * gs); sh.put(0.0); sh.put(-muP * A * VV);
+    sh.put(-muP * Bt * Vb); sh.put(-muP * Bt * Va); sh.put(muP * Bt * Vb); sh.put(muP * Bt * Va); sh.put(-muP * A);
+    sh.put(-muQ * Bt * VV); sh.put(-muQ * Bt * VV); sh.put(muQ * 2.0 * bs); sh.put(0.0); sh.put(muQ * Bt * VV);
+    sh.put(-muQ * A * Vb); sh.put(-muQ * A * Va); sh.put(muQ * A * Vb); sh.put(muQ * A * Va); sh.put(muQ * Bt);
+  } else if constexpr (FORM == PNRARV) {                       // :235-243  T3, v0/v1 = vi_b / vr_b
+    const double gs = st * T.hc[q], bs = st * T.hc[T.nhe + q];
+    const double G = st * T.hc[2 * T.nhe + q], B = st * T.hc[3 * T.nhe + q];
+    const double ra = vb0, ia = va0, rb = v1, ib = v0;
+    const double A2 = ra * ra + ia * ia, C = ra * rb + ia * ib, S = ra * ib - ia * rb;
+    if (want_pieces) {                                         // P: ((acc - p0) - p1) + p2 ; Q: ((acc + p3) + p4) + p5
+      gpq[0] = gs * A2; gpq[T.nhe] = G * C; gpq[2 * T.nhe] = B * S;
+      gpq[3 * T.nhe] = bs * A2; gpq[4 * T.nhe] = B * C; gpq[5 * T.nhe] = G * S;
+    }
+    // J: d/d(ra, ia, rb, ib)
+    sj.put(-2.0 * gs * ra - G * rb + B * ib); sj.put(-2.0 * gs * ia - G * ib - B * rb);
+    sj.put(-G * ra - B * ia); sj.put(-G * ia + B * ra);
+    sj.put(2.0 * bs * ra + B * rb + G * ib); sj.put(2.0 * bs * ia + B * ib - G * rb);
+    sj.put(B * ra - G * ia); sj.put(B * ia + G * ra);
+    // H: (ra,ra)(ia,ia)(rb,rb)(ib,ib)(ra,rb)(ia,ib)(ra,ib)(ia,rb)
+    sh.put(muP * -2.0 * gs); sh.put(muP * -2.0 * gs); sh.put(0.0); sh.put(0.0);
+    sh.put(-muP * G); sh.put(-muP * G); sh.put(muP * B); sh.put(-muP * B);
+    sh.put(muQ * 2.0 * bs); sh.put(muQ * 2.0 * bs); sh.put(0.0); sh.put(0.0);
+    sh.put(muQ * B); sh.put(muQ * B); sh.put(muQ * G); sh.put(-muQ * G);
   }
-  // shunt terms :256-279
-  const double Gl = B.Gl, Bl = B.Bl;
-  const int f0 = B.f0, f1 = B.f1;
-  if constexpr (is_polar(FORM)) {
-    const double V = vb0, V2 = V * V;
-    accP = accP - Gl * V2;
-    accQ = accQ + Bl * V2;
-    sj.put(-2.0 * Gl * V); sj.put(2.0 * Bl * V);
-    sh.put(-2.0 * Gl * muP); sh.put(2.0 * Bl * muQ);
-    for (int q = f0; q < f1; q++) {
-      const double bss = xs[T.xs_ + q];
-      accQ = accQ + bss * V2;
-      sj.put(V2); sj.put(2.0 * bss * V);
-      sh.put(0.0); sh.put(2.0 * bss * muQ); sh.put(2.0 * V * muQ);
-    }
-  } else if constexpr (FORM == PBRARV || FORM == CBRARV || FORM == PNRARV) {
-    const double r = vb0, im = va0, A2 = r * r + im * im;
-    accP = accP - Gl * A2;
-    accQ = accQ + Bl * A2;
-    sj.put(-2.0 * Gl * r); sj.put(-2.0 * Gl * im); sj.put(2.0 * Bl * r); sj.put(2.0 * Bl * im);
-    sh.put(-2.0 * Gl * muP); sh.put(-2.0 * Gl * muP); sh.put(2.0 * Bl * muQ); sh.put(2.0 * Bl * muQ);
-    for (int q = f0; q < f1; q++) {
-      const double bss = xs[T.xs_ + q];
-      accQ = accQ + bss * A2;
-      sj.put(A2); sj.put(2.0 * bss * r); sj.put(2.0 * bss * im);
-      sh.put(0.0); sh.put(2.0 * bss * muQ); sh.put(2.0 * bss * muQ);
-      sh.put(2.0 * r * muQ); sh.put(2.0 * im * muQ); sh.put(0.0);
-    }
-  } else if constexpr (FORM == CBRAWV) {
-    const double W = xs[T.xw + lu];
-    accP = accP - Gl * W;
-    accQ = accQ + Bl * W;
-    sj.put(-Gl); sj.put(Bl);
-    for (int q = f0; q < f1; q++) {
-      const double bss = xs[T.xs_ + q];
-      accQ = accQ + bss * W;
-      sj.put(W); sj.put(bss);
-      sh.put(0.0); sh.put(0.0); sh.put(muQ);
-    }
-  }
-  o.G(0, accP - xs[T.xl + lu]);                                // :291
-  o.G(1, accQ - xs[T.xl + T.nbt + lu]);                        // :292
 }
 
-// Power-branch-flow balances (PBRAPV / PBRARV, formulations.jl:188-196): the row is linear in the generator and
-// flow variables, so its Jacobian slots are, in JuMP's sorted-column order, [own voltage slots][pg | qg of the
-// bus's generators][Pij | Qij of Sij][Pji | Qji of Sji] -- the emission order -- and every entry but the voltage
-// ones is the constant 1 (times the branch status).  The constant slots are written once per CTA and stay in the
-// staging tile; per scenario a bus thread sums its injections and rewrites the 2-4 voltage-dependent slots.
+// Generator and shunt contributions of one bus (everything of the bus that is not a half-edge)
 template <int FORM>
-__device__ __forceinline__ void bus_rows_pb(const BusTile& T, const BusInv& B, const double* __restrict__ xs, BusOut& o,
-                                            bool wj, bool wh, int lu, bool has_status, bool fill_const) {
-  constexpr int NV = (FORM == PBRARV) ? 2 : 1;                 // (vi_i, vr_i) | V_i
-  const int len = NV + (B.g1 - B.g0) + (B.h1 - B.h0);          // slots of the P row == slots of the Q row
-  double* __restrict__ jP = T.sJ + B.jbase;
-  double* __restrict__ jQ = jP + len;
-  double accP = 0.0, accQ = 0.0;                               // formulations.jl:171-172
-  int c = NV;
-  for (int q = B.g0; q < B.g1; q++, c++) {                     // :177-180
+__device__ __forceinline__ void bus_own_terms(const DevPlan& P, const BusTile& T, const BusInv& B, const double* __restrict__ xs,
+                                              int lu, SeqW sjg, SeqW sjs, SeqW shs) {
+  for (int q = B.g0; q < B.g1; q++) { sjg.put(1.0); sjg.put(1.0); }     // :177-180
+  const double muP = shs.on ? xs[T.xm + 2 * lu] : 0.0, muQ = shs.on ? xs[T.xm + 2 * lu + 1] : 0.0;
+  const double va0 = xs[lu], vb0 = xs[T.nbt + lu];
+  const double Gl = B.Gl, Bl = B.Bl;
+  if constexpr (is_polar(FORM)) {                                       // :256-263
+    const double V = vb0, V2 = V * V;
+    sjs.put(-2.0 * Gl * V); sjs.put(2.0 * Bl * V);
+    shs.put(-2.0 * Gl * muP); shs.put(2.0 * Bl * muQ);
+    for (int q = B.f0; q < B.f1; q++) {
+      const double bss = xs[T.xs_ + q];
+      sjs.put(V2); sjs.put(2.0 * bss * V);
+      shs.put(0.0); shs.put(2.0 * bss * muQ); shs.put(2.0 * V * muQ);
+    }
+  } else if constexpr (FORM == PBRARV || FORM == CBRARV || FORM == PNRARV) {   // :264-271
+    const double r = vb0, im = va0, A2 = r * r + im * im;
+    sjs.put(-2.0 * Gl * r); sjs.put(-2.0 * Gl * im); sjs.put(2.0 * Bl * r); sjs.put(2.0 * Bl * im);
+    shs.put(-2.0 * Gl * muP); shs.put(-2.0 * Gl * muP); shs.put(2.0 * Bl * muQ); shs.put(2.0 * Bl * muQ);
+    for (int q = B.f0; q < B.f1; q++) {
+      const double bss = xs[T.xs_ + q];
+      sjs.put(A2); sjs.put(2.0 * bss * r); sjs.put(2.0 * bss * im);
+      shs.put(0.0); shs.put(2.0 * bss * muQ); shs.put(2.0 * bss * muQ);
+      shs.put(2.0 * r * muQ); shs.put(2.0 * im * muQ); shs.put(0.0);
+    }
+  } else if constexpr (FORM == CBRAWV) {                                // :272-279
+    const double W = xs[T.xw + lu];
+    sjs.put(-Gl); sjs.put(Bl);
+    for (int q = B.f0; q < B.f1; q++) {
+      const double bss = xs[T.xs_ + q];
+      sjs.put(W); sjs.put(bss);
+      shs.put(0.0); shs.put(0.0); shs.put(muQ);
+    }
+  }
+}
+
+// The two residuals of one bus from the staged pieces, in the reference's order and association (:171-292)
+template <int FORM>
+__device__ __forceinline__ void bus_residuals(const BusTile& T, const BusInv& B, const double* __restrict__ xs, int lu,
+                                              bool has_status, double& gP, double& gQ) {
+  double accP = 0.0, accQ = 0.0;                               // :171-172
+  for (int q = B.g0; q < B.g1; q++) {                          // :177-180
     accP = accP + xs[T.xg + 2 * q];
     accQ = accQ + xs[T.xg + 2 * q + 1];
-    if (fill_const) { jP[c] = 1.0; jQ[c] = 1.0; }
   }
-  for (int q = B.h0; q < B.h1; q++, c++) {                     // :188-196, Sij ascending then Sji ascending
-    const double st = has_status ? (double)T.sst[q] : 1.0;
-    accP = accP + st * xs[T.xh + 2 * q];
-    accQ = accQ + st * xs[T.xh + 2 * q + 1];
-    if (fill_const || (has_status && wj)) { jP[c] = st; jQ[c] = st; }
+  const int nh = T.nhe;
+  for (int q = B.h0; q < B.h1; q++) {                          // Sij ascending, then Sji ascending
+    const double* g = T.gp + q;
+    if constexpr (FORM == PBRAPV || FORM == PBRARV) {
+      const double st = has_status ? (double)T.sst[q] : 1.0;
+      accP = accP + st * xs[T.xh + 2 * q];
+      accQ = accQ + st * xs[T.xh + 2 * q + 1];
+    } else if constexpr (is_CB(FORM)) {
+      accP = (accP + g[0]) + g[nh];
+      accQ = (accQ + g[2 * nh]) - g[3 * nh];
+    } else if constexpr (FORM == PNPAPV || FORM == PNRAPV) {
+      accP = (accP - g[0]) - g[nh];
+      accQ = (accQ + g[2 * nh]) + g[3 * nh];
+    } else {
+      accP = ((accP - g[0]) - g[nh]) + g[2 * nh];
+      accQ = ((accQ + g[3 * nh]) + g[4 * nh]) + g[5 * nh];
+    }
   }
-  const double muP = wh ? xs[T.xm + 2 * lu] : 0.0, muQ = wh ? xs[T.xm + 2 * lu + 1] : 0.0;
-  double* __restrict__ hP = T.sH + B.hbase;
-  if constexpr (FORM == PBRARV) {                              // :264-266
-    const double im = xs[lu], r = xs[T.nbt + lu], A2 = r * r + im * im;
-    accP = accP - B.Gl * A2;
-    accQ = accQ + B.Bl * A2;
-    if (wj) { jP[0] = -2.0 * B.Gl * im; jP[1] = -2.0 * B.Gl * r; jQ[0] = 2.0 * B.Bl * im; jQ[1] = 2.0 * B.Bl * r; }
-    if (wh) { hP[0] = -2.0 * B.Gl * muP; hP[1] = -2.0 * B.Gl * muP; hP[2] = 2.0 * B.Bl * muQ; hP[3] = 2.0 * B.Bl * muQ; }
-  } else {                                                     // :256-258
-    const double V = xs[T.nbt + lu], V2 = V * V;
+  const double va0 = xs[lu], vb0 = xs[T.nbt + lu];
+  if constexpr (is_polar(FORM)) {
+    const double V2 = vb0 * vb0;
     accP = accP - B.Gl * V2;
     accQ = accQ + B.Bl * V2;
-    if (wj) { jP[0] = -2.0 * B.Gl * V; jQ[0] = 2.0 * B.Bl * V; }
-    if (wh) { hP[0] = -2.0 * B.Gl * muP; hP[1] = 2.0 * B.Bl * muQ; }
+    for (int q = B.f0; q < B.f1; q++) accQ = accQ + xs[T.xs_ + q] * V2;
+  } else if constexpr (FORM == PBRARV || FORM == CBRARV || FORM == PNRARV) {
+    const double A2 = vb0 * vb0 + va0 * va0;
+    accP = accP - B.Gl * A2;
+    accQ = accQ + B.Bl * A2;
+    for (int q = B.f0; q < B.f1; q++) accQ = accQ + xs[T.xs_ + q] * A2;
+  } else {
+    const double W = xs[T.xw + lu];
+    accP = accP - B.Gl * W;
+    accQ = accQ + B.Bl * W;
+    for (int q = B.f0; q < B.f1; q++) accQ = accQ + xs[T.xs_ + q] * W;
   }
-  o.G(0, accP - xs[T.xl + lu]);                                // :291
-  o.G(1, accQ - xs[T.xl + T.nbt + lu]);                        // :292
+  gP = accP - xs[T.xl + lu];                                   // :291
+  gQ = accQ - xs[T.xl + T.nbt + lu];                           // :292
 }
 
 // issue the cp.async gather of one scenario's inputs of a bus tile
@@ -830,6 +815,21 @@ __global__ void __launch_bounds__(TPB) branch_staged_kernel(const __grid_constan
   }
 }
 
+// Slots with several contributions (diagonal block of the nodal balances, parallel branches) are pre-reduced into the
+// cell of their first contribution, left to right in emission order; the list is sorted by contribution count so the
+// lanes of a warp run the same number of additions.  After that every slot has exactly one source cell.
+__device__ __forceinline__ void reduce_multi(double* cb, const uint16_t* mdst, const uint16_t* mptr, const uint16_t* mlist, int mn) {
+  for (int m = threadIdx.x; m < mn; m += TPB) {
+    const int d = mdst[m];
+    double v = cb[d];
+    for (int q = mptr[m], q1 = mptr[m + 1]; q < q1; q++) v = v + cb[mlist[q]];
+    cb[d] = v;
+  }
+}
+__device__ __forceinline__ void slots_out(double* __restrict__ dst, int n, const double* cb, const uint16_t* src) {
+  copy_aligned<TPB>(dst, n, threadIdx.x, [&](int e) { return cb[src[e]]; });
+}
+
 // Bus rows (nodal balances, formulations.jl:170-297) plus, in the last CTA column, the objective scalar.
 template <int FORM>
 __global__ void __launch_bounds__(TPB) bus_kernel(const __grid_constant__ DevPlan P, const __grid_constant__ EvalArgs A) {
@@ -840,9 +840,11 @@ __global__ void __launch_bounds__(TPB) bus_kernel(const __grid_constant__ DevPla
     return;
   }
   if constexpr (has_bus_rows(FORM)) {
+    constexpr int NJ = he_nj(FORM), NH = he_nh(FORM), NP = he_np(FORM);
     const Tile tl = P.tiles[blockIdx.x];
     const bool wg = (A.what & EV_G) != 0, wj = (A.what & EV_J) != 0, wh = (A.what & EV_H) != 0;
-    const int u = tl.u0 + threadIdx.x;
+    const int tid = threadIdx.x;
+    const int u = tl.u0 + tid;
     const bool act = u < tl.u1;
     const bool facts = (P.flags & FLAG_FACTS) != 0;
     BusTile T;
@@ -855,75 +857,126 @@ __global__ void __launch_bounds__(TPB) bus_kernel(const __grid_constant__ DevPla
     // gathered-input layout: own a | own b | half-edge pairs | generator pairs | Wd | bss | mu (P,Q) | Pd | Qd
     T.xh = 2 * T.nbt; T.xg = T.xh + 2 * T.nhe; T.xw = T.xg + 2 * T.ngt;
     T.xs_ = T.xw + (FORM == CBRAWV ? T.nbt : 0); T.xm = T.xs_ + T.nsh; T.xl = T.xm + 2 * T.nbt; T.nx = T.xl + 2 * T.nbt;
-    T.sG = smem; T.sJ = T.sG + tl.gn; T.sH = T.sJ + tl.jn;
-    T.xb0 = T.sH + tl.hn; T.xb1 = T.xb0 + T.nx;
+    T.cb = smem;
+    T.gp = T.cb + max(ncj, nch);
+    T.xb0 = T.gp + NP * T.nhe; T.xb1 = T.xb0 + T.nx;
     T.hc = T.xb1 + T.nx;
     T.heks = (int*)(T.hc + (is_PN(FORM) ? 4 * T.nhe : 0));
     T.hoth = T.heks + T.nhe;
     T.sgen = T.hoth + (is_PN(FORM) ? T.nhe : 0);
     T.ssh = T.sgen + T.ngt;
-    T.jpos = (uint16_t*)(T.ssh + T.nsh);
-    T.hpos = T.jpos + ncj;
-    T.sst = (uint8_t*)(T.hpos + nch);
+    T.hbus = (uint16_t*)(T.ssh + T.nsh);
+    T.jsrc = T.hbus + T.nhe;
+    T.hsrc = T.jsrc + tl.jn;
+    T.mdst = T.hsrc + tl.hn;                      // [mjn | mhn]
+    T.mptr = T.mdst + (tl.mjn + tl.mhn);          // [mjn + 1 | mhn + 1]
+    T.mlist = T.mptr + (tl.mjn + tl.mhn + 2);     // [mjln | mhln]
+    T.sst = (uint8_t*)(T.mlist + (tl.mjln + tl.mhln));
     // ---- scenario-independent staging (once per CTA)
-    for (int q = threadIdx.x; q < T.nhe; q += TPB) {
+    for (int q = tid; q < T.nhe; q += TPB) {
       T.heks[q] = P.he_ks[T.hp0 + q];
+      T.hbus[q] = (uint16_t)(P.he_bus[T.hp0 + q] - tl.u0);
       if constexpr (is_PN(FORM)) {
         T.hoth[q] = P.he_other[T.hp0 + q];
 #pragma unroll
         for (int c = 0; c < 4; c++) T.hc[c * T.nhe + q] = P.he_c[(long long)c * P.nhe + T.hp0 + q];
       }
     }
-    for (int q = threadIdx.x; q < T.ngt; q += TPB) T.sgen[q] = P.gen_idx[T.gp0 + q];
-    for (int q = threadIdx.x; q < T.nsh; q += TPB) T.ssh[q] = P.sh_idx[T.sp0 + q];
-    for (int q = threadIdx.x; q < ncj; q += TPB) T.jpos[q] = P.bus_jpos[T.cj0 + q];
-    for (int q = threadIdx.x; q < nch; q += TPB) T.hpos[q] = P.bus_hpos[T.ch0 + q];
+    for (int q = tid; q < T.ngt; q += TPB) T.sgen[q] = P.gen_idx[T.gp0 + q];
+    for (int q = tid; q < T.nsh; q += TPB) T.ssh[q] = P.sh_idx[T.sp0 + q];
+    for (int q = tid; q < tl.jn; q += TPB) T.jsrc[q] = (uint16_t)(P.jsrc[tl.j0 + q] - T.cj0);
+    for (int q = tid; q < tl.hn; q += TPB) T.hsrc[q] = (uint16_t)(P.hsrc[tl.h0 + q] - T.ch0);
+    for (int q = tid; q < tl.mjn; q += TPB) T.mdst[q] = (uint16_t)P.ms_dst[tl.mj0 + q];
+    for (int q = tid; q < tl.mhn; q += TPB) T.mdst[tl.mjn + q] = (uint16_t)P.ms_dst[tl.mh0 + q];
+    for (int q = tid; q <= tl.mjn; q += TPB) T.mptr[q] = (uint16_t)P.ms_ptr[tl.mj0 + q];
+    for (int q = tid; q <= tl.mhn; q += TPB) T.mptr[tl.mjn + 1 + q] = (uint16_t)P.ms_ptr[tl.mh0 + q];
+    for (int q = tid; q < tl.mjln; q += TPB) T.mlist[q] = (uint16_t)P.ms_list[tl.mjl0 + q];
+    for (int q = tid; q < tl.mhln; q += TPB) T.mlist[tl.mjln + q] = (uint16_t)P.ms_list[tl.mhl0 + q];
     BusInv B{};
     if (act) {
       B.g0 = P.gen_ptr[u] - T.gp0; B.g1 = P.gen_ptr[u + 1] - T.gp0;
       B.h0 = P.he_ptr[u] - T.hp0; B.h1 = P.he_ptr[u + 1] - T.hp0;
       B.f0 = P.sh_ptr[u] - T.sp0; B.f1 = facts ? P.sh_ptr[u + 1] - T.sp0 : B.f0;
-      B.jbase = P.jptr[2 * u] - tl.j0; B.hbase = P.hptr[2 * u] - tl.h0;
-      B.cjo = P.bus_jpp[u] - T.cj0; B.cho = P.bus_hpp[u] - T.ch0;
+      B.cj = P.bus_jpp[u] - T.cj0; B.ch = P.bus_hpp[u] - T.ch0;
       B.Gl = P.Gl[u]; B.Bl = P.Bl[u];
     }
+    // per-bus contribution bases the half-edge threads need: [cj of first half-edge, ch of first half-edge, first half-edge]
+    // (kept in the hbus-adjacent arrays would cost smem; they are cheap to recompute from the bus's invariants)
     const bool has_status = A.status != nullptr;
-    const bool pb_fast = P.pb_implicit && T.nsh == 0;          // implicit slot order verified by the plan builder
-    BusOut o;
-    o.g = T.sG + 2 * threadIdx.x; o.wg = wg; o.tol = A.viol_tol;
+    const bool need_g = wg || A.scal;
     __syncthreads();
     bus_gather<FORM>(P, A, T, tl, s0, T.xb0);
     cp_async_commit();
     for (int s = s0; s < s1; s++) {
       const bool odd = ((s - s0) & 1) != 0;
-      double* const xcur = odd ? T.xb1 : T.xb0;
+      double* const xs = odd ? T.xb1 : T.xb0;
       if (s + 1 < s1) bus_gather<FORM>(P, A, T, tl, s + 1, odd ? T.xb0 : T.xb1);   // one scenario ahead
       cp_async_commit();
       if (has_status) {
         const uint8_t* __restrict__ stp = A.status + (long long)s * A.ldst;
-        for (int q = threadIdx.x; q < T.nhe; q += TPB) T.sst[q] = stp[T.heks[q] >> 1];
+        for (int q = tid; q < T.nhe; q += TPB) T.sst[q] = stp[T.heks[q] >> 1];
       }
-      cp_async_wait<1>();                                                    // this scenario's gather has landed
+      cp_async_wait<1>();                                                          // this scenario's gather has landed
       __syncthreads();
-      o.vmax = 0.0; o.nviol = 0;
-      if (act) {
-        bool done = false;
-        if constexpr (FORM == PBRAPV || FORM == PBRARV) {
-          if (pb_fast) {
-            bus_rows_pb<FORM>(T, B, xcur, o, wj, wh, threadIdx.x, has_status, wj && s == s0);
-            done = true;
+      // ---- phase 1a: Jacobian contributions + residual pieces
+      if (wj || (need_g && NP > 0)) {
+        for (int q = tid; q < T.nhe; q += TPB) {
+          const int lb = T.hbus[q];
+          // the owning bus's first half-edge and contribution base, from the CSR pointers (L1-resident)
+          const int ub = tl.u0 + lb;
+          const int h0 = P.he_ptr[ub] - T.hp0;
+          const int cj = (P.bus_jpp[ub] - T.cj0) + 2 * (P.gen_ptr[ub + 1] - P.gen_ptr[ub]) + NJ * (q - h0);
+          SeqW sj{T.cb + cj, wj}, sh{nullptr, false};
+          he_terms<FORM>(T, xs, q, sj, sh, need_g, has_status);
+        }
+        if (act && wj) {
+          const int cjs = B.cj + 2 * (B.g1 - B.g0) + NJ * (B.h1 - B.h0);
+          bus_own_terms<FORM>(P, T, B, xs, tid, SeqW{T.cb + B.cj, true}, SeqW{T.cb + cjs, true}, SeqW{nullptr, false});
+        }
+      }
+      __syncthreads();
+      if (wj) {
+        reduce_multi(T.cb, T.mdst, T.mptr, T.mlist, tl.mjn);
+        __syncthreads();
+      }
+      // ---- phase 2a: Jacobian slots and residual rows
+      if (wj) slots_out(A.J + (long long)s * A.ldJ + tl.j0, tl.jn, T.cb, T.jsrc);
+      double vmax = 0.0;
+      int nviol = 0;
+      if (need_g && act) {
+        double gP, gQ;
+        bus_residuals<FORM>(T, B, xs, tid, has_status, gP, gQ);
+        if (wg) {
+          double* gd = A.g + (long long)s * A.ldg + tl.g0 + 2 * tid;
+          if ((reinterpret_cast<unsigned long long>(gd) & 15) == 0) *reinterpret_cast<double2*>(gd) = make_double2(gP, gQ);
+          else { gd[0] = gP; gd[1] = gQ; }
+        }
+        vmax = fmax(fabs(gP), fabs(gQ));
+        nviol = (fabs(gP) > A.viol_tol ? 1 : 0) + (fabs(gQ) > A.viol_tol ? 1 : 0);
+      }
+      reduce_scalars(A.scal ? A.scal + (long long)s * NSCAL : nullptr, vmax, nviol);
+      if (wh) {
+        __syncthreads();
+        // ---- phase 1b: Hessian contributions (same buffer)
+        if constexpr (NH > 0) {
+          for (int q = tid; q < T.nhe; q += TPB) {
+            const int ub = tl.u0 + T.hbus[q];
+            const int h0 = P.he_ptr[ub] - T.hp0;
+            const int ch = (P.bus_hpp[ub] - T.ch0) + NH * (q - h0);
+            SeqW sj{nullptr, false}, sh{T.cb + ch, true};
+            he_terms<FORM>(T, xs, q, sj, sh, false, has_status);
           }
         }
-        if (!done) {
-          Stream sj{T.sJ + B.jbase, T.jpos + B.cjo, wj}, sh{T.sH + B.hbase, T.hpos + B.cho, wh};
-          bus_rows<FORM>(P, T, B, xcur, o, sj, sh, threadIdx.x, has_status);
+        if (act) {
+          const int chs = B.ch + NH * (B.h1 - B.h0);
+          bus_own_terms<FORM>(P, T, B, xs, tid, SeqW{nullptr, false}, SeqW{nullptr, false}, SeqW{T.cb + chs, true});
         }
+        __syncthreads();
+        reduce_multi(T.cb, T.mdst + tl.mjn, T.mptr + tl.mjn + 1, T.mlist + tl.mjln, tl.mhn);
+        __syncthreads();
+        // ---- phase 2b: Hessian slots
+        slots_out(A.H + (long long)s * A.ldH + tl.h0, tl.hn, T.cb, T.hsrc);
       }
-      __syncthreads();
-      if (wg) copy_out(A.g + (long long)s * A.ldg + tl.g0, T.sG, tl.gn);
-      if (wj) copy_out(A.J + (long long)s * A.ldJ + tl.j0, T.sJ, tl.jn);
-      if (wh) copy_out(A.H + (long long)s * A.ldH + tl.h0, T.sH, tl.hn);
-      reduce_scalars(A.scal ? A.scal + (long long)s * NSCAL : nullptr, o.vmax, o.nviol);
       __syncthreads();
     }
   }

@@ -33,6 +33,8 @@ struct DevPlan {                    // passed to kernels by value (constant bank
   const int32_t *jptr, *hptr;
   const uint16_t *bus_jpos, *bus_hpos;
   const int32_t *bus_jpp, *bus_hpp;
+  const int32_t *he_bus;                            // half-edge -> bus
+  const int32_t *jsrc, *hsrc, *ms_dst, *ms_ptr, *ms_list;   // slot -> contribution maps of the bus block (ps_plan.h)
   const int32_t *he_ptr, *he_ks, *he_other;         // half-edges in bus order (Sij then Sji per bus)
   const double* he_c;                               // [4][nhe] PN* admittance entries staged per tile
   int nhe;

@@ -303,6 +303,7 @@ std::string build_plan(const HostNet& net, int form, int src, int flags, int tpb
         const int32_t k = idx[q];
         P.he_ks.push_back(2 * k + side);
         P.he_other.push_back(side ? net.f[k] : net.t[k]);
+        P.he_bus.push_back((int32_t)i);
       }
     }
     P.he_ptr[i + 1] = (int32_t)P.he_ks.size();
@@ -323,6 +324,27 @@ std::string build_plan(const HostNet& net, int form, int src, int flags, int tpb
         P.he_c[3 * nhe + q] = side ? net.Bt[k] : net.Bf[k];
       }
     }
+  }
+  // slot -> contribution maps of the bus block (inverse of the position streams, stable in emission order)
+  if (has_bus_rows(form)) {
+    auto invert = [&](const std::vector<uint16_t>& pos, const std::vector<int32_t>& pp, const std::vector<int32_t>& ptr,
+                      std::vector<int32_t>& sp, std::vector<int32_t>& perm) {
+      const int64_t nslots = ptr[2 * nb];
+      sp.assign(nslots + 1, 0);
+      perm.assign(pos.size(), 0);
+      for (int64_t i = 0; i < nb; i++)
+        for (int32_t c = pp[i]; c < pp[i + 1]; c++) sp[ptr[2 * i] + (pos[c] & 0x7fff) + 1]++;
+      for (int64_t e = 0; e < nslots; e++) sp[e + 1] += sp[e];
+      std::vector<int32_t> fill(sp.begin(), sp.end() - 1);
+      for (int64_t i = 0; i < nb; i++)
+        for (int32_t c = pp[i]; c < pp[i + 1]; c++) perm[fill[ptr[2 * i] + (pos[c] & 0x7fff)]++] = c;   // ascending c per slot
+    };
+    invert(P.bus_jpos, P.bus_jpp, P.jptr, P.jsp, P.jperm);
+    invert(P.bus_hpos, P.bus_hpp, P.hptr, P.hsp, P.hperm);
+    P.jsrc.resize(P.jsp.size() - 1);
+    for (size_t e = 0; e + 1 < P.jsp.size(); e++) P.jsrc[e] = P.jperm[P.jsp[e]];
+    P.hsrc.resize(P.hsp.size() - 1);
+    for (size_t e = 0; e + 1 < P.hsp.size(); e++) P.hsrc[e] = P.hperm[P.hsp[e]];
   }
   // PB* balances: check that the canonical slot order equals the emission order the specialised bus rows
   // assume ([voltage slots][gens][Sij][Sji], no accumulation); true whenever the adjacency lists are ascending
@@ -369,19 +391,20 @@ std::string build_plan(const HostNet& net, int form, int src, int flags, int tpb
     }
   }
   // bus tiles: greedy, at most tpb buses and at most `budget` bytes of shared memory per tile
+  const int npieces = is_CB(form) ? 4 : (form == PNRARV ? 6 : (is_PN(form) ? 4 : 0));   // g pieces per half-edge
   auto bus_tile_bytes = [&](int64_t u0, int64_t u1) -> int64_t {
     const int64_t nbt = u1 - u0, nh = P.he_ptr[u1] - P.he_ptr[u0], ngt = net.gen_ptr[u1] - net.gen_ptr[u0];
     const int64_t nsh = facts ? net.sh_ptr[u1] - net.sh_ptr[u0] : 0;
-    const int64_t outs = 2 * nbt + (P.jptr[2 * u1] - P.jptr[2 * u0]) + (P.hptr[2 * u1] - P.hptr[2 * u0]);
+    const int64_t jn = P.jptr[2 * u1] - P.jptr[2 * u0], hn = P.hptr[2 * u1] - P.hptr[2 * u0];
     const int64_t nx = 2 * nbt + 2 * nh + 2 * ngt + (form == CBRAWV ? nbt : 0) + nsh + 4 * nbt;
     const int64_t ncj = P.bus_jpp[u1] - P.bus_jpp[u0], nch = P.bus_hpp[u1] - P.bus_hpp[u0];
-    int64_t b = 8 * (outs + 2 * nx + (is_PN(form) ? 4 * nh : 0));
-    b += 4 * (nh + (is_PN(form) ? nh : 0) + ngt + nsh);
-    b += 2 * (ncj + nch + 4);
+    int64_t b = 8 * (std::max(ncj, nch) + npieces * nh + 2 * nx + (is_PN(form) ? 4 * nh : 0) + 2);
+    b += 4 * (nh + (is_PN(form) ? nh : 0) + ngt + nsh + 2);
+    b += 2 * (nh + jn + hn + 2 * ((ncj - jn) + (nch - hn)) + 2 * (jn + hn) / 4 + 16);   // hbus, jsrc, hsrc, multi-slot lists (upper bound)
     b += nh + 64;                                  // status bytes + alignment slack
     return b;
   };
-  const int64_t budget = 71 * 1024, hard = 220 * 1024;
+  const int64_t budget = 56 * 1024, hard = 220 * 1024;   // 4 CTAs / SM
   int64_t mx = 0;
   P.tiles.clear();
   if (has_bus_rows(form)) {
@@ -389,12 +412,39 @@ std::string build_plan(const HostNet& net, int form, int src, int flags, int tpb
     while (u0 < nb) {
       int64_t u1 = u0 + 1;
       if (bus_tile_bytes(u0, u1) > hard) return "a bus does not fit in shared memory (bus degree too large)";
-      while (u1 < nb && u1 - u0 < tpb && bus_tile_bytes(u0, u1 + 1) <= budget) u1++;
+      while (u1 < nb && u1 - u0 < tpb && bus_tile_bytes(u0, u1 + 1) <= budget &&
+             P.bus_jpp[u1 + 1] - P.bus_jpp[u0] < 60000 && P.bus_hpp[u1 + 1] - P.bus_hpp[u0] < 60000) u1++;
       Tile t{};
       t.kind = 0; t.u0 = (int32_t)u0; t.u1 = (int32_t)u1;
       t.g0 = (int32_t)(2 * u0); t.gn = (int32_t)(2 * (u1 - u0));
       t.j0 = P.jptr[2 * u0]; t.jn = P.jptr[2 * u1] - t.j0;
       t.h0 = P.hptr[2 * u0]; t.hn = P.hptr[2 * u1] - t.h0;
+      // multi-slot descriptors of this tile
+      auto multi = [&](const std::vector<int32_t>& sp, const std::vector<int32_t>& perm, int32_t e0, int32_t en, int32_t c0,
+                       int32_t& m0, int32_t& mn, int32_t& l0, int32_t& ln) {
+        std::vector<int32_t> ms;
+        for (int32_t e = e0; e < e0 + en; e++) if (sp[e + 1] - sp[e] > 1) ms.push_back(e);
+        std::stable_sort(ms.begin(), ms.end(), [&](int32_t a, int32_t b) { return sp[a + 1] - sp[a] > sp[b + 1] - sp[b]; });
+        m0 = (int32_t)P.ms_dst.size(); mn = (int32_t)ms.size(); l0 = (int32_t)P.ms_list.size();
+        int32_t run = 0;
+        for (int32_t e : ms) {
+          P.ms_dst.push_back(perm[sp[e]] - c0);
+          P.ms_ptr.push_back(run);
+          for (int32_t q = sp[e] + 1; q < sp[e + 1]; q++) { P.ms_list.push_back(perm[q] - c0); run++; }
+        }
+        P.ms_ptr.push_back(run);                   // one sentinel per tile and kind (mn + 1 entries)
+        ln = run;
+      };
+      // ms_ptr holds mn+1 entries per call, so its offset differs from ms_dst's: keep them in step with a pad
+      {
+        int32_t m0, mn, l0, ln;
+        while (P.ms_dst.size() < P.ms_ptr.size()) P.ms_dst.push_back(0);
+        multi(P.jsp, P.jperm, t.j0, t.jn, P.bus_jpp[u0], m0, mn, l0, ln);
+        t.mj0 = m0; t.mjn = mn; t.mjl0 = l0; t.mjln = ln;
+        while (P.ms_dst.size() < P.ms_ptr.size()) P.ms_dst.push_back(0);
+        multi(P.hsp, P.hperm, t.h0, t.hn, P.bus_hpp[u0], m0, mn, l0, ln);
+        t.mh0 = m0; t.mhn = mn; t.mhl0 = l0; t.mhln = ln;
+      }
       mx = std::max<int64_t>(mx, bus_tile_bytes(u0, u1));
       P.tiles.push_back(t);
       u0 = u1;

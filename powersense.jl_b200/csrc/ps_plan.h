@@ -25,6 +25,9 @@ struct Tile {                // one CTA work item: a contiguous range of buses o
   int32_t kind;              // 0 = bus rows, 1 = branch rows, 2 = objective scalar
   int32_t u0, u1;            // unit range
   int32_t g0, gn, j0, jn, h0, hn;  // output slot ranges (per scenario)
+  // bus tiles: slots with more than one contribution ("multi-slots"), sorted by contribution count (descending):
+  // descriptors [m0, m0+mn) in Plan::ms_dst / ms_ptr, extra-contribution lists from l0 (ln entries) in Plan::ms_list
+  int32_t mj0, mjn, mjl0, mjln, mh0, mhn, mhl0, mhln;
 };
 
 struct Plan {
@@ -48,6 +51,14 @@ struct Plan {
   std::vector<int32_t> he_ptr;                      // [nbus+1]
   std::vector<int32_t> he_ks;                       // branch * 2 + side (side 0: bus is the from end)
   std::vector<int32_t> he_other;                    // the bus at the other end
+  std::vector<int32_t> he_bus;                      // the bus a half-edge belongs to
+  // slot -> contributions of the bus block (contributions in the bus kernel's emission order, see bus_jpos):
+  // slot e of J sums CJ[jperm[jsp[e] .. jsp[e+1])] left to right (emission order); same for H
+  std::vector<int32_t> jsp, jperm, hsp, hperm;
+  // per bus tile (see Tile): jsrc / hsrc[e] = first contribution of slot e (global contribution index);
+  // ms_dst = tile-relative cell that receives the sum, ms_ptr = tile-relative [begin, end) into ms_list,
+  // ms_list = tile-relative contribution indices added in emission order
+  std::vector<int32_t> jsrc, hsrc, ms_dst, ms_ptr, ms_list;
   std::vector<double> he_c;                         // [4][nhe] staged constants of the PN* balances (g_s, b_s, c, d)
   // PB* balances without switched shunts: per-slot codes of the bus block for the slot-parallel fast path
   //   J: -1 -> 1.0 ; k >= 0 -> status of branch k ; -2 - (4*bus + w) -> voltage slot w (see pb_bus_jh_kernel)

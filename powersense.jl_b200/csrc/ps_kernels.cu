@@ -478,10 +478,11 @@ struct Branch {
 //            variables of a row: the diagonal block, parallel branches) and goes straight to HBM with warp-contiguous,
 //            sector-aligned stores; every bus row folds its pieces in the reference's association.
 // No atomics, bitwise reproducible, reference summation order.
-struct SeqW {                      // sequential writer of contributions
+struct SeqW {                      // writer of consecutive contributions (cells `stride` apart)
   double* p;
+  int stride;
   bool on;
-  __device__ __forceinline__ void put(double v) { if (on) *p = v; p++; }
+  __device__ __forceinline__ void put(double v) { if (on) *p = v; p += stride; }
 };
 
 __device__ __forceinline__ void cp_async8(void* smem_dst, const void* gsrc) {
@@ -491,16 +492,12 @@ __device__ __forceinline__ void cp_async8(void* smem_dst, const void* gsrc) {
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
 template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
 
-PS_HD constexpr int he_nj(int f) { return (f == PBRAPV || f == PBRARV) ? 2 : 8; }
-PS_HD constexpr int he_nh(int f) { return (f == PBRAPV || f == PBRARV) ? 0 : (is_CB(f) ? 12 : (f == PNRARV ? 16 : 20)); }
-PS_HD constexpr int he_np(int f) { return is_CB(f) ? 4 : (f == PNRARV ? 6 : (is_PN(f) ? 4 : 0)); }
-
 // shared-memory view of one bus tile
 struct BusTile {
   int nbt, nhe, ngt, nsh;            // buses, half-edges, generators, switched shunts in the tile
   int hp0, gp0, sp0, cj0, ch0;       // first global index of each list
   int xh, xg, xw, xs_, xm, xl, nx;   // offsets inside the gathered-input array
-  double *cb, *gp, *xb0, *xb1, *hc;  // contributions, g pieces [np][nhe], gathered inputs (x2), PN* constants [4][nhe]
+  double *cbj, *cbh, *gp, *xb0, *xb1, *hc;   // J / H contribution cells, g pieces [np][nhe], gathered inputs (x2), PN* constants
   int *heks, *hoth, *sgen, *ssh;
   uint16_t *hbus, *jsrc, *hsrc, *mdst, *mptr, *mlist;   // multi-slot arrays: J part then H part
   uint8_t* sst;
@@ -509,7 +506,7 @@ struct BusTile {
 // per-bus invariants, loaded once per CTA and kept in registers across the scenario loop
 struct BusInv {
   int g0, g1, h0, h1, f0, f1;        // tile-local ranges of the bus's generators / half-edges / switched shunts
-  int cj, ch;                        // tile-local first J / H contribution of the bus
+  int oj, oh;                        // tile-local first cell of the bus's own (generator / shunt) J and H contributions
   double Gl, Bl;
 };
 
@@ -857,8 +854,9 @@ __global__ void __launch_bounds__(TPB) bus_kernel(const __grid_constant__ DevPla
     // gathered-input layout: own a | own b | half-edge pairs | generator pairs | Wd | bss | mu (P,Q) | Pd | Qd
     T.xh = 2 * T.nbt; T.xg = T.xh + 2 * T.nhe; T.xw = T.xg + 2 * T.ngt;
     T.xs_ = T.xw + (FORM == CBRAWV ? T.nbt : 0); T.xm = T.xs_ + T.nsh; T.xl = T.xm + 2 * T.nbt; T.nx = T.xl + 2 * T.nbt;
-    T.cb = smem;
-    T.gp = T.cb + max(ncj, nch);
+    T.cbj = smem;
+    T.cbh = T.cbj + ncj;
+    T.gp = T.cbh + nch;
     T.xb0 = T.gp + NP * T.nhe; T.xb1 = T.xb0 + T.nx;
     T.hc = T.xb1 + T.nx;
     T.heks = (int*)(T.hc + (is_PN(FORM) ? 4 * T.nhe : 0));
@@ -884,8 +882,8 @@ __global__ void __launch_bounds__(TPB) bus_kernel(const __grid_constant__ DevPla
     }
     for (int q = tid; q < T.ngt; q += TPB) T.sgen[q] = P.gen_idx[T.gp0 + q];
     for (int q = tid; q < T.nsh; q += TPB) T.ssh[q] = P.sh_idx[T.sp0 + q];
-    for (int q = tid; q < tl.jn; q += TPB) T.jsrc[q] = (uint16_t)(P.jsrc[tl.j0 + q] - T.cj0);
-    for (int q = tid; q < tl.hn; q += TPB) T.hsrc[q] = (uint16_t)(P.hsrc[tl.h0 + q] - T.ch0);
+    for (int q = tid; q < tl.jn; q += TPB) T.jsrc[q] = (uint16_t)P.jsrc[tl.j0 + q];
+    for (int q = tid; q < tl.hn; q += TPB) T.hsrc[q] = (uint16_t)P.hsrc[tl.h0 + q];
     for (int q = tid; q < tl.mjn; q += TPB) T.mdst[q] = (uint16_t)P.ms_dst[tl.mj0 + q];
     for (int q = tid; q < tl.mhn; q += TPB) T.mdst[tl.mjn + q] = (uint16_t)P.ms_dst[tl.mh0 + q];
     for (int q = tid; q <= tl.mjn; q += TPB) T.mptr[q] = (uint16_t)P.ms_ptr[tl.mj0 + q];
@@ -897,11 +895,10 @@ __global__ void __launch_bounds__(TPB) bus_kernel(const __grid_constant__ DevPla
       B.g0 = P.gen_ptr[u] - T.gp0; B.g1 = P.gen_ptr[u + 1] - T.gp0;
       B.h0 = P.he_ptr[u] - T.hp0; B.h1 = P.he_ptr[u + 1] - T.hp0;
       B.f0 = P.sh_ptr[u] - T.sp0; B.f1 = facts ? P.sh_ptr[u + 1] - T.sp0 : B.f0;
-      B.cj = P.bus_jpp[u] - T.cj0; B.ch = P.bus_hpp[u] - T.ch0;
+      B.oj = NJ * T.nhe + (P.bus_jpp[u] - T.cj0) - NJ * B.h0;
+      B.oh = NH * T.nhe + (P.bus_hpp[u] - T.ch0) - NH * B.h0;
       B.Gl = P.Gl[u]; B.Bl = P.Bl[u];
     }
-    // per-bus contribution bases the half-edge threads need: [cj of first half-edge, ch of first half-edge, first half-edge]
-    // (kept in the hbus-adjacent arrays would cost smem; they are cheap to recompute from the bus's invariants)
     const bool has_status = A.status != nullptr;
     const bool need_g = wg || A.scal;
     __syncthreads();
@@ -918,29 +915,23 @@ __global__ void __launch_bounds__(TPB) bus_kernel(const __grid_constant__ DevPla
       }
       cp_async_wait<1>();                                                          // this scenario's gather has landed
       __syncthreads();
-      // ---- phase 1a: Jacobian contributions + residual pieces
-      if (wj || (need_g && NP > 0)) {
-        for (int q = tid; q < T.nhe; q += TPB) {
-          const int lb = T.hbus[q];
-          // the owning bus's first half-edge and contribution base, from the CSR pointers (L1-resident)
-          const int ub = tl.u0 + lb;
-          const int h0 = P.he_ptr[ub] - T.hp0;
-          const int cj = (P.bus_jpp[ub] - T.cj0) + 2 * (P.gen_ptr[ub + 1] - P.gen_ptr[ub]) + NJ * (q - h0);
-          SeqW sj{T.cb + cj, wj}, sh{nullptr, false};
-          he_terms<FORM>(T, xs, q, sj, sh, need_g, has_status);
-        }
-        if (act && wj) {
-          const int cjs = B.cj + 2 * (B.g1 - B.g0) + NJ * (B.h1 - B.h0);
-          bus_own_terms<FORM>(P, T, B, xs, tid, SeqW{T.cb + B.cj, true}, SeqW{T.cb + cjs, true}, SeqW{nullptr, false});
-        }
+      // ---- phase 1: half-edge-parallel contributions (J and H cells, residual pieces); the bus's own terms
+      for (int q = tid; q < T.nhe; q += TPB) {
+        SeqW sj{T.cbj + q, T.nhe, wj}, sh{T.cbh + q, T.nhe, wh};
+        he_terms<FORM>(T, xs, q, sj, sh, need_g, has_status);
+      }
+      if (act && (wj || wh)) {
+        const int ng2 = 2 * (B.g1 - B.g0);
+        bus_own_terms<FORM>(P, T, B, xs, tid, SeqW{T.cbj + B.oj, 1, wj}, SeqW{T.cbj + B.oj + ng2, 1, wj}, SeqW{T.cbh + B.oh, 1, wh});
       }
       __syncthreads();
-      if (wj) {
-        reduce_multi(T.cb, T.mdst, T.mptr, T.mlist, tl.mjn);
-        __syncthreads();
-      }
-      // ---- phase 2a: Jacobian slots and residual rows
-      if (wj) slots_out(A.J + (long long)s * A.ldJ + tl.j0, tl.jn, T.cb, T.jsrc);
+      // ---- phase 1.5: slots with several contributions
+      if (wj) reduce_multi(T.cbj, T.mdst, T.mptr, T.mlist, tl.mjn);
+      if (wh) reduce_multi(T.cbh, T.mdst + tl.mjn, T.mptr + tl.mjn + 1, T.mlist + tl.mjln, tl.mhn);
+      if (wj || wh) __syncthreads();
+      // ---- phase 2: slot-parallel output, residual rows
+      if (wj) slots_out(A.J + (long long)s * A.ldJ + tl.j0, tl.jn, T.cbj, T.jsrc);
+      if (wh) slots_out(A.H + (long long)s * A.ldH + tl.h0, tl.hn, T.cbh, T.hsrc);
       double vmax = 0.0;
       int nviol = 0;
       if (need_g && act) {
@@ -955,28 +946,6 @@ __global__ void __launch_bounds__(TPB) bus_kernel(const __grid_constant__ DevPla
         nviol = (fabs(gP) > A.viol_tol ? 1 : 0) + (fabs(gQ) > A.viol_tol ? 1 : 0);
       }
       reduce_scalars(A.scal ? A.scal + (long long)s * NSCAL : nullptr, vmax, nviol);
-      if (wh) {
-        __syncthreads();
-        // ---- phase 1b: Hessian contributions (same buffer)
-        if constexpr (NH > 0) {
-          for (int q = tid; q < T.nhe; q += TPB) {
-            const int ub = tl.u0 + T.hbus[q];
-            const int h0 = P.he_ptr[ub] - T.hp0;
-            const int ch = (P.bus_hpp[ub] - T.ch0) + NH * (q - h0);
-            SeqW sj{nullptr, false}, sh{T.cb + ch, true};
-            he_terms<FORM>(T, xs, q, sj, sh, false, has_status);
-          }
-        }
-        if (act) {
-          const int chs = B.ch + NH * (B.h1 - B.h0);
-          bus_own_terms<FORM>(P, T, B, xs, tid, SeqW{nullptr, false}, SeqW{nullptr, false}, SeqW{T.cb + chs, true});
-        }
-        __syncthreads();
-        reduce_multi(T.cb, T.mdst + tl.mjn, T.mptr + tl.mjn + 1, T.mlist + tl.mjln, tl.mhn);
-        __syncthreads();
-        // ---- phase 2b: Hessian slots
-        slots_out(A.H + (long long)s * A.ldH + tl.h0, tl.hn, T.cb, T.hsrc);
-      }
       __syncthreads();
     }
   }

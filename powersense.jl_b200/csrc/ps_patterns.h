@@ -213,4 +213,10 @@ PS_HD constexpr bool direct_ok(int form, int src) {
   return s.nj > 0 && s.nh > 0 && s.nj % 4 == 0 && s.nh % 4 == 0;
 }
 
+// contributions of one half-edge to its bus's two balance rows (emission order of ps_plan.cpp / he_terms): Jacobian,
+// Hessian, and the number of residual pieces staged for the bus thread
+PS_HD constexpr int he_nj(int f) { return (f == PBRAPV || f == PBRARV) ? 2 : 8; }
+PS_HD constexpr int he_nh(int f) { return (f == PBRAPV || f == PBRARV) ? 0 : (is_CB(f) ? 12 : (f == PNRARV ? 16 : 20)); }
+PS_HD constexpr int he_np(int f) { return is_CB(f) ? 4 : (f == PNRARV ? 6 : (is_PN(f) ? 4 : 0)); }
+
 }  // namespace ps

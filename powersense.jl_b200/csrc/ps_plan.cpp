@@ -341,10 +341,8 @@ std::string build_plan(const HostNet& net, int form, int src, int flags, int tpb
     };
     invert(P.bus_jpos, P.bus_jpp, P.jptr, P.jsp, P.jperm);
     invert(P.bus_hpos, P.bus_hpp, P.hptr, P.hsp, P.hperm);
-    P.jsrc.resize(P.jsp.size() - 1);
-    for (size_t e = 0; e + 1 < P.jsp.size(); e++) P.jsrc[e] = P.jperm[P.jsp[e]];
-    P.hsrc.resize(P.hsp.size() - 1);
-    for (size_t e = 0; e + 1 < P.hsp.size(); e++) P.hsrc[e] = P.hperm[P.hsp[e]];
+    P.jsrc.assign(P.jsp.size() - 1, 0);            // filled per tile below (tile-relative cells)
+    P.hsrc.assign(P.hsp.size() - 1, 0);
   }
   // PB* balances: check that the canonical slot order equals the emission order the specialised bus rows
   // assume ([voltage slots][gens][Sij][Sji], no accumulation); true whenever the adjacency lists are ascending
@@ -391,16 +389,27 @@ std::string build_plan(const HostNet& net, int form, int src, int flags, int tpb
     }
   }
   // bus tiles: greedy, at most tpb buses and at most `budget` bytes of shared memory per tile
-  const int npieces = is_CB(form) ? 4 : (form == PNRARV ? 6 : (is_PN(form) ? 4 : 0));   // g pieces per half-edge
+  const int npieces = he_np(form);                 // g pieces per half-edge
+  // prefix counts (per row) of slots with more than one contribution
+  std::vector<int64_t> nmJ(2 * nb + 1, 0), nmH(2 * nb + 1, 0);
+  if (has_bus_rows(form))
+    for (int64_t r = 0; r < 2 * nb; r++) {
+      int64_t cj = 0, ch = 0;
+      for (int32_t e = P.jptr[r]; e < P.jptr[r + 1]; e++) cj += (P.jsp[e + 1] - P.jsp[e] > 1);
+      for (int32_t e = P.hptr[r]; e < P.hptr[r + 1]; e++) ch += (P.hsp[e + 1] - P.hsp[e] > 1);
+      nmJ[r + 1] = nmJ[r] + cj;
+      nmH[r + 1] = nmH[r] + ch;
+    }
   auto bus_tile_bytes = [&](int64_t u0, int64_t u1) -> int64_t {
     const int64_t nbt = u1 - u0, nh = P.he_ptr[u1] - P.he_ptr[u0], ngt = net.gen_ptr[u1] - net.gen_ptr[u0];
     const int64_t nsh = facts ? net.sh_ptr[u1] - net.sh_ptr[u0] : 0;
     const int64_t jn = P.jptr[2 * u1] - P.jptr[2 * u0], hn = P.hptr[2 * u1] - P.hptr[2 * u0];
     const int64_t nx = 2 * nbt + 2 * nh + 2 * ngt + (form == CBRAWV ? nbt : 0) + nsh + 4 * nbt;
     const int64_t ncj = P.bus_jpp[u1] - P.bus_jpp[u0], nch = P.bus_hpp[u1] - P.bus_hpp[u0];
-    int64_t b = 8 * (std::max(ncj, nch) + npieces * nh + 2 * nx + (is_PN(form) ? 4 * nh : 0) + 2);
+    int64_t b = 8 * (ncj + nch + npieces * nh + 2 * nx + (is_PN(form) ? 4 * nh : 0) + 2);
     b += 4 * (nh + (is_PN(form) ? nh : 0) + ngt + nsh + 2);
-    b += 2 * (nh + jn + hn + 2 * ((ncj - jn) + (nch - hn)) + 2 * (jn + hn) / 4 + 16);   // hbus, jsrc, hsrc, multi-slot lists (upper bound)
+    const int64_t nm = (nmJ[2 * u1] - nmJ[2 * u0]) + (nmH[2 * u1] - nmH[2 * u0]);            // multi-slots of the tile
+    b += 2 * (nh + jn + hn + (2 * nm + 2) + ((ncj - jn) + (nch - hn)) + 16);   // hbus, jsrc, hsrc, mdst + mptr, mlist
     b += nh + 64;                                  // status bytes + alignment slack
     return b;
   };
@@ -420,17 +429,39 @@ std::string build_plan(const HostNet& net, int form, int src, int flags, int tpb
       t.j0 = P.jptr[2 * u0]; t.jn = P.jptr[2 * u1] - t.j0;
       t.h0 = P.hptr[2 * u0]; t.hn = P.hptr[2 * u1] - t.h0;
       // multi-slot descriptors of this tile
-      auto multi = [&](const std::vector<int32_t>& sp, const std::vector<int32_t>& perm, int32_t e0, int32_t en, int32_t c0,
-                       int32_t& m0, int32_t& mn, int32_t& l0, int32_t& ln) {
+      // Shared-memory cell of a contribution (tile-relative).  Half-edge contributions are stored type-major
+      // (cell = type * nhe_tile + half-edge: conflict-free stores by consecutive half-edge threads); the bus's own
+      // contributions (generators, shunt terms) follow in emission order.
+      const int32_t nhe_t = P.he_ptr[u1] - P.he_ptr[u0];
+      auto cell = [&](int32_t c, bool isJ) -> int32_t {
+        const std::vector<int32_t>& pp = isJ ? P.bus_jpp : P.bus_hpp;
+        const int64_t i = (std::upper_bound(pp.begin() + u0, pp.begin() + u1 + 1, c) - pp.begin()) - 1;   // owning bus
+        const int32_t per = isJ ? he_nj(form) : he_nh(form);
+        const int32_t ng2 = isJ ? 2 * (net.gen_ptr[i + 1] - net.gen_ptr[i]) : 0;
+        const int32_t deg = P.he_ptr[i + 1] - P.he_ptr[i];
+        const int32_t off = c - pp[i];
+        const int32_t own0 = per * nhe_t + (pp[i] - pp[u0]) - per * (P.he_ptr[i] - P.he_ptr[u0]);
+        if (off < ng2) return own0 + off;
+        if (off < ng2 + per * deg) {
+          const int32_t lh = (off - ng2) / per, ty = (off - ng2) % per;
+          return ty * nhe_t + (P.he_ptr[i] - P.he_ptr[u0]) + lh;
+        }
+        return own0 + off - per * deg;
+      };
+      auto multi = [&](const std::vector<int32_t>& sp, const std::vector<int32_t>& perm, std::vector<int32_t>& src, bool isJ,
+                       int32_t e0, int32_t en, int32_t& m0, int32_t& mn, int32_t& l0, int32_t& ln) {
         std::vector<int32_t> ms;
-        for (int32_t e = e0; e < e0 + en; e++) if (sp[e + 1] - sp[e] > 1) ms.push_back(e);
+        for (int32_t e = e0; e < e0 + en; e++) {
+          src[e] = cell(perm[sp[e]], isJ);
+          if (sp[e + 1] - sp[e] > 1) ms.push_back(e);
+        }
         std::stable_sort(ms.begin(), ms.end(), [&](int32_t a, int32_t b) { return sp[a + 1] - sp[a] > sp[b + 1] - sp[b]; });
         m0 = (int32_t)P.ms_dst.size(); mn = (int32_t)ms.size(); l0 = (int32_t)P.ms_list.size();
         int32_t run = 0;
         for (int32_t e : ms) {
-          P.ms_dst.push_back(perm[sp[e]] - c0);
+          P.ms_dst.push_back(src[e]);
           P.ms_ptr.push_back(run);
-          for (int32_t q = sp[e] + 1; q < sp[e + 1]; q++) { P.ms_list.push_back(perm[q] - c0); run++; }
+          for (int32_t q = sp[e] + 1; q < sp[e + 1]; q++) { P.ms_list.push_back(cell(perm[q], isJ)); run++; }
         }
         P.ms_ptr.push_back(run);                   // one sentinel per tile and kind (mn + 1 entries)
         ln = run;
@@ -439,10 +470,10 @@ std::string build_plan(const HostNet& net, int form, int src, int flags, int tpb
       {
         int32_t m0, mn, l0, ln;
         while (P.ms_dst.size() < P.ms_ptr.size()) P.ms_dst.push_back(0);
-        multi(P.jsp, P.jperm, t.j0, t.jn, P.bus_jpp[u0], m0, mn, l0, ln);
+        multi(P.jsp, P.jperm, P.jsrc, true, t.j0, t.jn, m0, mn, l0, ln);
         t.mj0 = m0; t.mjn = mn; t.mjl0 = l0; t.mjln = ln;
         while (P.ms_dst.size() < P.ms_ptr.size()) P.ms_dst.push_back(0);
-        multi(P.hsp, P.hperm, t.h0, t.hn, P.bus_hpp[u0], m0, mn, l0, ln);
+        multi(P.hsp, P.hperm, P.hsrc, false, t.h0, t.hn, m0, mn, l0, ln);
         t.mh0 = m0; t.mhn = mn; t.mhl0 = l0; t.mhln = ln;
       }
       mx = std::max<int64_t>(mx, bus_tile_bytes(u0, u1));

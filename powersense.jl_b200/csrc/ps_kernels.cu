@@ -719,9 +719,21 @@ __device__ __forceinline__ void copy_aligned(double* __restrict__ dst, int n, in
   if (tid < a) dst[tid] = get(tid);
   for (int e = a + tid; e < n; e += NTHR) dst[e] = get(e);
 }
+// same, one whole 32-byte sector (4 doubles) per thread and store: 4x fewer store instructions
+template <int NTHR, class F>
+__device__ __forceinline__ void copy_sectors(double* __restrict__ dst, int n, int tid, F get) {
+  const int a = min(n, (int)((4 - ((reinterpret_cast<unsigned long long>(dst) >> 3) & 3)) & 3));
+  const int nfull = (n - a) >> 2, tail = a + 4 * nfull;
+  for (int q = tid; q < nfull; q += NTHR) {
+    const int e = a + 4 * q;
+    st_v4(dst + e, get(e), get(e + 1), get(e + 2), get(e + 3));
+  }
+  if (tid < a) dst[tid] = get(tid);
+  if (tid < n - tail) dst[tail + tid] = get(tail + tid);
+}
 template <int N, int NP>
 __device__ __forceinline__ void copy_out_padded(double* __restrict__ dst, const double* tile, int n) {
-  copy_aligned<TPB>(dst, n, threadIdx.x, [&](int e) { return tile[e + (e / N) * (NP - N)]; });   // N: compile-time
+  copy_sectors<TPB>(dst, n, threadIdx.x, [&](int e) { return tile[e + (e / N) * (NP - N)]; });   // N: compile-time
 }
 __device__ __forceinline__ void copy_out(double* __restrict__ dst, const double* tile, int n) {
   copy_aligned<TPB>(dst, n, threadIdx.x, [&](int e) { return tile[e]; });

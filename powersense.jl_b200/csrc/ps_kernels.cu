@@ -19,10 +19,6 @@
 namespace ps {
 namespace {
 
-#ifndef PS_TRANSPOSE_MIN
-#define PS_TRANSPOSE_MIN 100000
-#endif
-
 // one full 32-byte sector per thread: the store shape that keeps HBM writes at copy bandwidth when every
 // thread owns a contiguous run of the output (8- and 16-byte stores of such runs are partial-sector writes and
 // run ~6x slower: profiles/r01_store_patterns.txt).  Streaming (evict-first): outputs are never re-read.
@@ -96,21 +92,31 @@ struct Branch {
     }
     template <int... Q> __device__ __forceinline__ void storeJ(double* p, std::integer_sequence<int, Q...>) const { (storeJ4<4 * Q>(p), ...); }
     template <int... Q> __device__ __forceinline__ void storeH(double* p, std::integer_sequence<int, Q...>) const { (storeH4<4 * Q>(p), ...); }
-    // same values into this thread's row of a per-warp shared staging buffer (16-byte stores)
-    template <int... Q> __device__ __forceinline__ void stageJ(double* row, std::integer_sequence<int, Q...>) const {
-      ((*reinterpret_cast<double2*>(row + 2 * Q) = make_double2(jsel<2 * Q>(), jsel<2 * Q + 1>())), ...);
+    // Blocks of 4k+2 doubles per branch (CBRARV / CBRAWV MATPOWER limits, PBRAPV PSS/E limits): the branches of an
+    // even/odd lane pair own 8k+4 doubles = whole sectors together.  The even lane writes its first k sectors and the
+    // boundary sector (its last two values + the odd lane's first two, fetched with a shuffle); the odd lane writes
+    // its remaining k sectors, which start on a sector boundary again.  All lanes of the warp must call this.
+    template <bool ISJ, int P> __device__ __forceinline__ double psel() const {
+      if constexpr (ISJ) return jsel<P>(); else return hsel<P>();
     }
-    template <int... Q> __device__ __forceinline__ void stageH(double* row, std::integer_sequence<int, Q...>) const {
-      ((*reinterpret_cast<double2*>(row + 2 * Q) = make_double2(hsel<2 * Q>(), hsel<2 * Q + 1>())), ...);
+    template <bool ISJ, int OFF, int... K> __device__ __forceinline__ void pair_sectors(double* p, std::integer_sequence<int, K...>) const {
+      (st_v4(p + OFF + 4 * K, psel<ISJ, OFF + 4 * K>(), psel<ISJ, OFF + 4 * K + 1>(), psel<ISJ, OFF + 4 * K + 2>(),
+             psel<ISJ, OFF + 4 * K + 3>()), ...);
+    }
+    template <bool ISJ, int R> __device__ __forceinline__ void store_pair(double* p, bool act, int lane, bool partner_act) const {
+      static_assert(R % 4 == 2, "pair mode is for blocks of 4k+2 doubles");
+      const double n0 = __shfl_down_sync(0xffffffffu, psel<ISJ, 0>(), 1), n1 = __shfl_down_sync(0xffffffffu, psel<ISJ, 1>(), 1);
+      if (!act) return;
+      if ((lane & 1) == 0) {
+        pair_sectors<ISJ, 0>(p, std::make_integer_sequence<int, (R - 2) / 4>{});
+        if (partner_act) st_v4(p + R - 2, psel<ISJ, R - 2>(), psel<ISJ, R - 1>(), n0, n1);
+        else { p[R - 2] = psel<ISJ, R - 2>(); p[R - 1] = psel<ISJ, R - 1>(); }
+      } else {
+        pair_sectors<ISJ, 2>(p, std::make_integer_sequence<int, (R - 2) / 4>{});
+      }
     }
   };
-  // Optional: blocks of at least PS_TRANSPOSE_MIN doubles per branch are transposed through a per-warp staging
-  // buffer so that every warp-wide store is 1 KB contiguous.  A store-only micro-benchmark favours it for wide
-  // blocks (profiles/r01_store_patterns.txt), the real kernel does not (measured 4.3 vs 4.8 TB/s on PBRARV): off.
-  static constexpr bool TJ = RJ >= PS_TRANSPOSE_MIN, TH = RH >= PS_TRANSPOSE_MIN;
-  static constexpr int WBUF = (TH ? 32 * RH : 0) > (TJ ? 32 * RJ : 0) ? (TH ? 32 * RH : 0) : (TJ ? 32 * RJ : 0);
-  static constexpr int WBUF_ALL = WBUF > 32 * NR ? WBUF : 32 * NR;
-  static constexpr bool DIRECT_OK = (RJ % 4 == 0) && (RH % 4 == 0) && RJ > 0 && RH > 0;
+  static constexpr bool DIRECT_OK = (RJ % 2 == 0) && (RH % 2 == 0) && RJ > 0 && RH > 0;   // whole sectors per branch or per branch pair
 
   struct Cst { double gf, bf, Gf, Bf, gt, bt, Gt, Bt, Imax; double d[8]; };   // d: c0..c3 per side
   struct In { double af, at, bf, bt, wf, wt, wr, wi, F0, F1, F2, F3, st; double mu[NR > 0 ? NR : 1]; };
@@ -1087,19 +1093,6 @@ __global__ void __launch_bounds__(TPB) objective_kernel(const __grid_constant__ 
 // Inputs of the next scenario are prefetched into registers while the current one is evaluated; the branch's
 // J and H blocks (whole 32-byte sectors) go straight from registers to HBM; g goes through a per-warp staging
 // row so that it is written with warp-contiguous stores.
-// write the first `nsec` 32-byte sectors of a per-warp staging buffer to `dst` (sector q by lane q % 32)
-template <int R>
-__device__ __forceinline__ void warp_flush(const double* sw, double* __restrict__ dst, int nsec, int lane) {
-#pragma unroll
-  for (int i = 0; i < R / 4; i++) {
-    const int q = i * 32 + lane;
-    if (q < nsec) {
-      const double2 a = *reinterpret_cast<const double2*>(sw + 4 * q), b = *reinterpret_cast<const double2*>(sw + 4 * q + 2);
-      st_v4(dst + 4 * q, a.x, a.y, b.x, b.y);
-    }
-  }
-}
-
 #ifndef PS_DIRECT_MINB
 #define PS_DIRECT_MINB 1
 #endif
@@ -1107,7 +1100,7 @@ template <int FORM, int SRC>
 __device__ __forceinline__ void branch_direct_body(const DevPlan& P, const EvalArgs& A, int bx) {
   using BR = Branch<FORM, SRC>;
   if constexpr (BR::DIRECT_OK) {
-    __shared__ __align__(16) double sW[TPB / 32][BR::WBUF_ALL];   // per-warp staging: transposed J / H blocks, then g
+    __shared__ __align__(16) double sW[TPB / 32][32 * BR::NR];     // per-warp staging row of g
     const int u = bx * TPB + threadIdx.x;
     const bool act = u < P.nr;
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
@@ -1138,26 +1131,16 @@ __device__ __forceinline__ void branch_direct_body(const DevPlan& P, const EvalA
       if (wj || wg || A.scal) {
         if (act) BR::run(oj, cst, cur);                            // pass 1: g + Jacobian tags
         if (wj) {
-          if constexpr (BR::TJ) {
-            if (act) oj.stageJ(sw + lane * BR::RJ, std::make_integer_sequence<int, BR::RJ / 2>{});
-            __syncwarp();
-            warp_flush<BR::RJ>(sw, A.J + (long long)s * A.ldJ + P.j_br0 + (long long)ubase * BR::RJ, nact * (BR::RJ / 4), lane);
-            __syncwarp();
-          } else if (act) {
-            oj.storeJ(A.J + (long long)s * A.ldJ + jb, std::make_integer_sequence<int, BR::RJ / 4>{});
-          }
+          double* jp = A.J + (long long)s * A.ldJ + jb;
+          if constexpr (BR::RJ % 4 == 0) { if (act) oj.storeJ(jp, std::make_integer_sequence<int, BR::RJ / 4>{}); }
+          else oj.template store_pair<true, BR::RJ>(jp, act, lane, u + 1 < P.nr);
         }
       }
       if (wh) {
         if (act) BR::run(oh, cst, cur);                            // pass 2: Hessian tags
-        if constexpr (BR::TH) {
-          if (act) oh.stageH(sw + lane * BR::RH, std::make_integer_sequence<int, BR::RH / 2>{});
-          __syncwarp();
-          warp_flush<BR::RH>(sw, A.H + (long long)s * A.ldH + P.h_br0 + (long long)ubase * BR::RH, nact * (BR::RH / 4), lane);
-          __syncwarp();
-        } else if (act) {
-          oh.storeH(A.H + (long long)s * A.ldH + hb, std::make_integer_sequence<int, BR::RH / 4>{});
-        }
+        double* hp = A.H + (long long)s * A.ldH + hb;
+        if constexpr (BR::RH % 4 == 0) { if (act) oh.storeH(hp, std::make_integer_sequence<int, BR::RH / 4>{}); }
+        else oh.template store_pair<false, BR::RH>(hp, act, lane, u + 1 < P.nr);
       }
       if (wg) {
         double* sg = sw;

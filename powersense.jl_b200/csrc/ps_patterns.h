@@ -207,10 +207,10 @@ PS_HD constexpr BranchSlots branch_slots(int form, int src) {
   return s;
 }
 
-// the direct (register -> 32-byte sector) store path needs whole sectors per branch
+// the direct (register -> 32-byte sector) store path needs whole sectors per branch or per pair of branches
 PS_HD constexpr bool direct_ok(int form, int src) {
   const BranchSlots s = branch_slots(form, src);
-  return s.nj > 0 && s.nh > 0 && s.nj % 4 == 0 && s.nh % 4 == 0;
+  return s.nj > 0 && s.nh > 0 && s.nj % 2 == 0 && s.nh % 2 == 0;
 }
 
 // contributions of one half-edge to its bus's two balance rows (emission order of ps_plan.cpp / he_terms): Jacobian,

@@ -307,3 +307,52 @@ def test_full_size_cases(F, case, S):
     _, _, H2, _ = _batch_eval(h, x, 2.0 * mu, Pd, Qd, what=4, scal=False)
     assert np.array_equal(H2, 2.0 * H)             # linearity in mu (scaling by 2 is exact in FP64)
     h.close()
+
+
+def test_config5_n1_contingency_sweep_full_size():
+    """BASELINE config 5 (evaluator part): case9241pegase PNPAPV, one scenario per outaged branch on the fixed
+    pattern.  A few scenarios are checked against the oracle run on the network rebuilt with that branch out of service
+    (g exactly; J / H through the rows / pairs the two structures share); size-independent properties for the rest:
+    the outaged branch's limit rows equal -Imax0^2 with Imax0 = 10000 (PowersenseData.jl:206-207), its Jacobian
+    and Hessian slots vanish, and every other branch row is bitwise equal to the no-outage evaluation."""
+    import copy
+    from powersense_b200.driver import contingency_status
+    from powersense_b200.synth import NAMED_CASES, synth_network
+    nb, nr, ng = NAMED_CASES["case9241pegase"]
+    net = synth_network(nb, nr, ng, seed=nb)
+    d = ps.create_PowersenseData(net)
+    F = ps.PNPAPVmodel
+    S = 12
+    x, Pd, Qd, _ = synth.scenario_batch(d, F, 1, seed=3)
+    x, Pd, Qd = np.repeat(x, S, 0), np.repeat(Pd, S, 0), np.repeat(Qd, S, 0)       # same point, different outages
+    h = capi.Handle(d, F.code, device=0)
+    mu = np.repeat(np.random.default_rng(2).normal(size=(1, h.m_nl)), S, 0)
+    st = contingency_status(d.nbr, s_begin=4000, s_count=S)
+    out = [int(np.argmin(r)) for r in st]
+    g0, J0, H0, _ = _batch_eval(h, x[:1], mu[:1], Pd[:1], Qd[:1])
+    g, J, H, _ = _batch_eval(h, x, mu, Pd, Qd, status=st)
+    jr, jc = h.jacobian_structure()
+    info = h.plan_info()
+    br_rows = 2 * d.nbus
+    for s, k in enumerate(out):
+        rows = np.array([br_rows + 2 * k, br_rows + 2 * k + 1])
+        assert np.all(g[s, rows] == -1.0e8)                                        # 0 - 10000^2
+        jsl = slice(info["j_br0"] + 8 * k, info["j_br0"] + 8 * k + 8)
+        hsl = slice(info["h_br0"] + 20 * k, info["h_br0"] + 20 * k + 20)
+        assert np.all(J[s, jsl] == 0.0) and np.all(H[s, hsl] == 0.0)
+        keep = np.ones(d.nbr, bool); keep[k] = False
+        assert np.array_equal(g[s, br_rows:].reshape(-1, 2)[keep], g0[0, br_rows:].reshape(-1, 2)[keep])
+        assert np.array_equal(J[s, info["j_br0"]:].reshape(-1, 8)[keep], J0[0, info["j_br0"]:].reshape(-1, 8)[keep])
+        # only the two end buses of the outaged branch see different balance rows
+        f, t = int(d.br[k][0]) - 1, int(d.br[k][1]) - 1
+        same = np.ones(d.nbus, bool); same[[f, t]] = False
+        assert np.array_equal(g[s, :br_rows].reshape(-1, 2)[same], g0[0, :br_rows].reshape(-1, 2)[same])
+    for s in (0, 5):                                                               # oracle on the rebuilt network
+        net2 = copy.deepcopy(net)
+        net2.br_status = net.br_status.copy(); net2.br_status[out[s]] = 0
+        d2 = ps.create_PowersenseData(net2)
+        o2 = c_oracle.COracle(d2, F.code)
+        g2, J2, H2 = o2.eval(x[s], mu[s], Pd[s], Qd[s])
+        gs2, _, _ = o2.condition_scale(x[s], mu[s], Pd[s], Qd[s])
+        assert tol_err_scaled(g[s], g2, gs2) <= 1.0
+    h.close()

@@ -195,6 +195,31 @@ int ps_csc_assemble(ps_csc* p, const double* dE, double* nzval);
 int ps_csc_assemble_batch(ps_csc* p, int64_t S, const double* dE, int64_t ldE, double* nzval, int64_t ldnz,
                           void* stream);
 
+/* ---- affine + quadratic rows of the solver-level model, on device ------------------------------ */
+/* Replaces the row evaluation Powersense.Optimizer does itself for the `@constraint` rows that precede the NLP block
+ * in g / J / lambda (src/opt/MOI_wrapper.jl:864-891 eval_function, :973-1002 fill_constraint_jacobian!, :1030-1042
+ * fill_hessian_lagrangian!, structures :780-800 and :834-839), so that a batched driver keeps the whole g / J / H on the
+ * device.  Row r (MOI.ScalarAffineFunction / ScalarQuadraticFunction) is given in CSR form, terms in MOI order:
+ *   value  = constant[r] + sum coef*x[var] + sum (var1 == var2 ? 0.5 : 1) * qcoef * x[var1] * x[var2]
+ *   J      : one entry per affine term (coef), then per quadratic term qcoef*x[var2] at (r,var1) and, when
+ *            var1 != var2, qcoef*x[var1] at (r,var2)
+ *   H      : one entry per quadratic term, lambda[r] * qcoef at (var1, var2)
+ * The objective is a 1-row block (lambda[0] = obj_factor; its "J" entries are the sparse gradient terms).
+ * Variable indices are 1-based; structures are 1-based with rows counted inside this block. */
+typedef struct ps_rows ps_rows;
+int ps_rows_create(int64_t n_var, int64_t m, const int64_t* aff_ptr, const int64_t* aff_var, const double* aff_coef,
+                   const int64_t* quad_ptr, const int64_t* quad_var1, const int64_t* quad_var2, const double* quad_coef,
+                   const double* constant, int device, ps_rows** out);
+void ps_rows_destroy(ps_rows* r);
+int ps_rows_dims(const ps_rows* r, int64_t* nnz_jac, int64_t* nnz_hess);
+int ps_rows_jacobian_structure(const ps_rows* r, int64_t* row, int64_t* col);
+int ps_rows_hessian_structure(const ps_rows* r, int64_t* row, int64_t* col);
+/* host pointers, one x (what: PS_EVAL_G | PS_EVAL_J | PS_EVAL_H; lambda needed for H only) */
+int ps_rows_eval(ps_rows* r, int what, const double* x, const double* lambda, double* g, double* J, double* H);
+/* DEVICE pointers, S scenarios, row s of an array at ptr + s*ld; asynchronous on `stream` */
+int ps_rows_eval_batch(ps_rows* r, int what, int64_t S, const double* x, int64_t ldx, const double* lambda, int64_t ldl,
+                       double* g, int64_t ldg, double* J, int64_t ldJ, double* H, int64_t ldH, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

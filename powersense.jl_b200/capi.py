@@ -78,6 +78,14 @@ _SIGS = {
     "ps_csc_structure": (C.c_int, [_VP, _P64, _P64]),
     "ps_csc_assemble": (C.c_int, [_VP, _PD, _PD]),
     "ps_csc_assemble_batch": (C.c_int, [_VP, C.c_int64, _VP, C.c_int64, _VP, C.c_int64, _VP]),
+    "ps_rows_create": (C.c_int, [C.c_int64, C.c_int64, _P64, _P64, _PD, _P64, _P64, _P64, _PD, _PD, C.c_int, C.POINTER(_VP)]),
+    "ps_rows_destroy": (None, [_VP]),
+    "ps_rows_dims": (C.c_int, [_VP, _P64, _P64]),
+    "ps_rows_jacobian_structure": (C.c_int, [_VP, _P64, _P64]),
+    "ps_rows_hessian_structure": (C.c_int, [_VP, _P64, _P64]),
+    "ps_rows_eval": (C.c_int, [_VP, C.c_int, _PD, _PD, _PD, _PD, _PD]),
+    "ps_rows_eval_batch": (C.c_int, [_VP, C.c_int, C.c_int64, _VP, C.c_int64, _VP, C.c_int64, _VP, C.c_int64, _VP, C.c_int64,
+                                     _VP, C.c_int64, _VP]),
 }
 EXPORTS = tuple(_SIGS)
 
@@ -384,3 +392,67 @@ class CscPattern:
         rc = lib().ps_csc_assemble_batch(self.p, dE.shape[0], dE.data_ptr(), dE.stride(0), nz.data_ptr(), nz.stride(0), stream)
         if rc != PS_OK:
             raise PowersenseError(rc, (lib().ps_last_error(None) or b"").decode())
+
+
+class RowsBlock:
+    """ps_rows: affine + quadratic rows of the solver-level model on the device (replaces the row evaluation of
+    src/opt/MOI_wrapper.jl:864-1042).  Terms in CSR form, 1-based variable indices, MOI term order."""
+
+    def __init__(self, n_var, aff_ptr, aff_var, aff_coef, quad_ptr, quad_var1, quad_var2, quad_coef, constant=None, device=-1):
+        i64 = lambda a: np.ascontiguousarray(a, dtype=np.int64)
+        f64 = lambda a: np.ascontiguousarray(a, dtype=np.float64)
+        self._keep = [i64(aff_ptr), i64(aff_var), f64(aff_coef), i64(quad_ptr), i64(quad_var1), i64(quad_var2), f64(quad_coef)]
+        ap, av, ac, qp, q1, q2, qc = self._keep
+        self.m = len(ap) - 1
+        self.n_var = int(n_var)
+        cst = f64(np.zeros(self.m) if constant is None else constant)
+        p = _VP()
+        rc = lib().ps_rows_create(self.n_var, self.m, _p64(ap), _p64(av), _pd(ac), _p64(qp), _p64(q1), _p64(q2), _pd(qc), _pd(cst),
+                                  int(device), C.byref(p))
+        if rc != PS_OK:
+            raise PowersenseError(rc, (lib().ps_last_error(None) or b"").decode())
+        self.p = p
+        a, b = C.c_int64(), C.c_int64()
+        lib().ps_rows_dims(self.p, C.byref(a), C.byref(b))
+        self.nnzJ, self.nnzH = a.value, b.value
+
+    def close(self):
+        if getattr(self, "p", None):
+            lib().ps_rows_destroy(self.p)
+            self.p = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc):
+        if rc != PS_OK:
+            raise PowersenseError(rc, (lib().ps_last_error(None) or b"").decode())
+
+    def jacobian_structure(self):
+        r, c = np.zeros(self.nnzJ, np.int64), np.zeros(self.nnzJ, np.int64)
+        self._check(lib().ps_rows_jacobian_structure(self.p, _p64(r), _p64(c)))
+        return r, c
+
+    def hessian_structure(self):
+        r, c = np.zeros(self.nnzH, np.int64), np.zeros(self.nnzH, np.int64)
+        self._check(lib().ps_rows_hessian_structure(self.p, _p64(r), _p64(c)))
+        return r, c
+
+    def eval(self, x, lam=None, what=7):
+        x = _f64(x, self.n_var)
+        lam = _f64(np.zeros(self.m) if lam is None else lam, self.m)
+        g, J, H = np.zeros(self.m), np.zeros(self.nnzJ), np.zeros(self.nnzH)
+        self._check(lib().ps_rows_eval(self.p, what, _pd(x), _pd(lam), _pd(g), _pd(J), _pd(H)))
+        return g, J, H
+
+    def eval_torch(self, what, x, lam, g, J, H, stream=None):
+        import torch
+        if stream is None:
+            stream = torch.cuda.current_stream(x.device).cuda_stream
+        p = lambda t: None if t is None else t.data_ptr()
+        ld = lambda t: 0 if t is None else t.stride(0)
+        self._check(lib().ps_rows_eval_batch(self.p, what, x.shape[0], p(x), ld(x), p(lam), ld(lam), p(g), ld(g), p(J), ld(J),
+                                             p(H), ld(H), stream))

@@ -87,6 +87,15 @@ struct ps_csc {
   std::string err;
 };
 
+struct ps_rows {
+  int64_t n_var = 0, m = 0, nnzj = 0, nnzh = 0;
+  std::vector<int64_t> jrow, jcol, hrow, hcol;   // 1-based structures
+  RowsDev dev{};
+  DevMem mem;
+  int device = 0;
+  double *d_x = nullptr, *d_lam = nullptr, *d_g = nullptr, *d_J = nullptr, *d_H = nullptr;
+};
+
 namespace {
 
 int fail(ps_handle* h, int code, const std::string& msg) {
@@ -730,6 +739,125 @@ int ps_csc_assemble_batch(ps_csc* p, int64_t S, const double* dE, int64_t ldE, d
   cudaError_t e = cudaSetDevice(p->device);
   if (e == cudaSuccess) e = launch_csc_assemble(p->d_segptr, p->d_perm, (int)p->nnz, S, dE, ldE, nzval, ldnz, (cudaStream_t)stream);
   if (e != cudaSuccess) { p->err = cudaGetErrorString(e); g_create_error = p->err; return PS_ERR_CUDA; }
+  return PS_OK;
+}
+
+// ---- affine + quadratic rows ---------------------------------------------------------------
+int ps_rows_create(int64_t n_var, int64_t m, const int64_t* aff_ptr, const int64_t* aff_var, const double* aff_coef,
+                   const int64_t* quad_ptr, const int64_t* quad_var1, const int64_t* quad_var2, const double* quad_coef,
+                   const double* constant, int device, ps_rows** out) {
+  if (!out) return PS_ERR_ARG;
+  *out = nullptr;
+  if (n_var <= 0 || m < 0 || (m && (!aff_ptr || !quad_ptr))) return fail(nullptr, PS_ERR_ARG, "bad rows arguments");
+  if (n_var >= (int64_t(1) << 31) || m >= (int64_t(1) << 31)) return fail(nullptr, PS_ERR_ARG, "rows block too large");
+  const int64_t na = m ? aff_ptr[m] : 0, nq = m ? quad_ptr[m] : 0;
+  if (m && (aff_ptr[0] != 0 || quad_ptr[0] != 0)) return fail(nullptr, PS_ERR_ARG, "row pointers must start at 0");
+  if ((na && (!aff_var || !aff_coef)) || (nq && (!quad_var1 || !quad_var2 || !quad_coef))) return fail(nullptr, PS_ERR_ARG, "null term arrays");
+  for (int64_t r = 0; r < m; r++)
+    if (aff_ptr[r + 1] < aff_ptr[r] || quad_ptr[r + 1] < quad_ptr[r]) return fail(nullptr, PS_ERR_ARG, "row pointers must be non-decreasing");
+  for (int64_t q = 0; q < na; q++) if (aff_var[q] < 1 || aff_var[q] > n_var) return fail(nullptr, PS_ERR_ARG, "affine variable index out of range");
+  for (int64_t q = 0; q < nq; q++)
+    if (quad_var1[q] < 1 || quad_var1[q] > n_var || quad_var2[q] < 1 || quad_var2[q] > n_var)
+      return fail(nullptr, PS_ERR_ARG, "quadratic variable index out of range");
+  ps_rows* R = new ps_rows();
+  R->n_var = n_var; R->m = m;
+  std::vector<int32_t> aptr(m + 1, 0), qptr(m + 1, 0), avar(na), qv1(nq), qv2(nq), jx, hrow;
+  std::vector<double> acoef(aff_coef, aff_coef + na), qcoef(quad_coef, quad_coef + nq), cst(m, 0.0), jc, hc;
+  for (int64_t r = 0; r <= m && m; r++) { aptr[r] = (int32_t)aff_ptr[r]; qptr[r] = (int32_t)quad_ptr[r]; }
+  for (int64_t q = 0; q < na; q++) avar[q] = (int32_t)(aff_var[q] - 1);
+  for (int64_t q = 0; q < nq; q++) { qv1[q] = (int32_t)(quad_var1[q] - 1); qv2[q] = (int32_t)(quad_var2[q] - 1); }
+  if (constant) cst.assign(constant, constant + m);
+  for (int64_t r = 0; r < m; r++) {
+    for (int64_t q = aff_ptr[r]; q < aff_ptr[r + 1]; q++) {                 // MOI_wrapper.jl:780-784, 973-979
+      R->jrow.push_back(r + 1); R->jcol.push_back(aff_var[q]);
+      jx.push_back(-1); jc.push_back(aff_coef[q]);
+    }
+    for (int64_t q = quad_ptr[r]; q < quad_ptr[r + 1]; q++) {               // :786-799, 981-1002
+      R->jrow.push_back(r + 1); R->jcol.push_back(quad_var1[q]);
+      jx.push_back((int32_t)(quad_var2[q] - 1)); jc.push_back(quad_coef[q]);
+      if (quad_var1[q] != quad_var2[q]) {
+        R->jrow.push_back(r + 1); R->jcol.push_back(quad_var2[q]);
+        jx.push_back((int32_t)(quad_var1[q] - 1)); jc.push_back(quad_coef[q]);
+      }
+      R->hrow.push_back(quad_var1[q]); R->hcol.push_back(quad_var2[q]);     // :834-839, 1030-1042
+      hrow.push_back((int32_t)r); hc.push_back(quad_coef[q]);
+    }
+  }
+  R->nnzj = (int64_t)jx.size(); R->nnzh = (int64_t)hc.size();
+  if (device == PS_DEVICE_NONE) { R->device = PS_DEVICE_NONE; *out = R; return PS_OK; }
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0) { delete R; return fail(nullptr, PS_ERR_CUDA, "no CUDA device available (no CPU fallback)"); }
+  if (device < 0) cudaGetDevice(&device);
+  if ((e = cudaSetDevice(device)) != cudaSuccess) { delete R; return cuda_fail(nullptr, e, "cudaSetDevice"); }
+  R->device = device;
+  DevMem& M = R->mem;
+  RowsDev& D = R->dev;
+  D.m = (int)m; D.nnzj = (int)R->nnzj; D.nnzh = (int)R->nnzh;
+  D.aptr = M.upload(aptr); D.avar = M.upload(avar); D.qptr = M.upload(qptr); D.qv1 = M.upload(qv1); D.qv2 = M.upload(qv2);
+  D.acoef = M.upload(acoef); D.qcoef = M.upload(qcoef); D.cst = M.upload(cst);
+  D.jx = M.upload(jx); D.jc = M.upload(jc); D.hrow = M.upload(hrow); D.hc = M.upload(hc);
+  R->d_x = M.alloc<double>(n_var); R->d_lam = M.alloc<double>(m); R->d_g = M.alloc<double>(m);
+  R->d_J = M.alloc<double>(R->nnzj); R->d_H = M.alloc<double>(R->nnzh);
+  if (M.err != cudaSuccess) { e = M.err; M.release(); delete R; return cuda_fail(nullptr, e, "rows upload"); }
+  *out = R;
+  return PS_OK;
+}
+
+void ps_rows_destroy(ps_rows* r) {
+  if (!r) return;
+  if (r->device != PS_DEVICE_NONE) { cudaSetDevice(r->device); r->mem.release(); }
+  delete r;
+}
+
+int ps_rows_dims(const ps_rows* r, int64_t* nnz_jac, int64_t* nnz_hess) {
+  if (!r) return PS_ERR_ARG;
+  if (nnz_jac) *nnz_jac = r->nnzj;
+  if (nnz_hess) *nnz_hess = r->nnzh;
+  return PS_OK;
+}
+int ps_rows_jacobian_structure(const ps_rows* r, int64_t* row, int64_t* col) {
+  if (!r || !row || !col) return PS_ERR_ARG;
+  std::copy(r->jrow.begin(), r->jrow.end(), row);
+  std::copy(r->jcol.begin(), r->jcol.end(), col);
+  return PS_OK;
+}
+int ps_rows_hessian_structure(const ps_rows* r, int64_t* row, int64_t* col) {
+  if (!r || !row || !col) return PS_ERR_ARG;
+  std::copy(r->hrow.begin(), r->hrow.end(), row);
+  std::copy(r->hcol.begin(), r->hcol.end(), col);
+  return PS_OK;
+}
+
+int ps_rows_eval_batch(ps_rows* r, int what, int64_t S, const double* x, int64_t ldx, const double* lambda, int64_t ldl,
+                       double* g, int64_t ldg, double* J, int64_t ldJ, double* H, int64_t ldH, void* stream) {
+  if (!r || S < 0) return PS_ERR_ARG;
+  if (r->device == PS_DEVICE_NONE) { g_create_error = "structure-only rows block (PS_DEVICE_NONE): no CPU fallback"; return PS_ERR_STATE; }
+  if (S == 0) return PS_OK;
+  if (!x || ldx < r->n_var || ((what & EV_G) && (!g || ldg < r->m)) || ((what & EV_J) && (!J || ldJ < r->nnzj)) ||
+      ((what & EV_H) && r->nnzh && (!H || ldH < r->nnzh || !lambda || ldl < r->m))) {
+    g_create_error = "ps_rows_eval_batch: null pointer or leading dimension too small";
+    return PS_ERR_ARG;
+  }
+  cudaError_t e = cudaSetDevice(r->device);
+  if (e == cudaSuccess) e = launch_rows_eval(r->dev, what, S, x, ldx, lambda, ldl, g, ldg, J, ldJ, H, ldH, (cudaStream_t)stream);
+  if (e != cudaSuccess) { g_create_error = std::string("rows kernels: ") + cudaGetErrorString(e); return PS_ERR_CUDA; }
+  return PS_OK;
+}
+
+int ps_rows_eval(ps_rows* r, int what, const double* x, const double* lambda, double* g, double* J, double* H) {
+  if (!r || !x) return PS_ERR_ARG;
+  if (r->device == PS_DEVICE_NONE) { g_create_error = "structure-only rows block (PS_DEVICE_NONE): no CPU fallback"; return PS_ERR_STATE; }
+  if (((what & EV_G) && !g) || ((what & EV_J) && !J) || ((what & EV_H) && r->nnzh && (!H || !lambda))) return PS_ERR_ARG;
+  cudaError_t e = cudaSetDevice(r->device);
+  if (e == cudaSuccess) e = cudaMemcpy(r->d_x, x, (size_t)r->n_var * 8, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess && (what & EV_H) && r->nnzh) e = cudaMemcpy(r->d_lam, lambda, (size_t)r->m * 8, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess)
+    e = launch_rows_eval(r->dev, what, 1, r->d_x, r->n_var, r->d_lam, r->m, r->d_g, r->m, r->d_J, r->nnzj, r->d_H, r->nnzh, nullptr);
+  if (e == cudaSuccess && (what & EV_G) && r->m) e = cudaMemcpy(g, r->d_g, (size_t)r->m * 8, cudaMemcpyDeviceToHost);
+  if (e == cudaSuccess && (what & EV_J) && r->nnzj) e = cudaMemcpy(J, r->d_J, (size_t)r->nnzj * 8, cudaMemcpyDeviceToHost);
+  if (e == cudaSuccess && (what & EV_H) && r->nnzh) e = cudaMemcpy(H, r->d_H, (size_t)r->nnzh * 8, cudaMemcpyDeviceToHost);
+  if (e != cudaSuccess) { g_create_error = std::string("ps_rows_eval: ") + cudaGetErrorString(e); return PS_ERR_CUDA; }
   return PS_OK;
 }
 

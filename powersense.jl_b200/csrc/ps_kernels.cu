@@ -10,6 +10,7 @@
 // reference summation order) into a shared-memory staging tile; the tile is then streamed to HBM
 // with fully coalesced stores.  HBM traffic per scenario = reads of x / mu / loads + exactly one
 // write of every output slot.  The path is sparse FP64 and HBM-bound: no tensor cores.
+#include <algorithm>
 #include <cstdio>
 #include <cstdlib>
 #include <utility>
@@ -1205,7 +1206,52 @@ __global__ void __launch_bounds__(256) csc_assemble_kernel(const int32_t* __rest
   nz[s * ldnz + j] = acc;
 }
 
+// ---- affine + quadratic rows (MOI_wrapper.jl:864-891, 973-1002, 1030-1042) -------------------------------------
+__global__ void __launch_bounds__(256) rows_g_kernel(const RowsDev R, const double* __restrict__ x, long long ldx,
+                                                     double* __restrict__ g, long long ldg) {
+  const int r = blockIdx.x * 256 + threadIdx.x;
+  if (r >= R.m) return;
+  const double* __restrict__ xs = x + (long long)blockIdx.y * ldx;
+  double v = R.cst[r];                                         // eval_function: constant, affine terms, quadratic terms
+  for (int q = R.aptr[r]; q < R.aptr[r + 1]; q++) v += R.acoef[q] * xs[R.avar[q]];
+  for (int q = R.qptr[r]; q < R.qptr[r + 1]; q++) {
+    const int i = R.qv1[q], j = R.qv2[q];
+    if (i == j) v += 0.5 * R.qcoef[q] * xs[i] * xs[j];
+    else v += R.qcoef[q] * xs[i] * xs[j];
+  }
+  g[(long long)blockIdx.y * ldg + r] = v;
+}
+__global__ void __launch_bounds__(256) rows_j_kernel(const RowsDev R, const double* __restrict__ x, long long ldx,
+                                                     double* __restrict__ J, long long ldJ) {
+  const int e = blockIdx.x * 256 + threadIdx.x;
+  if (e >= R.nnzj) return;
+  const int ix = R.jx[e];
+  const double c = R.jc[e];
+  J[(long long)blockIdx.y * ldJ + e] = ix < 0 ? c : c * x[(long long)blockIdx.y * ldx + ix];
+}
+__global__ void __launch_bounds__(256) rows_h_kernel(const RowsDev R, const double* __restrict__ lam, long long ldl,
+                                                     double* __restrict__ H, long long ldH) {
+  const int e = blockIdx.x * 256 + threadIdx.x;
+  if (e >= R.nnzh) return;
+  H[(long long)blockIdx.y * ldH + e] = lam[(long long)blockIdx.y * ldl + R.hrow[e]] * R.hc[e];
+}
+
 }  // namespace
+
+cudaError_t launch_rows_eval(const RowsDev& R, int what, int64_t S, const double* x, long long ldx, const double* lam,
+                             long long ldl, double* g, long long ldg, double* J, long long ldJ, double* H, long long ldH,
+                             cudaStream_t stream) {
+  for (int64_t s0 = 0; s0 < S; s0 += 65535) {                  // gridDim.y limit
+    const unsigned ny = (unsigned)std::min<int64_t>(65535, S - s0);
+    if ((what & EV_G) && R.m > 0)
+      rows_g_kernel<<<dim3((R.m + 255) / 256, ny), 256, 0, stream>>>(R, x + s0 * ldx, ldx, g + s0 * ldg, ldg);
+    if ((what & EV_J) && R.nnzj > 0)
+      rows_j_kernel<<<dim3((R.nnzj + 255) / 256, ny), 256, 0, stream>>>(R, x + s0 * ldx, ldx, J + s0 * ldJ, ldJ);
+    if ((what & EV_H) && R.nnzh > 0)
+      rows_h_kernel<<<dim3((R.nnzh + 255) / 256, ny), 256, 0, stream>>>(R, lam + s0 * ldl, ldl, H + s0 * ldH, ldH);
+  }
+  return cudaGetLastError();
+}
 
 cudaError_t configure_eval(int form, int src, int64_t smem_branch_bytes, int64_t smem_bus_bytes) {
   const size_t sb = (size_t)smem_branch_bytes, su = (size_t)smem_bus_bytes;

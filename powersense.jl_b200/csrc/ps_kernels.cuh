@@ -66,4 +66,16 @@ cudaError_t configure_eval(int form, int src, int64_t smem_branch_bytes, int64_t
 cudaError_t launch_csc_assemble(const int32_t* segptr, const int32_t* perm, int nnz_csc, int64_t S,
                                 const double* dE, long long ldE, double* nz, long long ldnz, cudaStream_t stream);
 
+// affine + quadratic rows (replaces src/opt/MOI_wrapper.jl:864-891, 973-1002, 1030-1042)
+struct RowsDev {
+  int m, nnzj, nnzh;
+  const int32_t *aptr, *avar, *qptr, *qv1, *qv2;   // CSR terms, 0-based variables
+  const double *acoef, *qcoef, *cst;
+  const int32_t *jx;  const double* jc;            // J entry e = jx[e] < 0 ? jc[e] : jc[e] * x[jx[e]]
+  const int32_t *hrow; const double* hc;           // H entry e = hc[e] * lambda[hrow[e]]
+};
+cudaError_t launch_rows_eval(const RowsDev& R, int what, int64_t S, const double* x, long long ldx, const double* lam,
+                             long long ldl, double* g, long long ldg, double* J, long long ldJ, double* H, long long ldH,
+                             cudaStream_t stream);
+
 }  // namespace ps

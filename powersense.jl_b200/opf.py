@@ -182,6 +182,36 @@ class OPFModel:
         L = sp.coo_matrix((H, (self.hrow, self.hcol)), shape=(self.n, self.n)).tocsr()      # lower triangle, duplicates summed
         return L + sp.tril(L, -1).T
 
+    def moi_rows(self):
+        """The affine / quadratic rows as Powersense.Optimizer stores them: every `Interval` row reaches it through JuMP's
+        SplitInterval bridge as one >= and one <= row, and rows are ordered [lin_le | lin_ge | lin_eq | quad_le | quad_ge |
+        quad_eq] in front of the NLP block (src/opt/MOI_wrapper.jl:767-773).  Returns (rows, lower, upper, g_order) with
+        rows = [(constant, [(coef, var)], [(coef, var1, var2)])], 1-based variables, MOI's quadratic convention (diagonal
+        coefficient doubled in storage, :884-888)."""
+        A, quad, lo, hi = self.rows.A, self.rows.quad, self.rows.lo, self.rows.hi
+        buckets = {k: [] for k in ("lin_le", "lin_ge", "lin_eq", "quad_le", "quad_ge", "quad_eq")}
+        for i in range(A.shape[0]):
+            a = A.getrow(i)
+            aff = [(float(v), int(c) + 1) for c, v in zip(a.indices, a.data)]
+            q = []
+            if quad[i] is not None:
+                Q = quad[i].tocoo()
+                q = [(float(v), int(r) + 1, int(c) + 1) for r, c, v in zip(Q.row, Q.col, Q.data) if r >= c]
+            kind = "quad" if q else "lin"
+            row = (0.0, aff, q)
+            if lo[i] == hi[i]:
+                buckets[kind + "_eq"].append((row, lo[i], hi[i]))
+            else:
+                if np.isfinite(hi[i]):
+                    buckets[kind + "_le"].append((row, -INF, hi[i]))
+                if np.isfinite(lo[i]):
+                    buckets[kind + "_ge"].append((row, lo[i], INF))
+        order = ("lin_le", "lin_ge", "lin_eq", "quad_le", "quad_ge", "quad_eq")
+        rows = [r for k in order for (r, _, _) in buckets[k]]
+        lower = np.array([l for k in order for (_, l, _) in buckets[k]])
+        upper = np.array([u for k in order for (_, _, u) in buckets[k]])
+        return rows, lower, upper, [len(buckets[k]) for k in order]
+
     def close(self):
         self.evaluator.close()
 

@@ -220,6 +220,25 @@ int ps_rows_eval(ps_rows* r, int what, const double* x, const double* lambda, do
 int ps_rows_eval_batch(ps_rows* r, int what, int64_t S, const double* x, int64_t ldx, const double* lambda, int64_t ldl,
                        double* g, int64_t ldg, double* J, int64_t ldJ, double* H, int64_t ldH, void* stream);
 
+/* ---- KKT / merit metrics of the SLP iteration, per scenario, on device ------------------------------ */
+/* Replaces, for a batch of scenarios, norm_violations (src/opt/algorithms/common.jl:76-98), norm_complementarity
+ * (:51-69), KT_residuals (:35-44, which row-slices a CSC once per row), and the merit value / directional derivative of
+ * the line search at alpha = 0 (src/opt/algorithms/slp.jl:108-131, 138-162; not the feasibility-restoration branch).
+ * The Jacobian comes assembled on the fixed CSC pattern of ps_csc_create (nzval from ps_csc_assemble_batch).
+ * out[s][0..PS_NKKT): 0 norm_violations p=1, 1 norm_violations p=Inf, 2 norm_complementarity p=Inf, 3 KT_residuals,
+ * 4 phi = f + sum nu_i * viol_i, 5 D = df'p - sum nu_i * viol_i, 6 ||df||_2, 7 max_i |lambda_i| * ||J[i,:]||_2. */
+#define PS_NKKT 8
+typedef struct ps_kkt ps_kkt;
+/* bounds: g_L, g_U [m], x_L, x_U [n] (host; +-Inf allowed); the pattern must outlive the ps_kkt */
+int ps_kkt_create(ps_csc* pattern, const double* g_L, const double* g_U, const double* x_L, const double* x_U, ps_kkt** out);
+void ps_kkt_destroy(ps_kkt* k);
+/* DEVICE pointers; row s of an array at ptr + s*ld; f [S]; nu / p may be NULL (out[4], out[5] are then f and 0);
+ * asynchronous on `stream` */
+int ps_kkt_eval_batch(ps_kkt* k, int64_t S, const double* E, int64_t ldE, const double* x, int64_t ldx,
+                      const double* lambda, int64_t ldl, const double* mult_x_U, const double* mult_x_L, int64_t ldm,
+                      const double* df, int64_t lddf, const double* nzval, int64_t ldnz, const double* nu, int64_t ldnu,
+                      const double* p, int64_t ldp, const double* f, double* out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -86,6 +86,10 @@ _SIGS = {
     "ps_rows_eval": (C.c_int, [_VP, C.c_int, _PD, _PD, _PD, _PD, _PD]),
     "ps_rows_eval_batch": (C.c_int, [_VP, C.c_int, C.c_int64, _VP, C.c_int64, _VP, C.c_int64, _VP, C.c_int64, _VP, C.c_int64,
                                      _VP, C.c_int64, _VP]),
+    "ps_kkt_create": (C.c_int, [_VP, _PD, _PD, _PD, _PD, C.POINTER(_VP)]),
+    "ps_kkt_destroy": (None, [_VP]),
+    "ps_kkt_eval_batch": (C.c_int, [_VP, C.c_int64, _VP, C.c_int64, _VP, C.c_int64, _VP, C.c_int64, _VP, _VP, C.c_int64,
+                                    _VP, C.c_int64, _VP, C.c_int64, _VP, C.c_int64, _VP, C.c_int64, _VP, _VP, _VP]),
 }
 EXPORTS = tuple(_SIGS)
 
@@ -456,3 +460,47 @@ class RowsBlock:
         ld = lambda t: 0 if t is None else t.stride(0)
         self._check(lib().ps_rows_eval_batch(self.p, what, x.shape[0], p(x), ld(x), p(lam), ld(lam), p(g), ld(g), p(J), ld(J),
                                              p(H), ld(H), stream))
+
+
+PS_NKKT = 8
+
+
+class KktMetrics:
+    """ps_kkt: per-scenario KKT / merit metrics on the device (replaces common.jl:35-98, slp.jl:108-162 at alpha = 0)."""
+
+    def __init__(self, pattern: CscPattern, g_L, g_U, x_L, x_U):
+        self.pattern = pattern
+        gl, gu = _f64(g_L, pattern.m), _f64(g_U, pattern.m)
+        xl, xu = _f64(x_L, pattern.n), _f64(x_U, pattern.n)
+        k = _VP()
+        rc = lib().ps_kkt_create(pattern.p, _pd(gl), _pd(gu), _pd(xl), _pd(xu), C.byref(k))
+        if rc != PS_OK:
+            raise PowersenseError(rc, (lib().ps_last_error(None) or b"").decode())
+        self.k = k
+
+    def close(self):
+        if getattr(self, "k", None):
+            lib().ps_kkt_destroy(self.k)
+            self.k = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def eval_torch(self, E, x, lam, mU, mL, df, nz, nu=None, p=None, f=None, out=None, stream=None):
+        import torch
+        S = E.shape[0]
+        if out is None:
+            out = torch.empty(S, PS_NKKT, dtype=torch.float64, device=E.device)
+        if stream is None:
+            stream = torch.cuda.current_stream(E.device).cuda_stream
+        P = lambda t: None if t is None else t.data_ptr()
+        ld = lambda t: 0 if t is None else t.stride(0)
+        assert mU.stride(0) == mL.stride(0)
+        rc = lib().ps_kkt_eval_batch(self.k, S, P(E), ld(E), P(x), ld(x), P(lam), ld(lam), P(mU), P(mL), ld(mU), P(df), ld(df),
+                                     P(nz), ld(nz), P(nu), ld(nu), P(p), ld(p), P(f), P(out), stream)
+        if rc != PS_OK:
+            raise PowersenseError(rc, (lib().ps_last_error(None) or b"").decode())
+        return out

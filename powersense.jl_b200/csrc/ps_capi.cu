@@ -96,6 +96,13 @@ struct ps_rows {
   double *d_x = nullptr, *d_lam = nullptr, *d_g = nullptr, *d_J = nullptr, *d_H = nullptr;
 };
 
+struct ps_kkt {
+  ps_csc* pat = nullptr;
+  KktDev dev{};
+  DevMem mem;
+  int device = 0;
+};
+
 namespace {
 
 int fail(ps_handle* h, int code, const std::string& msg) {
@@ -858,6 +865,60 @@ int ps_rows_eval(ps_rows* r, int what, const double* x, const double* lambda, do
   if (e == cudaSuccess && (what & EV_J) && r->nnzj) e = cudaMemcpy(J, r->d_J, (size_t)r->nnzj * 8, cudaMemcpyDeviceToHost);
   if (e == cudaSuccess && (what & EV_H) && r->nnzh) e = cudaMemcpy(H, r->d_H, (size_t)r->nnzh * 8, cudaMemcpyDeviceToHost);
   if (e != cudaSuccess) { g_create_error = std::string("ps_rows_eval: ") + cudaGetErrorString(e); return PS_ERR_CUDA; }
+  return PS_OK;
+}
+
+// ---- KKT / merit metrics -------------------------------------------------------------------
+int ps_kkt_create(ps_csc* pattern, const double* g_L, const double* g_U, const double* x_L, const double* x_U, ps_kkt** out) {
+  if (!out) return PS_ERR_ARG;
+  *out = nullptr;
+  if (!pattern || !g_L || !g_U || !x_L || !x_U) return fail(nullptr, PS_ERR_ARG, "ps_kkt_create: null argument");
+  cudaError_t e = cudaSetDevice(pattern->device);
+  if (e != cudaSuccess) return cuda_fail(nullptr, e, "cudaSetDevice");
+  ps_kkt* k = new ps_kkt();
+  k->pat = pattern; k->device = pattern->device;
+  const int64_t m = pattern->m, n = pattern->n, nnz = pattern->nnz;
+  std::vector<int32_t> colptr(n + 1), rowval(nnz), rptr(m + 1, 0), rperm(nnz);
+  for (int64_t c = 0; c <= n; c++) colptr[c] = (int32_t)(pattern->colptr[c] - 1);
+  for (int64_t q = 0; q < nnz; q++) { rowval[q] = (int32_t)(pattern->rowval[q] - 1); rptr[rowval[q] + 1]++; }
+  for (int64_t i = 0; i < m; i++) rptr[i + 1] += rptr[i];
+  { std::vector<int32_t> fill(rptr.begin(), rptr.end() - 1);
+    for (int64_t q = 0; q < nnz; q++) rperm[fill[rowval[q]]++] = (int32_t)q; }     // ascending column inside a row
+  KktDev& D = k->dev;
+  D.m = (int)m; D.n = (int)n;
+  D.gL = k->mem.upload(vec(g_L, m)); D.gU = k->mem.upload(vec(g_U, m));
+  D.xL = k->mem.upload(vec(x_L, n)); D.xU = k->mem.upload(vec(x_U, n));
+  D.colptr = k->mem.upload(colptr); D.rowval = k->mem.upload(rowval); D.rptr = k->mem.upload(rptr); D.rperm = k->mem.upload(rperm);
+  if (k->mem.err != cudaSuccess) { e = k->mem.err; k->mem.release(); delete k; return cuda_fail(nullptr, e, "kkt upload"); }
+  *out = k;
+  return PS_OK;
+}
+
+void ps_kkt_destroy(ps_kkt* k) {
+  if (!k) return;
+  cudaSetDevice(k->device);
+  k->mem.release();
+  delete k;
+}
+
+int ps_kkt_eval_batch(ps_kkt* k, int64_t S, const double* E, int64_t ldE, const double* x, int64_t ldx, const double* lambda,
+                      int64_t ldl, const double* mult_x_U, const double* mult_x_L, int64_t ldm, const double* df, int64_t lddf,
+                      const double* nzval, int64_t ldnz, const double* nu, int64_t ldnu, const double* p, int64_t ldp,
+                      const double* f, double* out, void* stream) {
+  if (!k || S < 0) return PS_ERR_ARG;
+  if (S == 0) return PS_OK;
+  const int64_t m = k->dev.m, n = k->dev.n;
+  if (!E || !x || !lambda || !mult_x_U || !mult_x_L || !df || !nzval || !out || ldE < m || ldx < n || ldl < m || ldm < n ||
+      lddf < n || ldnz < k->pat->nnz || (nu && ldnu < m) || (p && ldp < n)) {
+    g_create_error = "ps_kkt_eval_batch: null pointer or leading dimension too small";
+    return PS_ERR_ARG;
+  }
+  KktArgs A{};
+  A.E = E; A.x = x; A.lam = lambda; A.mU = mult_x_U; A.mL = mult_x_L; A.df = df; A.nz = nzval; A.nu = nu; A.p = p; A.f = f;
+  A.ldE = ldE; A.ldx = ldx; A.ldl = ldl; A.ldm = ldm; A.lddf = lddf; A.ldnz = ldnz; A.ldnu = ldnu; A.ldp = ldp; A.out = out;
+  cudaError_t e = cudaSetDevice(k->device);
+  if (e == cudaSuccess) e = launch_kkt(k->dev, A, S, (cudaStream_t)stream);
+  if (e != cudaSuccess) { g_create_error = std::string("kkt kernel: ") + cudaGetErrorString(e); return PS_ERR_CUDA; }
   return PS_OK;
 }
 

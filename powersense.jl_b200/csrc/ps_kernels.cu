@@ -1236,7 +1236,95 @@ __global__ void __launch_bounds__(256) rows_h_kernel(const RowsDev R, const doub
   H[(long long)blockIdx.y * ldH + e] = lam[(long long)blockIdx.y * ldl + R.hrow[e]] * R.hc[e];
 }
 
+// ---- KKT / merit metrics: one CTA per scenario, fixed-shape reductions (deterministic) ---------------------------
+constexpr int KT = 256;
+__device__ __forceinline__ double block_sum(double v, double* red) {
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  double t = 0.0;
+  for (int w = 0; w < KT / 32; w++) t += red[w];
+  return t;
+}
+__device__ __forceinline__ double block_max(double v, double* red) {
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, d));
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  double t = red[0];
+  for (int w = 1; w < KT / 32; w++) t = fmax(t, red[w]);
+  return t;
+}
+
+__global__ void __launch_bounds__(KT) kkt_kernel(const KktDev K, const KktArgs A) {
+  __shared__ double red[KT / 32];
+  const long long s = blockIdx.x;
+  const double* __restrict__ E = A.E + s * A.ldE;
+  const double* __restrict__ x = A.x + s * A.ldx;
+  const double* __restrict__ lam = A.lam + s * A.ldl;
+  const double* __restrict__ nz = A.nz + s * A.ldnz;
+  const double* __restrict__ df = A.df + s * A.lddf;
+  const double* __restrict__ nu = A.nu ? A.nu + s * A.ldnu : nullptr;
+  const double* __restrict__ pd = A.p ? A.p + s * A.ldp : nullptr;
+  double v1 = 0.0, vinf = 0.0, cinf = 0.0, den = 0.0, pen = 0.0, scal = 0.0;
+  for (int i = threadIdx.x; i < K.m; i += KT) {
+    const double e = E[i], lo = K.gL[i], hi = K.gU[i], l = lam[i];
+    double viol = 0.0;                                          // common.jl:84-90
+    if (e > hi) viol = e - hi;
+    else if (e < lo) viol = lo - e;
+    v1 += viol; vinf = fmax(vinf, viol);
+    if (nu) pen += nu[i] * viol;                                // slp.jl:124-128 / 155-159
+    if (lo != hi) {                                             // common.jl:59-66
+      double c = fmin(e - lo, hi - e) * l;
+      if (c != c) c = 0.0;
+      cinf = fmax(cinf, fabs(c));
+      den += l * l;
+    }
+    double rs = 0.0;                                            // ||J[i,:]||^2 (common.jl:40-42)
+    for (int q = K.rptr[i]; q < K.rptr[i + 1]; q++) { const double a = nz[K.rperm[q]]; rs += a * a; }
+    scal = fmax(scal, fabs(l) * sqrt(rs));
+  }
+  double kt = 0.0, dn = 0.0, dp = 0.0;
+  const double* __restrict__ mU = A.mU + s * A.ldm;
+  const double* __restrict__ mL = A.mL + s * A.ldm;
+  for (int j = threadIdx.x; j < K.n; j += KT) {
+    const double xj = x[j];
+    double viol = 0.0;                                          // common.jl:91-97
+    if (xj > K.xU[j]) viol = xj - K.xU[j];
+    else if (xj < K.xL[j]) viol = K.xL[j] - xj;
+    v1 += viol; vinf = fmax(vinf, viol);
+    double jt = 0.0;                                            // (J' lambda)_j over the column's stored entries
+    for (int q = K.colptr[j]; q < K.colptr[j + 1]; q++) jt += nz[q] * lam[K.rowval[q]];
+    const double r = df[j] - jt - mU[j] - mL[j];                // common.jl:38
+    kt += r * r;
+    dn += df[j] * df[j];
+    if (pd) dp += df[j] * pd[j];                                // slp.jl:153
+  }
+  const double V1 = block_sum(v1, red), VI = block_max(vinf, red), CI = block_max(cinf, red), DEN = block_sum(den, red);
+  const double PEN = block_sum(pen, red), SC = block_max(scal, red), KTS = block_sum(kt, red), DN = block_sum(dn, red);
+  const double DP = block_sum(dp, red);
+  if (threadIdx.x == 0) {
+    double* o = A.out + s * NKKT;
+    const double ndf = sqrt(DN);
+    o[0] = V1; o[1] = VI;
+    o[2] = CI / (1.0 + sqrt(DEN));                              // common.jl:68
+    o[3] = sqrt(KTS) / fmax(fmax(1.0, ndf), SC);                // common.jl:38-43
+    o[4] = (A.f ? A.f[s] : 0.0) + PEN;                          // slp.jl:121-129
+    o[5] = DP - PEN;                                            // slp.jl:153-160
+    o[6] = ndf; o[7] = SC;
+  }
+}
+
 }  // namespace
+
+cudaError_t launch_kkt(const KktDev& K, const KktArgs& A, int64_t S, cudaStream_t stream) {
+  if (S <= 0) return cudaSuccess;
+  kkt_kernel<<<(unsigned)S, KT, 0, stream>>>(K, A);
+  return cudaGetLastError();
+}
 
 cudaError_t launch_rows_eval(const RowsDev& R, int what, int64_t S, const double* x, long long ldx, const double* lam,
                              long long ldl, double* g, long long ldg, double* J, long long ldJ, double* H, long long ldH,

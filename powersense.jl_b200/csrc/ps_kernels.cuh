@@ -78,4 +78,19 @@ cudaError_t launch_rows_eval(const RowsDev& R, int what, int64_t S, const double
                              long long ldl, double* g, long long ldg, double* J, long long ldJ, double* H, long long ldH,
                              cudaStream_t stream);
 
+// KKT / merit metrics (replaces src/opt/algorithms/common.jl:35-98, slp.jl:108-162 at alpha = 0)
+constexpr int NKKT = 8;
+struct KktDev {
+  int m, n;
+  const double *gL, *gU, *xL, *xU;
+  const int32_t *colptr, *rowval;      // CSC pattern, 0-based
+  const int32_t *rptr, *rperm;         // the same entries grouped by row: row i owns rperm[rptr[i] .. rptr[i+1])
+};
+struct KktArgs {
+  const double *E, *x, *lam, *mU, *mL, *df, *nz, *nu, *p, *f;
+  long long ldE, ldx, ldl, ldm, lddf, ldnz, ldnu, ldp;
+  double* out;
+};
+cudaError_t launch_kkt(const KktDev& K, const KktArgs& A, int64_t S, cudaStream_t stream);
+
 }  // namespace ps

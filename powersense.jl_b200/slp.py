@@ -1,0 +1,320 @@
+"""Lock-step batched SLP line search: S scenarios (load cases / N-1 contingencies) of one OPF model solved together
+with the Powersense `OPT` algorithm, every evaluation on the GPU.
+
+Restates the reference's line-search SLP (src/opt/algorithms/slp_line_search.jl:80-278 `run!` / `compute_alpha`,
+src/opt/algorithms/slp.jl:83-162 `compute_nu!` / `compute_phi` / `compute_derivative`, the slack-augmented LP of
+src/opt/algorithms/subproblem.jl:55-334 and its dual extraction :657-700) with the per-iteration work split as:
+
+  device, one launch per batch   NL rows g / J (ps_batch_eval), affine + quadratic rows (ps_rows_eval_batch), objective
+                                 value and gradient terms (a 1-row ps_rows block), COO -> CSC assembly
+                                 (ps_csc_assemble_batch), primal / dual infeasibility, complementarity, merit value and
+                                 directional derivative (ps_kkt_eval_batch), and every backtracking trial point
+  host, per scenario             the LP subproblem (scipy `linprog` / HiGHS here, GLPK in the reference's tests): an
+                                 external serial simplex, out of scope of the GPU path
+
+Differences from the reference, stated: ConvexFeasibleInitialization is not run (the reference wraps it in try/catch and
+continues from the clamped start point when it fails, slp_line_search.jl:117-122); scenarios advance in lock-step, so a
+finished scenario simply stops updating.  The `@constraint` rows are shared by all scenarios, which holds for the
+formulations whose affine rows do not involve branch parameters (every formulation except CBRARV / CBRAWV when branch
+status masks are used)."""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Optional
+
+import numpy as np
+import scipy.sparse as sp
+from scipy.optimize import linprog
+
+from . import capi
+from .opf import OPFModel
+
+
+@dataclass
+class SlpOptions:                      # src/opt/parameters.jl:16-30
+    tol_direction: float = 1e-6
+    tol_residual: float = 0.01
+    tol_infeas: float = 0.01
+    tol_error: float = 0.0
+    max_iter: int = 200
+    eta: float = 0.4
+    tau: float = 0.9
+    min_alpha: float = 1e-8
+    delta: float = 1000.0              # sub_optimize!(slp, Δ = 1000.0), slp.jl:50
+
+class BatchedSlpLS:
+    def __init__(self, model: OPFModel, S: int, Pd=None, Qd=None, status=None, options: Optional[SlpOptions] = None):
+        import torch
+        self.torch = torch
+        self.model, self.S, self.opt = model, int(S), options or SlpOptions()
+        h = model.evaluator.handle
+        self.h = h
+        self.dev = torch.device("cuda", torch.cuda.current_device())
+        n = self.n = model.n
+        rows, lo, hi, g_order = model.moi_rows()
+        self.m_rows, self.m = len(rows), len(rows) + h.m_nl
+        self.g_order = g_order + [h.m_nl]
+        self.g_L = np.concatenate([lo, model.nl_lo])
+        self.g_U = np.concatenate([hi, model.nl_hi])
+        # device blocks: rows (N1), objective (1-row block), NL batch, CSC pattern (a11), metrics (N3)
+        from_rows = _rows_to_csr(rows)
+        self.rows = capi.RowsBlock(n, *from_rows[:7], constant=from_rows[7], device=self.dev.index)
+        obj_aff = [(float(c), int(j) + 1) for j, c in enumerate(model.c) if c != 0.0]
+        obj_quad = [(float(q), int(j) + 1, int(j) + 1) for j, q in enumerate(model.qdiag) if q != 0.0]
+        oc = _rows_to_csr([(model.c0, obj_aff, obj_quad)])
+        self.obj = capi.RowsBlock(n, *oc[:7], constant=oc[7], device=self.dev.index)
+        self.obj_jcol = torch.from_numpy(self.obj.jacobian_structure()[1] - 1).to(self.dev)
+        self.batch = capi.Batch(h, self.S)
+        if Pd is not None:
+            self.batch.set_loads(Pd, Qd)
+        if status is not None:
+            self.batch.set_branch_status(status)
+        rj_r, rj_c = self.rows.jacobian_structure()
+        nj_r, nj_c = h.jacobian_structure()
+        self.nnz_rows = len(rj_r)
+        jrow = np.concatenate([rj_r, nj_r + self.m_rows])        # MOI_wrapper.jl:810-830
+        jcol = np.concatenate([rj_c, nj_c])
+        self.pattern = capi.CscPattern(self.m, n, jrow, jcol, device=self.dev.index)
+        self.colptr, self.rowval = self.pattern.structure()
+        self.kkt = capi.KktMetrics(self.pattern, self.g_L, self.g_U, model.xl, model.xu)
+        f64 = torch.float64
+        Z = lambda *shape: torch.zeros(*shape, dtype=f64, device=self.dev)
+        S = self.S
+        self.X, self.Xt = Z(S, n), Z(S, n)
+        self.E, self.Et = Z(S, self.m), Z(S, self.m)
+        self.dE = Z(S, self.nnz_rows + h.nnzJ)
+        self.nz = Z(S, self.pattern.nnz)
+        self.lam, self.nu = Z(S, self.m), Z(S, self.m)
+        self.mU, self.mL, self.df, self.P = Z(S, n), Z(S, n), Z(S, n), Z(S, n)
+        self.f, self.ft = Z(S, 1), Z(S, 1)
+        self.gobj = Z(S, max(self.obj.nnzJ, 1))
+        self.metrics = Z(S, capi.PS_NKKT)
+        # row classes of the LP (subproblem.jl:141-318): le / ge / eq
+        le = np.isinf(self.g_L) & np.isfinite(self.g_U)
+        ge = np.isfinite(self.g_L) & np.isinf(self.g_U)
+        eq = self.g_L == self.g_U
+        if not np.all(le | ge | eq):
+            raise NotImplementedError("two-sided rows reach Powersense.Optimizer split by the SplitInterval bridge")
+        self.i_le, self.i_ge, self.i_eq = np.nonzero(le)[0], np.nonzero(ge)[0], np.nonzero(eq)[0]
+
+    # ---- device evaluations -------------------------------------------------------------------------------------
+    def _eval_g(self, X, E, f):
+        """E = [affine/quadratic rows | NL rows](X), f = objective(X) -- eval_g / eval_f of the closures of
+        MOI_wrapper.jl:1168-1180."""
+        self.rows.eval_torch(capi.EVAL_G, X, None, E, None, None)
+        self.batch.eval_torch(capi.EVAL_G, X, None, E[:, self.m_rows:], None, None, None)
+        self.obj.eval_torch(capi.EVAL_G, X, None, f, None, None)
+
+    def _eval_all(self):
+        t = self.torch
+        self.rows.eval_torch(capi.EVAL_G | capi.EVAL_J, self.X, None, self.E, self.dE, None)
+        self.batch.eval_torch(capi.EVAL_G | capi.EVAL_J, self.X, None, self.E[:, self.m_rows:], self.dE[:, self.nnz_rows:], None, None)
+        self.obj.eval_torch(capi.EVAL_G | capi.EVAL_J, self.X, None, self.f, self.gobj, None)
+        self.df.zero_()                                             # fill_gradient! (MOI_wrapper.jl:906-930): dense, duplicates added
+        if self.obj.nnzJ:
+            self.df.index_add_(1, self.obj_jcol, self.gobj)
+        self.pattern.assemble_torch(self.dE, self.nz)               # compute_jacobian_matrix (common.jl:12-20)
+
+    def _metrics(self, with_dir: bool):
+        self.kkt.eval_torch(self.E, self.X, self.lam, self.mU, self.mL, self.df, self.nz, self.nu if with_dir else None,
+                            self.P if with_dir else None, self.f.view(-1), out=self.metrics)
+        return self.metrics.cpu().numpy()
+
+    # ---- host: the LP subproblem of one scenario (subproblem.jl:55-334, 349-700) ---------------------------------
+    def _lp(self, nzval, E, df, x, restoration):
+        """Normal phase: min df'p  s.t.  g_L <= E + J p <= g_U, max(-Delta, x_L - x) <= p <= min(Delta, x_U - x) -- the
+        reference fixes every slack at zero there (subproblem.jl:520-540).  Feasibility restoration: min sum(slacks) over
+        the elastic rows (subproblem.jl:369-395; the reference parametrises the same LP with b shifted by |viol| and
+        slacks bounded below by -|viol|, :404-500 -- here the slacks are the standard non-negative ones, so their sum is
+        the linearised violation after the step, which is what compute_derivative adds, slp.jl:140-143)."""
+        n, m, o = self.n, self.m, self.opt
+        J = sp.csc_matrix((nzval, self.rowval - 1, self.colptr - 1), shape=(m, n)).tocsr()
+        le, ge, eq = self.i_le, self.i_ge, self.i_eq
+        nle, nge, neq = len(le), len(ge), len(eq)
+        ns = (nle + nge + 2 * neq) if restoration else 0
+        I = sp.identity
+        Zs = lambda r, c: sp.csr_matrix((r, c))
+        ub_blocks, eq_block = [], None
+        if restoration:        # columns: [p | s_le | s_ge | s1_eq | s2_eq]
+            if nle:
+                ub_blocks.append(sp.hstack([J[le], -I(nle), Zs(nle, nge + 2 * neq)]))              # A p - s <= c_ub - b
+            if nge:
+                ub_blocks.append(sp.hstack([-J[ge], Zs(nge, nle), -I(nge), Zs(nge, 2 * neq)]))     # A p + s >= c_lb - b
+            if neq:
+                eq_block = sp.hstack([J[eq], Zs(neq, nle + nge), I(neq), -I(neq)], format="csr")   # A p + s1 - s2 = c_lb - b
+        else:
+            if nle:
+                ub_blocks.append(J[le])
+            if nge:
+                ub_blocks.append(-J[ge])
+            if neq:
+                eq_block = J[eq]
+        A_ub = sp.vstack(ub_blocks, format="csr") if ub_blocks else None
+        b_ub = np.concatenate([self.g_U[le] - E[le], -(self.g_L[ge] - E[ge])]) if ub_blocks else None
+        b_eq = self.g_L[eq] - E[eq] if neq else None
+        if o.tol_error > 0:
+            if b_ub is not None:
+                b_ub[np.abs(b_ub) <= o.tol_error] = 0.0
+            if b_eq is not None:
+                b_eq[np.abs(b_eq) <= o.tol_error] = 0.0
+        c = np.concatenate([np.zeros(n) if restoration else df, np.ones(ns)])
+        ub = np.minimum(o.delta, self.model.xu - x)                # subproblem.jl:126-129
+        lb = np.maximum(-o.delta, self.model.xl - x)
+        bounds = np.column_stack([np.concatenate([lb, np.zeros(ns)]), np.concatenate([ub, np.full(ns, np.inf)])])
+        res = linprog(c, A_ub=A_ub, b_ub=b_ub, A_eq=eq_block, b_eq=b_eq, bounds=bounds, method="highs")
+        if res.status == 0:
+            p = res.x[:n]
+            lam = np.zeros(m)                                       # subproblem.jl:673-679 (MOI dual sign convention)
+            if ub_blocks:
+                lam[le] = res.ineqlin.marginals[:nle]
+                lam[ge] = -res.ineqlin.marginals[nle:]
+            if neq:
+                lam[eq] = res.eqlin.marginals
+            mU, mL = res.upper.marginals[:n].copy(), res.lower.marginals[:n].copy()
+            mU[p < self.model.xu - x] = 0.0                         # :686-693: the trust region is not a variable bound
+            mL[p > self.model.xl - x] = 0.0
+            return p, lam, mU, mL, float(res.x[n:].sum()), "OPTIMAL"
+        if res.status == 2:
+            return np.zeros(n), np.zeros(m), np.zeros(n), np.zeros(n), 0.0, "INFEASIBLE"
+        return np.zeros(n), np.zeros(m), np.zeros(n), np.zeros(n), 0.0, "OTHER"
+
+    # ---- the algorithm (slp_line_search.jl:80-249) -----------------------------------------------------------------
+    def run(self, x0: Optional[np.ndarray] = None):
+        t, o, S, n, m = self.torch, self.opt, self.S, self.n, self.m
+        x0 = self.model.x0 if x0 is None else x0
+        x0 = np.broadcast_to(np.asarray(x0, dtype=np.float64), (S, n)).copy()
+        xl, xu = self.model.xl, self.model.xu
+        x0 = np.where(xl > -np.inf, np.maximum(x0, xl), x0)        # :100-107 (clamp to the column bounds)
+        x0 = np.where(xu < np.inf, np.minimum(x0, xu), x0)
+        self.X.copy_(t.from_numpy(x0))
+        restoration = np.zeros(S, dtype=bool)
+        ret = np.full(S, -5)
+        done = np.zeros(S, dtype=bool)
+        iters = np.ones(S, dtype=np.int64)
+        slack_sum = np.zeros(S)
+        nu = np.zeros((S, m))
+        hist = []
+        it = 1
+        while not done.all():
+            self._eval_all()                                        # eval_functions!, slp.jl:201-206
+            mets = self._metrics(with_dir=False)
+            prim, dual, compl = mets[:, 1].copy(), mets[:, 3].copy(), mets[:, 2].copy()   # :141-143
+            nz, E, df, X = self.nz.cpu().numpy(), self.E.cpu().numpy(), self.df.cpu().numpy(), self.X.cpu().numpy()
+            P, lam, mU, mL = np.zeros((S, n)), np.zeros((S, m)), np.zeros((S, n)), np.zeros((S, n))
+            skip_step = np.zeros(S, dtype=bool)
+            for s in np.nonzero(~done)[0]:
+                p, l, a, b, ssum, status = self._lp(nz[s], E[s], df[s], X[s], restoration[s])      # :147-148
+                if status == "INFEASIBLE":                          # :160-175
+                    if restoration[s]:
+                        ret[s] = 6 if prim[s] <= o.tol_infeas else 2
+                        done[s] = True
+                    else:
+                        restoration[s] = True
+                        skip_step[s] = True
+                    continue
+                if status != "OPTIMAL":                             # :152-159
+                    ret[s] = 6 if prim[s] <= o.tol_infeas else -3
+                    done[s] = True
+                    continue
+                P[s], lam[s], mU[s], mL[s], slack_sum[s] = p, l, a, b, ssum
+                if it == 1 or iters[s] == 1:                        # compute_nu!, slp.jl:83-95
+                    norm_df = 1.0 if restoration[s] else np.linalg.norm(df[s])
+                    Js = sp.csc_matrix((nz[s], self.rowval - 1, self.colptr - 1), shape=(m, n)).tocsr()
+                    rn = np.sqrt(np.asarray(Js.multiply(Js).sum(axis=1)).ravel())
+                    nu[s] = np.maximum(1.0, norm_df / np.maximum(1.0, rn))
+                else:
+                    nu[s] = np.maximum(nu[s], np.abs(l))
+            active = ~done & ~skip_step
+            self.P.copy_(t.from_numpy(P)); self.lam.copy_(t.from_numpy(lam))
+            self.mU.copy_(t.from_numpy(mU)); self.mL.copy_(t.from_numpy(mL)); self.nu.copy_(t.from_numpy(nu))
+            mets = self._metrics(with_dir=True)                     # phi (slp.jl:108-131) and D (:138-162) at alpha = 0
+            viol1 = mets[:, 0]
+            phi0 = np.where(restoration, _viol_sum(E, self.g_L, self.g_U), mets[:, 4])
+            D = np.where(restoration, slack_sum - _viol_sum(E, self.g_L, self.g_U), mets[:, 5])
+            # ---- compute_alpha (:256-278): backtracking, every trial point of every scenario in one batch
+            alpha = np.ones(S)
+            valid = np.ones(S, dtype=bool)
+            searching = active.copy()
+            while searching.any():
+                self.Xt.copy_(self.X + t.from_numpy(alpha[:, None] * P).to(self.dev))
+                self._eval_g(self.Xt, self.Et, self.ft)
+                Et, ft = self.Et.cpu().numpy(), self.ft.cpu().numpy().ravel()
+                vs = _viol_rows(Et, self.g_L, self.g_U)
+                phi_t = np.where(restoration, vs.sum(axis=1), ft + (nu * vs).sum(axis=1))
+                ok = phi_t <= phi0 + o.eta * alpha * D
+                for s in np.nonzero(searching)[0]:
+                    if ok[s]:
+                        searching[s] = False
+                    elif alpha[s] < o.min_alpha:
+                        if restoration[s]:
+                            ret[s] = -3
+                        valid[s] = False
+                        searching[s] = False
+                    else:
+                        alpha[s] *= o.tau
+            hist.append({"iter": it, "prim_infeas": prim.copy(), "dual_infeas": dual.copy(), "compl": compl.copy(),
+                         "alpha": alpha.copy(), "f": self.f.cpu().numpy().ravel().copy(), "viol1": viol1.copy(),
+                         "phi": phi0.copy(), "D": D.copy(), "slack_sum": slack_sum.copy(), "restoration": restoration.copy(),
+                         "p_inf": np.abs(P).max(axis=1)})
+            step = np.zeros(S, dtype=bool)
+            for s in np.nonzero(active)[0]:
+                if slack_sum[s] <= o.tol_infeas:                    # :197-199
+                    restoration[s] = False
+                if iters[s] >= o.max_iter:                          # :202-208
+                    ret[s] = 6 if prim[s] <= o.tol_infeas else -1
+                    done[s] = True
+                    continue
+                pinf = np.abs(P[s]).max() if n else 0.0
+                if (prim[s] <= o.tol_infeas and compl[s] <= o.tol_residual) or pinf <= o.tol_direction:   # :210-222
+                    if restoration[s]:
+                        restoration[s] = False
+                        iters[s] += 1
+                        continue
+                    elif dual[s] <= o.tol_residual:
+                        ret[s] = 0
+                        done[s] = True
+                        continue
+                if not valid[s]:                                    # :225-240
+                    if ret[s] == -3:
+                        ret[s] = 6 if prim[s] <= o.tol_infeas else 2
+                        done[s] = True
+                    else:
+                        restoration[s] = True
+                        iters[s] += 1
+                    continue
+                step[s] = True
+                iters[s] += 1
+            iters[skip_step & ~done] += 0                           # `continue` without iter += 1 (:171-173)
+            upd = t.from_numpy((alpha * step)[:, None] * P).to(self.dev)
+            self.X += upd                                           # :243
+            it += 1
+            if it > 10 * o.max_iter:
+                break
+        self._eval_g(self.X, self.E, self.f)
+        return {"x": self.X.cpu().numpy(), "obj": self.f.cpu().numpy().ravel(), "status": ret, "iter": iters, "history": hist,
+                "g": self.E.cpu().numpy(), "lambda": self.lam.cpu().numpy()}
+
+    def close(self):
+        for o in (self.kkt, self.pattern, self.batch, self.rows, self.obj):
+            o.close()
+
+
+def _viol_rows(E, g_L, g_U):
+    return np.where(E > g_U, E - g_U, np.where(E < g_L, g_L - E, 0.0))
+
+
+def _viol_sum(E, g_L, g_U):
+    return _viol_rows(E, g_L, g_U).sum(axis=1)
+
+
+def _rows_to_csr(rows):
+    ap, av, ac, qp, q1, q2, qc, cst = [0], [], [], [0], [], [], [], []
+    for c, aff, quad in rows:
+        cst.append(c)
+        for coef, var in aff:
+            av.append(var); ac.append(coef)
+        for coef, i, j in quad:
+            q1.append(i); q2.append(j); qc.append(coef)
+        ap.append(len(av)); qp.append(len(q1))
+    return (np.array(ap, np.int64), np.array(av, np.int64), np.array(ac, np.float64), np.array(qp, np.int64),
+            np.array(q1, np.int64), np.array(q2, np.int64), np.array(qc, np.float64), np.array(cst, np.float64))

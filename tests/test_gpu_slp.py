@@ -1,0 +1,41 @@
+"""N4: the lock-step batched SLP line search (the reference's `OPT` algorithm, slp_line_search.jl:80-278) with every
+evaluation on the GPU -- NL rows, affine/quadratic rows, CSC assembly, KKT metrics, backtracking trial points -- and the LP
+subproblems on the host (scipy/HiGHS standing in for GLPK).  The reference's own SLP test asserts the 14-bus objective
+146.7 at rtol 0.1 with PNPAPVmodel (examples/opf/ACOPF_formulations_example.jl:7, test/opf/ACOPF_formulations.jl:9)."""
+import copy
+
+import numpy as np
+import pytest
+
+import powersense_b200 as ps
+from powersense_b200 import slp
+from powersense_b200.driver import contingency_status
+
+from cases import load_fixture
+
+pytestmark = pytest.mark.gpu
+
+
+def test_case14_slp_load_scenarios_and_contingencies():
+    M = copy.deepcopy(load_fixture("case14"))
+    model = ps.create_opf_model(M, formulation=ps.PNPAPVmodel, obj_type="linear")
+    S = 5
+    scale = np.array([1.0, 1.03, 0.97, 1.0, 1.0])
+    Pd, Qd = M.Pd[None, :] * scale[:, None], M.Qd[None, :] * scale[:, None]
+    st = np.ones((S, M.nbr), dtype=np.uint8)
+    st[3, 2] = 0                                         # N-1: branch 3 (2 -> 3) out
+    st[4, 9] = 0                                         # N-1: branch 10 out
+    drv = slp.BatchedSlpLS(model, S, Pd, Qd, status=st, options=slp.SlpOptions(max_iter=80))
+    res = drv.run()
+    assert np.all(res["status"] == 0), res["status"]     # LOCALLY_SOLVED for every scenario
+    assert res["obj"][0] == pytest.approx(146.7, rel=0.1)                 # the reference's assertion
+    assert res["obj"][0] == pytest.approx(146.77, rel=5e-3)               # and close to the NLP optimum found by SLSQP
+    assert res["obj"][1] > res["obj"][0] > res["obj"][2]                  # more load costs more
+    assert res["obj"][3] >= res["obj"][0] - 0.05 and res["obj"][4] >= res["obj"][0] - 0.05   # an outage cannot make it cheaper (SLP tolerance)
+    # primal feasibility at the reference's tolerance (tol_infeas = 0.01, parameters.jl:18) for every scenario
+    g = res["g"]
+    viol = np.maximum(np.maximum(g - drv.g_U, drv.g_L - g), 0.0).max(axis=1)
+    assert np.all(viol <= 0.01 + 1e-9), viol
+    assert np.all(res["iter"] < 80)
+    drv.close()
+    model.close()

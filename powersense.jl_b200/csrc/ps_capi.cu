@@ -150,12 +150,15 @@ int do_eval(ps_batch* b, int what, int64_t s_begin, int64_t s_count, const doubl
   const Plan& P = h->plan;
   if (s_count == 0) return PS_OK;
   if (s_begin < 0 || s_count < 0 || s_begin + s_count > b->S) return fail(h, PS_ERR_ARG, "scenario range outside the batch");
-  if (!(what & (EV_G | EV_J | EV_H)) && !scalars) return fail(h, PS_ERR_ARG, "nothing to evaluate");
   if (!x || ldx < P.n_var) return fail(h, PS_ERR_ARG, "x is null or ldx < n_var");
+  if (P.m_nl == 0) what &= ~EV_G;                    // empty blocks (e.g. a W-relaxation without branches): nothing to write
+  if (P.nnzJ == 0) what &= ~EV_J;
+  if (P.nnzH == 0) what &= ~EV_H;
   if ((what & EV_G) && (!g || ldg < P.m_nl)) return fail(h, PS_ERR_ARG, "g is null or ldg < m_nl");
   if ((what & EV_J) && (!J || ldJ < P.nnzJ)) return fail(h, PS_ERR_ARG, "J is null or ldJ < nnz_jac");
   if ((what & EV_H) && (!H || ldH < P.nnzH)) return fail(h, PS_ERR_ARG, "H is null or ldH < nnz_hess");
   if ((what & EV_H) && (!mu || ldmu < P.m_nl)) return fail(h, PS_ERR_ARG, "mu is null or ldmu < m_nl (needed for the Hessian)");
+  if (!(what & (EV_G | EV_J | EV_H)) && !scalars) return PS_OK;      // nothing to write
   if (s_count > 0x7fffffff) return fail(h, PS_ERR_ARG, "too many scenarios in one call");
   cudaError_t e;
   if (scalars) {
@@ -589,6 +592,9 @@ int ps_batch_eval_host(ps_batch* b, int what, int64_t s_begin, int64_t s_count, 
   if (s_count == 0) return PS_OK;
   if (s_begin < 0 || s_count < 0 || s_begin + s_count > b->S) return fail(h, PS_ERR_ARG, "scenario range outside the batch");
   if (!x || ldx < P.n_var) return fail(h, PS_ERR_ARG, "x is null or ldx < n_var");
+  if (P.m_nl == 0) what &= ~EV_G;                    // empty blocks (e.g. a W-relaxation without branches): nothing to write
+  if (P.nnzJ == 0) what &= ~EV_J;
+  if (P.nnzH == 0) what &= ~EV_H;
   if ((what & EV_G) && (!g || ldg < P.m_nl)) return fail(h, PS_ERR_ARG, "g is null or ldg < m_nl");
   if ((what & EV_J) && (!J || ldJ < P.nnzJ)) return fail(h, PS_ERR_ARG, "J is null or ldJ < nnz_jac");
   if ((what & EV_H) && (!H || ldH < P.nnzH)) return fail(h, PS_ERR_ARG, "H is null or ldH < nnz_hess");

@@ -356,3 +356,36 @@ def test_config5_n1_contingency_sweep_full_size():
         gs2, _, _ = o2.condition_scale(x[s], mu[s], Pd[s], Qd[s])
         assert tol_err_scaled(g[s], g2, gs2) <= 1.0
     h.close()
+
+
+@pytest.mark.parametrize("F", FORMS, ids=lambda f: f.name)
+def test_edge_networks(F):
+    """Degenerate inputs: a network without branches, an isolated bus without generator or load, a bus with two
+    generators, a single scenario, and a scenario count that does not divide the scenario chunk."""
+    from powersense_b200.data import Network
+    # (a) three buses, no branch at all
+    net = synth.synth_network(6, 5, 3, seed=1)
+    net0 = Network(**{**net.__dict__})
+    for k in ("f", "t", "br_r", "br_x", "g_fr", "b_fr", "g_to", "b_to", "tap", "shift", "br_status", "rate_a", "gfM", "bfM"):
+        setattr(net0, k, getattr(net, k)[:0])
+    d0 = ps.create_PowersenseData(net0)
+    # (b) bus 6 isolated (its only branches removed), two generators on bus 1
+    net1 = synth.synth_network(6, 7, 3, seed=2)
+    keep = (net1.f != 6) & (net1.t != 6)
+    for k in ("f", "t", "br_r", "br_x", "g_fr", "b_fr", "g_to", "b_to", "tap", "shift", "br_status", "rate_a", "gfM", "bfM"):
+        setattr(net1, k, getattr(net1, k)[keep])
+    net1.gen_bus[:] = [1, 1, 3]
+    d1 = ps.create_PowersenseData(net1)
+    for d, S in ((d0, 1), (d1, 1), (d1, 19)):
+        h = capi.Handle(d, F.code, device=0)
+        o = c_oracle.COracle(d, F.code)
+        assert (h.n_var, h.m_nl, h.nnzJ, h.nnzH) == (o.n_var, o.m_nl, o.nnzJ, o.nnzH)
+        x, Pd, Qd, _ = synth.scenario_batch(d, F, S, seed=3)
+        mu = np.random.default_rng(1).normal(size=(S, max(h.m_nl, 1)))[:, :h.m_nl]
+        if h.m_nl == 0:                                    # PNRAWV / PBRAWV without branches: nothing to evaluate
+            h.close()
+            continue
+        g, J, H, sc = _batch_eval(h, x, mu, Pd, Qd)
+        og, oJ, oH = o.eval_batch(x, mu, Pd, Qd)
+        assert tol_err(g, og) <= 1.0 and tol_err(J, oJ) <= 1.0 and tol_err(H, oH) <= 1.0
+        h.close()

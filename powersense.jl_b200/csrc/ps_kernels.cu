@@ -847,8 +847,11 @@ __device__ __forceinline__ void slots_out(double* __restrict__ dst, int n, const
 }
 
 // Bus rows (nodal balances, formulations.jl:170-297) plus, in the last CTA column, the objective scalar.
+#ifndef PS_BUS_MINB
+#define PS_BUS_MINB 5
+#endif
 template <int FORM>
-__global__ void __launch_bounds__(TPB) bus_kernel(const __grid_constant__ DevPlan P, const __grid_constant__ EvalArgs A) {
+__global__ void __launch_bounds__(TPB, PS_BUS_MINB) bus_kernel(const __grid_constant__ DevPlan P, const __grid_constant__ EvalArgs A) {
   extern __shared__ double smem[];
   const int s0 = blockIdx.y * A.chunk, s1 = min(A.S, s0 + A.chunk);
   if ((int)blockIdx.x >= P.n_bus_tiles) {

@@ -3,6 +3,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <utility>
 
 namespace ps {
@@ -413,7 +414,9 @@ std::string build_plan(const HostNet& net, int form, int src, int flags, int tpb
     b += nh + 64;                                  // status bytes + alignment slack
     return b;
   };
-  const int64_t budget = 56 * 1024, hard = 220 * 1024;   // 4 CTAs / SM
+  int64_t budget = 44 * 1024;                              // 5 CTAs / SM (bus_kernel is built for 5 resident CTAs)
+  if (const char* e = std::getenv("PS_BUS_SMEM_KB")) { const int v = std::atoi(e); if (v >= 8 && v <= 200) budget = (int64_t)v * 1024; }   // development knob
+  const int64_t hard = 220 * 1024;
   int64_t mx = 0;
   P.tiles.clear();
   if (has_bus_rows(form)) {

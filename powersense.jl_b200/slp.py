@@ -88,7 +88,7 @@ class BatchedSlpLS:
         self.mU, self.mL, self.df, self.P = Z(S, n), Z(S, n), Z(S, n), Z(S, n)
         self.f, self.ft = Z(S, 1), Z(S, 1)
         self.gobj = Z(S, max(self.obj.nnzJ, 1))
-        self.metrics = Z(S, capi.PS_NKKT)
+        self.metrics, self.metrics_t = Z(S, capi.PS_NKKT), Z(S, capi.PS_NKKT)
         # row classes of the LP (subproblem.jl:141-318): le / ge / eq
         le = np.isinf(self.g_L) & np.isfinite(self.g_U)
         ge = np.isfinite(self.g_L) & np.isinf(self.g_U)
@@ -238,9 +238,11 @@ class BatchedSlpLS:
             while searching.any():
                 self.Xt.copy_(self.X + t.from_numpy(alpha[:, None] * P).to(self.dev))
                 self._eval_g(self.Xt, self.Et, self.ft)
-                Et, ft = self.Et.cpu().numpy(), self.ft.cpu().numpy().ravel()
-                vs = _viol_rows(Et, self.g_L, self.g_U)
-                phi_t = np.where(restoration, vs.sum(axis=1), ft + (nu * vs).sum(axis=1))
+                # merit at the trial point on the device (compute_phi, slp.jl:108-131): out[4] = f + sum nu*viol, and
+                # out[0] = sum of violations (the step respects the column bounds, so only the rows contribute)
+                mt = self.kkt.eval_torch(self.Et, self.Xt, self.lam, self.mU, self.mL, self.df, self.nz, self.nu, self.P,
+                                         self.ft.view(-1), out=self.metrics_t).cpu().numpy()
+                phi_t = np.where(restoration, mt[:, 0], mt[:, 4])
                 ok = phi_t <= phi0 + o.eta * alpha * D
                 for s in np.nonzero(searching)[0]:
                     if ok[s]:

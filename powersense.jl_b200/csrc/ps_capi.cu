@@ -271,7 +271,6 @@ int ps_create(const ps_network* net, int formulation, int source_type, int flags
   D.ntiles = (int)P.tiles.size();
   D.n_bus_tiles = P.n_bus_tiles;
   D.j_br0 = P.jptr[P.bus_rows]; D.h_br0 = P.hptr[P.bus_rows];
-  D.pb_implicit = P.pb_implicit ? 1 : 0;
   D.pb_slots = P.pb_slots ? 1 : 0;
   D.pb_jcode = M.upload(P.pb_jcode); D.pb_hcode = M.upload(P.pb_hcode);
   D.cost_order = P.net.cost_order;
@@ -285,11 +284,7 @@ int ps_create(const ps_network* net, int formulation, int source_type, int flags
   D.k1 = P.net.c1.empty() ? nullptr : M.upload(P.net.c1);
   D.k2 = P.net.c2.empty() ? nullptr : M.upload(P.net.c2);
   D.gen_ptr = M.upload(P.net.gen_ptr); D.gen_idx = M.upload(P.net.gen_idx);
-  D.sij_ptr = M.upload(P.net.sij_ptr); D.sij_idx = M.upload(P.net.sij_idx);
-  D.sji_ptr = M.upload(P.net.sji_ptr); D.sji_idx = M.upload(P.net.sji_idx);
   D.sh_ptr = M.upload(P.net.sh_ptr); D.sh_idx = M.upload(P.net.sh_idx);
-  D.jptr = M.upload(P.jptr); D.hptr = M.upload(P.hptr);
-  D.bus_jpos = M.upload(P.bus_jpos); D.bus_hpos = M.upload(P.bus_hpos);
   D.bus_jpp = M.upload(P.bus_jpp); D.bus_hpp = M.upload(P.bus_hpp);
   D.he_ptr = M.upload(P.he_ptr); D.he_ks = M.upload(P.he_ks); D.he_other = M.upload(P.he_other);
   D.he_c = M.upload(P.he_c); D.nhe = (int)P.he_ks.size();

@@ -1,15 +1,20 @@
-// Hand-written sm_100a kernels: fused evaluation of the NL constraint block g(x), its sparse
-// Jacobian and the Hessian of the Lagrangian for every AC formulation of Powersense.jl
-// (math: src/opf/formulations.jl:170-428; closed-form derivatives: SURVEY.md Appendix F),
-// batched over scenarios.
+// Hand-written sm_100a kernels: evaluation of the NL constraint block g(x), its sparse Jacobian and the Hessian of
+// the Lagrangian for every AC formulation of Powersense.jl (math: src/opf/formulations.jl:170-428; closed-form
+// derivatives: SURVEY.md Appendix F), batched over scenarios; plus the affine / quadratic rows of the solver-level
+// model, the fixed-pattern COO -> CSC assembly and the SLP iteration's KKT / merit metrics.
 //
-// Work decomposition: a CTA owns one *tile* -- a contiguous range of buses or of branches, i.e. a
-// contiguous range of rows and therefore of g / J / H slots in JuMP order -- and loops over a chunk
-// of scenarios.  Per-branch network constants stay in registers across the scenario loop.  For
-// each scenario every thread evaluates its unit (branch-parallel or bus-parallel, no atomics,
-// reference summation order) into a shared-memory staging tile; the tile is then streamed to HBM
-// with fully coalesced stores.  HBM traffic per scenario = reads of x / mu / loads + exactly one
-// write of every output slot.  The path is sparse FP64 and HBM-bound: no tensor cores.
+// The path is sparse FP64 and HBM-bound (>= 84 % of the bytes are output writes): no tensor cores.  Outputs are
+// scenario-major [S][ld] in JuMP slot order, so what matters is that every store instruction writes whole 32-byte
+// sectors of a row.  One evaluation = the bus rows + the branch rows:
+//   branch rows   branch_direct_kernel: thread per branch, constants in registers across the scenario loop, next
+//                 scenario's inputs prefetched, values kept by compile-time tag and emitted in slot order as 32-byte
+//                 sector stores (the only topology dependence of the slot order, f < t, is a per-value select);
+//                 branch_staged_kernel: any block size / alignment, through a conflict-free shared staging tile.
+//   bus rows      bus_kernel: shared-memory staging of the tile's half-edge list, admittance entries and slot maps,
+//                 cp.async gather of the scenario's inputs one scenario ahead, contribution-major evaluation
+//                 (half-edge-parallel terms -> pre-reduced multi-slots -> slot-parallel stores);
+//                 pb_bus_g / pb_bus_jh kernels: slot-parallel fast path of the power-branch-flow balances.
+// No atomics on data (only order-independent ones on the per-scenario scalars); results are bitwise reproducible.
 #include <algorithm>
 #include <cstdio>
 #include <cstdlib>

@@ -23,16 +23,13 @@ struct DevPlan {                    // passed to kernels by value (constant bank
   int j_br0, h_br0;                                 // first J / H slot of the branch rows
   int pb_slots;                                     // PB* bus block: slot-parallel fast path available
   const int32_t *pb_jcode, *pb_hcode;               // per-slot codes of the bus block (see ps_plan.h)
-  int pb_implicit;                                  // PB* bus rows: slot order == emission order (see bus_rows_pb)
   int cost_order;
   const int32_t *f, *t;
   const double *Gf, *Bf, *Gt, *Bt, *gf, *bf, *gt, *bt, *Imax, *Gl, *Bl, *Pd0, *Qd0;
   const double *c0, *c1, *c2, *c3;                  // [2*nr] derived per-side constants
   const double *k0, *k1, *k2;                       // [ng] cost coefficients (may be null)
-  const int32_t *gen_ptr, *gen_idx, *sij_ptr, *sij_idx, *sji_ptr, *sji_idx, *sh_ptr, *sh_idx;
-  const int32_t *jptr, *hptr;
-  const uint16_t *bus_jpos, *bus_hpos;
-  const int32_t *bus_jpp, *bus_hpp;
+  const int32_t *gen_ptr, *gen_idx, *sh_ptr, *sh_idx;   // CSR lists per bus (Sij / Sji live in the half-edge tables)
+  const int32_t *bus_jpp, *bus_hpp;                 // per bus: first J / H contribution (emission order)
   const int32_t *he_bus;                            // half-edge -> bus
   const int32_t *jsrc, *hsrc, *ms_dst, *ms_ptr, *ms_list;   // slot -> contribution maps of the bus block (ps_plan.h)
   const int32_t *he_ptr, *he_ks, *he_other;         // half-edges in bus order (Sij then Sji per bus)

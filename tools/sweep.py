@@ -70,6 +70,25 @@ if __name__ == "__main__":
         run("case9241pegase", "PNPAPVmodel", 256, [4], steps=1)
     if sel == "ncu_cb":
         run("case13659pegase", "CBRARVmodel", 256, [4], steps=1)
+    if sel == "latency":
+        for case, Fname in (("case14", "PNPAPVmodel"), ("case2869pegase", "PNPAPVmodel"), ("case13659pegase", "PBRARVmodel")):
+            d = synth.named_case(case)
+            F = ps.BY_NAME[Fname]
+            h = capi.Handle(d, F.code, device=0)
+            x, _, _, _ = synth.scenario_batch(d, F, 1, seed=1)
+            x = x[0]
+            mu = np.random.default_rng(0).normal(size=h.m_nl)
+            g, J, H = np.zeros(h.m_nl), np.zeros(h.nnzJ), np.zeros(h.nnzH)
+            for name, fn in (("eval_constraint", lambda: h.eval_constraint(x, g)), ("eval_jacobian", lambda: h.eval_jacobian(x, J)),
+                             ("eval_hessian", lambda: h.eval_hessian(x, 1.0, mu, H)), ("eval_all", lambda: h.eval_all(x, mu))):
+                for _ in range(5):
+                    fn()
+                t0 = time.perf_counter()
+                for _ in range(50):
+                    fn()
+                dt = (time.perf_counter() - t0) / 50
+                print(f"{case} {Fname} {name}: {dt * 1e6:.0f} us per call (host pointers, synchronous)", flush=True)
+            h.close()
     if sel == "ncu":
         run("case13659pegase", "PBRARVmodel", 256, [4], steps=1)
     if sel in ("all", "others"):

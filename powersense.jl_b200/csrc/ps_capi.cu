@@ -10,6 +10,7 @@
 #include <cstring>
 #include <numeric>
 #include <string>
+#include <type_traits>
 #include <vector>
 
 #include "../../include/powersense_b200.h"
@@ -272,7 +273,42 @@ int ps_create(const ps_network* net, int formulation, int source_type, int flags
   D.n_bus_tiles = P.n_bus_tiles;
   D.j_br0 = P.jptr[P.bus_rows]; D.h_br0 = P.hptr[P.bus_rows];
   D.pb_slots = P.pb_slots ? 1 : 0;
-  D.pb_jcode = M.upload(P.pb_jcode); D.pb_hcode = M.upload(P.pb_hcode);
+  if (P.pb_slots) {
+    // PB* slot tables: slot e of the bus block is coefficient[e] * m, with m = x[index[e]] (own-voltage slots),
+    // 1 (generator slots: index -1) or the branch status (flow slots: index -2 - branch); the Hessian slots are
+    // coefficient[e] * mu[index[e]].  Four copies of each table, copy a shifted so that entry a + 4q sits on a
+    // 32-byte (values) / 16-byte (indices) boundary: the slot-parallel kernel reads the four entries of one output
+    // sector with one vector load whatever the row alignment a is.
+    const int64_t nj = (int64_t)P.pb_jcode.size(), nh = (int64_t)P.pb_hcode.size();
+    std::vector<double> jt((size_t)nj), ht((size_t)nh);
+    std::vector<int32_t> ji((size_t)nj), hi((size_t)nh);
+    for (int64_t e = 0; e < nj; e++) {
+      const int32_t c = P.pb_jcode[e];
+      if (c == -1) { jt[e] = 1.0; ji[e] = -1; }
+      else if (c >= 0) { jt[e] = 1.0; ji[e] = -2 - c; }
+      else {
+        const int32_t v = -2 - c, i = v >> 2, w = v & 3;
+        jt[e] = (w < 2) ? -2.0 * P.net.Gl[i] : 2.0 * P.net.Bl[i];
+        ji[e] = (int32_t)(((w & 1) ? P.o_b : P.o_a) + i);
+      }
+    }
+    for (int64_t e = 0; e < nh; e++) {
+      const int32_t c = P.pb_hcode[e], i = c >> 1;
+      ht[e] = (c & 1) ? 2.0 * P.net.Bl[i] : -2.0 * P.net.Gl[i];
+      hi[e] = c;
+    }
+    auto shifted = [&](const auto& v, int64_t& stride) {
+      using T = typename std::decay<decltype(v)>::type::value_type;
+      stride = ((int64_t)v.size() + 4 + 3) / 4 * 4;
+      std::vector<T> all((size_t)(4 * stride), T(0));
+      for (int a = 0; a < 4; a++) std::copy(v.begin(), v.end(), all.begin() + a * stride + (4 - a) % 4);
+      return all;
+    };
+    int64_t sj = 0, sh = 0;
+    D.pb_jt = M.upload(shifted(jt, sj)); D.pb_ji = M.upload(shifted(ji, sj));
+    D.pb_ht = M.upload(shifted(ht, sh)); D.pb_hi = M.upload(shifted(hi, sh));
+    D.pb_jstride = (int)sj; D.pb_hstride = (int)sh;
+  }
   D.cost_order = P.net.cost_order;
   D.f = M.upload(P.net.f); D.t = M.upload(P.net.t);
   D.Gf = M.upload(P.net.Gf); D.Bf = M.upload(P.net.Bf); D.Gt = M.upload(P.net.Gt); D.Bt = M.upload(P.net.Bt);

@@ -986,32 +986,26 @@ __global__ void __launch_bounds__(TPB, PS_BUS_MINB) bus_kernel(const __grid_cons
 // residuals of a bus by one thread that walks the bus's generator / Sij / Sji lists in the reference's order.
 constexpr int PBT = TPB;
 
-template <int FORM>
-__device__ __forceinline__ double pb_jval(const DevPlan& P, int code, const double* __restrict__ x, const uint8_t* __restrict__ st) {
-  if (code == -1) return 1.0;
-  if (code >= 0) return st ? (double)st[code] : 1.0;
-  const int v = -2 - code, i = v >> 2, w = v & 3;
-  const double coef = (w < 2) ? -2.0 * P.Gl[i] : 2.0 * P.Bl[i];
-  return coef * x[((w & 1) ? P.o_b : P.o_a) + i];
-}
-__device__ __forceinline__ double pb_hval(const DevPlan& P, int code, const double* __restrict__ mu) {
-  const int i = code >> 1;
-  return (code & 1) ? 2.0 * P.Bl[i] * mu[code] : -2.0 * P.Gl[i] * mu[code];
-}
-
-// writes dst[0..n) = f(e): the few elements before the first 32-byte boundary and after the last one with scalar
-// stores, everything else as whole sectors
+// dst[0..n) = coef[e] * m(idx[e]): the few elements before the first 32-byte boundary and after the last one with
+// scalar stores, everything else as whole sectors whose four table entries come from one vector load each
 template <class F>
-__device__ __forceinline__ void emit_sectors(double* __restrict__ dst, int n, int t, int nt, F f) {
+__device__ __forceinline__ void emit_sectors(double* __restrict__ dst, int n, int t, int nt, const double* __restrict__ coefs,
+                                             const int32_t* __restrict__ idxs, int stride, F m) {
   const int a = min(n, (int)((4 - ((reinterpret_cast<unsigned long long>(dst) >> 3) & 3)) & 3));
+  const long long off = (long long)(a & 3) * stride + ((4 - a) & 3);
+  const double* __restrict__ coef = coefs + off;
+  const int32_t* __restrict__ idx = idxs + off;
   const int nfull = (n - a) >> 2;
   for (int q = t; q < nfull; q += nt) {
     const int e = a + 4 * q;
-    st_v4(dst + e, f(e), f(e + 1), f(e + 2), f(e + 3));
+    const int4 c = *reinterpret_cast<const int4*>(idx + e);
+    const double4 k = *reinterpret_cast<const double4*>(coef + e);
+    const double m0 = m(c.x), m1 = m(c.y), m2 = m(c.z), m3 = m(c.w);
+    st_v4(dst + e, k.x * m0, k.y * m1, k.z * m2, k.w * m3);
   }
-  if (t < a) dst[t] = f(t);
+  if (t < a) dst[t] = coef[t] * m(idx[t]);
   const int tail = a + 4 * nfull;
-  if (t < n - tail) dst[tail + t] = f(tail + t);
+  if (t < n - tail) dst[tail + t] = coef[tail + t] * m(idx[tail + t]);
 }
 
 template <int FORM>
@@ -1020,12 +1014,19 @@ __device__ __forceinline__ void pb_bus_jh_body(const DevPlan& P, const EvalArgs&
   const int t = bx * PBT + threadIdx.x, nt = nbx * PBT;
   for (int s = s0; s < s1; s++) {
     const double* __restrict__ x = A.x + (long long)s * A.ldx;
-    const uint8_t* __restrict__ st = A.status ? A.status + (long long)s * A.ldst : nullptr;
-    if (A.what & EV_J)
-      emit_sectors(A.J + (long long)s * A.ldJ, P.j_br0, t, nt, [&](int e) { return pb_jval<FORM>(P, P.pb_jcode[e], x, st); });
+    if (A.what & EV_J) {
+      double* Jd = A.J + (long long)s * A.ldJ;
+      if (A.status) {
+        const uint8_t* __restrict__ st = A.status + (long long)s * A.ldst;
+        emit_sectors(Jd, P.j_br0, t, nt, P.pb_jt, P.pb_ji, P.pb_jstride,
+                     [&](int c) { return c >= 0 ? x[c] : (c == -1 ? 1.0 : (double)st[-2 - c]); });
+      } else {
+        emit_sectors(Jd, P.j_br0, t, nt, P.pb_jt, P.pb_ji, P.pb_jstride, [&](int c) { return c >= 0 ? x[c] : 1.0; });
+      }
+    }
     if (A.what & EV_H) {
       const double* __restrict__ mu = A.mu + (long long)s * A.ldmu;
-      emit_sectors(A.H + (long long)s * A.ldH, P.h_br0, t, nt, [&](int e) { return pb_hval(P, P.pb_hcode[e], mu); });
+      emit_sectors(A.H + (long long)s * A.ldH, P.h_br0, t, nt, P.pb_ht, P.pb_hi, P.pb_hstride, [&](int c) { return mu[c]; });
     }
   }
 }

@@ -22,7 +22,9 @@ struct DevPlan {                    // passed to kernels by value (constant bank
   int ntiles, n_bus_tiles;
   int j_br0, h_br0;                                 // first J / H slot of the branch rows
   int pb_slots;                                     // PB* bus block: slot-parallel fast path available
-  const int32_t *pb_jcode, *pb_hcode;               // per-slot codes of the bus block (see ps_plan.h)
+  const double *pb_jt, *pb_ht;                      // PB* slot tables (ps_capi.cu: upload): coefficients and
+  const int32_t *pb_ji, *pb_hi;                     // indices, 4 shifted copies each:
+  int pb_jstride, pb_hstride;                       // copy a at + a * stride + (4 - a) % 4 (aligned at entry a + 4q)
   int cost_order;
   const int32_t *f, *t;
   const double *Gf, *Bf, *Gt, *Bt, *gf, *bf, *gt, *bt, *Imax, *Gl, *Bl, *Pd0, *Qd0;

@@ -98,6 +98,13 @@ struct Branch {
     }
     template <int... Q> __device__ __forceinline__ void storeJ(double* p, std::integer_sequence<int, Q...>) const { (storeJ4<4 * Q>(p), ...); }
     template <int... Q> __device__ __forceinline__ void storeH(double* p, std::integer_sequence<int, Q...>) const { (storeH4<4 * Q>(p), ...); }
+    // the same values as 16-byte pairs into a (shared-memory) row, for the bulk-copy path
+    template <int... Q> __device__ __forceinline__ void rowJ(double* r, std::integer_sequence<int, Q...>) const {
+      ((*reinterpret_cast<double2*>(r + 2 * Q) = make_double2(jsel<2 * Q>(), jsel<2 * Q + 1>())), ...);
+    }
+    template <int... Q> __device__ __forceinline__ void rowH(double* r, std::integer_sequence<int, Q...>) const {
+      ((*reinterpret_cast<double2*>(r + 2 * Q) = make_double2(hsel<2 * Q>(), hsel<2 * Q + 1>())), ...);
+    }
     // Blocks of 4k+2 doubles per branch (CBRARV / CBRAWV MATPOWER limits, PBRAPV PSS/E limits): the branches of an
     // even/odd lane pair own 8k+4 doubles = whole sectors together.  The even lane writes its first k sectors and the
     // boundary sector (its last two values + the odd lane's first two, fetched with a shuffle); the odd lane writes
@@ -1106,6 +1113,9 @@ __global__ void __launch_bounds__(TPB) objective_kernel(const __grid_constant__ 
 #ifndef PS_DIRECT_MINB
 #define PS_DIRECT_MINB 1
 #endif
+#ifndef PS_PREFETCH2
+#define PS_PREFETCH2 1
+#endif
 template <int FORM, int SRC>
 __device__ __forceinline__ void branch_direct_body(const DevPlan& P, const EvalArgs& A, int bx) {
   using BR = Branch<FORM, SRC>;
@@ -1133,9 +1143,17 @@ __device__ __forceinline__ void branch_direct_body(const DevPlan& P, const EvalA
     const int nact = max(0, min(32, P.nr - ubase));               // active lanes of this warp
     const int ng = nact * BR::NR;
     const long long gb = P.bus_rows + (long long)ubase * BR::NR;
+#if PS_PREFETCH2
+    typename BR::In nx1{};
+    if (act && s0 + 1 < s1) nx1 = BR::load_in(P, A, s0 + 1, u, f, t);
+#endif
     for (int s = s0; s < s1; s++) {
       typename BR::In nxt{};
+#if PS_PREFETCH2
+      if (act && s + 2 < s1) nxt = BR::load_in(P, A, s + 2, u, f, t);   // two scenarios ahead
+#else
       if (act && s + 1 < s1) nxt = BR::load_in(P, A, s + 1, u, f, t);
+#endif
       oj.vmax = 0.0; oj.nviol = 0;
       double* sw = sW[w];
       if (wj || wg || A.scal) {
@@ -1163,9 +1181,166 @@ __device__ __forceinline__ void branch_direct_body(const DevPlan& P, const EvalA
         __syncwarp();
       }
       reduce_scalars(A.scal ? A.scal + (long long)s * NSCAL : nullptr, oj.vmax, oj.nviol);
+#if PS_PREFETCH2
+      cur = nx1; nx1 = nxt;
+#else
       if (s + 1 < s1) cur = nxt;
+#endif
     }
   }
+}
+
+// Bulk path of the branch rows: the same thread-per-branch evaluation, but every thread parks its J and H block in a
+// private, padded shared-memory row (conflict-free 16-byte stores) and hands it to the copy engine with one
+// cp.async.bulk per block (TMA, shared -> global).  The SM's load/store units then carry no global stores at all, the
+// HBM writes are issued as whole lines, and the copy of scenario s overlaps the evaluation of scenario s + 1 (a row is
+// only waited for right before it is overwritten).  No barrier: the rows and the bulk groups are per thread.
+// Needs 16-byte aligned blocks (even block lengths, even leading dimensions); see launch_eval.
+__device__ __forceinline__ void bulk_store(double* gdst, const double* ssrc, int bytes) {
+  const unsigned sa = (unsigned)__cvta_generic_to_shared(ssrc);
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(sa), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+#ifndef PS_BULK_WARP
+#define PS_BULK_WARP 1
+#endif
+#if PS_BULK_WARP
+constexpr int bulk_row_stride(int r) { return r; }   // rows of a warp contiguous: one copy per warp and block
+#else
+constexpr int bulk_row_stride(int r) { return ((r / 2) & 1) ? r : r + 2; }   // doubles; (stride / 2) odd: conflict-free 16-byte stores
+#endif
+
+#ifndef PS_BULK_MINB
+#define PS_BULK_MINB 2
+#endif
+template <int FORM, int SRC>
+__global__ void __launch_bounds__(TPB, PS_BULK_MINB) branch_bulk_kernel(const __grid_constant__ DevPlan P, const __grid_constant__ EvalArgs A) {
+  using BR = Branch<FORM, SRC>;
+  if constexpr (BR::DIRECT_OK) {
+    constexpr int SJ = bulk_row_stride(BR::RJ), SH = bulk_row_stride(BR::RH);
+    extern __shared__ __align__(16) double rows[];                 // [TPB][SJ] | [TPB][SH]
+    __shared__ __align__(16) double sW[TPB / 32][32 * BR::NR];     // per-warp staging row of g
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+#if PS_BULK_WARP
+    // rows of 8 consecutive branches are contiguous (one copy per 8 rows); 16 bytes of padding between the groups of a
+    // warp spread the 16-byte row stores of the 32 lanes over all banks
+    double* const rj = rows + threadIdx.x * SJ + (threadIdx.x >> 3) * 2;
+    double* const rh = rows + TPB * SJ + (TPB / 8) * 2 + threadIdx.x * SH + (threadIdx.x >> 3) * 2;
+#else
+    double* const rj = rows + threadIdx.x * SJ;
+    double* const rh = rows + TPB * SJ + threadIdx.x * SH;
+#endif
+    const int u = blockIdx.x * TPB + threadIdx.x;
+    const bool act = u < P.nr;
+    const int s0 = blockIdx.y * A.chunk, s1 = min(A.S, s0 + A.chunk);
+    const bool wg = (A.what & EV_G) != 0, wj = (A.what & EV_J) != 0, wh = (A.what & EV_H) != 0;
+    typename BR::template OutR<true, false> oj;
+    typename BR::template OutR<false, true> oh;
+    oj.tol = A.viol_tol; oh.tol = A.viol_tol;
+    typename BR::Cst cst{};
+    typename BR::In cur{};
+    int f = 0, t = 1;
+    if (act) {
+      f = P.f[u]; t = P.t[u];
+      cst = BR::load_cst(P, u);
+      cur = BR::load_in(P, A, s0, u, f, t);
+    }
+    oj.sw = oh.sw = f > t;
+    const long long jb = P.j_br0 + (long long)u * BR::RJ, hb = P.h_br0 + (long long)u * BR::RH;
+    const int ubase = blockIdx.x * TPB + w * 32;
+    const int nact = max(0, min(32, P.nr - ubase));
+    const int ng = nact * BR::NR;
+    const long long gb = P.bus_rows + (long long)ubase * BR::NR;
+    const bool lead = (lane & 7) == 0;                             // issues (and waits for) the copies of its 8 rows
+    const int nrow8 = max(0, min(8, P.nr - u));                    // rows of this lane's group (meaningful on lead lanes)
+#if PS_PREFETCH2
+    typename BR::In nx1{};
+    if (act && s0 + 1 < s1) nx1 = BR::load_in(P, A, s0 + 1, u, f, t);
+#endif
+    for (int s = s0; s < s1; s++) {
+      typename BR::In nxt{};
+#if PS_PREFETCH2
+      if (act && s + 2 < s1) nxt = BR::load_in(P, A, s + 2, u, f, t);   // two scenarios ahead
+#else
+      if (act && s + 1 < s1) nxt = BR::load_in(P, A, s + 1, u, f, t);
+#endif
+      oj.vmax = 0.0; oj.nviol = 0;
+      if (wj || wg || A.scal) {
+        if (act) BR::run(oj, cst, cur);                            // pass 1: g + Jacobian tags
+#if PS_BULK_WARP
+        if (wj) {
+          if (lead) bulk_wait_read<1>();                           // the copy that last read these rows (scenario s - 1) is done
+          __syncwarp();
+          if (act) oj.rowJ(rj, std::make_integer_sequence<int, BR::RJ / 2>{});
+          fence_async_smem();
+          __syncwarp();
+          if (lead && nrow8 > 0) bulk_store(A.J + (long long)s * A.ldJ + jb, rj, nrow8 * BR::RJ * 8);
+        }
+      }
+      if (lead) bulk_commit();
+      if (wh) {
+        if (act) BR::run(oh, cst, cur);                            // pass 2: Hessian tags
+        if (lead) bulk_wait_read<1>();
+        __syncwarp();
+        if (act) oh.rowH(rh, std::make_integer_sequence<int, BR::RH / 2>{});
+        fence_async_smem();
+        __syncwarp();
+        if (lead && nrow8 > 0) bulk_store(A.H + (long long)s * A.ldH + hb, rh, nrow8 * BR::RH * 8);
+      }
+      if (lead) bulk_commit();
+#else
+        if (wj && act) {
+          bulk_wait_read<1>();                                     // the copy that last read this row (scenario s - 1) is done
+          oj.rowJ(rj, std::make_integer_sequence<int, BR::RJ / 2>{});
+          fence_async_smem();
+          bulk_store(A.J + (long long)s * A.ldJ + jb, rj, BR::RJ * 8);
+        }
+      }
+      bulk_commit();
+      if (wh && act) {
+        BR::run(oh, cst, cur);                                     // pass 2: Hessian tags
+        bulk_wait_read<1>();
+        oh.rowH(rh, std::make_integer_sequence<int, BR::RH / 2>{});
+        fence_async_smem();
+        bulk_store(A.H + (long long)s * A.ldH + hb, rh, BR::RH * 8);
+      }
+      bulk_commit();
+#endif
+      if (wg) {
+        double* sg = sW[w];
+        if (act) {
+#pragma unroll
+          for (int r = 0; r < BR::NR; r++) sg[lane * BR::NR + r] = oj.gt[r];
+        }
+        __syncwarp();
+        copy_aligned<32>(A.g + (long long)s * A.ldg + gb, ng, lane, [&](int e) { return sg[e]; });
+        __syncwarp();
+      }
+      reduce_scalars(A.scal ? A.scal + (long long)s * NSCAL : nullptr, oj.vmax, oj.nviol);
+#if PS_PREFETCH2
+      cur = nx1; nx1 = nxt;
+#else
+      if (s + 1 < s1) cur = nxt;
+#endif
+    }
+    bulk_wait_read<0>();                                           // shared memory must outlive the copies that read it
+  }
+}
+
+template <int FORM>
+cudaError_t launch_bulk(const DevPlan& P, const EvalArgs& A, cudaStream_t st, dim3 grid) {
+  if (P.src == SRC_MATPOWER) {
+    using BR = Branch<FORM, SRC_MATPOWER>;
+    const size_t smem = (size_t)(TPB * (bulk_row_stride(BR::RJ) + bulk_row_stride(BR::RH)) + (TPB / 8) * 4) * 8;
+    branch_bulk_kernel<FORM, SRC_MATPOWER><<<grid, TPB, smem, st>>>(P, A);
+  } else {
+    using BR = Branch<FORM, SRC_ARPAE>;
+    const size_t smem = (size_t)(TPB * (bulk_row_stride(BR::RJ) + bulk_row_stride(BR::RH)) + (TPB / 8) * 4) * 8;
+    branch_bulk_kernel<FORM, SRC_ARPAE><<<grid, TPB, smem, st>>>(P, A);
+  }
+  return cudaGetLastError();
 }
 
 template <int FORM, int SRC>
@@ -1197,6 +1372,17 @@ template <int FORM>
 cudaError_t configure_form(int src, size_t smem_branch, size_t smem_bus) {
   cudaError_t e = cudaFuncSetAttribute(bus_kernel<FORM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bus);
   if (e != cudaSuccess) return e;
+  {
+    using BM = Branch<FORM, SRC_MATPOWER>;
+    using BA = Branch<FORM, SRC_ARPAE>;
+    if (src == SRC_MATPOWER && BM::DIRECT_OK)
+      e = cudaFuncSetAttribute(branch_bulk_kernel<FORM, SRC_MATPOWER>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               (TPB * (bulk_row_stride(BM::RJ) + bulk_row_stride(BM::RH)) + (TPB / 8) * 4) * 8);
+    if (src != SRC_MATPOWER && BA::DIRECT_OK)
+      e = cudaFuncSetAttribute(branch_bulk_kernel<FORM, SRC_ARPAE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               (TPB * (bulk_row_stride(BA::RJ) + bulk_row_stride(BA::RH)) + (TPB / 8) * 4) * 8);
+    if (e != cudaSuccess) return e;
+  }
   if (src == SRC_MATPOWER)
     return cudaFuncSetAttribute(branch_staged_kernel<FORM, SRC_MATPOWER>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_branch);
   return cudaFuncSetAttribute(branch_staged_kernel<FORM, SRC_ARPAE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_branch);
@@ -1425,6 +1611,11 @@ static cudaError_t launch_pb(const DevPlan& P, const EvalArgs& A, cudaStream_t s
   PS_FORM_SWITCH(PS_CALL)
 #undef PS_CALL
 }
+static cudaError_t launch_branch_bulk(const DevPlan& P, const EvalArgs& A, cudaStream_t stream, dim3 grid) {
+#define PS_CALL(F) launch_bulk<F>(P, A, stream, grid)
+  PS_FORM_SWITCH(PS_CALL)
+#undef PS_CALL
+}
 static cudaError_t launch_branch_direct(const DevPlan& P, const EvalArgs& A, cudaStream_t stream, dim3 grid) {
 #define PS_CALL(F) launch_direct<F>(P, A, stream, grid)
   PS_FORM_SWITCH(PS_CALL)
@@ -1486,8 +1677,16 @@ cudaError_t launch_eval(const DevPlan& P, const EvalArgs& A0, int64_t smem_branc
   bool direct = direct_ok(P.form, P.src) && !getenv("PS_NO_DIRECT");
   if (direct && (A.what & EV_J)) direct = sector_aligned(A.J, P.j_br0, A.ldJ);
   if (direct && (A.what & EV_H)) direct = sector_aligned(A.H, P.h_br0, A.ldH);
+  // bulk (TMA store) path: 16-byte aligned blocks are enough
+  auto pair_aligned = [](const double* p, long long first, long long ld) {
+    return ((reinterpret_cast<unsigned long long>(p) >> 3) + (unsigned long long)first) % 2 == 0 && ld % 2 == 0;
+  };
+  bool bulk = direct_ok(P.form, P.src) && !getenv("PS_NO_BULK");
+  if (bulk && (A.what & EV_J)) bulk = pair_aligned(A.J, P.j_br0, A.ldJ);
+  if (bulk && (A.what & EV_H)) bulk = pair_aligned(A.H, P.h_br0, A.ldH);
   if (launches) *launches += 1;
   KTimer kt(ev, ev_mask, stream, K_BRANCH);
+  if (bulk) return launch_branch_bulk(P, A, stream, dim3(nbt, (unsigned)nchunks));
   if (direct) return launch_branch_direct(P, A, stream, dim3(nbt, (unsigned)nchunks));
   return launch_staged(P, A, (size_t)smem_branch_bytes, stream, dim3(nbt, (unsigned)nchunks));
 }

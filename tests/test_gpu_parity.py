@@ -395,9 +395,10 @@ def test_edge_networks(F):
                                     (ps.PNPAPVmodel, "case2869pegase"), (ps.CBRARVmodel, "case2869pegase")],
                          ids=lambda v: getattr(v, "name", str(v)))
 def test_all_code_paths_agree_bitwise(F, case):
-    """The direct (register -> sector) and staged branch kernels, the slot-parallel PB* bus kernels and the generic
-    contribution-major bus kernel evaluate the same expressions in the same order: their outputs are bitwise equal, on
-    the preferred (sector-aligned) layout and on a plain one, and two runs are bitwise reproducible."""
+    """The bulk (TMA store), direct (register -> sector) and staged branch kernels, the slot-parallel PB* bus kernels and
+    the generic contribution-major bus kernel evaluate the same expressions in the same order: their outputs are bitwise
+    equal, on the preferred (sector-aligned) layout, on a 16-byte aligned one and on a plain one, and two runs are
+    bitwise reproducible."""
     import os
     torch = _torch()
     dev = torch.device("cuda:0")
@@ -411,10 +412,14 @@ def test_all_code_paths_agree_bitwise(F, case):
     tx, tmu = torch.from_numpy(x).to(dev), torch.from_numpy(mu).to(dev)
     (ldg, ldJ, ldH), (pg, pJ, pH) = h.preferred_layout()
 
-    def run(aligned):
+    def run(layout):
         def rows(width, ld, pad):
-            if not aligned:
-                return torch.full((S, width + 1), np.nan, dtype=torch.float64, device=dev)[:, :width]   # odd ld: never sector aligned
+            if layout == "plain":      # odd leading dimension: rows are only 8-byte aligned -> staged branch kernel
+                return torch.full((S, width + 1 + width % 2), np.nan, dtype=torch.float64, device=dev)[:, :width]
+            if layout == "pair":       # ld = 2 mod 4: 16-byte aligned blocks, sectors are not -> bulk (TMA) branch kernel only
+                ld2 = ld + 2
+                flat = torch.full((pad + S * ld2,), np.nan, dtype=torch.float64, device=dev)
+                return flat[pad:].view(S, ld2)[:, :width]
             flat = torch.full((pad + S * ld,), np.nan, dtype=torch.float64, device=dev)
             return flat[pad:].view(S, ld)[:, :width]
         g, J, H = rows(h.m_nl, ldg, pg), rows(h.nnzJ, ldJ, pJ), rows(h.nnzH, ldH, pH)
@@ -422,18 +427,20 @@ def test_all_code_paths_agree_bitwise(F, case):
         b.eval_torch(7, tx, tmu, g, J, H, sc)
         torch.cuda.synchronize()
         return g.cpu().numpy(), J.cpu().numpy(), H.cpu().numpy(), sc.cpu().numpy()
-    ref = run(True)
-    assert all(np.array_equal(a, c) for a, c in zip(ref, run(True)))              # reproducible
-    variants = [({}, False), ({"PS_NO_DIRECT": "1"}, True), ({"PS_NO_PBFAST": "1"}, True),
-                ({"PS_NO_DIRECT": "1", "PS_NO_PBFAST": "1"}, False), ({"PS_CHUNK": "1"}, True), ({"PS_CHUNK": "5"}, True)]
-    for env, aligned in variants:
+    ref = run("sector")
+    assert all(np.array_equal(a, c) for a, c in zip(ref, run("sector")))              # reproducible
+    variants = [({}, "plain"), ({}, "pair"), ({"PS_NO_BULK": "1"}, "sector"), ({"PS_NO_BULK": "1"}, "pair"),
+                ({"PS_NO_BULK": "1", "PS_NO_DIRECT": "1"}, "sector"), ({"PS_NO_PBFAST": "1"}, "sector"),
+                ({"PS_NO_BULK": "1", "PS_NO_DIRECT": "1", "PS_NO_PBFAST": "1"}, "plain"), ({"PS_CHUNK": "1"}, "sector"),
+                ({"PS_CHUNK": "5"}, "sector")]
+    for env, layout in variants:
         os.environ.update(env)
         try:
-            out = run(aligned)
+            out = run(layout)
         finally:
             for k in env:
                 del os.environ[k]
         for name, a, c in zip("gJHs", ref, out):
-            assert np.array_equal(a, c), (F.name, env, aligned, name)
+            assert np.array_equal(a, c), (F.name, env, layout, name)
     b.close()
     h.close()

@@ -73,6 +73,61 @@ __global__ void coalesced2(double2* __restrict__ out, long long n, double a) {
   for (; i < n; i += stride) out[i] = make_double2(a + (double)i, a);
 }
 
+
+// ---- three output arrays per thread (g: 4, J: 24, H: 36 doubles), like the branch rows of PBRARV
+__device__ __forceinline__ void stv4(double* p, double a, double b, double c, double d) {
+  asm volatile("st.global.v4.f64 [%0], {%1, %2, %3, %4};" ::"l"(p), "d"(a), "d"(b), "d"(c), "d"(d) : "memory");
+}
+__global__ void rows3_direct(double* __restrict__ g, double* __restrict__ J, double* __restrict__ H, long long n, double a) {
+  long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (; t < n; t += stride) {
+    const double v = a + (double)t;
+    stv4(g + t * 4, v, v + 1, v + 2, v + 3);
+#pragma unroll
+    for (int i = 0; i < 24; i += 4) stv4(J + t * 24 + i, v + i, v - i, v * 2, v + 1);
+#pragma unroll
+    for (int i = 0; i < 36; i += 4) stv4(H + t * 36 + i, v + i, v - i, v * 3, v + 1);
+  }
+}
+__device__ __forceinline__ void bulk_store(double* gdst, const double* ssrc, int bytes) {
+  const unsigned sa = (unsigned)__cvta_generic_to_shared(ssrc);
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(sa), "r"(bytes) : "memory");
+}
+// per-thread padded rows in shared memory (conflict-free 16-byte stores), one bulk copy per row and array
+template <int MODE>   // 0: per-thread bulk copies of padded rows; 1: linear rows, one bulk copy per warp and array
+__global__ void rows3_bulk(double* __restrict__ g, double* __restrict__ J, double* __restrict__ H, long long n, double a) {
+  extern __shared__ __align__(128) double sm[];
+  constexpr int PG = MODE ? 4 : 6, PJ = MODE ? 24 : 26, PH = MODE ? 36 : 38;
+  double* sg = sm;
+  double* sJ = sg + blockDim.x * PG;
+  double* sH = sJ + blockDim.x * PJ;
+  const int tid = threadIdx.x, lane = tid & 31;
+  long long t = blockIdx.x * (long long)blockDim.x + tid;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (; t < n; t += stride) {
+    const double v = a + (double)t;
+    double* rg = sg + tid * PG; double* rJ = sJ + tid * PJ; double* rH = sH + tid * PH;
+    *reinterpret_cast<double2*>(rg) = make_double2(v, v + 1); *reinterpret_cast<double2*>(rg + 2) = make_double2(v + 2, v + 3);
+#pragma unroll
+    for (int i = 0; i < 24; i += 2) *reinterpret_cast<double2*>(rJ + i) = make_double2(v + i, v - i);
+#pragma unroll
+    for (int i = 0; i < 36; i += 2) *reinterpret_cast<double2*>(rH + i) = make_double2(v + i, v * 3);
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    if (MODE == 0) {
+      bulk_store(g + t * 4, rg, 32); bulk_store(J + t * 24, rJ, 192); bulk_store(H + t * 36, rH, 288);
+    } else {
+      __syncwarp();
+      if (lane == 0) {
+        bulk_store(g + t * 4, rg, 32 * 32); bulk_store(J + t * 24, rJ, 32 * 192); bulk_store(H + t * 36, rH, 32 * 288);
+      }
+    }
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+    if (MODE == 1) __syncwarp();
+  }
+}
+
 template <class F> float timeit(F f, int reps = 5) {
   cudaEvent_t e0, e1;
   cudaEventCreate(&e0); cudaEventCreate(&e1);
@@ -110,6 +165,20 @@ int main() {
   printf("rows R=36 warp-transposed: %7.1f GB/s\n", (N / 36) * 36 * 8 / ms / 1e6);
   ms = timeit([&] { rows_warp_transposed<36, 1><<<148 * 6, 128>>>(out, (N / 36) / 32 * 32, 1.0); });
   printf("rows R=36 warp-transposed .cs: %7.1f GB/s\n", (N / 36) * 36 * 8 / ms / 1e6);
+  {
+    const long long n3 = (N / 64) / 128 * 128;
+    double *g3 = out, *J3 = out + n3 * 4, *H3 = J3 + n3 * 24;
+    ms = timeit([&] { rows3_direct<<<blocks, 128>>>(g3, J3, H3, n3, 1.0); });
+    printf("rows3 (4+24+36) direct v4        : %7.1f GB/s\n", n3 * 64 * 8 / ms / 1e6);
+    cudaFuncSetAttribute(rows3_bulk<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 70 * 8);
+    cudaFuncSetAttribute(rows3_bulk<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 64 * 8);
+    for (int bl : {148 * 2, 148 * 3, 148 * 6}) {
+      ms = timeit([&] { rows3_bulk<0><<<bl, 128, 128 * 70 * 8>>>(g3, J3, H3, n3, 1.0); });
+      printf("rows3 bulk per-thread rows grid=%4d: %7.1f GB/s\n", bl, n3 * 64 * 8 / ms / 1e6);
+      ms = timeit([&] { rows3_bulk<1><<<bl, 128, 128 * 64 * 8>>>(g3, J3, H3, n3, 1.0); });
+      printf("rows3 bulk per-warp linear  grid=%4d: %7.1f GB/s\n", bl, n3 * 64 * 8 / ms / 1e6);
+    }
+  }
   cudaError_t e = cudaDeviceSynchronize();
   printf("status %s\n", cudaGetErrorString(e));
   return 0;

@@ -297,7 +297,14 @@ def main():
     achieved_step = alg_bytes * S / (kernel_ms * 1e-3) / 1e9
     achieved = alg_branch * S / (kavg["branch"] * 1e-3) / 1e9      # the dominant kernel: branch rows
     info = h.plan_info()
-    kname = ("branch_direct_kernel" if info["direct_ok"] else "branch_staged_kernel") + f"<{args.formulation[:6]}>"
+    # ScenarioDriver allocates the preferred (sector-aligned) layout: the bulk (TMA store) branch kernel runs unless disabled
+    if info["direct_ok"]:
+        kname = "branch_direct_kernel" if os.environ.get("PS_NO_BULK") else "branch_bulk_kernel"
+        if os.environ.get("PS_NO_BULK") and os.environ.get("PS_NO_DIRECT"):
+            kname = "branch_staged_kernel"
+    else:
+        kname = "branch_staged_kernel"
+    kname += f"<{args.formulation[:6]}>"
     traffic = None
     tp = os.path.join(ROOT, "profiles", "traffic.json")             # dram bytes/launch from the committed ncu capture
     if os.path.exists(tp):

@@ -299,7 +299,10 @@ def main():
     info = h.plan_info()
     # ScenarioDriver allocates the preferred (sector-aligned) layout: the bulk (TMA store) branch kernel runs unless disabled
     if info["direct_ok"]:
-        kname = "branch_direct_kernel" if os.environ.get("PS_NO_BULK") else "branch_bulk_kernel"
+        nr_ = max(len(d.br), 1)
+        long_blocks = (h.nnzJ - info["j_br0"]) // nr_ + (h.nnzH - info["h_br0"]) // nr_ >= 48     # launch_eval's rule
+        use_bulk = (long_blocks or os.environ.get("PS_BULK")) and not os.environ.get("PS_NO_BULK")
+        kname = "branch_bulk_kernel" if use_bulk else "branch_direct_kernel"
         if os.environ.get("PS_NO_BULK") and os.environ.get("PS_NO_DIRECT"):
             kname = "branch_staged_kernel"
     else:

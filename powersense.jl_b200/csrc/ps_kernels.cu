@@ -1681,7 +1681,10 @@ cudaError_t launch_eval(const DevPlan& P, const EvalArgs& A0, int64_t smem_branc
   auto pair_aligned = [](const double* p, long long first, long long ld) {
     return ((reinterpret_cast<unsigned long long>(p) >> 3) + (unsigned long long)first) % 2 == 0 && ld % 2 == 0;
   };
-  bool bulk = direct_ok(P.form, P.src) && !getenv("PS_NO_BULK");
+  // ... and it pays for long blocks only (PB*: 60-68 doubles per branch); for the short blocks of the CB* / PN* models the
+  // per-warp copy set-up is not amortised and the direct path is a few percent faster (PS_BULK=1 forces it)
+  const BranchPat bp = branch_pattern(P.form, P.src);
+  bool bulk = direct_ok(P.form, P.src) && !getenv("PS_NO_BULK") && (bp.nj() + bp.nh() >= 48 || getenv("PS_BULK"));
   if (bulk && (A.what & EV_J)) bulk = pair_aligned(A.J, P.j_br0, A.ldJ);
   if (bulk && (A.what & EV_H)) bulk = pair_aligned(A.H, P.h_br0, A.ldH);
   if (launches) *launches += 1;

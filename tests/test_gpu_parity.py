@@ -429,7 +429,8 @@ def test_all_code_paths_agree_bitwise(F, case):
         return g.cpu().numpy(), J.cpu().numpy(), H.cpu().numpy(), sc.cpu().numpy()
     ref = run("sector")
     assert all(np.array_equal(a, c) for a, c in zip(ref, run("sector")))              # reproducible
-    variants = [({}, "plain"), ({}, "pair"), ({"PS_NO_BULK": "1"}, "sector"), ({"PS_NO_BULK": "1"}, "pair"),
+    variants = [({}, "plain"), ({}, "pair"), ({"PS_BULK": "1"}, "sector"), ({"PS_BULK": "1"}, "pair"),
+                ({"PS_NO_BULK": "1"}, "sector"), ({"PS_NO_BULK": "1"}, "pair"),
                 ({"PS_NO_BULK": "1", "PS_NO_DIRECT": "1"}, "sector"), ({"PS_NO_PBFAST": "1"}, "sector"),
                 ({"PS_NO_BULK": "1", "PS_NO_DIRECT": "1", "PS_NO_PBFAST": "1"}, "plain"), ({"PS_CHUNK": "1"}, "sector"),
                 ({"PS_CHUNK": "5"}, "sector")]

@@ -875,7 +875,10 @@ __global__ void __launch_bounds__(TPB, PS_BUS_MINB) bus_kernel(const __grid_cons
     const Tile tl = P.tiles[blockIdx.x];
     const bool wg = (A.what & EV_G) != 0, wj = (A.what & EV_J) != 0, wh = (A.what & EV_H) != 0;
     const int tid = threadIdx.x;
-    const int u = tl.u0 + tid;
+    // bus-owner threads are taken from the END of the CTA: the half-edge phase fills the first warps, so the per-bus
+    // work (own terms, residuals) runs on warps that would otherwise idle at the barrier instead of lengthening warp 0
+    const int lb = TPB - 1 - tid;                  // tile-local bus of this thread
+    const int u = tl.u0 + lb;
     const bool act = u < tl.u1;
     const bool facts = (P.flags & FLAG_FACTS) != 0;
     BusTile T;
@@ -956,7 +959,7 @@ __global__ void __launch_bounds__(TPB, PS_BUS_MINB) bus_kernel(const __grid_cons
       }
       if (act && (wj || wh)) {
         const int ng2 = 2 * (B.g1 - B.g0);
-        bus_own_terms<FORM>(P, T, B, xs, tid, SeqW{T.cbj + B.oj, 1, wj}, SeqW{T.cbj + B.oj + ng2, 1, wj}, SeqW{T.cbh + B.oh, 1, wh});
+        bus_own_terms<FORM>(P, T, B, xs, lb, SeqW{T.cbj + B.oj, 1, wj}, SeqW{T.cbj + B.oj + ng2, 1, wj}, SeqW{T.cbh + B.oh, 1, wh});
       }
       __syncthreads();
       // ---- phase 1.5: slots with several contributions
@@ -970,9 +973,9 @@ __global__ void __launch_bounds__(TPB, PS_BUS_MINB) bus_kernel(const __grid_cons
       int nviol = 0;
       if (need_g && act) {
         double gP, gQ;
-        bus_residuals<FORM>(T, B, xs, tid, has_status, gP, gQ);
+        bus_residuals<FORM>(T, B, xs, lb, has_status, gP, gQ);
         if (wg) {
-          double* gd = A.g + (long long)s * A.ldg + tl.g0 + 2 * tid;
+          double* gd = A.g + (long long)s * A.ldg + tl.g0 + 2 * lb;
           if ((reinterpret_cast<unsigned long long>(gd) & 15) == 0) *reinterpret_cast<double2*>(gd) = make_double2(gP, gQ);
           else { gd[0] = gP; gd[1] = gQ; }
         }

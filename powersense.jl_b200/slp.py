@@ -42,11 +42,16 @@ class SlpOptions:                      # src/opt/parameters.jl:16-30
     min_alpha: float = 1e-8
     delta: float = 1000.0              # sub_optimize!(slp, Δ = 1000.0), slp.jl:50
 
-class BatchedSlpLS:
-    def __init__(self, model: OPFModel, S: int, Pd=None, Qd=None, status=None, options: Optional[SlpOptions] = None):
+class GpuBackend:
+    """Device side of the iteration for an OPF model: every evaluation is one batched launch over the S scenarios
+    (ps_batch_eval, ps_rows_eval_batch, ps_csc_assemble_batch, ps_kkt_eval_batch).  BatchedSlpLS only needs the small
+    interface below (attributes dev, n, m, nnz, g_L, g_U, xl, xu, x0, colptr, rowval; eval_g, eval_all, metrics), which
+    the tests also implement on the CPU oracle to run the same algorithm on the reference's own toy problem."""
+
+    def __init__(self, model: OPFModel, S: int, Pd=None, Qd=None, status=None):
         import torch
         self.torch = torch
-        self.model, self.S, self.opt = model, int(S), options or SlpOptions()
+        self.model, self.S = model, int(S)
         h = model.evaluator.handle
         self.h = h
         self.dev = torch.device("cuda", torch.cuda.current_device())
@@ -56,6 +61,7 @@ class BatchedSlpLS:
         self.g_order = g_order + [h.m_nl]
         self.g_L = np.concatenate([lo, model.nl_lo])
         self.g_U = np.concatenate([hi, model.nl_hi])
+        self.xl, self.xu, self.x0 = model.xl, model.xu, model.x0
         # device blocks: rows (N1), objective (1-row block), NL batch, CSC pattern (a11), metrics (N3)
         from_rows = _rows_to_csr(rows)
         self.rows = capi.RowsBlock(n, *from_rows[:7], constant=from_rows[7], device=self.dev.index)
@@ -76,18 +82,57 @@ class BatchedSlpLS:
         jcol = np.concatenate([rj_c, nj_c])
         self.pattern = capi.CscPattern(self.m, n, jrow, jcol, device=self.dev.index)
         self.colptr, self.rowval = self.pattern.structure()
+        self.nnz = self.pattern.nnz
         self.kkt = capi.KktMetrics(self.pattern, self.g_L, self.g_U, model.xl, model.xu)
+        Z = lambda *shape: torch.zeros(*shape, dtype=torch.float64, device=self.dev)
+        self.dE = Z(self.S, self.nnz_rows + h.nnzJ)
+        self.gobj = Z(self.S, max(self.obj.nnzJ, 1))
+
+    def eval_g(self, X, E, f):
+        """E = [affine/quadratic rows | NL rows](X), f = objective(X) -- eval_g / eval_f of the closures of
+        MOI_wrapper.jl:1168-1180."""
+        self.rows.eval_torch(capi.EVAL_G, X, None, E, None, None)
+        self.batch.eval_torch(capi.EVAL_G, X, None, E[:, self.m_rows:], None, None, None)
+        self.obj.eval_torch(capi.EVAL_G, X, None, f, None, None)
+
+    def eval_all(self, X, E, f, df, nz):
+        self.rows.eval_torch(capi.EVAL_G | capi.EVAL_J, X, None, E, self.dE, None)
+        self.batch.eval_torch(capi.EVAL_G | capi.EVAL_J, X, None, E[:, self.m_rows:], self.dE[:, self.nnz_rows:], None, None)
+        self.obj.eval_torch(capi.EVAL_G | capi.EVAL_J, X, None, f, self.gobj, None)
+        df.zero_()                                                  # fill_gradient! (MOI_wrapper.jl:906-930): dense, duplicates added
+        if self.obj.nnzJ:
+            df.index_add_(1, self.obj_jcol, self.gobj)
+        self.pattern.assemble_torch(self.dE, nz)                    # compute_jacobian_matrix (common.jl:12-20)
+
+    def metrics(self, E, X, lam, mU, mL, df, nz, nu, P, f, out):
+        """[S, PS_NKKT]: viol1, viol_inf, complementarity, KKT residual, phi(0), D(0) (nu / P may be None)."""
+        return self.kkt.eval_torch(E, X, lam, mU, mL, df, nz, nu, P, f, out=out)
+
+    def close(self):
+        for o in (self.kkt, self.pattern, self.batch, self.rows, self.obj):
+            o.close()
+
+
+class BatchedSlpLS:
+    def __init__(self, model: Optional[OPFModel], S: int, Pd=None, Qd=None, status=None, options: Optional[SlpOptions] = None,
+                 backend=None):
+        import torch
+        self.torch = torch
+        self.S, self.opt = int(S), options or SlpOptions()
+        be = self.be = backend if backend is not None else GpuBackend(model, S, Pd, Qd, status)
+        self.dev = be.dev
+        n, m = self.n, self.m = be.n, be.m
+        self.g_L, self.g_U, self.xl, self.xu, self.x0 = be.g_L, be.g_U, be.xl, be.xu, be.x0
+        self.colptr, self.rowval = be.colptr, be.rowval
         f64 = torch.float64
         Z = lambda *shape: torch.zeros(*shape, dtype=f64, device=self.dev)
         S = self.S
         self.X, self.Xt = Z(S, n), Z(S, n)
-        self.E, self.Et = Z(S, self.m), Z(S, self.m)
-        self.dE = Z(S, self.nnz_rows + h.nnzJ)
-        self.nz = Z(S, self.pattern.nnz)
-        self.lam, self.nu = Z(S, self.m), Z(S, self.m)
+        self.E, self.Et = Z(S, m), Z(S, m)
+        self.nz = Z(S, be.nnz)
+        self.lam, self.nu = Z(S, m), Z(S, m)
         self.mU, self.mL, self.df, self.P = Z(S, n), Z(S, n), Z(S, n), Z(S, n)
         self.f, self.ft = Z(S, 1), Z(S, 1)
-        self.gobj = Z(S, max(self.obj.nnzJ, 1))
         self.metrics, self.metrics_t = Z(S, capi.PS_NKKT), Z(S, capi.PS_NKKT)
         # row classes of the LP (subproblem.jl:141-318): le / ge / eq
         le = np.isinf(self.g_L) & np.isfinite(self.g_U)
@@ -97,27 +142,16 @@ class BatchedSlpLS:
             raise NotImplementedError("two-sided rows reach Powersense.Optimizer split by the SplitInterval bridge")
         self.i_le, self.i_ge, self.i_eq = np.nonzero(le)[0], np.nonzero(ge)[0], np.nonzero(eq)[0]
 
-    # ---- device evaluations -------------------------------------------------------------------------------------
+    # ---- evaluations (device) ----------------------------------------------------------------------------------------
     def _eval_g(self, X, E, f):
-        """E = [affine/quadratic rows | NL rows](X), f = objective(X) -- eval_g / eval_f of the closures of
-        MOI_wrapper.jl:1168-1180."""
-        self.rows.eval_torch(capi.EVAL_G, X, None, E, None, None)
-        self.batch.eval_torch(capi.EVAL_G, X, None, E[:, self.m_rows:], None, None, None)
-        self.obj.eval_torch(capi.EVAL_G, X, None, f, None, None)
+        self.be.eval_g(X, E, f)
 
     def _eval_all(self):
-        t = self.torch
-        self.rows.eval_torch(capi.EVAL_G | capi.EVAL_J, self.X, None, self.E, self.dE, None)
-        self.batch.eval_torch(capi.EVAL_G | capi.EVAL_J, self.X, None, self.E[:, self.m_rows:], self.dE[:, self.nnz_rows:], None, None)
-        self.obj.eval_torch(capi.EVAL_G | capi.EVAL_J, self.X, None, self.f, self.gobj, None)
-        self.df.zero_()                                             # fill_gradient! (MOI_wrapper.jl:906-930): dense, duplicates added
-        if self.obj.nnzJ:
-            self.df.index_add_(1, self.obj_jcol, self.gobj)
-        self.pattern.assemble_torch(self.dE, self.nz)               # compute_jacobian_matrix (common.jl:12-20)
+        self.be.eval_all(self.X, self.E, self.f, self.df, self.nz)
 
     def _metrics(self, with_dir: bool):
-        self.kkt.eval_torch(self.E, self.X, self.lam, self.mU, self.mL, self.df, self.nz, self.nu if with_dir else None,
-                            self.P if with_dir else None, self.f.view(-1), out=self.metrics)
+        self.be.metrics(self.E, self.X, self.lam, self.mU, self.mL, self.df, self.nz, self.nu if with_dir else None,
+                        self.P if with_dir else None, self.f.view(-1), self.metrics)
         return self.metrics.cpu().numpy()
 
     # ---- host: the LP subproblem of one scenario (subproblem.jl:55-334, 349-700) ---------------------------------
@@ -158,8 +192,8 @@ class BatchedSlpLS:
             if b_eq is not None:
                 b_eq[np.abs(b_eq) <= o.tol_error] = 0.0
         c = np.concatenate([np.zeros(n) if restoration else df, np.ones(ns)])
-        ub = np.minimum(o.delta, self.model.xu - x)                # subproblem.jl:126-129
-        lb = np.maximum(-o.delta, self.model.xl - x)
+        ub = np.minimum(o.delta, self.xu - x)                      # subproblem.jl:126-129
+        lb = np.maximum(-o.delta, self.xl - x)
         bounds = np.column_stack([np.concatenate([lb, np.zeros(ns)]), np.concatenate([ub, np.full(ns, np.inf)])])
         res = linprog(c, A_ub=A_ub, b_ub=b_ub, A_eq=eq_block, b_eq=b_eq, bounds=bounds, method="highs")
         if res.status == 0:
@@ -171,8 +205,8 @@ class BatchedSlpLS:
             if neq:
                 lam[eq] = res.eqlin.marginals
             mU, mL = res.upper.marginals[:n].copy(), res.lower.marginals[:n].copy()
-            mU[p < self.model.xu - x] = 0.0                         # :686-693: the trust region is not a variable bound
-            mL[p > self.model.xl - x] = 0.0
+            mU[p < self.xu - x] = 0.0                               # :686-693: the trust region is not a variable bound
+            mL[p > self.xl - x] = 0.0
             return p, lam, mU, mL, float(res.x[n:].sum()), "OPTIMAL"
         if res.status == 2:
             return np.zeros(n), np.zeros(m), np.zeros(n), np.zeros(n), 0.0, "INFEASIBLE"
@@ -181,9 +215,9 @@ class BatchedSlpLS:
     # ---- the algorithm (slp_line_search.jl:80-249) -----------------------------------------------------------------
     def run(self, x0: Optional[np.ndarray] = None):
         t, o, S, n, m = self.torch, self.opt, self.S, self.n, self.m
-        x0 = self.model.x0 if x0 is None else x0
+        x0 = self.x0 if x0 is None else x0
         x0 = np.broadcast_to(np.asarray(x0, dtype=np.float64), (S, n)).copy()
-        xl, xu = self.model.xl, self.model.xu
+        xl, xu = self.xl, self.xu
         x0 = np.where(xl > -np.inf, np.maximum(x0, xl), x0)        # :100-107 (clamp to the column bounds)
         x0 = np.where(xu < np.inf, np.minimum(x0, xu), x0)
         self.X.copy_(t.from_numpy(x0))
@@ -240,8 +274,9 @@ class BatchedSlpLS:
                 self._eval_g(self.Xt, self.Et, self.ft)
                 # merit at the trial point on the device (compute_phi, slp.jl:108-131): out[4] = f + sum nu*viol, and
                 # out[0] = sum of violations (the step respects the column bounds, so only the rows contribute)
-                mt = self.kkt.eval_torch(self.Et, self.Xt, self.lam, self.mU, self.mL, self.df, self.nz, self.nu, self.P,
-                                         self.ft.view(-1), out=self.metrics_t).cpu().numpy()
+                self.be.metrics(self.Et, self.Xt, self.lam, self.mU, self.mL, self.df, self.nz, self.nu, self.P,
+                                self.ft.view(-1), self.metrics_t)
+                mt = self.metrics_t.cpu().numpy()
                 phi_t = np.where(restoration, mt[:, 0], mt[:, 4])
                 ok = phi_t <= phi0 + o.eta * alpha * D
                 for s in np.nonzero(searching)[0]:
@@ -297,8 +332,7 @@ class BatchedSlpLS:
                 "g": self.E.cpu().numpy(), "lambda": self.lam.cpu().numpy()}
 
     def close(self):
-        for o in (self.kkt, self.pattern, self.batch, self.rows, self.obj):
-            o.close()
+        self.be.close()
 
 
 def _viol_rows(E, g_L, g_U):

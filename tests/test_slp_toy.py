@@ -1,0 +1,76 @@
+"""N4 pinned on the reference's own SLP test: the toy NLP of test/opt/ext_solver.jl (and examples/opt/opt_example.jl),
+which test/runtests.jl:19-25 solves with Powersense.Optimizer + GLPK and checks as X = Y = -1 (rtol 1e-4),
+LOCALLY_SOLVED.  The product's lock-step SLP driver (powersense_b200.slp.BatchedSlpLS: the algorithm and the LP
+subproblem) runs here unchanged; only its evaluation backend is replaced by a test-only CPU one built on the oracle
+(the product has no CPU evaluation path: the default backend needs the CUDA library and a GPU)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import kkt_oracle
+from powersense_b200 import capi, slp
+
+
+class HostToyBackend:
+    """min X^2 + X  s.t.  X^2 - X == 2,  X*Y == 1,  X*Y >= 0,  X >= -2   (ext_solver.jl:31-38).
+    Row order as Powersense.Optimizer sees it (MOI_wrapper.jl:780-800): the affine row, then the NL rows."""
+
+    def __init__(self, S):
+        self.S, self.dev, self.n, self.m = S, torch.device("cpu"), 2, 4
+        inf = np.inf
+        self.g_L = np.array([-2.0, 2.0, 1.0, 0.0])
+        self.g_U = np.array([inf, 2.0, 1.0, inf])
+        self.xl, self.xu, self.x0 = np.full(2, -inf), np.full(2, inf), np.zeros(2)
+        # dense 4x2 Jacobian in CSC order, 1-based like ps_csc_structure
+        self.colptr = np.array([1, 5, 9], dtype=np.int64)
+        self.rowval = np.array([1, 2, 3, 4, 1, 2, 3, 4], dtype=np.int64)
+        self.nnz = 8
+
+    @staticmethod
+    def _g(x, y):
+        return np.array([x, x * x - x, x * y, x * y])
+
+    def eval_g(self, X, E, f):
+        for s in range(self.S):
+            x, y = X[s].tolist()
+            E[s] = torch.from_numpy(self._g(x, y))
+            f[s, 0] = x * x + x
+
+    def eval_all(self, X, E, f, df, nz):
+        self.eval_g(X, E, f)
+        for s in range(self.S):
+            x, y = X[s].tolist()
+            df[s] = torch.tensor([2 * x + 1, 0.0], dtype=torch.float64)
+            nz[s] = torch.tensor([1.0, 2 * x - 1, y, y, 0.0, 0.0, x, x], dtype=torch.float64)
+
+    def metrics(self, E, X, lam, mU, mL, df, nz, nu, P, f, out):
+        for s in range(self.S):
+            Jac = nz[s].numpy().reshape(2, 4).T
+            e, x = E[s].numpy(), X[s].numpy()
+            out[s, 0] = kkt_oracle.norm_violations(e, self.g_L, self.g_U, x, self.xl, self.xu, 1)
+            out[s, 1] = kkt_oracle.norm_violations(e, self.g_L, self.g_U, x, self.xl, self.xu, np.inf)
+            out[s, 2] = kkt_oracle.norm_complementarity(e, self.g_L, self.g_U, lam[s].numpy())
+            out[s, 3] = kkt_oracle.KT_residuals(df[s].numpy(), lam[s].numpy(), mU[s].numpy(), mL[s].numpy(), Jac)
+            fs = float(f[s])
+            out[s, 4] = kkt_oracle.compute_phi0(fs, e, self.g_L, self.g_U, nu[s].numpy()) if nu is not None else fs
+            out[s, 5] = (kkt_oracle.compute_derivative(df[s].numpy(), P[s].numpy(), e, self.g_L, self.g_U, nu[s].numpy())
+                         if nu is not None and P is not None else 0.0)
+        return out
+
+    def close(self):
+        pass
+
+
+@pytest.mark.parametrize("S", [1, 3])
+def test_reference_toy_problem_known_answer(S):
+    be = HostToyBackend(S)
+    drv = slp.BatchedSlpLS(None, S, backend=be, options=slp.SlpOptions())
+    x0 = np.zeros((S, 2))
+    if S > 1:                                  # scenarios started elsewhere advance in lock-step to the same point
+        x0[1] = [-0.5, -0.5]
+        x0[2] = [-2.0, -3.0]
+    out = drv.run(x0)
+    assert (out["status"] == 0).all(), out["status"]                     # LOCALLY_SOLVED
+    np.testing.assert_allclose(out["x"], -1.0, rtol=1e-4)                # test/runtests.jl:20-21
+    np.testing.assert_allclose(out["obj"], 0.0, atol=1e-6)
+    drv.close()

@@ -46,7 +46,7 @@ class GpuBackend:
     """Device side of the iteration for an OPF model: every evaluation is one batched launch over the S scenarios
     (ps_batch_eval, ps_rows_eval_batch, ps_csc_assemble_batch, ps_kkt_eval_batch).  BatchedSlpLS only needs the small
     interface below (attributes dev, n, m, nnz, g_L, g_U, xl, xu, x0, colptr, rowval; eval_g, eval_all, metrics), which
-    the tests also implement on the CPU oracle to run the same algorithm on the reference's own toy problem."""
+    the tests also implement on a CPU checker to run the same algorithm on the reference's own toy problem."""
 
     def __init__(self, model: OPFModel, S: int, Pd=None, Qd=None, status=None):
         import torch

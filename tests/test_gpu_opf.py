@@ -1,6 +1,7 @@
-"""End-to-end known answer (the only numeric answer the reference's tests hold on this path): the 14-bus PSS/E case
-solved with obj_type = :linear gives cost ~ 146.7 at rtol 0.1 for PNPAPV, PBRARV + box and CBRARV +- box
-(test/opf/ACOPF_formulations.jl:7-9, examples/opf/ACOPF_formulations_example.jl:5-19).  The NL block is served by the
+"""End-to-end known answers (the numeric answers the reference's tests and examples hold on this path): the 14-bus
+PSS/E case solved with obj_type = :linear gives cost ~ 146.7 at rtol 0.1 for PNPAPV, PBRARV + box and CBRARV +- box
+(test/opf/ACOPF_formulations.jl:7-9, examples/opf/ACOPF_formulations_example.jl:5-19), and MATPOWER case300 with the
+quadratic objective gives 7.1973e+05 (example :23-27).  The NL block is served by the
 GPU evaluator through the MOI-style callbacks; the NLP solver is scipy's SLSQP (no Ipopt / GLPK here)."""
 import copy
 
@@ -31,6 +32,22 @@ def test_case14_known_objective(F, box):
     assert M.Pg.shape == (5,) and np.all(M.Pg >= M.Pmin - 1e-6) and np.all(M.Pg <= M.Pmax + 1e-6)
     if F is ps.PNPAPVmodel:
         assert np.all(M.V >= 0.9 - 1e-6) and np.all(M.V <= 1.1 + 1e-6)
+    model.close()
+
+
+def test_case300_known_objective():
+    """The reference's second example (examples/opf/ACOPF_formulations_example.jl:23-27): MATPOWER case300, PNPAPV,
+    obj_type = :quadratic, quoted there as 7.1973e+05 (MATPOWER's published AC-OPF optimum of the case is 719725.1).
+    Dense SLSQP on 738 variables: about a minute of host time."""
+    M = copy.deepcopy(load_fixture("case300"))
+    res = ps.run_opf(M, formulation=ps.PNPAPVmodel, obj_type="quadratic", maxiter=300)
+    model = M.model
+    g = model.nl_value(res.x)
+    viol = np.maximum(np.maximum(g - model.nl_hi, model.nl_lo - g), 0.0).max()
+    rv = model.rows_value(res.x)
+    viol = max(viol, np.maximum(np.maximum(rv - model.rows.hi, model.rows.lo - rv), 0.0).max())
+    assert viol < 1e-5, viol
+    assert M.cost == pytest.approx(7.1973e5, rel=1e-4), M.cost
     model.close()
 
 

@@ -862,18 +862,14 @@ __device__ __forceinline__ void slots_out(double* __restrict__ dst, int n, const
 #ifndef PS_BUS_MINB
 #define PS_BUS_MINB 5
 #endif
-template <int FORM>
-__global__ void __launch_bounds__(TPB, PS_BUS_MINB) bus_kernel(const __grid_constant__ DevPlan P, const __grid_constant__ EvalArgs A) {
-  extern __shared__ double smem[];
-  const int s0 = blockIdx.y * A.chunk, s1 = min(A.S, s0 + A.chunk);
-  if ((int)blockIdx.x >= P.n_bus_tiles) {
-    if (A.scal) objective_tile(P, A, s0, s1, smem);
-    return;
-  }
+// FULL = the whole evaluation (g + J + H) without a status mask: the output flags are compile-time constants there,
+// which keeps the hot instantiation free of predicated stores and of the loop versions the compiler otherwise clones
+template <int FORM, bool FULL>
+__device__ __forceinline__ void bus_tile_body(const DevPlan& P, const EvalArgs& A, double* smem, int s0, int s1) {
   if constexpr (has_bus_rows(FORM)) {
     constexpr int NJ = he_nj(FORM), NH = he_nh(FORM), NP = he_np(FORM);
     const Tile tl = P.tiles[blockIdx.x];
-    const bool wg = (A.what & EV_G) != 0, wj = (A.what & EV_J) != 0, wh = (A.what & EV_H) != 0;
+    const bool wg = FULL || (A.what & EV_G) != 0, wj = FULL || (A.what & EV_J) != 0, wh = FULL || (A.what & EV_H) != 0;
     const int tid = threadIdx.x;
     // bus-owner threads are taken from the END of the CTA: the half-edge phase fills the first warps, so the per-bus
     // work (own terms, residuals) runs on warps that would otherwise idle at the barrier instead of lengthening warp 0
@@ -936,7 +932,7 @@ __global__ void __launch_bounds__(TPB, PS_BUS_MINB) bus_kernel(const __grid_cons
       B.oh = NH * T.nhe + (P.bus_hpp[u] - T.ch0) - NH * B.h0;
       B.Gl = P.Gl[u]; B.Bl = P.Bl[u];
     }
-    const bool has_status = A.status != nullptr;
+    const bool has_status = !FULL && A.status != nullptr;
     const bool need_g = wg || A.scal;
     __syncthreads();
     bus_gather<FORM>(P, A, T, tl, s0, T.xb0);
@@ -986,6 +982,18 @@ __global__ void __launch_bounds__(TPB, PS_BUS_MINB) bus_kernel(const __grid_cons
       __syncthreads();
     }
   }
+}
+
+template <int FORM>
+__global__ void __launch_bounds__(TPB, PS_BUS_MINB) bus_kernel(const __grid_constant__ DevPlan P, const __grid_constant__ EvalArgs A) {
+  extern __shared__ double smem[];
+  const int s0 = blockIdx.y * A.chunk, s1 = min(A.S, s0 + A.chunk);
+  if ((int)blockIdx.x >= P.n_bus_tiles) {
+    if (A.scal) objective_tile(P, A, s0, s1, smem);
+    return;
+  }
+  if ((A.what & (EV_G | EV_J | EV_H)) == (EV_G | EV_J | EV_H) && A.status == nullptr) bus_tile_body<FORM, true>(P, A, smem, s0, s1);
+  else bus_tile_body<FORM, false>(P, A, smem, s0, s1);
 }
 
 // ---- PB* balances, fast path (PBRAPV / PBRARV without switched shunts) ------------------------------------------

@@ -225,7 +225,7 @@ int ps_create(const ps_network* net, int formulation, int source_type, int flags
   hn.cost_order = net->cost_order;
 
   ps_handle* h = new ps_handle();
-  const std::string msg = build_plan(hn, formulation, source_type, flags, TPB, h->plan);
+  const std::string msg = build_plan(hn, formulation, source_type, flags, TPB, BTPB, h->plan);
   if (!msg.empty()) {
     const bool arg = msg.rfind("unknown", 0) == 0;
     delete h;

@@ -696,7 +696,7 @@ template <int FORM>
 __device__ __forceinline__ void bus_gather(const DevPlan& P, const EvalArgs& A, const BusTile& T, const Tile& tl, int s, double* xs) {
   const double* __restrict__ x = A.x + (long long)s * A.ldx;
   const int tid = threadIdx.x;
-  for (int q = tid; q < T.nbt; q += TPB) {
+  for (int q = tid; q < T.nbt; q += BTPB) {
     cp_async8(xs + q, x + P.o_a + tl.u0 + q);
     cp_async8(xs + T.nbt + q, x + P.o_b + tl.u0 + q);
     if constexpr (FORM == CBRAWV) cp_async8(xs + T.xw + q, x + P.o_Wd + tl.u0 + q);
@@ -707,9 +707,9 @@ __device__ __forceinline__ void bus_gather(const DevPlan& P, const EvalArgs& A, 
   }
   if (A.what & EV_H) {
     const double* __restrict__ mu = A.mu + (long long)s * A.ldmu + 2 * tl.u0;
-    for (int q = tid; q < 2 * T.nbt; q += TPB) cp_async8(xs + T.xm + q, mu + q);
+    for (int q = tid; q < 2 * T.nbt; q += BTPB) cp_async8(xs + T.xm + q, mu + q);
   }
-  for (int q = tid; q < T.nhe; q += TPB) {
+  for (int q = tid; q < T.nhe; q += BTPB) {
     const int ks = T.heks[q], k = ks >> 1, side = ks & 1;
     if constexpr (is_PN(FORM)) {
       const int b = T.hoth[q];
@@ -720,12 +720,12 @@ __device__ __forceinline__ void bus_gather(const DevPlan& P, const EvalArgs& A, 
       cp_async8(xs + T.xh + 2 * q + 1, x + P.o_f[1 + 2 * side] + k);
     }
   }
-  for (int q = tid; q < T.ngt; q += TPB) {
+  for (int q = tid; q < T.ngt; q += BTPB) {
     const int g = T.sgen[q];
     cp_async8(xs + T.xg + 2 * q, x + P.o_pg + g);
     cp_async8(xs + T.xg + 2 * q + 1, x + P.o_qg + g);
   }
-  for (int q = tid; q < T.nsh; q += TPB) cp_async8(xs + T.xs_ + q, x + P.o_bss + T.ssh[q]);
+  for (int q = tid; q < T.nsh; q += BTPB) cp_async8(xs + T.xs_ + q, x + P.o_bss + T.ssh[q]);
 }
 
 // ------------------------------------------------------------------------------- helpers
@@ -847,7 +847,7 @@ __global__ void __launch_bounds__(TPB) branch_staged_kernel(const __grid_constan
 // cell of their first contribution, left to right in emission order; the list is sorted by contribution count so the
 // lanes of a warp run the same number of additions.  After that every slot has exactly one source cell.
 __device__ __forceinline__ void reduce_multi(double* cb, const uint16_t* mdst, const uint16_t* mptr, const uint16_t* mlist, int mn) {
-  for (int m = threadIdx.x; m < mn; m += TPB) {
+  for (int m = threadIdx.x; m < mn; m += BTPB) {
     const int d = mdst[m];
     double v = cb[d];
     for (int q = mptr[m], q1 = mptr[m + 1]; q < q1; q++) v = v + cb[mlist[q]];
@@ -855,13 +855,14 @@ __device__ __forceinline__ void reduce_multi(double* cb, const uint16_t* mdst, c
   }
 }
 __device__ __forceinline__ void slots_out(double* __restrict__ dst, int n, const double* cb, const uint16_t* src) {
-  copy_aligned<TPB>(dst, n, threadIdx.x, [&](int e) { return cb[src[e]]; });
+  copy_aligned<BTPB>(dst, n, threadIdx.x, [&](int e) { return cb[src[e]]; });
 }
 
 // Bus rows (nodal balances, formulations.jl:170-297) plus, in the last CTA column, the objective scalar.
 #ifndef PS_BUS_MINB
 #define PS_BUS_MINB 5
 #endif
+// threads per bus-tile CTA (the plan sizes the bus tiles for it: ps_capi.cu passes BTPB to build_plan)
 // FULL = the whole evaluation (g + J + H) without a status mask: the output flags are compile-time constants there,
 // which keeps the hot instantiation free of predicated stores and of the loop versions the compiler otherwise clones
 template <int FORM, bool FULL>
@@ -873,7 +874,7 @@ __device__ __forceinline__ void bus_tile_body(const DevPlan& P, const EvalArgs& 
     const int tid = threadIdx.x;
     // bus-owner threads are taken from the END of the CTA: the half-edge phase fills the first warps, so the per-bus
     // work (own terms, residuals) runs on warps that would otherwise idle at the barrier instead of lengthening warp 0
-    const int lb = TPB - 1 - tid;                  // tile-local bus of this thread
+    const int lb = BTPB - 1 - tid;                  // tile-local bus of this thread
     const int u = tl.u0 + lb;
     const bool act = u < tl.u1;
     const bool facts = (P.flags & FLAG_FACTS) != 0;
@@ -904,7 +905,7 @@ __device__ __forceinline__ void bus_tile_body(const DevPlan& P, const EvalArgs& 
     T.mlist = T.mptr + (tl.mjn + tl.mhn + 2);     // [mjln | mhln]
     T.sst = (uint8_t*)(T.mlist + (tl.mjln + tl.mhln));
     // ---- scenario-independent staging (once per CTA)
-    for (int q = tid; q < T.nhe; q += TPB) {
+    for (int q = tid; q < T.nhe; q += BTPB) {
       T.heks[q] = P.he_ks[T.hp0 + q];
       T.hbus[q] = (uint16_t)(P.he_bus[T.hp0 + q] - tl.u0);
       if constexpr (is_PN(FORM)) {
@@ -913,16 +914,16 @@ __device__ __forceinline__ void bus_tile_body(const DevPlan& P, const EvalArgs& 
         for (int c = 0; c < 4; c++) T.hc[c * T.nhe + q] = P.he_c[(long long)c * P.nhe + T.hp0 + q];
       }
     }
-    for (int q = tid; q < T.ngt; q += TPB) T.sgen[q] = P.gen_idx[T.gp0 + q];
-    for (int q = tid; q < T.nsh; q += TPB) T.ssh[q] = P.sh_idx[T.sp0 + q];
-    for (int q = tid; q < tl.jn; q += TPB) T.jsrc[q] = (uint16_t)P.jsrc[tl.j0 + q];
-    for (int q = tid; q < tl.hn; q += TPB) T.hsrc[q] = (uint16_t)P.hsrc[tl.h0 + q];
-    for (int q = tid; q < tl.mjn; q += TPB) T.mdst[q] = (uint16_t)P.ms_dst[tl.mj0 + q];
-    for (int q = tid; q < tl.mhn; q += TPB) T.mdst[tl.mjn + q] = (uint16_t)P.ms_dst[tl.mh0 + q];
-    for (int q = tid; q <= tl.mjn; q += TPB) T.mptr[q] = (uint16_t)P.ms_ptr[tl.mj0 + q];
-    for (int q = tid; q <= tl.mhn; q += TPB) T.mptr[tl.mjn + 1 + q] = (uint16_t)P.ms_ptr[tl.mh0 + q];
-    for (int q = tid; q < tl.mjln; q += TPB) T.mlist[q] = (uint16_t)P.ms_list[tl.mjl0 + q];
-    for (int q = tid; q < tl.mhln; q += TPB) T.mlist[tl.mjln + q] = (uint16_t)P.ms_list[tl.mhl0 + q];
+    for (int q = tid; q < T.ngt; q += BTPB) T.sgen[q] = P.gen_idx[T.gp0 + q];
+    for (int q = tid; q < T.nsh; q += BTPB) T.ssh[q] = P.sh_idx[T.sp0 + q];
+    for (int q = tid; q < tl.jn; q += BTPB) T.jsrc[q] = (uint16_t)P.jsrc[tl.j0 + q];
+    for (int q = tid; q < tl.hn; q += BTPB) T.hsrc[q] = (uint16_t)P.hsrc[tl.h0 + q];
+    for (int q = tid; q < tl.mjn; q += BTPB) T.mdst[q] = (uint16_t)P.ms_dst[tl.mj0 + q];
+    for (int q = tid; q < tl.mhn; q += BTPB) T.mdst[tl.mjn + q] = (uint16_t)P.ms_dst[tl.mh0 + q];
+    for (int q = tid; q <= tl.mjn; q += BTPB) T.mptr[q] = (uint16_t)P.ms_ptr[tl.mj0 + q];
+    for (int q = tid; q <= tl.mhn; q += BTPB) T.mptr[tl.mjn + 1 + q] = (uint16_t)P.ms_ptr[tl.mh0 + q];
+    for (int q = tid; q < tl.mjln; q += BTPB) T.mlist[q] = (uint16_t)P.ms_list[tl.mjl0 + q];
+    for (int q = tid; q < tl.mhln; q += BTPB) T.mlist[tl.mjln + q] = (uint16_t)P.ms_list[tl.mhl0 + q];
     BusInv B{};
     if (act) {
       B.g0 = P.gen_ptr[u] - T.gp0; B.g1 = P.gen_ptr[u + 1] - T.gp0;
@@ -944,12 +945,12 @@ __device__ __forceinline__ void bus_tile_body(const DevPlan& P, const EvalArgs& 
       cp_async_commit();
       if (has_status) {
         const uint8_t* __restrict__ stp = A.status + (long long)s * A.ldst;
-        for (int q = tid; q < T.nhe; q += TPB) T.sst[q] = stp[T.heks[q] >> 1];
+        for (int q = tid; q < T.nhe; q += BTPB) T.sst[q] = stp[T.heks[q] >> 1];
       }
       cp_async_wait<1>();                                                          // this scenario's gather has landed
       __syncthreads();
       // ---- phase 1: half-edge-parallel contributions (J and H cells, residual pieces); the bus's own terms
-      for (int q = tid; q < T.nhe; q += TPB) {
+      for (int q = tid; q < T.nhe; q += BTPB) {
         SeqW sj{T.cbj + q, T.nhe, wj}, sh{T.cbh + q, T.nhe, wh};
         he_terms<FORM>(T, xs, q, sj, sh, need_g, has_status);
       }
@@ -985,13 +986,9 @@ __device__ __forceinline__ void bus_tile_body(const DevPlan& P, const EvalArgs& 
 }
 
 template <int FORM>
-__global__ void __launch_bounds__(TPB, PS_BUS_MINB) bus_kernel(const __grid_constant__ DevPlan P, const __grid_constant__ EvalArgs A) {
+__global__ void __launch_bounds__(BTPB, PS_BUS_MINB) bus_kernel(const __grid_constant__ DevPlan P, const __grid_constant__ EvalArgs A) {
   extern __shared__ double smem[];
   const int s0 = blockIdx.y * A.chunk, s1 = min(A.S, s0 + A.chunk);
-  if ((int)blockIdx.x >= P.n_bus_tiles) {
-    if (A.scal) objective_tile(P, A, s0, s1, smem);
-    return;
-  }
   if ((A.what & (EV_G | EV_J | EV_H)) == (EV_G | EV_J | EV_H) && A.status == nullptr) bus_tile_body<FORM, true>(P, A, smem, s0, s1);
   else bus_tile_body<FORM, false>(P, A, smem, s0, s1);
 }
@@ -1375,7 +1372,7 @@ cudaError_t launch_form(const DevPlan& P, const EvalArgs& A, size_t smem, cudaSt
 
 template <int FORM>
 cudaError_t launch_bus_form(const DevPlan& P, const EvalArgs& A, size_t smem, cudaStream_t st, dim3 grid) {
-  bus_kernel<FORM><<<grid, TPB, smem, st>>>(P, A);
+  bus_kernel<FORM><<<grid, BTPB, smem, st>>>(P, A);
   return cudaGetLastError();
 }
 
@@ -1671,12 +1668,19 @@ cudaError_t launch_eval(const DevPlan& P, const EvalArgs& A0, int64_t smem_branc
     A.chunk = env_int("PS_CHUNK_BUS", (int)(c < 1 ? 1 : (c > 32 ? 32 : c)));
     const int nchunks = (A.S + A.chunk - 1) / A.chunk;
     if (nchunks > 65535) return cudaErrorInvalidConfiguration;
-    if (launches) *launches += 1;
-    {
+    if (P.n_bus_tiles > 0) {
+      if (launches) *launches += 1;
       KTimer kt(ev, ev_mask, stream, K_BUS);
-      e = launch_bus(P, A, (size_t)smem_bus_bytes, stream, dim3((unsigned)P.n_bus_tiles + 1, (unsigned)nchunks));
+      e = launch_bus(P, A, (size_t)smem_bus_bytes, stream, dim3((unsigned)P.n_bus_tiles, (unsigned)nchunks));
     }
     if (e != cudaSuccess) return e;
+    if (A.scal) {                                  // objective scalar: its own small launch (fixed reduction shape)
+      if (launches) *launches += 1;
+      KTimer kt(ev, ev_mask, stream, K_OBJ);
+      objective_kernel<<<dim3((unsigned)nchunks), TPB, 0, stream>>>(P, A);
+      e = cudaGetLastError();
+      if (e != cudaSuccess) return e;
+    }
   }
   if (P.nr == 0 || !(A.what & (EV_G | EV_J | EV_H)) ) {
     if (P.nr == 0 || !A.scal) return e;

@@ -11,7 +11,11 @@ namespace ps {
 #ifndef PS_TPB
 #define PS_TPB 128
 #endif
-constexpr int TPB = PS_TPB;         // threads per CTA == units (branches / buses) per tile
+constexpr int TPB = PS_TPB;         // threads per CTA == branches per tile
+#ifndef PS_BUS_TPB
+#define PS_BUS_TPB 128
+#endif
+constexpr int BTPB = PS_BUS_TPB;    // threads per bus-tile CTA (at most BTPB buses per tile)
 constexpr int NSCAL = 4;            // PS_NSCALARS
 
 struct DevPlan {                    // passed to kernels by value (constant bank)

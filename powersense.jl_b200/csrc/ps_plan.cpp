@@ -66,7 +66,7 @@ void append_row(Plan& P, int64_t row, const RowCanon& c, bool eq) {
 
 }  // namespace
 
-std::string build_plan(const HostNet& net, int form, int src, int flags, int tpb, Plan& P) {
+std::string build_plan(const HostNet& net, int form, int src, int flags, int tpb, int bus_tpb, Plan& P) {
   if (form < 0 || form >= NFORM) return "unknown formulation code";
   if (src != SRC_MATPOWER && src != SRC_ARPAE) return "unknown source_type code";
   P = Plan();
@@ -424,7 +424,7 @@ std::string build_plan(const HostNet& net, int form, int src, int flags, int tpb
     while (u0 < nb) {
       int64_t u1 = u0 + 1;
       if (bus_tile_bytes(u0, u1) > hard) return "a bus does not fit in shared memory (bus degree too large)";
-      while (u1 < nb && u1 - u0 < tpb && bus_tile_bytes(u0, u1 + 1) <= budget &&
+      while (u1 < nb && u1 - u0 < bus_tpb && bus_tile_bytes(u0, u1 + 1) <= budget &&
              P.bus_jpp[u1 + 1] - P.bus_jpp[u0] < 60000 && P.bus_hpp[u1 + 1] - P.bus_hpp[u0] < 60000) u1++;
       Tile t{};
       t.kind = 0; t.u0 = (int32_t)u0; t.u1 = (int32_t)u1;
@@ -484,7 +484,7 @@ std::string build_plan(const HostNet& net, int form, int src, int flags, int tpb
       u0 = u1;
     }
   }
-  P.tile_units_bus = tpb;
+  P.tile_units_bus = bus_tpb;
   P.n_bus_tiles = (int)P.tiles.size();
   P.NRP = pat.nrows | 1; P.RJP = P.RJ | 1; P.RHP = P.RH | 1;
   const int64_t mxb = nr > 0 ? (int64_t)8 * tpb * (P.NRP + P.RJP + P.RHP) : 0;

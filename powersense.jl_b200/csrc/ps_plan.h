@@ -80,6 +80,6 @@ struct Plan {
 };
 
 // returns "" on success, else an error message
-std::string build_plan(const HostNet& net, int form, int src, int flags, int tpb, Plan& out);
+std::string build_plan(const HostNet& net, int form, int src, int flags, int tpb, int bus_tpb, Plan& out);
 
 }  // namespace ps

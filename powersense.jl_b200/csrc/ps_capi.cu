@@ -327,6 +327,13 @@ int ps_create(const ps_network* net, int formulation, int source_type, int flags
   D.he_bus = M.upload(P.he_bus); D.jsrc = M.upload(P.jsrc); D.hsrc = M.upload(P.hsrc);
   D.ms_dst = M.upload(P.ms_dst); D.ms_ptr = M.upload(P.ms_ptr); D.ms_list = M.upload(P.ms_list);
   D.tiles = M.upload(P.tiles);
+  D.n_wtiles = (int)P.wtiles.size();
+  D.wtiles = M.upload(P.wtiles);
+  D.wt_jspace = P.wt_jspace; D.wt_hspace = P.wt_hspace; D.wt_gspace = P.wt_gspace; D.wt_lists = P.wt_lists_max;
+  D.wt_dst = M.upload(P.wt_dst); D.wt_mdst = M.upload(P.wt_mdst); D.wt_mx0 = M.upload(P.wt_mx0);
+  D.wt_mcnt = M.upload(P.wt_mcnt); D.wt_ownj = M.upload(P.wt_ownj); D.wt_ownh = M.upload(P.wt_ownh);
+  D.wt_owng = M.upload(P.wt_owng);
+  D.wt_ownj_ptr = M.upload(P.wt_ownj_ptr); D.wt_ownh_ptr = M.upload(P.wt_ownh_ptr); D.wt_owng_ptr = M.upload(P.wt_owng_ptr);
   // single-scenario staging
   const int64_t n_in = P.n_var + P.m_nl, n_out = P.m_nl + P.nnzJ + P.nnzH + NSCAL;
   h->d_x = M.alloc<double>(P.n_var); h->d_mu = M.alloc<double>(P.m_nl);
@@ -336,7 +343,7 @@ int ps_create(const ps_network* net, int formulation, int source_type, int flags
   if ((e = cudaHostAlloc((void**)&h->h_in, std::max<int64_t>(n_in, 1) * sizeof(double), cudaHostAllocDefault)) != cudaSuccess ||
       (e = cudaHostAlloc((void**)&h->h_out, std::max<int64_t>(n_out, 1) * sizeof(double), cudaHostAllocDefault)) != cudaSuccess ||
       (e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking)) != cudaSuccess ||
-      (e = configure_eval(P.form, P.src, P.smem_branch_bytes, P.smem_bus_bytes)) != cudaSuccess) {
+      (e = configure_eval(P.form, P.src, P.smem_branch_bytes, P.smem_bus_bytes, wt_smem_bytes(D))) != cudaSuccess) {
     ps_destroy(h);
     return cuda_fail(nullptr, e, "handle setup");
   }

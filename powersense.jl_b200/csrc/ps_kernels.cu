@@ -510,6 +510,14 @@ __device__ __forceinline__ void cp_async8(void* smem_dst, const void* gsrc) {
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
 template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
+// TMA bulk copy shared -> global (SASS UBLKCP): the copy engine writes whole lines, the LSU carries no global stores
+__device__ __forceinline__ void bulk_store(double* gdst, const double* ssrc, int bytes) {
+  const unsigned sa = (unsigned)__cvta_generic_to_shared(ssrc);
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(sa), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 // shared-memory view of one bus tile
 struct BusTile {
@@ -531,40 +539,45 @@ struct BusInv {
 
 // One half-edge: contributions in the emission order of ps_plan.cpp (which is the reference's source order), and the
 // pieces of the flow term for the residual.  xs = gathered inputs of this scenario.
-template <int FORM>
-__device__ __forceinline__ void he_terms(const BusTile& T, const double* __restrict__ xs, int q, SeqW& sj, SeqW& sh,
-                                         bool want_pieces, bool has_status) {
-  const int side = T.heks[q] & 1;
-  const int lb = T.hbus[q];
-  const double st = has_status ? (double)T.sst[q] : 1.0;
-  const double v0 = xs[T.xh + 2 * q], v1 = xs[T.xh + 2 * q + 1];
-  const double va0 = xs[lb], vb0 = xs[T.nbt + lb];             // own voltage: (theta_i, V_i) | (vi_i, vr_i)
-  const double muP = sh.on ? xs[T.xm + 2 * lb] : 0.0, muQ = sh.on ? xs[T.xm + 2 * lb + 1] : 0.0;
-  double* gpq = T.gp + q;
+// inputs of one half-edge: side, status, the two x entries of the far end (PN*: neighbour voltage) or of the branch
+// (flow / current variables), the own voltage (theta_i, V_i) | (vi_i, vr_i), the row multipliers, PN* constants
+struct HeIn {
+  int side;
+  double st, v0, v1, va0, vb0, muP, muQ, c0, c1, c2, c3;
+};
+struct PieceW {                    // residual pieces of the CTA-tile kernel: [np][nhe]
+  double* p;
+  int stride;
+  __device__ __forceinline__ void operator()(int k, double v) const { p[k * stride] = v; }
+};
+template <int FORM, class WJ, class WH, class PC>
+__device__ __forceinline__ void he_math(const HeIn& in, WJ& sj, WH& sh, const PC& piece, bool want_pieces) {
+  const int side = in.side;
+  const double st = in.st, v0 = in.v0, v1 = in.v1, va0 = in.va0, vb0 = in.vb0, muP = in.muP, muQ = in.muQ;
   if constexpr (FORM == PBRAPV || FORM == PBRARV) {            // :188-196
     sj.put(st);
     sj.put(st);
   } else if constexpr (FORM == CBRARV || FORM == CBRAWV) {     // :206-214  T4, v0/v1 = Ir / Ii
     const double Ir = v0, Ii = v1, ra = vb0, ia = va0;
     if (want_pieces) {
-      gpq[0] = st * (ra * Ir); gpq[T.nhe] = st * (ia * Ii);
-      gpq[2 * T.nhe] = st * (ia * Ir); gpq[3 * T.nhe] = st * (ra * Ii);
+      piece(0, st * (ra * Ir)); piece(1, st * (ia * Ii));
+      piece(2, st * (ia * Ir)); piece(3, st * (ra * Ii));
     }
     sj.put(st * Ir); sj.put(st * Ii); sj.put(st * ra); sj.put(st * ia);          // P: d/d(ra, ia, Ir, Ii)
     sj.put(-st * Ii); sj.put(st * Ir); sj.put(st * ia); sj.put(-st * ra);        // Q
     sh.put(0.0); sh.put(0.0); sh.put(st * muP); sh.put(0.0); sh.put(0.0); sh.put(st * muP);
     sh.put(0.0); sh.put(0.0); sh.put(st * muQ); sh.put(0.0); sh.put(0.0); sh.put(-st * muQ);
   } else if constexpr (FORM == PNPAPV || FORM == PNRAPV) {     // :215-234  T2 / T1, v0/v1 = theta_b / V_b
-    const double gs = st * T.hc[q], bs = st * T.hc[T.nhe + q];
+    const double gs = st * in.c0, bs = st * in.c1;
     const double thb = v0, Vb = v1, Va = vb0, dl = va0 - thb;
     double A, Bt;
     if constexpr (FORM == PNPAPV) {
-      const double Y = st * T.hc[2 * T.nhe + q], phi = T.hc[3 * T.nhe + q];
+      const double Y = st * in.c2, phi = in.c3;
       double s, c;
       sincos(dl - phi, &s, &c);
       A = Y * c; Bt = -(Y * s);
     } else {
-      const double G = st * T.hc[2 * T.nhe + q], B = st * T.hc[3 * T.nhe + q];
+      const double G = st * in.c2, B = st * in.c3;
       double s, c;
       sincos(dl, &s, &c);
       A = G * c + B * s; Bt = B * c - G * s;
@@ -572,8 +585,8 @@ __device__ __forceinline__ void he_terms(const BusTile& T, const double* __restr
     const double Vf = side ? Vb : Va, Vt = side ? Va : Vb;    // source order V[f]*V[t]
     const double VV = Va * Vb;
     if (want_pieces) {                                         // acc = (acc -/+ p1) -/+ p2
-      gpq[0] = gs * (Va * Va); gpq[T.nhe] = A * Vf * Vt;
-      gpq[2 * T.nhe] = bs * (Va * Va); gpq[3 * T.nhe] = Bt * Vf * Vt;
+      piece(0, gs * (Va * Va)); piece(1, A * Vf * Vt);
+      piece(2, bs * (Va * Va)); piece(3, Bt * Vf * Vt);
     }
     // J: d/d(th_a, th_b, V_a, V_b)
     sj.put(-Bt * VV); sj.put(Bt * VV); sj.put(-2.0 * gs * Va - A * Vb); sj.put(-A * Va);
@@ -584,13 +597,13 @@ __device__ __forceinline__ void he_terms(const BusTile& T, const double* __restr
     sh.put(-muQ * Bt * VV); sh.put(-muQ * Bt * VV); sh.put(muQ * 2.0 * bs); sh.put(0.0); sh.put(muQ * Bt * VV);
     sh.put(-muQ * A * Vb); sh.put(-muQ * A * Va); sh.put(muQ * A * Vb); sh.put(muQ * A * Va); sh.put(muQ * Bt);
   } else if constexpr (FORM == PNRARV) {                       // :235-243  T3, v0/v1 = vi_b / vr_b
-    const double gs = st * T.hc[q], bs = st * T.hc[T.nhe + q];
-    const double G = st * T.hc[2 * T.nhe + q], B = st * T.hc[3 * T.nhe + q];
+    const double gs = st * in.c0, bs = st * in.c1;
+    const double G = st * in.c2, B = st * in.c3;
     const double ra = vb0, ia = va0, rb = v1, ib = v0;
     const double A2 = ra * ra + ia * ia, C = ra * rb + ia * ib, S = ra * ib - ia * rb;
     if (want_pieces) {                                         // P: ((acc - p0) - p1) + p2 ; Q: ((acc + p3) + p4) + p5
-      gpq[0] = gs * A2; gpq[T.nhe] = G * C; gpq[2 * T.nhe] = B * S;
-      gpq[3 * T.nhe] = bs * A2; gpq[4 * T.nhe] = B * C; gpq[5 * T.nhe] = G * S;
+      piece(0, gs * A2); piece(1, G * C); piece(2, B * S);
+      piece(3, bs * A2); piece(4, B * C); piece(5, G * S);
     }
     // J: d/d(ra, ia, rb, ib)
     sj.put(-2.0 * gs * ra - G * rb + B * ib); sj.put(-2.0 * gs * ia - G * ib - B * rb);
@@ -605,20 +618,41 @@ __device__ __forceinline__ void he_terms(const BusTile& T, const double* __restr
   }
 }
 
-// Generator and shunt contributions of one bus (everything of the bus that is not a half-edge)
+// the CTA-tile kernel's view: inputs from the gathered shared array, contributions to type-major cells
 template <int FORM>
-__device__ __forceinline__ void bus_own_terms(const DevPlan& P, const BusTile& T, const BusInv& B, const double* __restrict__ xs,
-                                              int lu, SeqW sjg, SeqW sjs, SeqW shs) {
-  for (int q = B.g0; q < B.g1; q++) { sjg.put(1.0); sjg.put(1.0); }     // :177-180
-  const double muP = shs.on ? xs[T.xm + 2 * lu] : 0.0, muQ = shs.on ? xs[T.xm + 2 * lu + 1] : 0.0;
-  const double va0 = xs[lu], vb0 = xs[T.nbt + lu];
-  const double Gl = B.Gl, Bl = B.Bl;
+__device__ __forceinline__ void he_terms(const BusTile& T, const double* __restrict__ xs, int q, SeqW& sj, SeqW& sh,
+                                         bool want_pieces, bool has_status) {
+  HeIn in;
+  in.side = T.heks[q] & 1;
+  const int lb = T.hbus[q];
+  in.st = has_status ? (double)T.sst[q] : 1.0;
+  in.v0 = xs[T.xh + 2 * q]; in.v1 = xs[T.xh + 2 * q + 1];
+  in.va0 = xs[lb]; in.vb0 = xs[T.nbt + lb];                    // own voltage: (theta_i, V_i) | (vi_i, vr_i)
+  in.muP = sh.on ? xs[T.xm + 2 * lb] : 0.0; in.muQ = sh.on ? xs[T.xm + 2 * lb + 1] : 0.0;
+  if constexpr (is_PN(FORM)) { in.c0 = T.hc[q]; in.c1 = T.hc[T.nhe + q]; in.c2 = T.hc[2 * T.nhe + q]; in.c3 = T.hc[3 * T.nhe + q]; }
+  else { in.c0 = in.c1 = in.c2 = in.c3 = 0.0; }
+  he_math<FORM>(in, sj, sh, PieceW{T.gp + q, T.nhe}, want_pieces);
+}
+
+// Generator and shunt contributions of one bus (everything of the bus that is not a half-edge).
+// bss(q) = value of the q-th switched-shunt variable of the bus; sjg / sjs / shs = writers of the generator J entries,
+// the shunt J entries and the shunt H entries (emission order of ps_plan.cpp)
+struct OwnIn {
+  double va0, vb0, W, muP, muQ, Gl, Bl;
+  int ngen, nsh;
+};
+template <int FORM, class BSS, class WJ, class WH>
+__device__ __forceinline__ void own_math(const OwnIn& o, const BSS& bssv, WJ& sjg, WJ& sjs, WH& shs) {
+  for (int q = 0; q < o.ngen; q++) { sjg.put(1.0); sjg.put(1.0); }     // :177-180
+  const double muP = o.muP, muQ = o.muQ;
+  const double va0 = o.va0, vb0 = o.vb0;
+  const double Gl = o.Gl, Bl = o.Bl;
   if constexpr (is_polar(FORM)) {                                       // :256-263
     const double V = vb0, V2 = V * V;
     sjs.put(-2.0 * Gl * V); sjs.put(2.0 * Bl * V);
     shs.put(-2.0 * Gl * muP); shs.put(2.0 * Bl * muQ);
-    for (int q = B.f0; q < B.f1; q++) {
-      const double bss = xs[T.xs_ + q];
+    for (int q = 0; q < o.nsh; q++) {
+      const double bss = bssv(q);
       sjs.put(V2); sjs.put(2.0 * bss * V);
       shs.put(0.0); shs.put(2.0 * bss * muQ); shs.put(2.0 * V * muQ);
     }
@@ -626,69 +660,104 @@ __device__ __forceinline__ void bus_own_terms(const DevPlan& P, const BusTile& T
     const double r = vb0, im = va0, A2 = r * r + im * im;
     sjs.put(-2.0 * Gl * r); sjs.put(-2.0 * Gl * im); sjs.put(2.0 * Bl * r); sjs.put(2.0 * Bl * im);
     shs.put(-2.0 * Gl * muP); shs.put(-2.0 * Gl * muP); shs.put(2.0 * Bl * muQ); shs.put(2.0 * Bl * muQ);
-    for (int q = B.f0; q < B.f1; q++) {
-      const double bss = xs[T.xs_ + q];
+    for (int q = 0; q < o.nsh; q++) {
+      const double bss = bssv(q);
       sjs.put(A2); sjs.put(2.0 * bss * r); sjs.put(2.0 * bss * im);
       shs.put(0.0); shs.put(2.0 * bss * muQ); shs.put(2.0 * bss * muQ);
       shs.put(2.0 * r * muQ); shs.put(2.0 * im * muQ); shs.put(0.0);
     }
   } else if constexpr (FORM == CBRAWV) {                                // :272-279
-    const double W = xs[T.xw + lu];
+    const double W = o.W;
     sjs.put(-Gl); sjs.put(Bl);
-    for (int q = B.f0; q < B.f1; q++) {
-      const double bss = xs[T.xs_ + q];
+    for (int q = 0; q < o.nsh; q++) {
+      const double bss = bssv(q);
       sjs.put(W); sjs.put(bss);
       shs.put(0.0); shs.put(0.0); shs.put(muQ);
     }
   }
 }
+template <int FORM>
+__device__ __forceinline__ void bus_own_terms(const DevPlan& P, const BusTile& T, const BusInv& B, const double* __restrict__ xs,
+                                              int lu, SeqW sjg, SeqW sjs, SeqW shs) {
+  OwnIn o;
+  o.muP = shs.on ? xs[T.xm + 2 * lu] : 0.0; o.muQ = shs.on ? xs[T.xm + 2 * lu + 1] : 0.0;
+  o.va0 = xs[lu]; o.vb0 = xs[T.nbt + lu];
+  o.W = 0.0;
+  if constexpr (FORM == CBRAWV) o.W = xs[T.xw + lu];
+  o.Gl = B.Gl; o.Bl = B.Bl;
+  o.ngen = B.g1 - B.g0; o.nsh = B.f1 - B.f0;
+  own_math<FORM>(o, [&](int q) { return xs[T.xs_ + B.f0 + q]; }, sjg, sjs, shs);
+}
 
-// The two residuals of one bus from the staged pieces, in the reference's order and association (:171-292)
+// The two residuals of one bus from the staged pieces, in the reference's order and association (:171-292).
+// gen(q, pg, qg): injections of the bus's q-th generator; flow(q, st, fp, fq): status and flow variables of its q-th
+// half-edge (PB*); piece(q, k): k-th staged piece of its q-th half-edge; bssv(q): switched-shunt variables
+template <int FORM, class GEN, class FLOW, class PIECE, class BSS>
+__device__ __forceinline__ void residual_math(const OwnIn& o, int deg, double Pd, double Qd, const GEN& gen, const FLOW& flow,
+                                              const PIECE& g, const BSS& bssv, double& gP, double& gQ) {
+  double accP = 0.0, accQ = 0.0;                               // :171-172
+  for (int q = 0; q < o.ngen; q++) {                           // :177-180
+    double pg, qg;
+    gen(q, pg, qg);
+    accP = accP + pg;
+    accQ = accQ + qg;
+  }
+  for (int q = 0; q < deg; q++) {                              // Sij ascending, then Sji ascending
+    if constexpr (FORM == PBRAPV || FORM == PBRARV) {
+      double st, fp, fq;
+      flow(q, st, fp, fq);
+      accP = accP + st * fp;
+      accQ = accQ + st * fq;
+    } else if constexpr (is_CB(FORM)) {
+      accP = (accP + g(q, 0)) + g(q, 1);
+      accQ = (accQ + g(q, 2)) - g(q, 3);
+    } else if constexpr (FORM == PNPAPV || FORM == PNRAPV) {
+      accP = (accP - g(q, 0)) - g(q, 1);
+      accQ = (accQ + g(q, 2)) + g(q, 3);
+    } else {
+      accP = ((accP - g(q, 0)) - g(q, 1)) + g(q, 2);
+      accQ = ((accQ + g(q, 3)) + g(q, 4)) + g(q, 5);
+    }
+  }
+  const double va0 = o.va0, vb0 = o.vb0;
+  if constexpr (is_polar(FORM)) {
+    const double V2 = vb0 * vb0;
+    accP = accP - o.Gl * V2;
+    accQ = accQ + o.Bl * V2;
+    for (int q = 0; q < o.nsh; q++) accQ = accQ + bssv(q) * V2;
+  } else if constexpr (FORM == PBRARV || FORM == CBRARV || FORM == PNRARV) {
+    const double A2 = vb0 * vb0 + va0 * va0;
+    accP = accP - o.Gl * A2;
+    accQ = accQ + o.Bl * A2;
+    for (int q = 0; q < o.nsh; q++) accQ = accQ + bssv(q) * A2;
+  } else {
+    const double W = o.W;
+    accP = accP - o.Gl * W;
+    accQ = accQ + o.Bl * W;
+    for (int q = 0; q < o.nsh; q++) accQ = accQ + bssv(q) * W;
+  }
+  gP = accP - Pd;                                              // :291
+  gQ = accQ - Qd;                                              // :292
+}
 template <int FORM>
 __device__ __forceinline__ void bus_residuals(const BusTile& T, const BusInv& B, const double* __restrict__ xs, int lu,
                                               bool has_status, double& gP, double& gQ) {
-  double accP = 0.0, accQ = 0.0;                               // :171-172
-  for (int q = B.g0; q < B.g1; q++) {                          // :177-180
-    accP = accP + xs[T.xg + 2 * q];
-    accQ = accQ + xs[T.xg + 2 * q + 1];
-  }
+  OwnIn o;
+  o.va0 = xs[lu]; o.vb0 = xs[T.nbt + lu];
+  o.W = 0.0;
+  if constexpr (FORM == CBRAWV) o.W = xs[T.xw + lu];
+  o.muP = o.muQ = 0.0;
+  o.Gl = B.Gl; o.Bl = B.Bl;
+  o.ngen = B.g1 - B.g0; o.nsh = B.f1 - B.f0;
   const int nh = T.nhe;
-  for (int q = B.h0; q < B.h1; q++) {                          // Sij ascending, then Sji ascending
-    const double* g = T.gp + q;
-    if constexpr (FORM == PBRAPV || FORM == PBRARV) {
-      const double st = has_status ? (double)T.sst[q] : 1.0;
-      accP = accP + st * xs[T.xh + 2 * q];
-      accQ = accQ + st * xs[T.xh + 2 * q + 1];
-    } else if constexpr (is_CB(FORM)) {
-      accP = (accP + g[0]) + g[nh];
-      accQ = (accQ + g[2 * nh]) - g[3 * nh];
-    } else if constexpr (FORM == PNPAPV || FORM == PNRAPV) {
-      accP = (accP - g[0]) - g[nh];
-      accQ = (accQ + g[2 * nh]) + g[3 * nh];
-    } else {
-      accP = ((accP - g[0]) - g[nh]) + g[2 * nh];
-      accQ = ((accQ + g[3 * nh]) + g[4 * nh]) + g[5 * nh];
-    }
-  }
-  const double va0 = xs[lu], vb0 = xs[T.nbt + lu];
-  if constexpr (is_polar(FORM)) {
-    const double V2 = vb0 * vb0;
-    accP = accP - B.Gl * V2;
-    accQ = accQ + B.Bl * V2;
-    for (int q = B.f0; q < B.f1; q++) accQ = accQ + xs[T.xs_ + q] * V2;
-  } else if constexpr (FORM == PBRARV || FORM == CBRARV || FORM == PNRARV) {
-    const double A2 = vb0 * vb0 + va0 * va0;
-    accP = accP - B.Gl * A2;
-    accQ = accQ + B.Bl * A2;
-    for (int q = B.f0; q < B.f1; q++) accQ = accQ + xs[T.xs_ + q] * A2;
-  } else {
-    const double W = xs[T.xw + lu];
-    accP = accP - B.Gl * W;
-    accQ = accQ + B.Bl * W;
-    for (int q = B.f0; q < B.f1; q++) accQ = accQ + xs[T.xs_ + q] * W;
-  }
-  gP = accP - xs[T.xl + lu];                                   // :291
-  gQ = accQ - xs[T.xl + T.nbt + lu];                           // :292
+  residual_math<FORM>(
+      o, B.h1 - B.h0, xs[T.xl + lu], xs[T.xl + T.nbt + lu],
+      [&](int q, double& pg, double& qg) { pg = xs[T.xg + 2 * (B.g0 + q)]; qg = xs[T.xg + 2 * (B.g0 + q) + 1]; },
+      [&](int q, double& st, double& fp, double& fq) {
+        st = has_status ? (double)T.sst[B.h0 + q] : 1.0;
+        fp = xs[T.xh + 2 * (B.h0 + q)]; fq = xs[T.xh + 2 * (B.h0 + q) + 1];
+      },
+      [&](int q, int k) { return T.gp[k * nh + B.h0 + q]; }, [&](int q) { return xs[T.xs_ + B.f0 + q]; }, gP, gQ);
 }
 
 // issue the cp.async gather of one scenario's inputs of a bus tile
@@ -993,6 +1062,287 @@ __global__ void __launch_bounds__(BTPB, PS_BUS_MINB) bus_kernel(const __grid_con
   else bus_tile_body<FORM, false>(P, A, smem, s0, s1);
 }
 
+// ---- bus rows, warp tiles ---------------------------------------------------------------------------------------
+// The same nodal balances, restructured so that a WARP owns a small tile (<= 32 half-edges, ps_plan.h: WTile) and
+// nothing is shared between warps: no CTA barrier, no cp.async staging, one shared-memory store per contribution.
+// Everything is a slot that sums its contributions left to right in emission order -- the J and H entries and also
+// the two residuals of a bus, written as flat sums of signed terms (x - y == x + (-y) exactly) in the reference's
+// order: generator injections, the pieces of every half-edge, shunt terms, - load.  Per scenario
+//   1. lane = half-edge: inputs straight from global memory (prefetched one scenario ahead in registers); he_math
+//      writes every contribution to its DESTINATION: the slot's own position in a shared-memory image of the tile's
+//      J / H / g block when it is the slot's first contribution, an extra cell behind the image otherwise.  The
+//      destinations (uint16, fixed per lane) live in registers for the whole scenario loop;
+//   2. lane = bus: generator and shunt contributions, the load terms;
+//   3. lane = multi-contribution slot (lists sorted by count): slot += its extra cells, which are contiguous;
+//   4. the image *is* the output: one cp.async.bulk (TMA) per J / H block hands it to the copy engine, which writes
+//      whole lines to HBM while the warp evaluates the next scenario.  An odd first slot is matched by shifting the
+//      image by one double, so that image and destination share their 16-byte phase (any other layout: a coalesced
+//      copy loop).  The residual rows are stored, and folded into the violation scalars, by the lanes.
+#ifndef PS_WT_WPC
+#define PS_WT_WPC 4
+#endif
+constexpr int WPC = PS_WT_WPC;     // warps (= tiles) per CTA
+
+struct RegW {                      // writer through register-held destinations (two uint16 per register)
+  double* base;
+  const uint32_t* d;
+  int k;
+  bool on;
+  __device__ __forceinline__ void put(double v) {
+    if (on) base[(d[k >> 1] >> ((k & 1) * 16)) & 0xffffu] = v;
+    k++;
+  }
+};
+struct ListW {                     // writer through a destination list in shared memory
+  double* base;
+  const uint16_t* d;
+  bool on;
+  __device__ __forceinline__ void put(double v) {
+    if (on) base[*d] = v;
+    d++;
+  }
+};
+// slot += its extra cells, left to right; lane per multi-contribution slot
+__device__ __forceinline__ void reduce_multi_warp(double* sp, const uint16_t* mdst, const uint16_t* mx0, const uint16_t* mcnt,
+                                                  int mn, int lane) {
+  for (int m = lane; m < mn; m += 32) {
+    const int d = mdst[m], n = mcnt[m];
+    const double* xp = sp + mx0[m];
+    double v = sp[d];
+    int q = 0;
+    for (; q + 1 < n; q += 2) { const double a = xp[q], b = xp[q + 1]; v = (v + a) + b; }
+    if (q < n) v = v + xp[q];
+    sp[d] = v;
+  }
+}
+// hand a finished block image to the copy engine (or copy it with the warp when the 16-byte phases differ)
+__device__ __forceinline__ void wt_store_block(double* __restrict__ g, const double* img, int n, int lane) {
+  const unsigned gph = (unsigned)(reinterpret_cast<unsigned long long>(g) >> 3) & 1u;
+  const unsigned sph = ((unsigned)__cvta_generic_to_shared(img) >> 3) & 1u;
+  if (gph == sph) {
+    const int head = (int)gph, mid = (n - head) & ~1;
+    if (lane == 0 && mid > 0) bulk_store(g + head, img + head, mid * 8);
+    if (lane == 1 && head && n > 0) g[0] = img[0];
+    if (lane == 2 && head + mid < n) g[n - 1] = img[n - 1];
+  } else {
+    for (int e = lane; e < n; e += 32) g[e] = img[e];
+  }
+}
+__device__ __forceinline__ void reduce_scalars_redux(double* scal, double vmax, int nviol) {
+  if (!scal) return;
+  if (!(vmax >= 0.0)) vmax = 0.0;                               // NaN is ignored, like fmax does
+  const unsigned long long b = (unsigned long long)__double_as_longlong(vmax);   // non-negative doubles order like their bits
+  const unsigned hi = __reduce_max_sync(0xffffffffu, (unsigned)(b >> 32));
+  const unsigned lo = __reduce_max_sync(0xffffffffu, (unsigned)(b >> 32) == hi ? (unsigned)b : 0u);
+  const int nv = __reduce_add_sync(0xffffffffu, nviol);
+  if ((threadIdx.x & 31) == 0) {
+    const unsigned long long m = ((unsigned long long)hi << 32) | lo;
+    if (m) atomicMax((unsigned long long*)(scal + 1), m);
+    if (nv) atomicAdd(scal + 2, (double)nv);
+  }
+}
+
+template <int FORM, bool FULL>
+__device__ __forceinline__ void bus_warp_body(const DevPlan& P, const EvalArgs& A, double* region, int tile, int s0, int s1) {
+  if constexpr (has_bus_rows(FORM)) {
+    constexpr int NJ = he_nj(FORM), NH = he_nh(FORM), NG = he_npg(FORM);
+    constexpr int ND = (NJ + NH + NG + 1) / 2;
+    constexpr bool PB = (FORM == PBRAPV || FORM == PBRARV);
+    const WTile t = P.wtiles[tile];
+    const int lane = threadIdx.x & 31;
+    const bool wg = FULL || (A.what & EV_G) != 0, wj = FULL || (A.what & EV_J) != 0, wh = FULL || (A.what & EV_H) != 0;
+    const bool has_status = !FULL && A.status != nullptr;
+    const bool need_g = wg || A.scal;
+    const bool facts = (P.flags & FLAG_FACTS) != 0;
+    double* const spJ = region;
+    double* const spH = spJ + P.wt_jspace;
+    double* const spG = spH + P.wt_hspace;
+    const int nm = t.mjn + t.mhn + t.mgn;
+    uint16_t* const mdst = (uint16_t*)(spG + P.wt_gspace);      // [mjn | mhn | mgn] x (dst, first extra cell, count)
+    uint16_t* const mx0 = mdst + nm;
+    uint16_t* const mcnt = mx0 + nm;
+    const int oj0 = P.wt_ownj_ptr[t.u0], noj = P.wt_ownj_ptr[t.u1] - oj0;
+    const int oh0 = P.wt_ownh_ptr[t.u0], noh = P.wt_ownh_ptr[t.u1] - oh0;
+    const int og0 = P.wt_owng_ptr[t.u0], nog = P.wt_owng_ptr[t.u1] - og0;
+    uint16_t* const ownj = mcnt + nm;
+    uint16_t* const ownh = ownj + noj;
+    uint16_t* const owng = ownh + noh;
+    // ---- scenario-independent set-up
+    for (int q = lane; q < nm; q += 32) {
+      const int src = q < t.mjn ? t.mj0 + q : (q < t.mjn + t.mhn ? t.mh0 + (q - t.mjn) : t.mg0 + (q - t.mjn - t.mhn));
+      mdst[q] = P.wt_mdst[src]; mx0[q] = P.wt_mx0[src]; mcnt[q] = P.wt_mcnt[src];
+    }
+    for (int q = lane; q < noj; q += 32) ownj[q] = P.wt_ownj[oj0 + q];
+    for (int q = lane; q < noh; q += 32) ownh[q] = P.wt_ownh[oh0 + q];
+    for (int q = lane; q < nog; q += 32) owng[q] = P.wt_owng[og0 + q];
+    // lane = half-edge
+    const bool hact = lane < t.nhe;
+    int ks = 0, hb = t.u0, oth = 0;
+    double c0 = 0.0, c1 = 0.0, c2 = 0.0, c3 = 0.0;
+    uint32_t d[ND];
+#pragma unroll
+    for (int i = 0; i < ND; i++) d[i] = 0;
+    if (hact) {
+      const int q = t.he0 + lane;
+      ks = P.he_ks[q]; hb = P.he_bus[q];
+      if constexpr (is_PN(FORM)) {
+        oth = P.he_other[q];
+        c0 = P.he_c[q]; c1 = P.he_c[(long long)P.nhe + q]; c2 = P.he_c[2LL * P.nhe + q]; c3 = P.he_c[3LL * P.nhe + q];
+      }
+      const uint16_t* dt = P.wt_dst + t.dst0 + lane;
+#pragma unroll
+      for (int i = 0; i < ND; i++) {
+        const unsigned lo = dt[(2 * i) * 32], hi = (2 * i + 1 < NJ + NH + NG) ? dt[(2 * i + 1) * 32] : 0u;
+        d[i] = lo | (hi << 16);
+      }
+    }
+    const int k = ks >> 1, side = ks & 1;
+    const int xo0 = is_PN(FORM) ? P.o_a + oth : P.o_f[0 + 2 * side] + k;
+    const int xo1 = is_PN(FORM) ? P.o_b + oth : P.o_f[1 + 2 * side] + k;
+    const int xa = P.o_a + hb, xb = P.o_b + hb;
+    // lane = bus
+    const int nbt = t.u1 - t.u0, u = t.u0 + lane;
+    const bool bact = lane < nbt;
+    int g0 = 0, ngen = 0, h0l = 0, deg = 0, f0 = 0, nsh = 0, oj = 0, oh = 0, og = 0;
+    double Gl = 0.0, Bl = 0.0;
+    if (bact) {
+      g0 = P.gen_ptr[u]; ngen = P.gen_ptr[u + 1] - g0;
+      h0l = P.he_ptr[u] - t.he0; deg = P.he_ptr[u + 1] - P.he_ptr[u];
+      if (facts) { f0 = P.sh_ptr[u]; nsh = P.sh_ptr[u + 1] - f0; }
+      oj = P.wt_ownj_ptr[u] - oj0; oh = P.wt_ownh_ptr[u] - oh0; og = P.wt_owng_ptr[u] - og0;
+      Gl = P.Gl[u]; Bl = P.Bl[u];
+    }
+    const int own_src = deg > 0 ? h0l : lane;                   // lane that holds this bus's own voltage / multipliers
+    // row pointers of the current scenario (warp-uniform); the images share the 16-byte phase of their destination
+    const double* __restrict__ xrow = A.x + (long long)s0 * A.ldx;
+    const double* __restrict__ murow = wh ? A.mu + (long long)s0 * A.ldmu : nullptr;
+    const double* __restrict__ pdrow = A.Pd ? A.Pd + (long long)s0 * A.ldl : P.Pd0;
+    const double* __restrict__ qdrow = A.Qd ? A.Qd + (long long)s0 * A.ldl : P.Qd0;
+    const long long ldload = A.Pd ? A.ldl : 0, ldloadq = A.Qd ? A.ldl : 0;
+    const uint8_t* __restrict__ strow = has_status ? A.status + (long long)s0 * A.ldst : nullptr;
+    double* jrow = wj ? A.J + (long long)s0 * A.ldJ + t.j0 : nullptr;
+    double* hrow = wh ? A.H + (long long)s0 * A.ldH + t.h0 : nullptr;
+    double* grow = wg ? A.g + (long long)s0 * A.ldg + 2 * t.u0 : nullptr;
+    double* const imgJ = spJ + ((reinterpret_cast<unsigned long long>(jrow) >> 3) & 1);
+    double* const imgH = spH + ((reinterpret_cast<unsigned long long>(hrow) >> 3) & 1);
+    double* const imgG = spG;
+    struct Raw { double v0, v1, va0, vb0, muP, muQ, st, Pd, Qd; };
+    auto load = [&](const double* __restrict__ x, const double* __restrict__ mu, const double* __restrict__ pd,
+                    const double* __restrict__ qd, const uint8_t* __restrict__ stp) {
+      Raw r;
+      r.v0 = r.v1 = r.va0 = r.vb0 = r.muP = r.muQ = r.Pd = r.Qd = 0.0; r.st = 1.0;
+      if (hact) {
+        r.v0 = x[xo0]; r.v1 = x[xo1]; r.va0 = x[xa]; r.vb0 = x[xb];
+        if (wh) { r.muP = mu[2 * hb]; r.muQ = mu[2 * hb + 1]; }
+        if (has_status) r.st = (double)stp[k];
+      }
+      if (bact && need_g) { r.Pd = pd[u]; r.Qd = qd[u]; }
+      return r;
+    };
+    Raw cur = load(xrow, murow, pdrow, qdrow, strow);
+    __syncwarp();
+    for (int s = s0; s < s1; s++) {
+      Raw nxt = cur;
+      if (s + 1 < s1)                                            // one scenario ahead
+        nxt = load(xrow + A.ldx, wh ? murow + A.ldmu : nullptr, pdrow + ldload, qdrow + ldloadq, has_status ? strow + A.ldst : nullptr);
+      const double* __restrict__ x = xrow;
+      if (s > s0 && lane == 0) bulk_wait_read<0>();             // the copy engine has read the previous images
+      __syncwarp();
+      // ---- 1. half-edge contributions
+      if (hact) {
+        HeIn in;
+        in.side = side; in.st = cur.st; in.v0 = cur.v0; in.v1 = cur.v1; in.va0 = cur.va0; in.vb0 = cur.vb0;
+        in.muP = cur.muP; in.muQ = cur.muQ; in.c0 = c0; in.c1 = c1; in.c2 = c2; in.c3 = c3;
+        RegW sj{imgJ, d, 0, wj}, sh{imgH, d, NJ, wh};
+        auto gput = [&](int kk, double v) {
+          imgG[(d[(NJ + NH + kk) >> 1] >> (((NJ + NH + kk) & 1) * 16)) & 0xffffu] = piece_neg(FORM, kk) ? -v : v;
+        };
+        he_math<FORM>(in, sj, sh, gput, need_g);
+        if constexpr (PB) {
+          if (need_g) { gput(0, cur.st * cur.v0); gput(1, cur.st * cur.v1); }
+        }
+      }
+      // ---- 2. the bus's own terms (own voltage / multipliers come from the bus's first half-edge lane)
+      OwnIn o;
+      o.va0 = __shfl_sync(0xffffffffu, cur.va0, own_src); o.vb0 = __shfl_sync(0xffffffffu, cur.vb0, own_src);
+      o.muP = __shfl_sync(0xffffffffu, cur.muP, own_src); o.muQ = __shfl_sync(0xffffffffu, cur.muQ, own_src);
+      o.W = 0.0; o.Gl = Gl; o.Bl = Bl; o.ngen = ngen; o.nsh = nsh;
+      if (bact) {
+        if (deg == 0) {                                         // isolated bus: nobody loaded its inputs
+          o.va0 = x[P.o_a + u]; o.vb0 = x[P.o_b + u];
+          o.muP = wh ? murow[2 * u] : 0.0; o.muQ = wh ? murow[2 * u + 1] : 0.0;
+        }
+        if constexpr (FORM == CBRAWV) o.W = x[P.o_Wd + u];
+        auto bssv = [&](int q) { return x[P.o_bss + P.sh_idx[f0 + q]]; };
+        if (wj || wh) {
+          ListW lj{imgJ, ownj + oj, wj}, lh{imgH, ownh + oh, wh};
+          own_math<FORM>(o, bssv, lj, lj, lh);
+        }
+        if (need_g) {                                           // residual terms: :177-180, :256-279, :291-292
+          ListW lg{imgG, owng + og, true};
+          for (int q = 0; q < ngen; q++) {
+            const int gi = P.gen_idx[g0 + q];
+            lg.put(x[P.o_pg + gi]); lg.put(x[P.o_qg + gi]);
+          }
+          double m2;                                            // |V|^2 of the shunt terms
+          if constexpr (is_polar(FORM)) m2 = o.vb0 * o.vb0;
+          else if constexpr (FORM == PBRARV || FORM == CBRARV || FORM == PNRARV) m2 = o.vb0 * o.vb0 + o.va0 * o.va0;
+          else m2 = o.W;
+          lg.put(-(Gl * m2)); lg.put(Bl * m2);
+          for (int q = 0; q < nsh; q++) lg.put(bssv(q) * m2);
+          lg.put(-cur.Pd); lg.put(-cur.Qd);
+        }
+      }
+      __syncwarp();
+      // ---- 3. slots with several contributions
+      if (wj) reduce_multi_warp(imgJ, mdst, mx0, mcnt, t.mjn, lane);
+      if (wh) reduce_multi_warp(imgH, mdst + t.mjn, mx0 + t.mjn, mcnt + t.mjn, t.mhn, lane);
+      if (need_g) reduce_multi_warp(imgG, mdst + t.mjn + t.mhn, mx0 + t.mjn + t.mhn, mcnt + t.mjn + t.mhn, t.mgn, lane);
+      // ---- 4. the images go out
+      fence_async_smem();
+      __syncwarp();
+      if (wj) wt_store_block(jrow, imgJ, t.jn, lane);
+      if (wh) wt_store_block(hrow, imgH, t.hn, lane);
+      if (lane == 0) bulk_commit();
+      if (need_g) {
+        double vmax = 0.0;
+        int nviol = 0;
+        for (int e = lane; e < 2 * nbt; e += 32) {
+          const double v = imgG[e];
+          if (wg) grow[e] = v;
+          vmax = fmax(vmax, fabs(v));
+          nviol += fabs(v) > A.viol_tol ? 1 : 0;
+        }
+        reduce_scalars_redux(A.scal ? A.scal + (long long)s * NSCAL : nullptr, vmax, nviol);
+      }
+      cur = nxt;
+      xrow += A.ldx; pdrow += ldload; qdrow += ldloadq;
+      if (wh) { murow += A.ldmu; hrow += A.ldH; }
+      if (wj) jrow += A.ldJ;
+      if (wg) grow += A.ldg;
+      if (has_status) strow += A.ldst;
+    }
+    if (lane == 0) bulk_wait_read<0>();                         // shared memory must outlive the copies that read it
+  }
+}
+
+#ifndef PS_WT_MINB
+#define PS_WT_MINB 4
+#endif
+__host__ __device__ inline int wt_region_doubles(const DevPlan& P) {   // per-warp shared memory, doubles (even)
+  return P.wt_jspace + P.wt_hspace + P.wt_gspace + ((P.wt_lists + 7) / 8) * 2;
+}
+template <int FORM>
+__global__ void __launch_bounds__(32 * WPC, PS_WT_MINB) bus_warp_kernel(const __grid_constant__ DevPlan P, const __grid_constant__ EvalArgs A) {
+  extern __shared__ __align__(16) double smem[];
+  const int tile = blockIdx.x * WPC + (threadIdx.x >> 5);
+  if (tile >= P.n_wtiles) return;
+  const int s0 = blockIdx.y * A.chunk, s1 = min(A.S, s0 + A.chunk);
+  double* r = smem + (threadIdx.x >> 5) * wt_region_doubles(P);
+  if ((A.what & (EV_G | EV_J | EV_H)) == (EV_G | EV_J | EV_H) && A.status == nullptr) bus_warp_body<FORM, true>(P, A, r, tile, s0, s1);
+  else bus_warp_body<FORM, false>(P, A, r, tile, s0, s1);
+}
+
 // ---- PB* balances, fast path (PBRAPV / PBRARV without switched shunts) ------------------------------------------
 // The nodal balance of a power-branch-flow model is linear in the generator and flow variables
 // (formulations.jl:188-196): its Jacobian entries are the constant 1 (times the branch status) except the 1-2
@@ -1204,13 +1554,6 @@ __device__ __forceinline__ void branch_direct_body(const DevPlan& P, const EvalA
 // HBM writes are issued as whole lines, and the copy of scenario s overlaps the evaluation of scenario s + 1 (a row is
 // only waited for right before it is overwritten).  No barrier: the rows and the bulk groups are per thread.
 // Needs 16-byte aligned blocks (even block lengths, even leading dimensions); see launch_eval.
-__device__ __forceinline__ void bulk_store(double* gdst, const double* ssrc, int bytes) {
-  const unsigned sa = (unsigned)__cvta_generic_to_shared(ssrc);
-  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(sa), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
-template <int N> __device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
-__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 #ifndef PS_BULK_WARP
 #define PS_BULK_WARP 1
 #endif
@@ -1377,9 +1720,19 @@ cudaError_t launch_bus_form(const DevPlan& P, const EvalArgs& A, size_t smem, cu
 }
 
 template <int FORM>
-cudaError_t configure_form(int src, size_t smem_branch, size_t smem_bus) {
+cudaError_t launch_bus_warp_form(const DevPlan& P, const EvalArgs& A, size_t smem, cudaStream_t st, dim3 grid) {
+  bus_warp_kernel<FORM><<<grid, 32 * WPC, smem, st>>>(P, A);
+  return cudaGetLastError();
+}
+
+template <int FORM>
+cudaError_t configure_form(int src, size_t smem_branch, size_t smem_bus, size_t smem_wt) {
   cudaError_t e = cudaFuncSetAttribute(bus_kernel<FORM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bus);
   if (e != cudaSuccess) return e;
+  if (smem_wt > 0) {
+    e = cudaFuncSetAttribute(bus_warp_kernel<FORM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_wt);
+    if (e != cudaSuccess) return e;
+  }
   {
     using BM = Branch<FORM, SRC_MATPOWER>;
     using BA = Branch<FORM, SRC_ARPAE>;
@@ -1544,18 +1897,23 @@ cudaError_t launch_rows_eval(const RowsDev& R, int what, int64_t S, const double
   return cudaGetLastError();
 }
 
-cudaError_t configure_eval(int form, int src, int64_t smem_branch_bytes, int64_t smem_bus_bytes) {
-  const size_t sb = (size_t)smem_branch_bytes, su = (size_t)smem_bus_bytes;
+int64_t wt_smem_bytes(const DevPlan& P) {
+  if (P.n_wtiles <= 0) return 0;
+  return (int64_t)WPC * wt_region_doubles(P) * 8;
+}
+
+cudaError_t configure_eval(int form, int src, int64_t smem_branch_bytes, int64_t smem_bus_bytes, int64_t smem_wt_bytes) {
+  const size_t sb = (size_t)smem_branch_bytes, su = (size_t)smem_bus_bytes, sw = (size_t)smem_wt_bytes;
   switch (form) {
-    case PBRAPV: return configure_form<PBRAPV>(src, sb, su);
-    case PBRARV: return configure_form<PBRARV>(src, sb, su);
-    case PBRAWV: return configure_form<PBRAWV>(src, sb, su);
-    case CBRARV: return configure_form<CBRARV>(src, sb, su);
-    case CBRAWV: return configure_form<CBRAWV>(src, sb, su);
-    case PNPAPV: return configure_form<PNPAPV>(src, sb, su);
-    case PNRAPV: return configure_form<PNRAPV>(src, sb, su);
-    case PNRARV: return configure_form<PNRARV>(src, sb, su);
-    case PNRAWV: return configure_form<PNRAWV>(src, sb, su);
+    case PBRAPV: return configure_form<PBRAPV>(src, sb, su, sw);
+    case PBRARV: return configure_form<PBRARV>(src, sb, su, sw);
+    case PBRAWV: return configure_form<PBRAWV>(src, sb, su, sw);
+    case CBRARV: return configure_form<CBRARV>(src, sb, su, sw);
+    case CBRAWV: return configure_form<CBRAWV>(src, sb, su, sw);
+    case PNPAPV: return configure_form<PNPAPV>(src, sb, su, sw);
+    case PNRAPV: return configure_form<PNRAPV>(src, sb, su, sw);
+    case PNRARV: return configure_form<PNRARV>(src, sb, su, sw);
+    case PNRAWV: return configure_form<PNRAWV>(src, sb, su, sw);
   }
   return cudaErrorInvalidValue;
 }
@@ -1581,6 +1939,11 @@ static cudaError_t launch_staged(const DevPlan& P, const EvalArgs& A, size_t sme
 }
 static cudaError_t launch_bus(const DevPlan& P, const EvalArgs& A, size_t smem, cudaStream_t stream, dim3 grid) {
 #define PS_CALL(F) launch_bus_form<F>(P, A, smem, stream, grid)
+  PS_FORM_SWITCH(PS_CALL)
+#undef PS_CALL
+}
+static cudaError_t launch_bus_warp(const DevPlan& P, const EvalArgs& A, size_t smem, cudaStream_t stream, dim3 grid) {
+#define PS_CALL(F) launch_bus_warp_form<F>(P, A, smem, stream, grid)
   PS_FORM_SWITCH(PS_CALL)
 #undef PS_CALL
 }
@@ -1663,15 +2026,19 @@ cudaError_t launch_eval(const DevPlan& P, const EvalArgs& A0, int64_t smem_branc
     if (e != cudaSuccess) return e;
   } else if (P.n_bus_tiles > 0 || A.scal) {
     // bus tiles are few and pay a per-CTA staging cost: longer scenario chunks than the branch kernel
+    const int64_t smem_wt = wt_smem_bytes(P);
+    const bool warp_tiles = smem_wt > 0 && smem_wt <= 200 * 1024 && !getenv("PS_NO_WARPBUS");
     const long long want = 148LL * 4 * 6;
     long long c = ((long long)A.S * (P.n_bus_tiles + 1)) / want;
-    A.chunk = env_int("PS_CHUNK_BUS", (int)(c < 1 ? 1 : (c > 32 ? 32 : c)));
+    const long long cw = ((long long)A.S * ((P.n_wtiles + WPC - 1) / WPC)) / (148LL * PS_WT_MINB * 8);
+    A.chunk = warp_tiles ? env_int("PS_CHUNK_WT", (int)(cw < 1 ? 1 : (cw > 16 ? 16 : cw))) : env_int("PS_CHUNK_BUS", (int)(c < 1 ? 1 : (c > 32 ? 32 : c)));
     const int nchunks = (A.S + A.chunk - 1) / A.chunk;
     if (nchunks > 65535) return cudaErrorInvalidConfiguration;
     if (P.n_bus_tiles > 0) {
       if (launches) *launches += 1;
       KTimer kt(ev, ev_mask, stream, K_BUS);
-      e = launch_bus(P, A, (size_t)smem_bus_bytes, stream, dim3((unsigned)P.n_bus_tiles, (unsigned)nchunks));
+      if (warp_tiles) e = launch_bus_warp(P, A, (size_t)smem_wt, stream, dim3((unsigned)((P.n_wtiles + WPC - 1) / WPC), (unsigned)nchunks));
+      else e = launch_bus(P, A, (size_t)smem_bus_bytes, stream, dim3((unsigned)P.n_bus_tiles, (unsigned)nchunks));
     }
     if (e != cudaSuccess) return e;
     if (A.scal) {                                  // objective scalar: its own small launch (fixed reduction shape)

@@ -42,6 +42,11 @@ struct DevPlan {                    // passed to kernels by value (constant bank
   const double* he_c;                               // [4][nhe] PN* admittance entries staged per tile
   int nhe;
   const Tile* tiles;
+  // warp tiles of bus_warp_kernel (ps_plan.h: WTile); n_wtiles == 0 -> the CTA-tile bus_kernel runs
+  const WTile* wtiles;
+  int n_wtiles, wt_jspace, wt_hspace, wt_gspace, wt_lists;
+  const uint16_t *wt_dst, *wt_mdst, *wt_mx0, *wt_mcnt, *wt_ownj, *wt_ownh, *wt_owng;
+  const int32_t *wt_ownj_ptr, *wt_ownh_ptr, *wt_owng_ptr;
 };
 
 struct EvalArgs {
@@ -63,7 +68,9 @@ enum KernelId : int { K_BUS = 0, K_BUS_JH = 1, K_OBJ = 2, K_BRANCH = 3, K_COUNT 
 cudaError_t launch_eval(const DevPlan& P, const EvalArgs& A, int64_t smem_branch_bytes, int64_t smem_bus_bytes,
                         cudaStream_t stream, int64_t* launches, cudaEvent_t* ev = nullptr, unsigned* ev_mask = nullptr);
 // opt the kernels of one formulation into the needed dynamic shared memory (once per device)
-cudaError_t configure_eval(int form, int src, int64_t smem_branch_bytes, int64_t smem_bus_bytes);
+cudaError_t configure_eval(int form, int src, int64_t smem_branch_bytes, int64_t smem_bus_bytes, int64_t smem_wt_bytes = 0);
+// dynamic shared memory of one bus_warp_kernel CTA (0 when the plan has no warp tiles)
+int64_t wt_smem_bytes(const DevPlan& P);
 
 // COO -> CSC assembly (replaces src/opt/algorithms/common.jl:12-20): nz[j] = sum_{q in seg j} dE[perm[q]]
 cudaError_t launch_csc_assemble(const int32_t* segptr, const int32_t* perm, int nnz_csc, int64_t S,

@@ -218,5 +218,11 @@ PS_HD constexpr bool direct_ok(int form, int src) {
 PS_HD constexpr int he_nj(int f) { return (f == PBRAPV || f == PBRARV) ? 2 : 8; }
 PS_HD constexpr int he_nh(int f) { return (f == PBRAPV || f == PBRARV) ? 0 : (is_CB(f) ? 12 : (f == PNRARV ? 16 : 20)); }
 PS_HD constexpr int he_np(int f) { return is_CB(f) ? 4 : (f == PNRARV ? 6 : (is_PN(f) ? 4 : 0)); }
+// The residual of a nodal balance as a flat left-to-right sum of signed terms (formulations.jl:171-292): per half-edge
+// he_npg terms -- the staged pieces above, or for the PB* models status * flow variable for the P and the Q row --
+// term k belongs to row piece_row (0 = P, 1 = Q) and enters with the sign piece_neg (x - y == x + (-y) exactly)
+PS_HD constexpr int he_npg(int f) { return (f == PBRAPV || f == PBRARV) ? 2 : he_np(f); }
+PS_HD constexpr int piece_row(int f, int k) { return (f == PBRAPV || f == PBRARV) ? k : (f == PNRARV ? (k >= 3 ? 1 : 0) : (k >= 2 ? 1 : 0)); }
+PS_HD constexpr bool piece_neg(int f, int k) { return is_PN(f) ? (k < 2) : (is_CB(f) ? (k == 3) : false); }
 
 }  // namespace ps

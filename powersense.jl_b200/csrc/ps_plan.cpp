@@ -484,6 +484,101 @@ std::string build_plan(const HostNet& net, int form, int src, int flags, int tpb
       u0 = u1;
     }
   }
+  // ---- warp tiles (bus_warp_kernel): contiguous bus ranges with at most 32 half-edges and 32 buses.  Every
+  // contribution gets a destination in the tile's J (H, G) space: the first contribution of a slot goes to the slot's
+  // own position in the output image, later ones (diagonal block, parallel branches, every further term of a residual)
+  // to extra cells behind the image, contiguous per slot; the kernel adds them left to right in emission order.
+  P.wtiles.clear();
+  if (has_bus_rows(form) && nb > 0) {
+    const int NJ = he_nj(form), NH = he_nh(form), NG = he_npg(form);
+    bool ok = true;
+    for (int64_t i = 0; i < nb && ok; i++) ok = P.he_ptr[i + 1] - P.he_ptr[i] <= 32;
+    P.wt_ownj_ptr.assign(nb + 1, 0);
+    P.wt_ownh_ptr.assign(nb + 1, 0);
+    P.wt_owng_ptr.assign(nb + 1, 0);
+    int64_t u0 = 0;
+    while (ok && u0 < nb) {
+      int64_t u1 = u0 + 1;
+      while (u1 < nb && u1 - u0 < 32 && P.he_ptr[u1 + 1] - P.he_ptr[u0] <= 32) u1++;
+      WTile t{};
+      t.u0 = (int32_t)u0; t.u1 = (int32_t)u1;
+      t.j0 = P.jptr[2 * u0]; t.jn = P.jptr[2 * u1] - t.j0;
+      t.h0 = P.hptr[2 * u0]; t.hn = P.hptr[2 * u1] - t.h0;
+      t.he0 = P.he_ptr[u0]; t.nhe = P.he_ptr[u1] - t.he0;
+      const int32_t cj0 = P.bus_jpp[u0], ncj = P.bus_jpp[u1] - cj0, ch0 = P.bus_hpp[u0], nch = P.bus_hpp[u1] - ch0;
+      // residual terms of the tile in emission order, and the row (slot) each one belongs to
+      std::vector<int32_t> gslot, gbus0(u1 - u0 + 1, 0);
+      for (int64_t i = u0; i < u1; i++) {
+        const int32_t r0 = (int32_t)(2 * (i - u0));
+        const int32_t ngen = net.gen_ptr[i + 1] - net.gen_ptr[i], deg = P.he_ptr[i + 1] - P.he_ptr[i];
+        const int32_t nshi = facts ? net.sh_ptr[i + 1] - net.sh_ptr[i] : 0;
+        for (int32_t q = 0; q < ngen; q++) { gslot.push_back(r0); gslot.push_back(r0 + 1); }
+        for (int32_t lh = 0; lh < deg; lh++) for (int k = 0; k < NG; k++) gslot.push_back(r0 + piece_row(form, k));
+        gslot.push_back(r0); gslot.push_back(r0 + 1);                   // shunt terms
+        for (int32_t q = 0; q < nshi; q++) gslot.push_back(r0 + 1);     // switched shunts (Q row)
+        gslot.push_back(r0); gslot.push_back(r0 + 1);                   // - Pd, - Qd
+        gbus0[i - u0 + 1] = (int32_t)gslot.size();
+      }
+      const int32_t ncg = (int32_t)gslot.size(), gn = (int32_t)(2 * (u1 - u0));
+      if (ncj + 2 >= 65536 || nch + 2 >= 65536 || ncg + 2 >= 65536) { ok = false; break; }
+      std::vector<int32_t> cdj(ncj, 0), cdh(nch, 0), cdg(ncg, 0);
+      // slot -> contributions (tile-local ids, ascending = emission order)
+      std::vector<std::vector<int32_t>> lj(t.jn), lh_(t.hn), lg(gn);
+      for (int32_t e = 0; e < t.jn; e++) for (int32_t q = P.jsp[t.j0 + e]; q < P.jsp[t.j0 + e + 1]; q++) lj[e].push_back(P.jperm[q] - cj0);
+      for (int32_t e = 0; e < t.hn; e++) for (int32_t q = P.hsp[t.h0 + e]; q < P.hsp[t.h0 + e + 1]; q++) lh_[e].push_back(P.hperm[q] - ch0);
+      for (int32_t c = 0; c < ncg; c++) lg[gslot[c]].push_back(c);
+      auto spaces = [&](const std::vector<std::vector<int32_t>>& sl, std::vector<int32_t>& cd, int32_t& nx, int32_t& m0, int32_t& mn) {
+        const int32_t en = (int32_t)sl.size();
+        std::vector<int32_t> ms, x0(en, 0);
+        nx = 0;
+        for (int32_t e = 0; e < en; e++) {
+          cd[sl[e][0]] = e;
+          x0[e] = en + nx;
+          for (size_t q = 1; q < sl[e].size(); q++) cd[sl[e][q]] = en + nx++;
+          if (sl[e].size() > 1) ms.push_back(e);
+        }
+        std::stable_sort(ms.begin(), ms.end(), [&](int32_t a, int32_t b) { return sl[a].size() > sl[b].size(); });
+        m0 = (int32_t)P.wt_mdst.size(); mn = (int32_t)ms.size();
+        for (int32_t e : ms) {
+          P.wt_mdst.push_back((uint16_t)e);
+          P.wt_mx0.push_back((uint16_t)x0[e]);
+          P.wt_mcnt.push_back((uint16_t)(sl[e].size() - 1));
+        }
+      };
+      spaces(lj, cdj, t.jx, t.mj0, t.mjn);
+      spaces(lh_, cdh, t.hx, t.mh0, t.mhn);
+      spaces(lg, cdg, t.gx, t.mg0, t.mgn);
+      t.dst0 = (int32_t)P.wt_dst.size();
+      P.wt_dst.resize(P.wt_dst.size() + (size_t)(NJ + NH + NG) * 32, 0);
+      uint16_t* dst = P.wt_dst.data() + t.dst0;
+      for (int64_t i = u0; i < u1; i++) {
+        const int32_t ngen = net.gen_ptr[i + 1] - net.gen_ptr[i], ng2 = 2 * ngen, deg = P.he_ptr[i + 1] - P.he_ptr[i];
+        const int32_t cJ = P.bus_jpp[i] - cj0, cH = P.bus_hpp[i] - ch0, cG = gbus0[i - u0], lane0 = P.he_ptr[i] - t.he0;
+        for (int32_t lh = 0; lh < deg; lh++) {
+          for (int ty = 0; ty < NJ; ty++) dst[ty * 32 + lane0 + lh] = (uint16_t)cdj[cJ + ng2 + lh * NJ + ty];
+          for (int ty = 0; ty < NH; ty++) dst[(NJ + ty) * 32 + lane0 + lh] = (uint16_t)cdh[cH + lh * NH + ty];
+          for (int ty = 0; ty < NG; ty++) dst[(NJ + NH + ty) * 32 + lane0 + lh] = (uint16_t)cdg[cG + ng2 + lh * NG + ty];
+        }
+        for (int32_t c = cJ; c < cJ + ng2; c++) P.wt_ownj.push_back((uint16_t)cdj[c]);
+        for (int32_t c = cJ + ng2 + NJ * deg; c < P.bus_jpp[i + 1] - cj0; c++) P.wt_ownj.push_back((uint16_t)cdj[c]);
+        for (int32_t c = cH + NH * deg; c < P.bus_hpp[i + 1] - ch0; c++) P.wt_ownh.push_back((uint16_t)cdh[c]);
+        for (int32_t c = cG; c < cG + ng2; c++) P.wt_owng.push_back((uint16_t)cdg[c]);
+        for (int32_t c = cG + ng2 + NG * deg; c < gbus0[i - u0 + 1]; c++) P.wt_owng.push_back((uint16_t)cdg[c]);
+        P.wt_ownj_ptr[i + 1] = (int32_t)P.wt_ownj.size();
+        P.wt_ownh_ptr[i + 1] = (int32_t)P.wt_ownh.size();
+        P.wt_owng_ptr[i + 1] = (int32_t)P.wt_owng.size();
+      }
+      const int32_t lists = 3 * (t.mjn + t.mhn + t.mgn) + (P.wt_ownj_ptr[u1] - P.wt_ownj_ptr[u0]) +
+                            (P.wt_ownh_ptr[u1] - P.wt_ownh_ptr[u0]) + (P.wt_owng_ptr[u1] - P.wt_owng_ptr[u0]);
+      P.wt_lists_max = std::max(P.wt_lists_max, lists);
+      P.wt_jspace = std::max(P.wt_jspace, (ncj + 3) & ~1);          // + 1 for the 16-byte phase of the image, even
+      P.wt_hspace = std::max(P.wt_hspace, (nch + 3) & ~1);
+      P.wt_gspace = std::max(P.wt_gspace, (ncg + 3) & ~1);
+      P.wtiles.push_back(t);
+      u0 = u1;
+    }
+    if (!ok) { P.wtiles.clear(); P.wt_dst.clear(); P.wt_mdst.clear(); P.wt_mx0.clear(); P.wt_mcnt.clear(); }
+  }
   P.tile_units_bus = bus_tpb;
   P.n_bus_tiles = (int)P.tiles.size();
   P.NRP = pat.nrows | 1; P.RJP = P.RJ | 1; P.RHP = P.RH | 1;

@@ -30,6 +30,19 @@ struct Tile {                // one CTA work item: a contiguous range of buses o
   int32_t mj0, mjn, mjl0, mjln, mh0, mhn, mhl0, mhln;
 };
 
+// One warp's work item of bus_warp_kernel: a contiguous range of buses with at most 32 half-edges.  The warp keeps a
+// shared-memory *image* of the tile's J block, H block and residual rows (exactly the bytes that go to HBM), each
+// followed by extra cells for the second and later contributions of multi-contribution slots ("J / H / G space").
+// The extra cells of one slot are contiguous and in emission order.
+struct WTile {
+  int32_t u0, u1;            // buses
+  int32_t j0, jn, h0, hn;    // output slot ranges (per scenario); the residual rows are 2*u0 .. 2*u1
+  int32_t he0, nhe;          // half-edges (global, bus order)
+  int32_t jx, hx, gx;        // extra cells of the J / H / G space
+  int32_t dst0;              // Plan::wt_dst: [he_nj + he_nh + he_npg][32] destinations of lane's contributions (type-major)
+  int32_t mj0, mjn, mh0, mhn, mg0, mgn;   // multi-slots (sorted by count, descending): Plan::wt_mdst / wt_mx0 / wt_mcnt
+};
+
 struct Plan {
   int form = 0, src = 0, flags = 0;
   HostNet net;
@@ -71,6 +84,16 @@ struct Plan {
   // derived per-side constants (side 0 = from, 1 = to), each [2*nbr]
   std::vector<double> c0, c1, c2, c3;
   std::vector<Tile> tiles;
+  // warp tiles of bus_warp_kernel (empty when a bus has more than 32 half-edges: the CTA-tile bus_kernel runs then)
+  std::vector<WTile> wtiles;
+  std::vector<uint16_t> wt_dst;
+  std::vector<uint16_t> wt_mdst, wt_mx0, wt_mcnt;   // multi-slot: destination slot, first extra cell, number of extra cells
+  // destinations of the buses' own contributions: J (generators, shunt), H (shunt), G (generator injections (P, Q) per
+  // generator, then P shunt, Q shunt, Q switched-shunt terms, -Pd, -Qd)
+  std::vector<uint16_t> wt_ownj, wt_ownh, wt_owng;
+  std::vector<int32_t> wt_ownj_ptr, wt_ownh_ptr, wt_owng_ptr;    // per bus [nbus+1]
+  int32_t wt_lists_max = 0;                         // uint16 entries of the per-warp staged lists (max over tiles)
+  int32_t wt_jspace = 0, wt_hspace = 0, wt_gspace = 0;   // doubles of the spaces incl. alignment slack (max over tiles)
   int n_bus_tiles = 0;
   int tile_units_bus = 0, tile_units_br = 0;
   int64_t smem_doubles = 0;                         // max over tiles of staged outputs (padded)

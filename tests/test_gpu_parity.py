@@ -392,11 +392,13 @@ def test_edge_networks(F):
 
 
 @pytest.mark.parametrize("F,case", [(ps.PBRARVmodel, "case13659pegase"), (ps.PBRAPVmodel, "case2869pegase"),
-                                    (ps.PNPAPVmodel, "case2869pegase"), (ps.CBRARVmodel, "case2869pegase")],
+                                    (ps.PNPAPVmodel, "case2869pegase"), (ps.CBRARVmodel, "case2869pegase"),
+                                    (ps.PNRARVmodel, "case2869pegase"), (ps.PNRAPVmodel, "case118"),
+                                    (ps.CBRAWVmodel, "case118")],
                          ids=lambda v: getattr(v, "name", str(v)))
 def test_all_code_paths_agree_bitwise(F, case):
-    """The bulk (TMA store), direct (register -> sector) and staged branch kernels, the slot-parallel PB* bus kernels and
-    the generic contribution-major bus kernel evaluate the same expressions in the same order: their outputs are bitwise
+    """The bulk (TMA store), direct (register -> sector) and staged branch kernels, the slot-parallel PB* bus kernels, the
+    warp-tile bus kernel and the CTA-tile contribution-major bus kernel evaluate the same expressions in the same order: their outputs are bitwise
     equal, on the preferred (sector-aligned) layout, on a 16-byte aligned one and on a plain one, and two runs are
     bitwise reproducible."""
     import os
@@ -433,7 +435,11 @@ def test_all_code_paths_agree_bitwise(F, case):
                 ({"PS_NO_BULK": "1"}, "sector"), ({"PS_NO_BULK": "1"}, "pair"),
                 ({"PS_NO_BULK": "1", "PS_NO_DIRECT": "1"}, "sector"), ({"PS_NO_PBFAST": "1"}, "sector"),
                 ({"PS_NO_BULK": "1", "PS_NO_DIRECT": "1", "PS_NO_PBFAST": "1"}, "plain"), ({"PS_CHUNK": "1"}, "sector"),
-                ({"PS_CHUNK": "5"}, "sector")]
+                ({"PS_CHUNK": "5"}, "sector"),
+                # bus rows: warp-tile kernel (default) against the CTA-tile kernel, and its scenario chunking
+                ({"PS_NO_WARPBUS": "1"}, "sector"), ({"PS_NO_WARPBUS": "1"}, "plain"),
+                ({"PS_NO_WARPBUS": "1", "PS_NO_PBFAST": "1"}, "pair"), ({"PS_CHUNK_WT": "1"}, "sector"),
+                ({"PS_CHUNK_WT": "5", "PS_NO_PBFAST": "1"}, "plain")]
     for env, layout in variants:
         os.environ.update(env)
         try:

@@ -46,6 +46,13 @@ def run(case, Fname, S, chunks, what=7, steps=5, scal=True):
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1) / steps
         print(f"{case} {Fname} S={S} what={what} scal={scal} chunk={c}: {ms:.3f} ms  {S / ms * 1e3:.0f} evals/s  {ab * S / ms / 1e6:.0f} GB/s", flush=True)
+    b.enable_timing(True)
+    b.eval_torch(what, x, mu, g, J, H, sc)
+    kt = b.kernel_times()
+    abr = h.algorithmic_bytes_branch(what)
+    print(f"   kernels (ms): {kt}; branch rows {abr * S / max(kt['branch'], 1e-9) / 1e6:.0f} GB/s, "
+          f"bus rows {(ab - abr) * S / max(kt['bus'] + kt['bus_jh'], 1e-9) / 1e6:.0f} GB/s", flush=True)
+    b.enable_timing(False)
     b.close()
     h.close()
 

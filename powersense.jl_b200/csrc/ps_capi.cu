@@ -330,8 +330,8 @@ int ps_create(const ps_network* net, int formulation, int source_type, int flags
   D.n_wtiles = (int)P.wtiles.size();
   D.wtiles = M.upload(P.wtiles);
   D.wt_jspace = P.wt_jspace; D.wt_hspace = P.wt_hspace; D.wt_gspace = P.wt_gspace; D.wt_lists = P.wt_lists_max;
-  D.wt_dst = M.upload(P.wt_dst); D.wt_mdst = M.upload(P.wt_mdst); D.wt_mx0 = M.upload(P.wt_mx0);
-  D.wt_mcnt = M.upload(P.wt_mcnt); D.wt_ownj = M.upload(P.wt_ownj); D.wt_ownh = M.upload(P.wt_ownh);
+  D.wt_dst = M.upload(P.wt_dst); D.wt_multi = M.upload(P.wt_multi);
+  D.wt_ownj = M.upload(P.wt_ownj); D.wt_ownh = M.upload(P.wt_ownh);
   D.wt_owng = M.upload(P.wt_owng);
   D.wt_ownj_ptr = M.upload(P.wt_ownj_ptr); D.wt_ownh_ptr = M.upload(P.wt_ownh_ptr); D.wt_owng_ptr = M.upload(P.wt_owng_ptr);
   // single-scenario staging

@@ -1102,17 +1102,22 @@ struct ListW {                     // writer through a destination list in share
     d++;
   }
 };
-// slot += its extra cells, left to right; lane per multi-contribution slot
-__device__ __forceinline__ void reduce_multi_warp(double* sp, const uint16_t* mdst, const uint16_t* mx0, const uint16_t* mcnt,
-                                                  int mn, int lane) {
+// slot += its extra cells, left to right; lane per multi-contribution slot of any of the three spaces (one list,
+// sorted by count, so the lanes of a round run about the same number of additions)
+__device__ __forceinline__ void reduce_multi_warp(double* imgJ, double* imgH, double* imgG, bool wj, bool wh, bool wgg,
+                                                  const uint64_t* multi, int mn, int lane) {
   for (int m = lane; m < mn; m += 32) {
-    const int d = mdst[m], n = mcnt[m];
-    const double* xp = sp + mx0[m];
-    double v = sp[d];
+    const uint64_t w = multi[m];
+    const int kind = (int)(w >> 14) & 3, n = (int)(w >> 32);
+    if (!(kind == 0 ? wj : (kind == 1 ? wh : wgg))) continue;
+    double* sp = kind == 0 ? imgJ : (kind == 1 ? imgH : imgG);
+    double* dp = sp + ((unsigned)w & 0x3fffu);
+    const double* xp = sp + (((unsigned)w >> 16) & 0xffffu);
+    double v = *dp;
     int q = 0;
     for (; q + 1 < n; q += 2) { const double a = xp[q], b = xp[q + 1]; v = (v + a) + b; }
     if (q < n) v = v + xp[q];
-    sp[d] = v;
+    *dp = v;
   }
 }
 // hand a finished block image to the copy engine (or copy it with the warp when the 16-byte phases differ)
@@ -1157,21 +1162,15 @@ __device__ __forceinline__ void bus_warp_body(const DevPlan& P, const EvalArgs& 
     double* const spJ = region;
     double* const spH = spJ + P.wt_jspace;
     double* const spG = spH + P.wt_hspace;
-    const int nm = t.mjn + t.mhn + t.mgn;
-    uint16_t* const mdst = (uint16_t*)(spG + P.wt_gspace);      // [mjn | mhn | mgn] x (dst, first extra cell, count)
-    uint16_t* const mx0 = mdst + nm;
-    uint16_t* const mcnt = mx0 + nm;
+    uint64_t* const multi = (uint64_t*)(spG + P.wt_gspace);     // multi-slot descriptors (ps_plan.h: wt_multi)
     const int oj0 = P.wt_ownj_ptr[t.u0], noj = P.wt_ownj_ptr[t.u1] - oj0;
     const int oh0 = P.wt_ownh_ptr[t.u0], noh = P.wt_ownh_ptr[t.u1] - oh0;
     const int og0 = P.wt_owng_ptr[t.u0], nog = P.wt_owng_ptr[t.u1] - og0;
-    uint16_t* const ownj = mcnt + nm;
+    uint16_t* const ownj = (uint16_t*)(multi + t.mn);
     uint16_t* const ownh = ownj + noj;
     uint16_t* const owng = ownh + noh;
     // ---- scenario-independent set-up
-    for (int q = lane; q < nm; q += 32) {
-      const int src = q < t.mjn ? t.mj0 + q : (q < t.mjn + t.mhn ? t.mh0 + (q - t.mjn) : t.mg0 + (q - t.mjn - t.mhn));
-      mdst[q] = P.wt_mdst[src]; mx0[q] = P.wt_mx0[src]; mcnt[q] = P.wt_mcnt[src];
-    }
+    for (int q = lane; q < t.mn; q += 32) multi[q] = P.wt_multi[t.m0 + q];
     for (int q = lane; q < noj; q += 32) ownj[q] = P.wt_ownj[oj0 + q];
     for (int q = lane; q < noh; q += 32) ownh[q] = P.wt_ownh[oh0 + q];
     for (int q = lane; q < nog; q += 32) owng[q] = P.wt_owng[og0 + q];
@@ -1295,9 +1294,7 @@ __device__ __forceinline__ void bus_warp_body(const DevPlan& P, const EvalArgs& 
       }
       __syncwarp();
       // ---- 3. slots with several contributions
-      if (wj) reduce_multi_warp(imgJ, mdst, mx0, mcnt, t.mjn, lane);
-      if (wh) reduce_multi_warp(imgH, mdst + t.mjn, mx0 + t.mjn, mcnt + t.mjn, t.mhn, lane);
-      if (need_g) reduce_multi_warp(imgG, mdst + t.mjn + t.mhn, mx0 + t.mjn + t.mhn, mcnt + t.mjn + t.mhn, t.mgn, lane);
+      reduce_multi_warp(imgJ, imgH, imgG, wj, wh, need_g, multi, t.mn, lane);
       // ---- 4. the images go out
       fence_async_smem();
       __syncwarp();
@@ -2044,7 +2041,9 @@ cudaError_t launch_eval(const DevPlan& P, const EvalArgs& A0, int64_t smem_branc
     if (A.scal) {                                  // objective scalar: its own small launch (fixed reduction shape)
       if (launches) *launches += 1;
       KTimer kt(ev, ev_mask, stream, K_OBJ);
-      objective_kernel<<<dim3((unsigned)nchunks), TPB, 0, stream>>>(P, A);
+      EvalArgs Ao = A;                             // one CTA per few scenarios, whatever the bus kernel's chunk is
+      Ao.chunk = A.S >= 65535 * 2 ? (A.S + 65534) / 65535 : 2;
+      objective_kernel<<<dim3((unsigned)((A.S + Ao.chunk - 1) / Ao.chunk)), TPB, 0, stream>>>(P, Ao);
       e = cudaGetLastError();
       if (e != cudaSuccess) return e;
     }

@@ -45,7 +45,8 @@ struct DevPlan {                    // passed to kernels by value (constant bank
   // warp tiles of bus_warp_kernel (ps_plan.h: WTile); n_wtiles == 0 -> the CTA-tile bus_kernel runs
   const WTile* wtiles;
   int n_wtiles, wt_jspace, wt_hspace, wt_gspace, wt_lists;
-  const uint16_t *wt_dst, *wt_mdst, *wt_mx0, *wt_mcnt, *wt_ownj, *wt_ownh, *wt_owng;
+  const uint16_t *wt_dst, *wt_ownj, *wt_ownh, *wt_owng;
+  const uint64_t* wt_multi;
   const int32_t *wt_ownj_ptr, *wt_ownh_ptr, *wt_owng_ptr;
 };
 

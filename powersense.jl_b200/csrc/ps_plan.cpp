@@ -527,27 +527,25 @@ std::string build_plan(const HostNet& net, int form, int src, int flags, int tpb
       for (int32_t e = 0; e < t.jn; e++) for (int32_t q = P.jsp[t.j0 + e]; q < P.jsp[t.j0 + e + 1]; q++) lj[e].push_back(P.jperm[q] - cj0);
       for (int32_t e = 0; e < t.hn; e++) for (int32_t q = P.hsp[t.h0 + e]; q < P.hsp[t.h0 + e + 1]; q++) lh_[e].push_back(P.hperm[q] - ch0);
       for (int32_t c = 0; c < ncg; c++) lg[gslot[c]].push_back(c);
-      auto spaces = [&](const std::vector<std::vector<int32_t>>& sl, std::vector<int32_t>& cd, int32_t& nx, int32_t& m0, int32_t& mn) {
+      struct MS { int32_t kind, e, x0, cnt; };
+      std::vector<MS> ms;
+      auto spaces = [&](int kind, const std::vector<std::vector<int32_t>>& sl, std::vector<int32_t>& cd, int32_t& nx) {
         const int32_t en = (int32_t)sl.size();
-        std::vector<int32_t> ms, x0(en, 0);
         nx = 0;
         for (int32_t e = 0; e < en; e++) {
           cd[sl[e][0]] = e;
-          x0[e] = en + nx;
+          if (sl[e].size() > 1) ms.push_back(MS{kind, e, en + nx, (int32_t)sl[e].size() - 1});
           for (size_t q = 1; q < sl[e].size(); q++) cd[sl[e][q]] = en + nx++;
-          if (sl[e].size() > 1) ms.push_back(e);
-        }
-        std::stable_sort(ms.begin(), ms.end(), [&](int32_t a, int32_t b) { return sl[a].size() > sl[b].size(); });
-        m0 = (int32_t)P.wt_mdst.size(); mn = (int32_t)ms.size();
-        for (int32_t e : ms) {
-          P.wt_mdst.push_back((uint16_t)e);
-          P.wt_mx0.push_back((uint16_t)x0[e]);
-          P.wt_mcnt.push_back((uint16_t)(sl[e].size() - 1));
         }
       };
-      spaces(lj, cdj, t.jx, t.mj0, t.mjn);
-      spaces(lh_, cdh, t.hx, t.mh0, t.mhn);
-      spaces(lg, cdg, t.gx, t.mg0, t.mgn);
+      spaces(0, lj, cdj, t.jx);
+      spaces(1, lh_, cdh, t.hx);
+      spaces(2, lg, cdg, t.gx);
+      if (ncj + 2 >= 16384 || nch + 2 >= 16384 || ncg + 2 >= 16384) { ok = false; break; }
+      std::stable_sort(ms.begin(), ms.end(), [](const MS& a, const MS& b) { return a.cnt > b.cnt; });
+      t.m0 = (int32_t)P.wt_multi.size(); t.mn = (int32_t)ms.size();
+      for (const MS& m : ms)
+        P.wt_multi.push_back((uint64_t)m.e | ((uint64_t)m.kind << 14) | ((uint64_t)m.x0 << 16) | ((uint64_t)m.cnt << 32));
       t.dst0 = (int32_t)P.wt_dst.size();
       P.wt_dst.resize(P.wt_dst.size() + (size_t)(NJ + NH + NG) * 32, 0);
       uint16_t* dst = P.wt_dst.data() + t.dst0;
@@ -568,7 +566,7 @@ std::string build_plan(const HostNet& net, int form, int src, int flags, int tpb
         P.wt_ownh_ptr[i + 1] = (int32_t)P.wt_ownh.size();
         P.wt_owng_ptr[i + 1] = (int32_t)P.wt_owng.size();
       }
-      const int32_t lists = 3 * (t.mjn + t.mhn + t.mgn) + (P.wt_ownj_ptr[u1] - P.wt_ownj_ptr[u0]) +
+      const int32_t lists = 4 * t.mn + (P.wt_ownj_ptr[u1] - P.wt_ownj_ptr[u0]) +
                             (P.wt_ownh_ptr[u1] - P.wt_ownh_ptr[u0]) + (P.wt_owng_ptr[u1] - P.wt_owng_ptr[u0]);
       P.wt_lists_max = std::max(P.wt_lists_max, lists);
       P.wt_jspace = std::max(P.wt_jspace, (ncj + 3) & ~1);          // + 1 for the 16-byte phase of the image, even
@@ -577,7 +575,7 @@ std::string build_plan(const HostNet& net, int form, int src, int flags, int tpb
       P.wtiles.push_back(t);
       u0 = u1;
     }
-    if (!ok) { P.wtiles.clear(); P.wt_dst.clear(); P.wt_mdst.clear(); P.wt_mx0.clear(); P.wt_mcnt.clear(); }
+    if (!ok) { P.wtiles.clear(); P.wt_dst.clear(); P.wt_multi.clear(); }
   }
   P.tile_units_bus = bus_tpb;
   P.n_bus_tiles = (int)P.tiles.size();

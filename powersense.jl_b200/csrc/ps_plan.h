@@ -40,7 +40,7 @@ struct WTile {
   int32_t he0, nhe;          // half-edges (global, bus order)
   int32_t jx, hx, gx;        // extra cells of the J / H / G space
   int32_t dst0;              // Plan::wt_dst: [he_nj + he_nh + he_npg][32] destinations of lane's contributions (type-major)
-  int32_t mj0, mjn, mh0, mhn, mg0, mgn;   // multi-slots (sorted by count, descending): Plan::wt_mdst / wt_mx0 / wt_mcnt
+  int32_t m0, mn;            // multi-slots of all three spaces, sorted by count (descending): Plan::wt_multi
 };
 
 struct Plan {
@@ -87,7 +87,8 @@ struct Plan {
   // warp tiles of bus_warp_kernel (empty when a bus has more than 32 half-edges: the CTA-tile bus_kernel runs then)
   std::vector<WTile> wtiles;
   std::vector<uint16_t> wt_dst;
-  std::vector<uint16_t> wt_mdst, wt_mx0, wt_mcnt;   // multi-slot: destination slot, first extra cell, number of extra cells
+  // multi-slot descriptor: bits 0-13 destination slot, 14-15 space (0 J, 1 H, 2 G), 16-31 first extra cell, 32-47 count
+  std::vector<uint64_t> wt_multi;
   // destinations of the buses' own contributions: J (generators, shunt), H (shunt), G (generator injections (P, Q) per
   // generator, then P shunt, Q shunt, Q switched-shunt terms, -Pd, -Qd)
   std::vector<uint16_t> wt_ownj, wt_ownh, wt_owng;

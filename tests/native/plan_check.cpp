@@ -96,12 +96,13 @@ static int check(const Plan& P, int kind) {
     }
     if (c != nc) { printf("contribution count mismatch %d != %d (kind %d)\n", c, nc, kind); return 1; }
     for (char h : hit) if (!h) { printf("unwritten cell\n"); return 1; }
-    const int m0 = kind == 0 ? t.mj0 : (kind == 1 ? t.mh0 : t.mg0), mn = kind == 0 ? t.mjn : (kind == 1 ? t.mhn : t.mgn);
-    for (int m = 0; m < mn; m++) {
-      const int d = P.wt_mdst[m0 + m];
-      if (m > 0 && P.wt_mcnt[m0 + m] > P.wt_mcnt[m0 + m - 1]) { printf("multi-slots not sorted by count\n"); return 1; }
+    for (int m = 0; m < t.mn; m++) {
+      const uint64_t w = P.wt_multi[t.m0 + m];
+      if (m > 0 && ((w >> 32) & 0xffff) > ((P.wt_multi[t.m0 + m - 1] >> 32) & 0xffff)) { printf("multi-slots not sorted by count\n"); return 1; }
+      if ((int)((w >> 14) & 3) != kind) continue;
+      const int d = (int)(w & 0x3fff), x0 = (int)((w >> 16) & 0xffff), cnt = (int)((w >> 32) & 0xffff);
       double v = sp_[d];
-      for (int q = 0; q < P.wt_mcnt[m0 + m]; q++) v = v + sp_[P.wt_mx0[m0 + m] + q];
+      for (int q = 0; q < cnt; q++) v = v + sp_[x0 + q];
       sp_[d] = v;
     }
     for (int e = 0; e < en; e++) {

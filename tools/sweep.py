@@ -73,6 +73,9 @@ if __name__ == "__main__":
         for cpb in (2, 4, 8, 16):
             os.environ["PS_CHUNK_PB"] = str(cpb)
             run("case13659pegase", "PBRARVmodel", 2048, [4, 8, 16])
+    if sel == "pn":
+        run("case9241pegase", "PNPAPVmodel", 512, [16])
+        run("case13659pegase", "CBRARVmodel", 512, [16])
     if sel == "ncu_pn":
         run("case9241pegase", "PNPAPVmodel", 256, [4], steps=1)
     if sel == "ncu_cb":

@@ -502,6 +502,7 @@ struct SeqW {                      // writer of consecutive contributions (cells
   int stride;
   bool on;
   __device__ __forceinline__ void put(double v) { if (on) *p = v; p += stride; }
+  __device__ __forceinline__ void zero() { put(0.0); }          // a structural zero (ps_patterns.h: he_h_zero)
 };
 
 __device__ __forceinline__ void cp_async8(void* smem_dst, const void* gsrc) {
@@ -565,8 +566,8 @@ __device__ __forceinline__ void he_math(const HeIn& in, WJ& sj, WH& sh, const PC
     }
     sj.put(st * Ir); sj.put(st * Ii); sj.put(st * ra); sj.put(st * ia);          // P: d/d(ra, ia, Ir, Ii)
     sj.put(-st * Ii); sj.put(st * Ir); sj.put(st * ia); sj.put(-st * ra);        // Q
-    sh.put(0.0); sh.put(0.0); sh.put(st * muP); sh.put(0.0); sh.put(0.0); sh.put(st * muP);
-    sh.put(0.0); sh.put(0.0); sh.put(st * muQ); sh.put(0.0); sh.put(0.0); sh.put(-st * muQ);
+    sh.zero(); sh.zero(); sh.put(st * muP); sh.zero(); sh.zero(); sh.put(st * muP);
+    sh.zero(); sh.zero(); sh.put(st * muQ); sh.zero(); sh.zero(); sh.put(-st * muQ);
   } else if constexpr (FORM == PNPAPV || FORM == PNRAPV) {     // :215-234  T2 / T1, v0/v1 = theta_b / V_b
     const double gs = st * in.c0, bs = st * in.c1;
     const double thb = v0, Vb = v1, Va = vb0, dl = va0 - thb;
@@ -592,9 +593,9 @@ __device__ __forceinline__ void he_math(const HeIn& in, WJ& sj, WH& sh, const PC
     sj.put(-Bt * VV); sj.put(Bt * VV); sj.put(-2.0 * gs * Va - A * Vb); sj.put(-A * Va);
     sj.put(-A * VV); sj.put(A * VV); sj.put(2.0 * bs * Va + Bt * Vb); sj.put(Bt * Va);
     // H clique order over [th_a, th_b, V_a, V_b]: aa bb VaVa VbVb ab aVa aVb bVa bVb VaVb
-    sh.put(muP * A * VV); sh.put(muP * A * VV); sh.put(muP * -2.0 * gs); sh.put(0.0); sh.put(-muP * A * VV);
+    sh.put(muP * A * VV); sh.put(muP * A * VV); sh.put(muP * -2.0 * gs); sh.zero(); sh.put(-muP * A * VV);
     sh.put(-muP * Bt * Vb); sh.put(-muP * Bt * Va); sh.put(muP * Bt * Vb); sh.put(muP * Bt * Va); sh.put(-muP * A);
-    sh.put(-muQ * Bt * VV); sh.put(-muQ * Bt * VV); sh.put(muQ * 2.0 * bs); sh.put(0.0); sh.put(muQ * Bt * VV);
+    sh.put(-muQ * Bt * VV); sh.put(-muQ * Bt * VV); sh.put(muQ * 2.0 * bs); sh.zero(); sh.put(muQ * Bt * VV);
     sh.put(-muQ * A * Vb); sh.put(-muQ * A * Va); sh.put(muQ * A * Vb); sh.put(muQ * A * Va); sh.put(muQ * Bt);
   } else if constexpr (FORM == PNRARV) {                       // :235-243  T3, v0/v1 = vi_b / vr_b
     const double gs = st * in.c0, bs = st * in.c1;
@@ -611,9 +612,9 @@ __device__ __forceinline__ void he_math(const HeIn& in, WJ& sj, WH& sh, const PC
     sj.put(2.0 * bs * ra + B * rb + G * ib); sj.put(2.0 * bs * ia + B * ib - G * rb);
     sj.put(B * ra - G * ia); sj.put(B * ia + G * ra);
     // H: (ra,ra)(ia,ia)(rb,rb)(ib,ib)(ra,rb)(ia,ib)(ra,ib)(ia,rb)
-    sh.put(muP * -2.0 * gs); sh.put(muP * -2.0 * gs); sh.put(0.0); sh.put(0.0);
+    sh.put(muP * -2.0 * gs); sh.put(muP * -2.0 * gs); sh.zero(); sh.zero();
     sh.put(-muP * G); sh.put(-muP * G); sh.put(muP * B); sh.put(-muP * B);
-    sh.put(muQ * 2.0 * bs); sh.put(muQ * 2.0 * bs); sh.put(0.0); sh.put(0.0);
+    sh.put(muQ * 2.0 * bs); sh.put(muQ * 2.0 * bs); sh.zero(); sh.zero();
     sh.put(muQ * B); sh.put(muQ * B); sh.put(muQ * G); sh.put(-muQ * G);
   }
 }
@@ -1092,6 +1093,7 @@ struct RegW {                      // writer through register-held destinations 
     if (on) base[(d[k >> 1] >> ((k & 1) * 16)) & 0xffffu] = v;
     k++;
   }
+  __device__ __forceinline__ void zero() { k++; }               // structural zeros are never written (the plan drops them)
 };
 struct ListW {                     // writer through a destination list in shared memory
   double* base;
@@ -1171,6 +1173,7 @@ __device__ __forceinline__ void bus_warp_body(const DevPlan& P, const EvalArgs& 
     uint16_t* const owng = ownh + noh;
     // ---- scenario-independent set-up
     for (int q = lane; q < t.mn; q += 32) multi[q] = P.wt_multi[t.m0 + q];
+    for (int q = lane; q < P.wt_hspace; q += 32) spH[q] = 0.0;  // slots whose contributions are all structural zeros stay 0
     for (int q = lane; q < noj; q += 32) ownj[q] = P.wt_ownj[oj0 + q];
     for (int q = lane; q < noh; q += 32) ownh[q] = P.wt_ownh[oh0 + q];
     for (int q = lane; q < nog; q += 32) owng[q] = P.wt_owng[og0 + q];

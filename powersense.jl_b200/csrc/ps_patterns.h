@@ -218,6 +218,11 @@ PS_HD constexpr bool direct_ok(int form, int src) {
 PS_HD constexpr int he_nj(int f) { return (f == PBRAPV || f == PBRARV) ? 2 : 8; }
 PS_HD constexpr int he_nh(int f) { return (f == PBRAPV || f == PBRARV) ? 0 : (is_CB(f) ? 12 : (f == PNRARV ? 16 : 20)); }
 PS_HD constexpr int he_np(int f) { return is_CB(f) ? 4 : (f == PNRARV ? 6 : (is_PN(f) ? 4 : 0)); }
+// Hessian contributions of a half-edge that are structurally present but always 0.0 (he_math emits them with zero()):
+// the warp-tile kernel never writes them (x + 0.0 == x; an all-zero slot is zeroed once)
+PS_HD constexpr bool he_h_zero(int f, int ty) {
+  return is_CB(f) ? (ty % 3 != 2) : (f == PNRARV ? ((ty & 7) == 2 || (ty & 7) == 3) : (is_PN(f) ? (ty % 10 == 3) : false));
+}
 // The residual of a nodal balance as a flat left-to-right sum of signed terms (formulations.jl:171-292): per half-edge
 // he_npg terms -- the staged pieces above, or for the PB* models status * flow variable for the P and the Q row --
 // term k belongs to row piece_row (0 = P, 1 = Q) and enters with the sign piece_neg (x - y == x + (-y) exactly)

@@ -525,7 +525,17 @@ std::string build_plan(const HostNet& net, int form, int src, int flags, int tpb
       // slot -> contributions (tile-local ids, ascending = emission order)
       std::vector<std::vector<int32_t>> lj(t.jn), lh_(t.hn), lg(gn);
       for (int32_t e = 0; e < t.jn; e++) for (int32_t q = P.jsp[t.j0 + e]; q < P.jsp[t.j0 + e + 1]; q++) lj[e].push_back(P.jperm[q] - cj0);
-      for (int32_t e = 0; e < t.hn; e++) for (int32_t q = P.hsp[t.h0 + e]; q < P.hsp[t.h0 + e + 1]; q++) lh_[e].push_back(P.hperm[q] - ch0);
+      // structural zeros of the half-edge Hessian terms are dropped from the sums (x + 0.0 == x); a slot made of zeros
+      // only keeps one of them: the kernel zeroes the H space once and never writes such a contribution
+      std::vector<char> zh(nch, 0);
+      for (int64_t i = u0; i < u1; i++) {
+        const int32_t cH = P.bus_hpp[i] - ch0, deg = P.he_ptr[i + 1] - P.he_ptr[i];
+        for (int32_t lh = 0; lh < deg; lh++) for (int ty = 0; ty < NH; ty++) zh[cH + lh * NH + ty] = he_h_zero(form, ty);
+      }
+      for (int32_t e = 0; e < t.hn; e++) {
+        for (int32_t q = P.hsp[t.h0 + e]; q < P.hsp[t.h0 + e + 1]; q++) if (!zh[P.hperm[q] - ch0]) lh_[e].push_back(P.hperm[q] - ch0);
+        if (lh_[e].empty()) lh_[e].push_back(P.hperm[P.hsp[t.h0 + e]] - ch0);
+      }
       for (int32_t c = 0; c < ncg; c++) lg[gslot[c]].push_back(c);
       struct MS { int32_t kind, e, x0, cnt; };
       std::vector<MS> ms;

@@ -71,17 +71,27 @@ static int check(const Plan& P, int kind) {
       }
     }
     const int nc = (int)cslot.size();
-    if (en + nx != nc) { printf("space size mismatch\n"); return 1; }
+    // structural zeros of the half-edge Hessian terms: value 0.0, never written by the kernel
+    std::vector<char> zero(nc, 0);
+    if (kind == 1) {
+      for (int i = t.u0; i < t.u1; i++) {
+        const int cH = P.bus_hpp[i] - P.bus_hpp[t.u0], deg = P.he_ptr[i + 1] - P.he_ptr[i];
+        for (int lh = 0; lh < deg; lh++) for (int ty = 0; ty < NH; ty++) zero[cH + lh * NH + ty] = he_h_zero(P.form, ty);
+      }
+    }
+    if (en + nx > nc || (kind != 1 && en + nx != nc)) { printf("space size mismatch\n"); return 1; }
     if (en + nx + 2 > (kind == 0 ? P.wt_jspace : (kind == 1 ? P.wt_hspace : P.wt_gspace))) { printf("space max too small\n"); return 1; }
-    std::vector<double> val(nc), sp_(en + nx, -1e300), want(en, 0.0);
+    std::vector<double> val(nc), sp_(en + nx, kind == 1 ? 0.0 : -1e300), want(en, 0.0);
     std::vector<char> hit(en + nx, 0), seen(en, 0);
     for (int c = 0; c < nc; c++) {
-      val[c] = (double)(rng() % 100000) / 7.0 - 5000.0;
+      val[c] = zero[c] ? 0.0 : (double)(rng() % 100000) / 7.0 - 5000.0;
       if (cslot[c] < 0 || cslot[c] >= en) { printf("contribution without slot\n"); return 1; }
       want[cslot[c]] = seen[cslot[c]] ? want[cslot[c]] + val[c] : val[c];
       seen[cslot[c]] = 1;
     }
+    int cc = 0;                                           // running contribution index of the replay below
     auto put = [&](int dst, double v) {
+      if (zero[cc]) return;                               // RegW::zero(): skipped
       if (dst < 0 || dst >= en + nx || hit[dst]) { printf("bad destination %d\n", dst); exit(1); }
       hit[dst] = 1; sp_[dst] = v;
     };
@@ -89,13 +99,13 @@ static int check(const Plan& P, int kind) {
     for (int i = t.u0; i < t.u1; i++) {
       const int ng2 = kind == 1 ? 0 : 2 * (P.net.gen_ptr[i + 1] - P.net.gen_ptr[i]), deg = P.he_ptr[i + 1] - P.he_ptr[i];
       int o = optr[i];
-      for (int q = 0; q < ng2; q++) put(own[o++], val[c++]);
+      for (int q = 0; q < ng2; q++) { cc = c; put(own[o++], val[c++]); }
       for (int lh = 0; lh < deg; lh++)
-        for (int ty = 0; ty < per; ty++) put(P.wt_dst[t.dst0 + (ty0 + ty) * 32 + (P.he_ptr[i] - t.he0) + lh], val[c++]);
-      while (o < optr[i + 1]) put(own[o++], val[c++]);
+        for (int ty = 0; ty < per; ty++) { cc = c; put(P.wt_dst[t.dst0 + (ty0 + ty) * 32 + (P.he_ptr[i] - t.he0) + lh], val[c++]); }
+      while (o < optr[i + 1]) { cc = c; put(own[o++], val[c++]); }
     }
     if (c != nc) { printf("contribution count mismatch %d != %d (kind %d)\n", c, nc, kind); return 1; }
-    for (char h : hit) if (!h) { printf("unwritten cell\n"); return 1; }
+    if (kind != 1) for (char h : hit) if (!h) { printf("unwritten cell\n"); return 1; }
     for (int m = 0; m < t.mn; m++) {
       const uint64_t w = P.wt_multi[t.m0 + m];
       if (m > 0 && ((w >> 32) & 0xffff) > ((P.wt_multi[t.m0 + m - 1] >> 32) & 0xffff)) { printf("multi-slots not sorted by count\n"); return 1; }

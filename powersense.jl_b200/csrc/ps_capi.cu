@@ -640,9 +640,9 @@ int ps_batch_eval_host(ps_batch* b, int what, int64_t s_begin, int64_t s_count, 
   cudaError_t e = cudaSetDevice(h->device);
   if (e != cudaSuccess) return cuda_fail(h, e, "cudaSetDevice");
   if (!b->st_in) {
-    // staging chunk: ~256 MB of outputs per set
+    // staging chunk: ~128 MB of outputs per set (short pipeline fill; the copies stay at PCIe rate: tools/pcie_probe.py)
     const int64_t per = (P.m_nl + P.nnzJ + P.nnzH + P.n_var) * 8;
-    int64_t C = std::max<int64_t>(1, std::min<int64_t>(b->S, (int64_t(256) << 20) / std::max<int64_t>(per, 1)));
+    int64_t C = std::max<int64_t>(1, std::min<int64_t>(b->S, (int64_t(128) << 20) / std::max<int64_t>(per, 1)));
     if (const char* env = getenv("PS_STAGE")) { const int64_t c = atoll(env); if (c > 0) C = std::min<int64_t>(c, b->S); }
     b->stage_S = C;
     for (int q = 0; q < 2; q++) {
@@ -663,14 +663,20 @@ int ps_batch_eval_host(ps_batch* b, int what, int64_t s_begin, int64_t s_count, 
   }
   const int64_t C = b->stage_S;
   int64_t it = 0;
+  // rows that are contiguous on the host go as one linear copy (the driver splits pitched copies per row)
+  auto copy_rows = [](void* dst, int64_t dpitch, const void* src, int64_t spitch, int64_t width, int64_t rows, cudaMemcpyKind kind,
+                      cudaStream_t st) {
+    if (dpitch == width && spitch == width) return cudaMemcpyAsync(dst, src, (size_t)(width * rows), kind, st);
+    return cudaMemcpy2DAsync(dst, (size_t)dpitch, src, (size_t)spitch, (size_t)width, (size_t)rows, kind, st);
+  };
   for (int64_t c0 = 0; c0 < s_count; c0 += C, it++) {
     const int q = (int)(it & 1);
     const int64_t n = std::min<int64_t>(C, s_count - c0);
     // the staging set is free once the copy-out of chunk it-2 is done (inputs: once its kernel is done)
     if (it >= 2) { cudaStreamWaitEvent(b->st_in, b->ev_k[q], 0); }
-    e = cudaMemcpy2DAsync(b->sx[q], P.n_var * 8, x + c0 * ldx, ldx * 8, P.n_var * 8, n, cudaMemcpyHostToDevice, b->st_in);
+    e = copy_rows(b->sx[q], P.n_var * 8, x + c0 * ldx, ldx * 8, P.n_var * 8, n, cudaMemcpyHostToDevice, b->st_in);
     if (e == cudaSuccess && (what & EV_H))
-      e = cudaMemcpy2DAsync(b->smu[q], P.m_nl * 8, mu + c0 * ldmu, ldmu * 8, P.m_nl * 8, n, cudaMemcpyHostToDevice, b->st_in);
+      e = copy_rows(b->smu[q], P.m_nl * 8, mu + c0 * ldmu, ldmu * 8, P.m_nl * 8, n, cudaMemcpyHostToDevice, b->st_in);
     if (e != cudaSuccess) return cuda_fail(h, e, "H2D copy");
     cudaEventRecord(b->ev_in[q], b->st_in);
     cudaStreamWaitEvent(b->st_k, b->ev_in[q], 0);
@@ -680,11 +686,11 @@ int ps_batch_eval_host(ps_batch* b, int what, int64_t s_begin, int64_t s_count, 
     if (rc != PS_OK) return rc;
     cudaEventRecord(b->ev_k[q], b->st_k);
     cudaStreamWaitEvent(b->st_out, b->ev_k[q], 0);
-    if (what & EV_G) e = cudaMemcpy2DAsync(g + c0 * ldg, ldg * 8, b->sg[q], P.m_nl * 8, P.m_nl * 8, n, cudaMemcpyDeviceToHost, b->st_out);
+    if (what & EV_G) e = copy_rows(g + c0 * ldg, ldg * 8, b->sg[q], P.m_nl * 8, P.m_nl * 8, n, cudaMemcpyDeviceToHost, b->st_out);
     if (e == cudaSuccess && (what & EV_J))
-      e = cudaMemcpy2DAsync(J + c0 * ldJ, ldJ * 8, b->sJ[q], P.nnzJ * 8, P.nnzJ * 8, n, cudaMemcpyDeviceToHost, b->st_out);
+      e = copy_rows(J + c0 * ldJ, ldJ * 8, b->sJ[q], P.nnzJ * 8, P.nnzJ * 8, n, cudaMemcpyDeviceToHost, b->st_out);
     if (e == cudaSuccess && (what & EV_H))
-      e = cudaMemcpy2DAsync(H + c0 * ldH, ldH * 8, b->sH[q], P.nnzH * 8, P.nnzH * 8, n, cudaMemcpyDeviceToHost, b->st_out);
+      e = copy_rows(H + c0 * ldH, ldH * 8, b->sH[q], P.nnzH * 8, P.nnzH * 8, n, cudaMemcpyDeviceToHost, b->st_out);
     if (e == cudaSuccess && scalars)
       e = cudaMemcpyAsync(scalars + c0 * NSCAL, b->sscal[q], (size_t)n * NSCAL * 8, cudaMemcpyDeviceToHost, b->st_out);
     if (e != cudaSuccess) return cuda_fail(h, e, "D2H copy");

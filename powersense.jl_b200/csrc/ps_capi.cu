@@ -63,6 +63,7 @@ struct ps_batch {
   DevMem mem;
   double *d_Pd = nullptr, *d_Qd = nullptr;
   uint8_t* d_status = nullptr;
+  double* d_diag = nullptr;          // CB* fast path scratch [S][4*nbus] (allocated on first use)
   double viol_tol = 1e-6;
   int64_t launches = 0;
   int chunk_override = 0;
@@ -176,6 +177,14 @@ int do_eval(ps_batch* b, int what, int64_t s_begin, int64_t s_count, const doubl
   A.ldst = P.net.nbr;
   A.g = g; A.ldg = ldg; A.J = J; A.ldJ = ldJ; A.H = H; A.ldH = ldH;
   A.scal = scalars; A.viol_tol = b->viol_tol;
+  A.diag = nullptr; A.lddiag = 4 * P.net.nbus;
+  if (h->dev.cb_slots && !A.status && (what & EV_J)) {
+    if (!b->d_diag) {
+      b->d_diag = b->mem.alloc<double>((size_t)b->S * 4 * P.net.nbus);
+      if (!b->d_diag) return cuda_fail(h, b->mem.err, "cudaMalloc(CB diagonal scratch)");
+    }
+    A.diag = b->d_diag + s_begin * 4 * P.net.nbus;
+  }
   b->tmask = 0;
   e = launch_eval(h->dev, A, P.smem_branch_bytes, P.smem_bus_bytes, stream, &b->launches, b->timing ? b->tev : nullptr, &b->tmask);
   if (e != cudaSuccess) return cuda_fail(h, e, "eval_kernel launch");
@@ -308,6 +317,66 @@ int ps_create(const ps_network* net, int formulation, int source_type, int flags
     D.pb_jt = M.upload(shifted(jt, sj)); D.pb_ji = M.upload(shifted(ji, sj));
     D.pb_ht = M.upload(shifted(ht, sh)); D.pb_hi = M.upload(shifted(hi, sh));
     D.pb_jstride = (int)sj; D.pb_hstride = (int)sh;
+  }
+  D.cb_slots = 0;
+  if (is_CB(P.form) && nb > 0 && P.bus_rows == 2 * nb) {
+    // CB* slot tables (same layout and kernel as the PB* ones).  Every entry of the bus block is coefficient * m:
+    //   J  own-voltage slots: m = the sum the residual kernel leaves in the scratch (index -2 - (4*bus + w), w = P-vr, P-vi,
+    //      Q-vr, Q-vi); generator / W slots: constants (index -1); current slots: +-1 * x[own voltage] (formulations.jl:206-214)
+    //   H  coefficient * mu[row]: +-1 for the (voltage, current) pairs, -2Gl / 2Bl for the shunt diagonal, 0 elsewhere
+    bool ok = true;
+    if (P.flags & FLAG_FACTS) for (int64_t i = 0; i < nb; i++) ok = ok && P.net.sh_ptr[i + 1] == P.net.sh_ptr[i];
+    const int64_t nj = D.j_br0, nh = D.h_br0;
+    std::vector<double> jt((size_t)nj), ht((size_t)nh);
+    std::vector<int32_t> ji((size_t)nj), hi((size_t)nh);
+    auto flow_q = [&](int64_t v) -> int { for (int q = 0; q < 4; q++) if (v >= P.o_f[q] && v < P.o_f[q] + nr) return q; return -1; };
+    for (int64_t r = 0; r < 2 * nb && ok; r++) {
+      const int64_t i = r >> 1; const int pq = (int)(r & 1);
+      const int64_t vr = P.o_b + i, vi = P.o_a + i;
+      for (int32_t e = P.jptr[r]; e < P.jptr[r + 1] && ok; e++) {
+        const int64_t v = P.jcol[e] - 1;
+        const int q = flow_q(v);
+        if (v == vr) { jt[e] = 1.0; ji[e] = (int32_t)(-2 - (4 * i + (pq ? 2 : 0))); }
+        else if (v == vi) { jt[e] = 1.0; ji[e] = (int32_t)(-2 - (4 * i + (pq ? 3 : 1))); }
+        else if ((v >= P.o_pg && v < P.o_pg + ng) || (v >= P.o_qg && v < P.o_qg + ng)) { jt[e] = 1.0; ji[e] = -1; }
+        else if (P.form == CBRAWV && v == P.o_Wd + i) { jt[e] = pq ? P.net.Bl[i] : -P.net.Gl[i]; ji[e] = -1; }
+        else if (q >= 0) {
+          const bool isIr = (q & 1) == 0;
+          if (pq == 0) { jt[e] = 1.0; ji[e] = (int32_t)(isIr ? vr : vi); }
+          else { jt[e] = isIr ? 1.0 : -1.0; ji[e] = (int32_t)(isIr ? vi : vr); }
+        } else ok = false;
+      }
+      for (int32_t e = P.hptr[r]; e < P.hptr[r + 1] && ok; e++) {
+        int64_t a = P.hrow[e] - 1, c = P.hcol[e] - 1;
+        ht[e] = 0.0; hi[e] = -1;
+        if (a == c) {
+          if (P.form == CBRARV && (a == vr || a == vi)) { ht[e] = pq ? 2.0 * P.net.Bl[i] : -2.0 * P.net.Gl[i]; hi[e] = (int32_t)r; }
+          continue;
+        }
+        if (a != vr && a != vi) std::swap(a, c);
+        const int q = flow_q(c);
+        if ((a != vr && a != vi) || q < 0) { ok = false; break; }
+        const bool isIr = (q & 1) == 0, own_r = (a == vr);
+        // P: (vr, Ir), (vi, Ii) -> +mu_P ; Q: (vi, Ir) -> +mu_Q, (vr, Ii) -> -mu_Q ; the other pairs do not occur
+        if (pq == 0) { if (own_r != isIr) { ok = false; break; } ht[e] = 1.0; }
+        else { if (own_r == isIr) { ok = false; break; } ht[e] = own_r ? -1.0 : 1.0; }
+        hi[e] = (int32_t)r;
+      }
+    }
+    if (ok) {
+      auto shifted = [&](const auto& v, int64_t& stride) {
+        using T = typename std::decay<decltype(v)>::type::value_type;
+        stride = ((int64_t)v.size() + 4 + 3) / 4 * 4;
+        std::vector<T> all((size_t)(4 * stride), T(0));
+        for (int a = 0; a < 4; a++) std::copy(v.begin(), v.end(), all.begin() + a * stride + (4 - a) % 4);
+        return all;
+      };
+      int64_t sj = 0, sh = 0;
+      D.pb_jt = M.upload(shifted(jt, sj)); D.pb_ji = M.upload(shifted(ji, sj));
+      D.pb_ht = M.upload(shifted(ht, sh)); D.pb_hi = M.upload(shifted(hi, sh));
+      D.pb_jstride = (int)sj; D.pb_hstride = (int)sh;
+      D.cb_slots = 1;
+    }
   }
   D.cost_order = P.net.cost_order;
   D.f = M.upload(P.net.f); D.t = M.upload(P.net.t);

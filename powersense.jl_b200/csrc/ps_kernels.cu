@@ -1458,6 +1458,91 @@ __global__ void __launch_bounds__(PBT) pb_bus_g_kernel(const __grid_constant__ D
 }
 
 // objective scalar only (used with the PB* fast path, where no bus_kernel runs)
+// ---- CB* balances, fast path (CBRARV / CBRAWV without switched shunts and without a status mask) --------------------
+// The current-branch-flow balances are bilinear in (own voltage, branch current) (formulations.jl:206-214): every
+// Jacobian entry of a current variable is +-1 * an own-voltage entry of x, every Hessian entry is +-1 (or the shunt's
+// -2Gl / 2Bl) * the row multiplier or a structural 0, and the only sums are the four own-voltage Jacobian entries of a
+// bus.  So: cb_bus_g_kernel, thread per bus, walks the bus's generator / Sij / Sji lists in the reference's order and
+// leaves the two residuals and those four sums (scratch [S][4 nb]); cb_bus_jh_kernel then produces the whole bus block
+// of J and H slot-parallel as coefficient[e] * m(index[e]) -- one 32-byte sector per thread, tables read with vector
+// loads -- exactly like the PB* fast path.
+template <int FORM>
+__global__ void __launch_bounds__(PBT) cb_bus_g_kernel(const __grid_constant__ DevPlan P, const __grid_constant__ EvalArgs A) {
+  const int s0 = blockIdx.y * A.chunk, s1 = min(A.S, s0 + A.chunk);
+  const int i = blockIdx.x * PBT + threadIdx.x;
+  const bool act = i < P.nb;
+  int g0 = 0, g1 = 0, h0 = 0, h1 = 0;
+  double Gl = 0.0, Bl = 0.0;
+  if (act) { g0 = P.gen_ptr[i]; g1 = P.gen_ptr[i + 1]; h0 = P.he_ptr[i]; h1 = P.he_ptr[i + 1]; Gl = P.Gl[i]; Bl = P.Bl[i]; }
+  const bool wg = (A.what & EV_G) != 0, wd = (A.what & EV_J) != 0 && A.diag != nullptr;
+  for (int s = s0; s < s1; s++) {
+    double vmax = 0.0;
+    int nviol = 0;
+    if (act) {
+      const double* __restrict__ x = A.x + (long long)s * A.ldx;
+      const double ia = x[P.o_a + i], ra = x[P.o_b + i];
+      double accP = 0.0, accQ = 0.0;                           // formulations.jl:171-172
+      for (int q = g0; q < g1; q++) {                          // :177-180
+        const int g = P.gen_idx[q];
+        accP = accP + x[P.o_pg + g];
+        accQ = accQ + x[P.o_qg + g];
+      }
+      double d0 = 0.0, d1 = 0.0, d2 = 0.0, d3 = 0.0;           // d/d(vr) P, d/d(vi) P, d/d(vr) Q, d/d(vi) Q
+      bool first = true;
+      for (int q = h0; q < h1; q++) {                          // :206-214, Sij ascending then Sji ascending
+        const int ks = P.he_ks[q], k = ks >> 1, side = ks & 1;
+        const double Ir = x[P.o_f[0 + 2 * side] + k], Ii = x[P.o_f[1 + 2 * side] + k];
+        accP = (accP + ra * Ir) + ia * Ii;
+        accQ = (accQ + ia * Ir) - ra * Ii;
+        if (first) { d0 = Ir; d1 = Ii; d2 = -Ii; d3 = Ir; first = false; }
+        else { d0 = d0 + Ir; d1 = d1 + Ii; d2 = d2 + (-Ii); d3 = d3 + Ir; }
+      }
+      if constexpr (FORM == CBRARV) {                          // :264-266
+        const double A2 = ra * ra + ia * ia;
+        accP = accP - Gl * A2;
+        accQ = accQ + Bl * A2;
+        const double t0 = -2.0 * Gl * ra, t1 = -2.0 * Gl * ia, t2 = 2.0 * Bl * ra, t3 = 2.0 * Bl * ia;
+        if (first) { d0 = t0; d1 = t1; d2 = t2; d3 = t3; }
+        else { d0 = d0 + t0; d1 = d1 + t1; d2 = d2 + t2; d3 = d3 + t3; }
+      } else {                                                 // :272-274
+        const double W = x[P.o_Wd + i];
+        accP = accP - Gl * W;
+        accQ = accQ + Bl * W;
+      }
+      if (wd) *reinterpret_cast<double4*>(A.diag + (long long)s * A.lddiag + 4 * i) = make_double4(d0, d1, d2, d3);
+      const double* pd = A.Pd ? A.Pd + (long long)s * A.ldl : P.Pd0;
+      const double* qd = A.Qd ? A.Qd + (long long)s * A.ldl : P.Qd0;
+      const double gP = accP - pd[i], gQ = accQ - qd[i];       // :291-292
+      if (wg) {
+        double* gd = A.g + (long long)s * A.ldg + 2 * i;
+        if ((reinterpret_cast<unsigned long long>(gd) & 15) == 0) *reinterpret_cast<double2*>(gd) = make_double2(gP, gQ);
+        else { gd[0] = gP; gd[1] = gQ; }
+      }
+      vmax = fmax(fabs(gP), fabs(gQ));
+      nviol = (fabs(gP) > A.viol_tol ? 1 : 0) + (fabs(gQ) > A.viol_tol ? 1 : 0);
+    }
+    reduce_scalars(A.scal ? A.scal + (long long)s * NSCAL : nullptr, vmax, nviol);
+  }
+}
+
+__global__ void __launch_bounds__(PBT) cb_bus_jh_kernel(const __grid_constant__ DevPlan P, const __grid_constant__ EvalArgs A) {
+  const int s0 = blockIdx.y * A.chunk, s1 = min(A.S, s0 + A.chunk);
+  const int t = blockIdx.x * PBT + threadIdx.x, nt = gridDim.x * PBT;
+  for (int s = s0; s < s1; s++) {
+    if (A.what & EV_J) {
+      const double* __restrict__ x = A.x + (long long)s * A.ldx;
+      const double* __restrict__ dg = A.diag + (long long)s * A.lddiag;
+      emit_sectors(A.J + (long long)s * A.ldJ, P.j_br0, t, nt, P.pb_jt, P.pb_ji, P.pb_jstride,
+                   [&](int c) { return c >= 0 ? x[c] : (c == -1 ? 1.0 : dg[-2 - c]); });
+    }
+    if (A.what & EV_H) {
+      const double* __restrict__ mu = A.mu + (long long)s * A.ldmu;
+      emit_sectors(A.H + (long long)s * A.ldH, P.h_br0, t, nt, P.pb_ht, P.pb_hi, P.pb_hstride,
+                   [&](int c) { return c >= 0 ? mu[c] : 1.0; });
+    }
+  }
+}
+
 __global__ void __launch_bounds__(TPB) objective_kernel(const __grid_constant__ DevPlan P, const __grid_constant__ EvalArgs A) {
   __shared__ double red[TPB / 32];
   const int s0 = blockIdx.x * A.chunk, s1 = min(A.S, s0 + A.chunk);
@@ -1982,6 +2067,32 @@ static cudaError_t launch_pb(const DevPlan& P, const EvalArgs& A, cudaStream_t s
   PS_FORM_SWITCH(PS_CALL)
 #undef PS_CALL
 }
+static cudaError_t launch_cb(const DevPlan& P, const EvalArgs& A, cudaStream_t st, int nchunks, int64_t* launches,
+                             cudaEvent_t* ev, unsigned* ev_mask) {
+  auto rec = [&](int id, int end) { if (ev) { cudaEventRecord(ev[2 * id + end], st); if (end && ev_mask) *ev_mask |= 1u << id; } };
+  if ((A.what & (EV_G | EV_J)) || A.scal) {
+    const dim3 grid((unsigned)((P.nb + PBT - 1) / PBT), (unsigned)nchunks);
+    rec(K_BUS, 0);
+    if (P.form == CBRARV) cb_bus_g_kernel<CBRARV><<<grid, PBT, 0, st>>>(P, A);
+    else cb_bus_g_kernel<CBRAWV><<<grid, PBT, 0, st>>>(P, A);
+    rec(K_BUS, 1);
+    if (launches) *launches += 1;
+  }
+  if (A.what & (EV_J | EV_H)) {
+    const int n = (P.j_br0 > P.h_br0 ? P.j_br0 : P.h_br0) / 4 + 1;
+    rec(K_BUS_JH, 0);
+    cb_bus_jh_kernel<<<dim3((unsigned)((n + PBT - 1) / PBT), (unsigned)nchunks), PBT, 0, st>>>(P, A);
+    rec(K_BUS_JH, 1);
+    if (launches) *launches += 1;
+  }
+  if (A.scal) {
+    rec(K_OBJ, 0);
+    objective_kernel<<<dim3((unsigned)nchunks), TPB, 0, st>>>(P, A);
+    rec(K_OBJ, 1);
+    if (launches) *launches += 1;
+  }
+  return cudaGetLastError();
+}
 static cudaError_t launch_branch_bulk(const DevPlan& P, const EvalArgs& A, cudaStream_t stream, dim3 grid) {
 #define PS_CALL(F) launch_bulk<F>(P, A, stream, grid)
   PS_FORM_SWITCH(PS_CALL)
@@ -2018,7 +2129,14 @@ cudaError_t launch_eval(const DevPlan& P, const EvalArgs& A0, int64_t smem_branc
   EvalArgs A = A0;
   cudaError_t e = cudaSuccess;
   const bool pb_fast = P.pb_slots && !getenv("PS_NO_PBFAST");
-  if (pb_fast) {
+  const bool cb_fast = P.cb_slots && !A.status && (A.diag || !(A.what & EV_J)) && !getenv("PS_NO_CBFAST");
+  if (cb_fast) {
+    A.chunk = env_int("PS_CHUNK_PB", 4);
+    const int nchunks = (A.S + A.chunk - 1) / A.chunk;
+    if (nchunks > 65535) return cudaErrorInvalidConfiguration;
+    e = launch_cb(P, A, stream, nchunks, launches, ev, ev_mask);
+    if (e != cudaSuccess) return e;
+  } else if (pb_fast) {
     A.chunk = env_int("PS_CHUNK_PB", 4);
     const int nchunks = (A.S + A.chunk - 1) / A.chunk;
     if (nchunks > 65535) return cudaErrorInvalidConfiguration;

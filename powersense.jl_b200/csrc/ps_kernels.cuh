@@ -26,6 +26,7 @@ struct DevPlan {                    // passed to kernels by value (constant bank
   int ntiles, n_bus_tiles;
   int j_br0, h_br0;                                 // first J / H slot of the branch rows
   int pb_slots;                                     // PB* bus block: slot-parallel fast path available
+  int cb_slots;                                     // CB* bus block: slot-parallel fast path available (same tables, see ps_capi.cu)
   const double *pb_jt, *pb_ht;                      // PB* slot tables (ps_capi.cu: upload): coefficients and
   const int32_t *pb_ji, *pb_hi;                     // indices, 4 shifted copies each:
   int pb_jstride, pb_hstride;                       // copy a at + a * stride + (4 - a) % 4 (aligned at entry a + 4q)
@@ -60,6 +61,7 @@ struct EvalArgs {
   double* J; long long ldJ;
   double* H; long long ldH;
   double* scal;                                        // [S][NSCAL] (nullptr -> skip); must be zeroed
+  double* diag; long long lddiag;                      // CB* fast path: scratch [S][4*nb] own-voltage Jacobian sums (nullptr -> generic path)
   double viol_tol;
 };
 

@@ -436,10 +436,13 @@ def test_all_code_paths_agree_bitwise(F, case):
                 ({"PS_NO_BULK": "1", "PS_NO_DIRECT": "1"}, "sector"), ({"PS_NO_PBFAST": "1"}, "sector"),
                 ({"PS_NO_BULK": "1", "PS_NO_DIRECT": "1", "PS_NO_PBFAST": "1"}, "plain"), ({"PS_CHUNK": "1"}, "sector"),
                 ({"PS_CHUNK": "5"}, "sector"),
-                # bus rows: warp-tile kernel (default) against the CTA-tile kernel, and its scenario chunking
-                ({"PS_NO_WARPBUS": "1"}, "sector"), ({"PS_NO_WARPBUS": "1"}, "plain"),
-                ({"PS_NO_WARPBUS": "1", "PS_NO_PBFAST": "1"}, "pair"), ({"PS_CHUNK_WT": "1"}, "sector"),
-                ({"PS_CHUNK_WT": "5", "PS_NO_PBFAST": "1"}, "plain")]
+                # bus rows: the slot-parallel CB* kernels (default for CB*) against the warp-tile kernel (default otherwise)
+                # against the CTA-tile kernel, and the warp-tile kernel's scenario chunking
+                ({"PS_NO_CBFAST": "1"}, "sector"), ({"PS_NO_CBFAST": "1"}, "plain"),
+                ({"PS_NO_CBFAST": "1", "PS_NO_WARPBUS": "1"}, "sector"), ({"PS_NO_CBFAST": "1", "PS_NO_WARPBUS": "1"}, "plain"),
+                ({"PS_NO_CBFAST": "1", "PS_NO_WARPBUS": "1", "PS_NO_PBFAST": "1"}, "pair"),
+                ({"PS_NO_CBFAST": "1", "PS_CHUNK_WT": "1"}, "sector"),
+                ({"PS_NO_CBFAST": "1", "PS_CHUNK_WT": "5", "PS_NO_PBFAST": "1"}, "plain"), ({"PS_CHUNK_PB": "3"}, "pair")]
     for env, layout in variants:
         os.environ.update(env)
         try:

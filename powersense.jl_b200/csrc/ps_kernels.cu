@@ -10,10 +10,13 @@
 //                 scenario's inputs prefetched, values kept by compile-time tag and emitted in slot order as 32-byte
 //                 sector stores (the only topology dependence of the slot order, f < t, is a per-value select);
 //                 branch_staged_kernel: any block size / alignment, through a conflict-free shared staging tile.
-//   bus rows      bus_kernel: shared-memory staging of the tile's half-edge list, admittance entries and slot maps,
-//                 cp.async gather of the scenario's inputs one scenario ahead, contribution-major evaluation
-//                 (half-edge-parallel terms -> pre-reduced multi-slots -> slot-parallel stores);
-//                 pb_bus_g / pb_bus_jh kernels: slot-parallel fast path of the power-branch-flow balances.
+//   bus rows      bus_warp_kernel: a warp per tile of <= 32 half-edges; contributions are scattered straight into a
+//                 shared-memory image of the tile's J / H / g block (destinations held in registers), multi-contribution
+//                 slots and the residuals are ordered sums over contiguous extra cells, the image leaves through TMA;
+//                 bus_kernel: its CTA-tile predecessor (cp.async staging, type-major cells, slot maps), kept for
+//                 networks with a bus of more than 32 half-edges;
+//                 pb_bus_g / pb_bus_jh and cb_bus_g / cb_bus_jh kernels: slot-parallel fast paths of the power- and
+//                 current-branch-flow balances (coefficient / index tables, one 32-byte sector per thread).
 // No atomics on data (only order-independent ones on the per-scenario scalars); results are bitwise reproducible.
 #include <algorithm>
 #include <cstdio>
@@ -538,8 +541,6 @@ struct BusInv {
   double Gl, Bl;
 };
 
-// One half-edge: contributions in the emission order of ps_plan.cpp (which is the reference's source order), and the
-// pieces of the flow term for the residual.  xs = gathered inputs of this scenario.
 // inputs of one half-edge: side, status, the two x entries of the far end (PN*: neighbour voltage) or of the branch
 // (flow / current variables), the own voltage (theta_i, V_i) | (vi_i, vr_i), the row multipliers, PN* constants
 struct HeIn {
@@ -551,6 +552,8 @@ struct PieceW {                    // residual pieces of the CTA-tile kernel: [n
   int stride;
   __device__ __forceinline__ void operator()(int k, double v) const { p[k * stride] = v; }
 };
+// One half-edge: contributions in the emission order of ps_plan.cpp (which is the reference's source order) through the
+// writers sj / sh, and the pieces of the flow term for the residual through piece(k, value).
 template <int FORM, class WJ, class WH, class PC>
 __device__ __forceinline__ void he_math(const HeIn& in, WJ& sj, WH& sh, const PC& piece, bool want_pieces) {
   const int side = in.side;

@@ -254,6 +254,60 @@ def test_errors_and_partial_what():
     h.close()
 
 
+@pytest.mark.parametrize("F", FORMS, ids=lambda f: f.name)
+def test_partial_what_matches_full_evaluation(F):
+    """eval_constraint / eval_constraint_jacobian / eval_hessian_lagrangian are separate callbacks (the SLP line search
+    only asks for g, the LP set-up for g + J): every subset of {g, J, H}, with and without the scalars, with and without a
+    status mask and on a sub-range of the batch, writes exactly the requested blocks of the full evaluation -- bitwise
+    -- and leaves the others untouched.  Covers the warp-tile bus kernel and the slot-parallel PB* / CB* kernels (whose
+    Jacobian depends on the scratch the residual kernel leaves)."""
+    torch = _torch()
+    dev = torch.device("cuda:0")
+    d = synthetic("case118")
+    S = 6
+    x, Pd, Qd, _ = synth.scenario_batch(d, F, S, seed=5)
+    h = capi.Handle(d, F.code, device=0)
+    mu = np.random.default_rng(6).normal(size=(S, h.m_nl))
+    tx, tmu = torch.from_numpy(x).to(dev), torch.from_numpy(mu).to(dev)
+    nr = len(d.br)
+    for masked in (False, True):
+        b = capi.Batch(h, S)
+        b.set_loads(Pd, Qd)
+        if masked:
+            st = np.ones((S, nr), dtype=np.uint8)
+            for s in range(S):
+                st[s, (7 * s + 3) % nr] = 0
+            b.set_branch_status(st)
+
+        def run(what, scal, lo=0):
+            n = S - lo
+            g = torch.full((n, h.m_nl), np.nan, dtype=torch.float64, device=dev)
+            J = torch.full((n, h.nnzJ), np.nan, dtype=torch.float64, device=dev)
+            H = torch.full((n, h.nnzH), np.nan, dtype=torch.float64, device=dev)
+            sc = torch.full((n, capi.PS_NSCALARS), np.nan, dtype=torch.float64, device=dev) if scal else None
+            b.eval_torch(what, tx[lo:], tmu[lo:] if what & 4 else None, g if what & 1 else None, J if what & 2 else None,
+                         H if what & 4 else None, sc, s_begin=lo)
+            torch.cuda.synchronize()
+            return g.cpu().numpy(), J.cpu().numpy(), H.cpu().numpy(), None if sc is None else sc.cpu().numpy()
+        full = run(7, True)
+        assert not any(np.isnan(a).any() for a in full)
+        for what in (1, 2, 3, 4, 5, 6, 7):
+            for scal in (False, True):
+                for lo in (0, 2):
+                    out = run(what, scal, lo)
+                    for bit, a, r in ((1, out[0], full[0]), (2, out[1], full[1]), (4, out[2], full[2])):
+                        if what & bit:
+                            assert np.array_equal(a, r[lo:]), (F.name, masked, what, scal, lo, bit)
+                        else:
+                            assert np.isnan(a).all(), (F.name, masked, what, scal, lo, bit)
+                    if scal:
+                        assert np.array_equal(out[3], full[3][lo:]), (F.name, masked, what, lo, "scalars")
+        out = run(0, True)                                   # scalars only
+        assert np.array_equal(out[3], full[3]) and all(np.isnan(a).all() for a in out[:3])
+        b.close()
+    h.close()
+
+
 def test_host_streaming_matches_device_path():
     d = synthetic("case118")
     F = ps.PBRARVmodel

@@ -396,6 +396,7 @@ int ps_create(const ps_network* net, int formulation, int source_type, int flags
   D.he_bus = M.upload(P.he_bus); D.jsrc = M.upload(P.jsrc); D.hsrc = M.upload(P.hsrc);
   D.ms_dst = M.upload(P.ms_dst); D.ms_ptr = M.upload(P.ms_ptr); D.ms_list = M.upload(P.ms_list);
   D.tiles = M.upload(P.tiles);
+  D.tile_map = nullptr; D.n_hub_tiles = (int)P.hub_tiles.size(); D.hub_tiles = M.upload(P.hub_tiles);
   D.n_wtiles = (int)P.wtiles.size();
   D.wtiles = M.upload(P.wtiles);
   D.wt_jspace = P.wt_jspace; D.wt_hspace = P.wt_hspace; D.wt_gspace = P.wt_gspace; D.wt_lists = P.wt_lists_max;

@@ -942,7 +942,7 @@ template <int FORM, bool FULL>
 __device__ __forceinline__ void bus_tile_body(const DevPlan& P, const EvalArgs& A, double* smem, int s0, int s1) {
   if constexpr (has_bus_rows(FORM)) {
     constexpr int NJ = he_nj(FORM), NH = he_nh(FORM), NP = he_np(FORM);
-    const Tile tl = P.tiles[blockIdx.x];
+    const Tile tl = P.tiles[P.tile_map ? P.tile_map[blockIdx.x] : blockIdx.x];
     const bool wg = FULL || (A.what & EV_G) != 0, wj = FULL || (A.what & EV_J) != 0, wh = FULL || (A.what & EV_H) != 0;
     const int tid = threadIdx.x;
     // bus-owner threads are taken from the END of the CTA: the half-edge phase fills the first warps, so the per-bus
@@ -2158,8 +2158,15 @@ cudaError_t launch_eval(const DevPlan& P, const EvalArgs& A0, int64_t smem_branc
     if (P.n_bus_tiles > 0) {
       if (launches) *launches += 1;
       KTimer kt(ev, ev_mask, stream, K_BUS);
-      if (warp_tiles) e = launch_bus_warp(P, A, (size_t)smem_wt, stream, dim3((unsigned)((P.n_wtiles + WPC - 1) / WPC), (unsigned)nchunks));
-      else e = launch_bus(P, A, (size_t)smem_bus_bytes, stream, dim3((unsigned)P.n_bus_tiles, (unsigned)nchunks));
+      if (warp_tiles) {
+        e = launch_bus_warp(P, A, (size_t)smem_wt, stream, dim3((unsigned)((P.n_wtiles + WPC - 1) / WPC), (unsigned)nchunks));
+        if (e == cudaSuccess && P.n_hub_tiles > 0) {     // the CTA tiles with a bus of more than 32 half-edges
+          DevPlan Ph = P;
+          Ph.tile_map = P.hub_tiles;
+          if (launches) *launches += 1;
+          e = launch_bus(Ph, A, (size_t)smem_bus_bytes, stream, dim3((unsigned)P.n_hub_tiles, (unsigned)nchunks));
+        }
+      } else e = launch_bus(P, A, (size_t)smem_bus_bytes, stream, dim3((unsigned)P.n_bus_tiles, (unsigned)nchunks));
     }
     if (e != cudaSuccess) return e;
     if (A.scal) {                                  // objective scalar: its own small launch (fixed reduction shape)

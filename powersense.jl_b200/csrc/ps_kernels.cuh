@@ -43,6 +43,8 @@ struct DevPlan {                    // passed to kernels by value (constant bank
   const double* he_c;                               // [4][nhe] PN* admittance entries staged per tile
   int nhe;
   const Tile* tiles;
+  const int32_t* tile_map;                          // bus_kernel: CTA -> tile (nullptr: identity); ps_plan.h: hub_tiles
+  const int32_t* hub_tiles; int n_hub_tiles;
   // warp tiles of bus_warp_kernel (ps_plan.h: WTile); n_wtiles == 0 -> the CTA-tile bus_kernel runs
   const WTile* wtiles;
   int n_wtiles, wt_jspace, wt_hspace, wt_gspace, wt_lists;

@@ -492,14 +492,31 @@ std::string build_plan(const HostNet& net, int form, int src, int flags, int tpb
   if (has_bus_rows(form) && nb > 0) {
     const int NJ = he_nj(form), NH = he_nh(form), NG = he_npg(form);
     bool ok = true;
-    for (int64_t i = 0; i < nb && ok; i++) ok = P.he_ptr[i + 1] - P.he_ptr[i] <= 32;
+    // CTA tiles holding a bus that does not fit a warp stay with bus_kernel; skip[i] = end of the hub tile that starts at i
+    P.hub_tiles.clear();
+    std::vector<int64_t> skip(nb + 1, -1);
+    for (int32_t ti = 0; ti < (int32_t)P.tiles.size(); ti++) {
+      const Tile& ct = P.tiles[ti];
+      if (ct.kind != 0) continue;
+      bool hub = false;
+      for (int64_t i = ct.u0; i < ct.u1; i++) hub = hub || P.he_ptr[i + 1] - P.he_ptr[i] > 32;
+      if (hub) { P.hub_tiles.push_back(ti); skip[ct.u0] = ct.u1; }
+    }
     P.wt_ownj_ptr.assign(nb + 1, 0);
     P.wt_ownh_ptr.assign(nb + 1, 0);
     P.wt_owng_ptr.assign(nb + 1, 0);
+    auto own_gap = [&](int64_t a, int64_t b) {       // buses a .. b belong to a hub tile: no own lists
+      for (int64_t i = a; i < b; i++) {
+        P.wt_ownj_ptr[i + 1] = (int32_t)P.wt_ownj.size();
+        P.wt_ownh_ptr[i + 1] = (int32_t)P.wt_ownh.size();
+        P.wt_owng_ptr[i + 1] = (int32_t)P.wt_owng.size();
+      }
+    };
     int64_t u0 = 0;
     while (ok && u0 < nb) {
+      if (skip[u0] >= 0) { own_gap(u0, skip[u0]); u0 = skip[u0]; continue; }
       int64_t u1 = u0 + 1;
-      while (u1 < nb && u1 - u0 < 32 && P.he_ptr[u1 + 1] - P.he_ptr[u0] <= 32) u1++;
+      while (u1 < nb && skip[u1] < 0 && u1 - u0 < 32 && P.he_ptr[u1 + 1] - P.he_ptr[u0] <= 32) u1++;
       WTile t{};
       t.u0 = (int32_t)u0; t.u1 = (int32_t)u1;
       t.j0 = P.jptr[2 * u0]; t.jn = P.jptr[2 * u1] - t.j0;
@@ -585,7 +602,7 @@ std::string build_plan(const HostNet& net, int form, int src, int flags, int tpb
       P.wtiles.push_back(t);
       u0 = u1;
     }
-    if (!ok) { P.wtiles.clear(); P.wt_dst.clear(); P.wt_multi.clear(); }
+    if (!ok) { P.wtiles.clear(); P.wt_dst.clear(); P.wt_multi.clear(); P.hub_tiles.clear(); }
   }
   P.tile_units_bus = bus_tpb;
   P.n_bus_tiles = (int)P.tiles.size();

@@ -84,8 +84,10 @@ struct Plan {
   // derived per-side constants (side 0 = from, 1 = to), each [2*nbr]
   std::vector<double> c0, c1, c2, c3;
   std::vector<Tile> tiles;
-  // warp tiles of bus_warp_kernel (empty when a bus has more than 32 half-edges: the CTA-tile bus_kernel runs then)
+  // warp tiles of bus_warp_kernel.  A bus with more than 32 half-edges does not fit a warp: the CTA tiles (`tiles`) that
+  // contain such a bus are listed in hub_tiles and run through bus_kernel; the warp tiles cover all other buses
   std::vector<WTile> wtiles;
+  std::vector<int32_t> hub_tiles;
   std::vector<uint16_t> wt_dst;
   // multi-slot descriptor: bits 0-13 destination slot, 14-15 space (0 J, 1 H, 2 G), 16-31 first extra cell, 32-47 count
   std::vector<uint64_t> wt_multi;

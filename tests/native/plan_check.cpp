@@ -120,7 +120,12 @@ static int check(const Plan& P, int kind) {
       covered++;
     }
   }
-  const int64_t want_n = kind == 0 ? P.jptr[P.bus_rows] : (kind == 1 ? P.hptr[P.bus_rows] : P.bus_rows);
+  int64_t want_n = kind == 0 ? P.jptr[P.bus_rows] : (kind == 1 ? P.hptr[P.bus_rows] : P.bus_rows);
+  for (int32_t ti : P.hub_tiles) {                       // CTA tiles that stay with bus_kernel
+    const Tile& ct = P.tiles[ti];
+    want_n -= kind == 0 ? ct.jn : (kind == 1 ? ct.hn : 2 * (ct.u1 - ct.u0));
+    for (const WTile& t : P.wtiles) if (t.u0 < ct.u1 && ct.u0 < t.u1) { printf("warp tile overlaps a hub tile\n"); return 1; }
+  }
   if (!P.wtiles.empty() && covered != want_n) { printf("coverage %lld != %lld\n", (long long)covered, (long long)want_n); return 1; }
   return 0;
 }
@@ -136,11 +141,16 @@ int main() {
       Plan P;
       const std::string msg = build_plan(n, form, SRC_MATPOWER, 0, 128, 128, P);
       if (!msg.empty()) { printf("form %d cfg %d: %s\n", form, cfg, msg.c_str()); bad++; continue; }
-      if (cfg == 3) {                                   // a hub bus with more than 32 half-edges: no warp tiles
-        if (!P.wtiles.empty()) { printf("form %d: hub network should not get warp tiles\n", form); bad++; }
+      if (cfg == 3 && P.hub_tiles.empty()) {            // a hub bus with more than 32 half-edges stays with the CTA-tile kernel
+        printf("form %d: hub network without hub tiles\n", form); bad++; continue;
+      }
+      if (cfg != 3 && !P.hub_tiles.empty()) { printf("form %d cfg %d: unexpected hub tiles\n", form, cfg); bad++; continue; }
+      if (P.wtiles.empty()) {                            // fine only when the hub tiles hold every bus
+        int64_t held = 0;
+        for (int32_t ti : P.hub_tiles) held += P.tiles[ti].u1 - P.tiles[ti].u0;
+        if (held != nb) { printf("form %d cfg %d: no warp tiles\n", form, cfg); bad++; }
         continue;
       }
-      if (P.wtiles.empty()) { printf("form %d cfg %d: no warp tiles\n", form, cfg); bad++; continue; }
       with_tiles++;
       for (int kind = 0; kind < 3; kind++) bad += check(P, kind);
     }

@@ -1125,17 +1125,30 @@ __device__ __forceinline__ void reduce_multi_warp(double* imgJ, double* imgH, do
     *dp = v;
   }
 }
-// hand a finished block image to the copy engine (or copy it with the warp when the 16-byte phases differ)
-__device__ __forceinline__ void wt_store_block(double* __restrict__ g, const double* img, int n, int lane) {
-  const unsigned gph = (unsigned)(reinterpret_cast<unsigned long long>(g) >> 3) & 1u;
-  const unsigned sph = ((unsigned)__cvta_generic_to_shared(img) >> 3) & 1u;
-  if (gph == sph) {
-    const int head = (int)gph, mid = (n - head) & ~1;
-    if (lane == 0 && mid > 0) bulk_store(g + head, img + head, mid * 8);
-    if (lane == 1 && head && n > 0) g[0] = img[0];
-    if (lane == 2 && head + mid < n) g[n - 1] = img[n - 1];
+// hand a finished block image to the copy engine: [head][mid doubles, 16-byte aligned on both sides][tail]; when the
+// 16-byte phases of image and destination differ (odd leading dimension) the warp copies it
+struct WtBlock {
+  unsigned simg;         // shared-memory address of the first bulk-copied double
+  int head, mid, n;      // 0 / 1 leading doubles stored by a lane, bulk-copied doubles, block length
+  bool bulk;
+};
+__device__ __forceinline__ WtBlock wt_block(const double* img, int n, bool bulk) {
+  WtBlock b;
+  b.head = (int)(((unsigned)__cvta_generic_to_shared(img) >> 3) & 1u);
+  b.mid = (n - b.head) & ~1;
+  b.n = n;
+  b.simg = (unsigned)__cvta_generic_to_shared(img + b.head);
+  b.bulk = bulk;
+  return b;
+}
+__device__ __forceinline__ void wt_store_block(double* __restrict__ g, const double* img, const WtBlock& b, int lane) {
+  if (b.bulk) {
+    if (lane == 0 && b.mid > 0)
+      asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(g + b.head), "r"(b.simg), "r"(b.mid * 8) : "memory");
+    if (lane == 1 && b.head && b.n > 0) g[0] = img[0];
+    if (lane == 2 && b.head + b.mid < b.n) g[b.n - 1] = img[b.n - 1];
   } else {
-    for (int e = lane; e < n; e += 32) g[e] = img[e];
+    for (int e = lane; e < b.n; e += 32) g[e] = img[e];
   }
 }
 __device__ __forceinline__ void reduce_scalars_redux(double* scal, double vmax, int nviol) {
@@ -1231,6 +1244,10 @@ __device__ __forceinline__ void bus_warp_body(const DevPlan& P, const EvalArgs& 
     double* const imgJ = spJ + ((reinterpret_cast<unsigned long long>(jrow) >> 3) & 1);
     double* const imgH = spH + ((reinterpret_cast<unsigned long long>(hrow) >> 3) & 1);
     double* const imgG = spG;
+    // image and destination share their 16-byte phase in every scenario iff the leading dimension is even
+    const WtBlock blkJ = wt_block(imgJ, t.jn, (A.ldJ & 1) == 0), blkH = wt_block(imgH, t.hn, (A.ldH & 1) == 0);
+    // the generator entries of J are the constant 1 (:177-180): written once, the image persists across scenarios
+    if (bact && wj) for (int q = 0; q < 2 * ngen; q++) imgJ[P.wt_ownj[oj0 + oj + q]] = 1.0;
     struct Raw { double v0, v1, va0, vb0, muP, muQ, st, Pd, Qd; };
     auto load = [&](const double* __restrict__ x, const double* __restrict__ mu, const double* __restrict__ pd,
                     const double* __restrict__ qd, const uint8_t* __restrict__ stp) {
@@ -1271,7 +1288,7 @@ __device__ __forceinline__ void bus_warp_body(const DevPlan& P, const EvalArgs& 
       OwnIn o;
       o.va0 = __shfl_sync(0xffffffffu, cur.va0, own_src); o.vb0 = __shfl_sync(0xffffffffu, cur.vb0, own_src);
       o.muP = __shfl_sync(0xffffffffu, cur.muP, own_src); o.muQ = __shfl_sync(0xffffffffu, cur.muQ, own_src);
-      o.W = 0.0; o.Gl = Gl; o.Bl = Bl; o.ngen = ngen; o.nsh = nsh;
+      o.W = 0.0; o.Gl = Gl; o.Bl = Bl; o.ngen = 0; o.nsh = nsh;  // ngen = 0: the generator J entries are already in the image
       if (bact) {
         if (deg == 0) {                                         // isolated bus: nobody loaded its inputs
           o.va0 = x[P.o_a + u]; o.vb0 = x[P.o_b + u];
@@ -1280,7 +1297,7 @@ __device__ __forceinline__ void bus_warp_body(const DevPlan& P, const EvalArgs& 
         if constexpr (FORM == CBRAWV) o.W = x[P.o_Wd + u];
         auto bssv = [&](int q) { return x[P.o_bss + P.sh_idx[f0 + q]]; };
         if (wj || wh) {
-          ListW lj{imgJ, ownj + oj, wj}, lh{imgH, ownh + oh, wh};
+          ListW lj{imgJ, ownj + oj + 2 * ngen, wj}, lh{imgH, ownh + oh, wh};
           own_math<FORM>(o, bssv, lj, lj, lh);
         }
         if (need_g) {                                           // residual terms: :177-180, :256-279, :291-292
@@ -1304,8 +1321,8 @@ __device__ __forceinline__ void bus_warp_body(const DevPlan& P, const EvalArgs& 
       // ---- 4. the images go out
       fence_async_smem();
       __syncwarp();
-      if (wj) wt_store_block(jrow, imgJ, t.jn, lane);
-      if (wh) wt_store_block(hrow, imgH, t.hn, lane);
+      if (wj) wt_store_block(jrow, imgJ, blkJ, lane);
+      if (wh) wt_store_block(hrow, imgH, blkH, lane);
       if (lane == 0) bulk_commit();
       if (need_g) {
         double vmax = 0.0;

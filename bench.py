@@ -323,6 +323,24 @@ def main():
           f"{achieved:.0f} GB/s; scalars[0]={sc[0].tolist()}",
           file=sys.stderr, flush=True)
 
+    # ---- the other callbacks of the boundary: the SLP line search asks for g only, its LP set-up for g + J.
+    # Not part of `value`; per GPU, device-resident, CUDA events, 5 passes each after one warm-up pass
+    callbacks = {}
+    drv.batch.enable_timing(False)
+    for name, w in (("g", 1), ("g+J", 3)):
+        if (args.what & w) != w:
+            continue
+        drv.evaluate(w)
+        torch.cuda.synchronize()
+        c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        c0.record()
+        for _ in range(5):
+            drv.evaluate(w)
+        c1.record()
+        torch.cuda.synchronize()
+        ms = c0.elapsed_time(c1) / 5
+        ab = h.algorithmic_bytes(w)
+        callbacks[name] = {"evals_per_s_per_gpu": S / (ms * 1e-3), "ms_per_pass": ms, "algorithmic_gbs": ab * S / (ms * 1e-3) / 1e9}
     # ---- e2e: host buffers through ps_batch_eval_host
     e2e = None
     if not args.no_e2e:
@@ -368,6 +386,7 @@ def main():
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
                 "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
                 "data": "synthetic", "config": cfg, "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
+                "callbacks": callbacks,
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                              "traffic": traffic, "peak_source": peak_src, "kernel": kname,
                              "kernel_ms_per_launch": kavg["branch"], "units_per_launch": S,

@@ -68,15 +68,15 @@ struct Branch {
   // constants) and emitted in slot order as full 32-byte sectors, st.global.v4.f64, by the owning thread.
   template <int P> struct JI { static constexpr int t0 = SL.jinv[0][P], t1 = SL.jinv[1][P]; };
   template <int P> struct HI { static constexpr int t0 = SL.hinv[0][P], t1 = SL.hinv[1][P]; };
-  template <bool WJ, bool WH>
+  template <bool WJ, bool WH, bool WG = WJ>
   struct OutR {                      // WJ / WH are compile-time: a J pass and an H pass keep register pressure low
-    static constexpr bool wj = WJ, wh = WH;
+    static constexpr bool wj = WJ, wh = WH;   // (WG alone: the residual-only pass of branch_g_kernel)
     double gt[NR > 0 ? NR : 1], jt[WJ && RJ > 0 ? RJ : 1], ht[WH && RH > 0 ? RH : 1];
     bool sw, track;
     double vmax, tol;
     int nviol;
     template <int R> __device__ __forceinline__ void G(double v, bool eq) {
-      if constexpr (WJ) {            // g and the violation scalars belong to the J pass
+      if constexpr (WG) {            // g and the violation scalars belong to the J pass
         gt[R] = v;
         const double vv = eq ? fabs(v) : v;
         vmax = fmax(vmax, vv);
@@ -1804,6 +1804,61 @@ __global__ void __launch_bounds__(TPB, PS_DIRECT_MINB) branch_direct_kernel(cons
   branch_direct_body<FORM, SRC>(P, A, blockIdx.x);
 }
 
+// Residual-only pass of the branch rows (eval_constraint alone: every trial point of the SLP line search, and the
+// violation scalars): the derivative tags are compile-time dead, so this is the flow / limit expressions and nothing
+// else; g leaves through a per-warp staging row as warp-contiguous, sector-aligned stores.  Any layout.
+template <int FORM, int SRC>
+__global__ void __launch_bounds__(TPB) branch_g_kernel(const __grid_constant__ DevPlan P, const __grid_constant__ EvalArgs A) {
+  using BR = Branch<FORM, SRC>;
+  if constexpr (BR::NR > 0) {
+    __shared__ __align__(16) double sW[TPB / 32][32 * BR::NR];
+    const int u = blockIdx.x * TPB + threadIdx.x;
+    const bool act = u < P.nr;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int s0 = blockIdx.y * A.chunk, s1 = min(A.S, s0 + A.chunk);
+    const bool wg = (A.what & EV_G) != 0;
+    typename BR::template OutR<false, false, true> og;
+    og.tol = A.viol_tol;
+    typename BR::Cst cst{};
+    typename BR::In cur{};
+    int f = 0, t = 1;
+    if (act) {
+      f = P.f[u]; t = P.t[u];
+      cst = BR::load_cst(P, u);
+      cur = BR::load_in(P, A, s0, u, f, t);
+    }
+    og.sw = f > t;
+    const int ubase = blockIdx.x * TPB + w * 32;
+    const int nact = max(0, min(32, P.nr - ubase));
+    const int ng = nact * BR::NR;
+    const long long gb = P.bus_rows + (long long)ubase * BR::NR;
+    for (int s = s0; s < s1; s++) {
+      typename BR::In nxt{};
+      if (act && s + 1 < s1) nxt = BR::load_in(P, A, s + 1, u, f, t);
+      og.vmax = 0.0; og.nviol = 0;
+      if (act) BR::run(og, cst, cur);
+      if (wg) {
+        double* sg = sW[w];
+        if (act) {
+#pragma unroll
+          for (int r = 0; r < BR::NR; r++) sg[lane * BR::NR + r] = og.gt[r];
+        }
+        __syncwarp();
+        copy_aligned<32>(A.g + (long long)s * A.ldg + gb, ng, lane, [&](int e) { return sg[e]; });
+        __syncwarp();
+      }
+      reduce_scalars(A.scal ? A.scal + (long long)s * NSCAL : nullptr, og.vmax, og.nviol);
+      if (s + 1 < s1) cur = nxt;
+    }
+  }
+}
+template <int FORM>
+cudaError_t launch_branch_g_form(const DevPlan& P, const EvalArgs& A, cudaStream_t st, dim3 grid) {
+  if (P.src == SRC_MATPOWER) branch_g_kernel<FORM, SRC_MATPOWER><<<grid, TPB, 0, st>>>(P, A);
+  else branch_g_kernel<FORM, SRC_ARPAE><<<grid, TPB, 0, st>>>(P, A);
+  return cudaGetLastError();
+}
+
 template <int FORM>
 cudaError_t launch_direct(const DevPlan& P, const EvalArgs& A, cudaStream_t st, dim3 grid) {
   if (P.src == SRC_MATPOWER) branch_direct_kernel<FORM, SRC_MATPOWER><<<grid, TPB, 0, st>>>(P, A);
@@ -2118,6 +2173,11 @@ static cudaError_t launch_branch_bulk(const DevPlan& P, const EvalArgs& A, cudaS
   PS_FORM_SWITCH(PS_CALL)
 #undef PS_CALL
 }
+static cudaError_t launch_branch_g(const DevPlan& P, const EvalArgs& A, cudaStream_t stream, dim3 grid) {
+#define PS_CALL(F) launch_branch_g_form<F>(P, A, stream, grid)
+  PS_FORM_SWITCH(PS_CALL)
+#undef PS_CALL
+}
 static cudaError_t launch_branch_direct(const DevPlan& P, const EvalArgs& A, cudaStream_t stream, dim3 grid) {
 #define PS_CALL(F) launch_direct<F>(P, A, stream, grid)
   PS_FORM_SWITCH(PS_CALL)
@@ -2218,6 +2278,7 @@ cudaError_t launch_eval(const DevPlan& P, const EvalArgs& A0, int64_t smem_branc
   if (bulk && (A.what & EV_H)) bulk = pair_aligned(A.H, P.h_br0, A.ldH);
   if (launches) *launches += 1;
   KTimer kt(ev, ev_mask, stream, K_BRANCH);
+  if (!(A.what & (EV_J | EV_H)) && !getenv("PS_NO_GONLY")) return launch_branch_g(P, A, stream, dim3(nbt, (unsigned)nchunks));
   if (bulk) return launch_branch_bulk(P, A, stream, dim3(nbt, (unsigned)nchunks));
   if (direct) return launch_branch_direct(P, A, stream, dim3(nbt, (unsigned)nchunks));
   return launch_staged(P, A, (size_t)smem_branch_bytes, stream, dim3(nbt, (unsigned)nchunks));

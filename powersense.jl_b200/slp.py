@@ -229,15 +229,23 @@ class BatchedSlpLS:
         nu = np.zeros((S, m))
         hist = []
         it = 1
+        import time
+        tm = {"gpu_eval_s": 0.0, "host_lp_s": 0.0, "lp_calls": 0, "trial_batches": 0}   # where the wall time goes
+        t_run = time.perf_counter()
         while not done.all():
+            t0 = time.perf_counter()
             self._eval_all()                                        # eval_functions!, slp.jl:201-206
             mets = self._metrics(with_dir=False)
+            tm["gpu_eval_s"] += time.perf_counter() - t0
             prim, dual, compl = mets[:, 1].copy(), mets[:, 3].copy(), mets[:, 2].copy()   # :141-143
             nz, E, df, X = self.nz.cpu().numpy(), self.E.cpu().numpy(), self.df.cpu().numpy(), self.X.cpu().numpy()
             P, lam, mU, mL = np.zeros((S, n)), np.zeros((S, m)), np.zeros((S, n)), np.zeros((S, n))
             skip_step = np.zeros(S, dtype=bool)
             for s in np.nonzero(~done)[0]:
+                t0 = time.perf_counter()
                 p, l, a, b, ssum, status = self._lp(nz[s], E[s], df[s], X[s], restoration[s])      # :147-148
+                tm["host_lp_s"] += time.perf_counter() - t0
+                tm["lp_calls"] += 1
                 if status == "INFEASIBLE":                          # :160-175
                     if restoration[s]:
                         ret[s] = 6 if prim[s] <= o.tol_infeas else 2
@@ -270,6 +278,8 @@ class BatchedSlpLS:
             valid = np.ones(S, dtype=bool)
             searching = active.copy()
             while searching.any():
+                t0 = time.perf_counter()
+                tm["trial_batches"] += 1
                 self.Xt.copy_(self.X + t.from_numpy(alpha[:, None] * P).to(self.dev))
                 self._eval_g(self.Xt, self.Et, self.ft)
                 # merit at the trial point on the device (compute_phi, slp.jl:108-131): out[4] = f + sum nu*viol, and
@@ -277,6 +287,7 @@ class BatchedSlpLS:
                 self.be.metrics(self.Et, self.Xt, self.lam, self.mU, self.mL, self.df, self.nz, self.nu, self.P,
                                 self.ft.view(-1), self.metrics_t)
                 mt = self.metrics_t.cpu().numpy()
+                tm["gpu_eval_s"] += time.perf_counter() - t0
                 phi_t = np.where(restoration, mt[:, 0], mt[:, 4])
                 ok = phi_t <= phi0 + o.eta * alpha * D
                 for s in np.nonzero(searching)[0]:
@@ -328,8 +339,9 @@ class BatchedSlpLS:
             if it > 10 * o.max_iter:
                 break
         self._eval_g(self.X, self.E, self.f)
+        tm["total_s"] = time.perf_counter() - t_run
         return {"x": self.X.cpu().numpy(), "obj": self.f.cpu().numpy().ravel(), "status": ret, "iter": iters, "history": hist,
-                "g": self.E.cpu().numpy(), "lambda": self.lam.cpu().numpy()}
+                "g": self.E.cpu().numpy(), "lambda": self.lam.cpu().numpy(), "timing": tm}
 
     def close(self):
         self.be.close()

@@ -39,3 +39,31 @@ def test_case14_slp_load_scenarios_and_contingencies():
     assert np.all(res["iter"] < 80)
     drv.close()
     model.close()
+
+
+def test_case14_n1_branch_contingency_sweep():
+    """BASELINE config 5 at fixture scale: base case + every single-branch outage of the 14-bus case in one lock-step
+    batch (tools/n1_sweep.py prints the table).  Every outage that leaves the network connected is LOCALLY_SOLVED with an
+    objective at or above the base case's (to the SLP tolerance); opening the radial branch 7 - 8 islands the condenser
+    bus, which the SLP reports as not solved to optimality."""
+    M = copy.deepcopy(load_fixture("case14"))
+    model = ps.create_opf_model(M, formulation=ps.PNPAPVmodel, obj_type="linear")
+    S = M.nbr + 1
+    st = np.ones((S, M.nbr), dtype=np.uint8)
+    for k in range(M.nbr):
+        st[k + 1, k] = 0
+    drv = slp.BatchedSlpLS(model, S, np.tile(M.Pd, (S, 1)), np.tile(M.Qd, (S, 1)), status=st, options=slp.SlpOptions(max_iter=100))
+    res = drv.run()
+    radial = 1 + [tuple(b) for b in M.br.tolist()].index((7, 8))
+    connected = np.array([s != radial for s in range(S)])
+    assert np.all(res["status"][connected] == 0), res["status"]
+    assert res["status"][radial] != 0
+    assert res["obj"][0] == pytest.approx(146.7, rel=0.1)
+    assert np.all(res["obj"][connected] >= res["obj"][0] - 0.05) and np.all(res["obj"][connected] < 148.0)
+    g = res["g"]
+    viol = np.maximum(np.maximum(g - drv.g_U, drv.g_L - g), 0.0).max(axis=1)
+    assert np.all(viol[connected] <= 0.01 + 1e-9)
+    tm = res["timing"]
+    assert tm["lp_calls"] > 0 and tm["gpu_eval_s"] > 0.0
+    drv.close()
+    model.close()

@@ -1573,9 +1573,13 @@ __global__ void __launch_bounds__(TPB) objective_kernel(const __grid_constant__ 
 // Inputs of the next scenario are prefetched into registers while the current one is evaluated; the branch's
 // J and H blocks (whole 32-byte sectors) go straight from registers to HBM; g goes through a per-warp staging
 // row so that it is written with warp-contiguous stores.
+// resident CTAs the direct kernel is compiled for: the short-block models (CB*, PN*: <= 178 registers unbounded) gain from
+// a third CTA per SM (170 registers, no spills: PNPAPV branch rows 4.4 -> 4.9 TB/s), the PB* fallback (216 registers)
+// would spill; four CTAs spill everywhere (3.5 TB/s)
 #ifndef PS_DIRECT_MINB
-#define PS_DIRECT_MINB 1
+#define PS_DIRECT_MINB 3
 #endif
+constexpr int direct_minb(int form) { return is_PB(form) ? 1 : PS_DIRECT_MINB; }
 #ifndef PS_PREFETCH2
 #define PS_PREFETCH2 1
 #endif
@@ -1800,7 +1804,7 @@ cudaError_t launch_bulk(const DevPlan& P, const EvalArgs& A, cudaStream_t st, di
 }
 
 template <int FORM, int SRC>
-__global__ void __launch_bounds__(TPB, PS_DIRECT_MINB) branch_direct_kernel(const __grid_constant__ DevPlan P, const __grid_constant__ EvalArgs A) {
+__global__ void __launch_bounds__(TPB, direct_minb(FORM)) branch_direct_kernel(const __grid_constant__ DevPlan P, const __grid_constant__ EvalArgs A) {
   branch_direct_body<FORM, SRC>(P, A, blockIdx.x);
 }
 

@@ -188,3 +188,14 @@ def test_condition_scale_flags_ill_conditioned_limit_rows():
     gs, Js, Hs = o.condition_scale(x[0], np.ones(o.m_nl), Pd[0], Qd[0])
     lim = slice(2 * d.nbus, None)
     assert (gs[lim] / np.maximum(np.abs(g[lim]), 1e-300)).max() > 1e3
+
+
+def test_synthetic_branch_orders_are_the_same_network():
+    """synth_network(branch_order="file") lists the same branches as the default random permutation, in (mostly)
+    ascending from-bus order like the reference's shipped case files."""
+    from powersense_b200 import synth
+    a = synth.synth_network(300, 411, 69, seed=7, branch_order="random")
+    b = synth.synth_network(300, 411, 69, seed=7, branch_order="file")
+    assert sorted(zip(a.f.tolist(), a.t.tolist())) == sorted(zip(b.f.tolist(), b.t.tolist()))
+    descents = int(np.sum(np.diff(b.f) < 0))
+    assert descents <= 0.1 * len(b.f) < int(np.sum(np.diff(a.f) < 0))

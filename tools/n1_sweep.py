@@ -1,7 +1,8 @@
 """BASELINE config 5 at fixture scale: the N-1 branch-contingency sweep of the reference's 14-bus case solved with the
 lock-step batched SLP line search (powersense_b200.slp.BatchedSlpLS): one scenario per branch outage plus the base case,
 every evaluation on the GPU, the LP subproblems on the host.  Prints status / objective / iterations per scenario and
-where the wall time goes.  usage: python tools/n1_sweep.py [formulation]"""
+where the wall time goes.  usage: python tools/n1_sweep.py [formulation [case [n_outages]]] -- case: case14 (the
+reference's fixture, default) or a synthetic named case (powersense_b200.synth), e.g. case118"""
 import copy
 import os
 import sys
@@ -18,11 +19,14 @@ from cases import load_fixture  # noqa: E402
 
 def main():
     F = ps.BY_NAME[sys.argv[1]] if len(sys.argv) > 1 else ps.PNPAPVmodel
-    M = copy.deepcopy(load_fixture("case14"))
-    model = ps.create_opf_model(M, formulation=F, obj_type="linear")
-    S = M.nbr + 1
+    case = sys.argv[2] if len(sys.argv) > 2 else "case14"
+    M = copy.deepcopy(load_fixture(case) if case == "case14" else __import__("powersense_b200.synth", fromlist=["x"]).named_case(case))
+    obj = "linear" if case == "case14" else "quadratic"
+    model = ps.create_opf_model(M, formulation=F, obj_type=obj)
+    nout = min(int(sys.argv[3]), M.nbr) if len(sys.argv) > 3 else M.nbr
+    S = nout + 1
     st = np.ones((S, M.nbr), dtype=np.uint8)
-    for k in range(M.nbr):
+    for k in range(nout):
         st[k + 1, k] = 0
     Pd, Qd = np.tile(M.Pd, (S, 1)), np.tile(M.Qd, (S, 1))
     drv = slp.BatchedSlpLS(model, S, Pd, Qd, status=st, options=slp.SlpOptions(max_iter=100))
@@ -31,8 +35,10 @@ def main():
              -5: "OTHER"}
     g = res["g"]
     viol = np.maximum(np.maximum(g - drv.g_U, drv.g_L - g), 0.0).max(axis=1)
-    print(f"{F.name}: {S} scenarios (base + {M.nbr} single-branch outages)")
-    for s in range(S):
+    print(f"{F.name} {case}: {S} scenarios (base + {nout} single-branch outages)")
+    import collections
+    print("  status counts:", dict(collections.Counter(names.get(int(v), int(v)) for v in res["status"])))
+    for s in range(S if S <= 40 else 0):
         what = "base case" if s == 0 else f"branch {s} ({M.br[s - 1][0]} - {M.br[s - 1][1]}) out"
         print(f"  {what:28s} {names.get(int(res['status'][s]), res['status'][s]):22s} objective {res['obj'][s]:9.3f}  "
               f"iterations {int(res['iter'][s]):3d}  max violation {viol[s]:.2e}")

@@ -24,9 +24,8 @@ from typing import Optional
 
 import numpy as np
 import scipy.sparse as sp
-from scipy.optimize import linprog
 
-from . import capi
+from . import capi, lp_host
 from .opf import OPFModel
 
 
@@ -41,6 +40,7 @@ class SlpOptions:                      # src/opt/parameters.jl:16-30
     tau: float = 0.9
     min_alpha: float = 1e-8
     delta: float = 1000.0              # sub_optimize!(slp, Δ = 1000.0), slp.jl:50
+    lp_workers: int = 0                # > 0: the scenarios' LPs of one iteration are solved by that many worker processes
 
 class GpuBackend:
     """Device side of the iteration for an OPF model: every evaluation is one batched launch over the S scenarios
@@ -141,6 +141,11 @@ class BatchedSlpLS:
         if not np.all(le | ge | eq):
             raise NotImplementedError("two-sided rows reach Powersense.Optimizer split by the SplitInterval bridge")
         self.i_le, self.i_ge, self.i_eq = np.nonzero(le)[0], np.nonzero(ge)[0], np.nonzero(eq)[0]
+        self._lp_static = lp_host.LpStatic(n=n, m=m, colptr=np.asarray(self.colptr), rowval=np.asarray(self.rowval), i_le=self.i_le,
+                                           i_ge=self.i_ge, i_eq=self.i_eq, g_L=np.asarray(self.g_L), g_U=np.asarray(self.g_U),
+                                           xl=np.asarray(self.xl), xu=np.asarray(self.xu), delta=self.opt.delta,
+                                           tol_error=self.opt.tol_error)
+        self._lp_pool = lp_host.LpPool(self._lp_static, self.opt.lp_workers) if self.opt.lp_workers > 0 else None
 
     # ---- evaluations (device) ----------------------------------------------------------------------------------------
     def _eval_g(self, X, E, f):
@@ -156,61 +161,8 @@ class BatchedSlpLS:
 
     # ---- host: the LP subproblem of one scenario (subproblem.jl:55-334, 349-700) ---------------------------------
     def _lp(self, nzval, E, df, x, restoration):
-        """Normal phase: min df'p  s.t.  g_L <= E + J p <= g_U, max(-Delta, x_L - x) <= p <= min(Delta, x_U - x) -- the
-        reference fixes every slack at zero there (subproblem.jl:520-540).  Feasibility restoration: min sum(slacks) over
-        the elastic rows (subproblem.jl:369-395; the reference parametrises the same LP with b shifted by |viol| and
-        slacks bounded below by -|viol|, :404-500 -- here the slacks are the standard non-negative ones, so their sum is
-        the linearised violation after the step, which is what compute_derivative adds, slp.jl:140-143)."""
-        n, m, o = self.n, self.m, self.opt
-        J = sp.csc_matrix((nzval, self.rowval - 1, self.colptr - 1), shape=(m, n)).tocsr()
-        le, ge, eq = self.i_le, self.i_ge, self.i_eq
-        nle, nge, neq = len(le), len(ge), len(eq)
-        ns = (nle + nge + 2 * neq) if restoration else 0
-        I = sp.identity
-        Zs = lambda r, c: sp.csr_matrix((r, c))
-        ub_blocks, eq_block = [], None
-        if restoration:        # columns: [p | s_le | s_ge | s1_eq | s2_eq]
-            if nle:
-                ub_blocks.append(sp.hstack([J[le], -I(nle), Zs(nle, nge + 2 * neq)]))              # A p - s <= c_ub - b
-            if nge:
-                ub_blocks.append(sp.hstack([-J[ge], Zs(nge, nle), -I(nge), Zs(nge, 2 * neq)]))     # A p + s >= c_lb - b
-            if neq:
-                eq_block = sp.hstack([J[eq], Zs(neq, nle + nge), I(neq), -I(neq)], format="csr")   # A p + s1 - s2 = c_lb - b
-        else:
-            if nle:
-                ub_blocks.append(J[le])
-            if nge:
-                ub_blocks.append(-J[ge])
-            if neq:
-                eq_block = J[eq]
-        A_ub = sp.vstack(ub_blocks, format="csr") if ub_blocks else None
-        b_ub = np.concatenate([self.g_U[le] - E[le], -(self.g_L[ge] - E[ge])]) if ub_blocks else None
-        b_eq = self.g_L[eq] - E[eq] if neq else None
-        if o.tol_error > 0:
-            if b_ub is not None:
-                b_ub[np.abs(b_ub) <= o.tol_error] = 0.0
-            if b_eq is not None:
-                b_eq[np.abs(b_eq) <= o.tol_error] = 0.0
-        c = np.concatenate([np.zeros(n) if restoration else df, np.ones(ns)])
-        ub = np.minimum(o.delta, self.xu - x)                      # subproblem.jl:126-129
-        lb = np.maximum(-o.delta, self.xl - x)
-        bounds = np.column_stack([np.concatenate([lb, np.zeros(ns)]), np.concatenate([ub, np.full(ns, np.inf)])])
-        res = linprog(c, A_ub=A_ub, b_ub=b_ub, A_eq=eq_block, b_eq=b_eq, bounds=bounds, method="highs")
-        if res.status == 0:
-            p = res.x[:n]
-            lam = np.zeros(m)                                       # subproblem.jl:673-679 (MOI dual sign convention)
-            if ub_blocks:
-                lam[le] = res.ineqlin.marginals[:nle]
-                lam[ge] = -res.ineqlin.marginals[nle:]
-            if neq:
-                lam[eq] = res.eqlin.marginals
-            mU, mL = res.upper.marginals[:n].copy(), res.lower.marginals[:n].copy()
-            mU[p < self.xu - x] = 0.0                               # :686-693: the trust region is not a variable bound
-            mL[p > self.xl - x] = 0.0
-            return p, lam, mU, mL, float(res.x[n:].sum()), "OPTIMAL"
-        if res.status == 2:
-            return np.zeros(n), np.zeros(m), np.zeros(n), np.zeros(n), 0.0, "INFEASIBLE"
-        return np.zeros(n), np.zeros(m), np.zeros(n), np.zeros(n), 0.0, "OTHER"
+        """The LP subproblem of one scenario (lp_host.solve_lp; subproblem.jl:55-334, 657-700)."""
+        return lp_host.solve_lp(self._lp_static, nzval, E, df, x, restoration)
 
     # ---- the algorithm (slp_line_search.jl:80-249) -----------------------------------------------------------------
     def run(self, x0: Optional[np.ndarray] = None):
@@ -241,11 +193,13 @@ class BatchedSlpLS:
             nz, E, df, X = self.nz.cpu().numpy(), self.E.cpu().numpy(), self.df.cpu().numpy(), self.X.cpu().numpy()
             P, lam, mU, mL = np.zeros((S, n)), np.zeros((S, m)), np.zeros((S, n)), np.zeros((S, n))
             skip_step = np.zeros(S, dtype=bool)
-            for s in np.nonzero(~done)[0]:
-                t0 = time.perf_counter()
-                p, l, a, b, ssum, status = self._lp(nz[s], E[s], df[s], X[s], restoration[s])      # :147-148
-                tm["host_lp_s"] += time.perf_counter() - t0
-                tm["lp_calls"] += 1
+            todo = np.nonzero(~done)[0]
+            t0 = time.perf_counter()
+            jobs = [(nz[s], E[s], df[s], X[s], bool(restoration[s])) for s in todo]
+            sols = self._lp_pool.solve_many(jobs) if self._lp_pool is not None else [self._lp(*j) for j in jobs]   # :147-148
+            tm["host_lp_s"] += time.perf_counter() - t0
+            tm["lp_calls"] += len(jobs)
+            for s, (p, l, a, b, ssum, status) in zip(todo, sols):
                 if status == "INFEASIBLE":                          # :160-175
                     if restoration[s]:
                         ret[s] = 6 if prim[s] <= o.tol_infeas else 2
@@ -344,6 +298,9 @@ class BatchedSlpLS:
                 "g": self.E.cpu().numpy(), "lambda": self.lam.cpu().numpy(), "timing": tm}
 
     def close(self):
+        if self._lp_pool is not None:
+            self._lp_pool.close()
+            self._lp_pool = None
         self.be.close()
 
 

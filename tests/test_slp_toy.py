@@ -74,3 +74,19 @@ def test_reference_toy_problem_known_answer(S):
     np.testing.assert_allclose(out["x"], -1.0, rtol=1e-4)                # test/runtests.jl:20-21
     np.testing.assert_allclose(out["obj"], 0.0, atol=1e-6)
     drv.close()
+
+
+def test_pooled_lps_reproduce_the_serial_run():
+    """The LP subproblems of one lock-step iteration are independent; solved by worker processes (SlpOptions.lp_workers)
+    they give exactly the iterates of the serial run."""
+    S = 3
+    x0 = np.array([[0.0, 0.0], [-0.5, -0.5], [-2.0, -3.0]])
+    runs = []
+    for workers in (0, 2):
+        drv = slp.BatchedSlpLS(None, S, backend=HostToyBackend(S), options=slp.SlpOptions(lp_workers=workers))
+        runs.append(drv.run(x0))
+        drv.close()
+    a, b = runs
+    assert np.array_equal(a["status"], b["status"]) and np.array_equal(a["iter"], b["iter"])
+    assert np.array_equal(a["x"], b["x"]) and np.array_equal(a["lambda"], b["lambda"])
+    assert b["timing"]["lp_calls"] == a["timing"]["lp_calls"] > 0

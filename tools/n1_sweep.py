@@ -1,7 +1,7 @@
 """BASELINE config 5 at fixture scale: the N-1 branch-contingency sweep of the reference's 14-bus case solved with the
 lock-step batched SLP line search (powersense_b200.slp.BatchedSlpLS): one scenario per branch outage plus the base case,
 every evaluation on the GPU, the LP subproblems on the host.  Prints status / objective / iterations per scenario and
-where the wall time goes.  usage: python tools/n1_sweep.py [formulation [case [n_outages]]] -- case: case14 (the
+where the wall time goes.  usage: python tools/n1_sweep.py [formulation [case [n_outages [lp_workers]]]] -- case: case14 (the
 reference's fixture, default) or a synthetic named case (powersense_b200.synth), e.g. case118"""
 import copy
 import os
@@ -29,7 +29,8 @@ def main():
     for k in range(nout):
         st[k + 1, k] = 0
     Pd, Qd = np.tile(M.Pd, (S, 1)), np.tile(M.Qd, (S, 1))
-    drv = slp.BatchedSlpLS(model, S, Pd, Qd, status=st, options=slp.SlpOptions(max_iter=100))
+    workers = int(sys.argv[4]) if len(sys.argv) > 4 else 0
+    drv = slp.BatchedSlpLS(model, S, Pd, Qd, status=st, options=slp.SlpOptions(max_iter=100, lp_workers=workers))
     res = drv.run()
     names = {0: "LOCALLY_SOLVED", 2: "LOCALLY_INFEASIBLE", 6: "ALMOST_LOCALLY_SOLVED", -1: "ITERATION_LIMIT", -3: "NUMERICAL_ERROR",
              -5: "OTHER"}
@@ -43,7 +44,7 @@ def main():
         print(f"  {what:28s} {names.get(int(res['status'][s]), res['status'][s]):22s} objective {res['obj'][s]:9.3f}  "
               f"iterations {int(res['iter'][s]):3d}  max violation {viol[s]:.2e}")
     tm = res["timing"]
-    print(f"wall {tm['total_s']:.2f} s: host LPs {tm['host_lp_s']:.2f} s ({tm['lp_calls']} calls, serial), GPU evaluations + metrics "
+    print(f"wall {tm['total_s']:.2f} s: host LPs {tm['host_lp_s']:.2f} s ({tm['lp_calls']} calls, {f"{workers} worker processes" if workers else "serial"}), GPU evaluations + metrics "
           f"{tm['gpu_eval_s']:.2f} s ({len(res['history'])} lock-step iterations, {tm['trial_batches']} batched trial points)")
     drv.close()
     model.close()

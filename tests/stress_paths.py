@@ -1,8 +1,9 @@
-"""Randomised cross-check of the kernel paths (development tool, needs a GPU): many small seeded networks -- parallel
+"""Randomised cross-check of the kernel paths (test infrastructure, needs a GPU; test_gpu_stress.py runs a short pass,
+`python tests/stress_paths.py 200` the long one): many small seeded networks -- parallel
 branches, out-of-service elements, switched shunts, both source types, hubs, isolated buses -- every formulation, random
 layouts; the default path, the warp-tile path (PS_NO_CBFAST / PS_NO_PBFAST) and the CTA-tile path (PS_NO_WARPBUS) must
 agree bitwise, with and without a status mask, and the default path must match the CPU oracle.
-usage: python tools/stress_paths.py [n_networks]"""
+usage: python tests/stress_paths.py [n_networks]"""
 import os
 import sys
 
@@ -11,7 +12,6 @@ import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
-import torch  # noqa: E402
 
 import powersense_b200 as ps  # noqa: E402
 from powersense_b200 import capi, synth  # noqa: E402
@@ -20,6 +20,7 @@ from cases import tol_err_scaled  # noqa: E402
 
 
 def main(n):
+    import torch
     dev = torch.device("cuda:0")
     rng = np.random.default_rng(int(os.environ.get("PS_STRESS_SEED", "2024")))
     bad = 0

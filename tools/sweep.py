@@ -73,6 +73,9 @@ if __name__ == "__main__":
         for cpb in (2, 4, 8, 16):
             os.environ["PS_CHUNK_PB"] = str(cpb)
             run("case13659pegase", "PBRARVmodel", 2048, [4, 8, 16])
+    if sel == "all9":
+        for F in ps.ALL_FORMULATIONS:
+            run("case13659pegase", F.name, 512, [16])
     if sel == "pn":
         run("case9241pegase", "PNPAPVmodel", 512, [16])
         run("case13659pegase", "CBRARVmodel", 512, [16])

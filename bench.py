@@ -57,7 +57,9 @@ def parse_args():
 def workload_config(args, h=None):
     cfg = {"workload": f"{args.case} (synthetic topology, published dimensions) {args.formulation} g+J+H batched evaluation",
            "case": args.case, "formulation": args.formulation, "what": args.what,
-           "scenarios_per_gpu": args.scenarios, "l2": "inputs+outputs per step >> 126 MB L2 (no flush needed)"}
+           "scenarios_per_gpu": args.scenarios, "l2": "inputs+outputs per step >> 126 MB L2 (no flush needed)",
+           "synthetic_branch_order": os.environ.get("PS_SYNTH_ORDER", "random") + " (random = permuted branch list, the adversarial order "
+                                     "for the gathers; file = ascending from-bus like real case files)"}
     return cfg
 
 

@@ -1082,8 +1082,10 @@ __global__ void __launch_bounds__(BTPB, PS_BUS_MINB) bus_kernel(const __grid_con
 //      whole lines to HBM while the warp evaluates the next scenario.  An odd first slot is matched by shifting the
 //      image by one double, so that image and destination share their 16-byte phase (any other layout: a coalesced
 //      copy loop).  The residual rows are stored, and folded into the violation scalars, by the lanes.
+// one warp per CTA: the warps share nothing, and a CTA of several tiles holds its registers and shared memory until its
+// slowest tile is done (4 warps per CTA: 3 % slower)
 #ifndef PS_WT_WPC
-#define PS_WT_WPC 4
+#define PS_WT_WPC 1
 #endif
 constexpr int WPC = PS_WT_WPC;     // warps (= tiles) per CTA
 
@@ -1347,7 +1349,7 @@ __device__ __forceinline__ void bus_warp_body(const DevPlan& P, const EvalArgs& 
 }
 
 #ifndef PS_WT_MINB
-#define PS_WT_MINB 4
+#define PS_WT_MINB 16               // 16 warps / SM: 128 registers per thread
 #endif
 __host__ __device__ inline int wt_region_doubles(const DevPlan& P) {   // per-warp shared memory, doubles (even)
   return P.wt_jspace + P.wt_hspace + P.wt_gspace + ((P.wt_lists + 7) / 8) * 2;

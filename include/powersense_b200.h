@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define PS_ABI_VERSION 1
+#define PS_ABI_VERSION 2
 /* `device` argument of ps_create: CUDA ordinal, PS_DEVICE_CURRENT, or PS_DEVICE_NONE for a structure-only
  * handle (ps_dims / ps_constraint_bounds / ps_*_structure / ps_variable_offsets work; every evaluation entry
  * point returns PS_ERR_STATE -- there is no CPU evaluation path) */
@@ -106,6 +106,27 @@ int ps_constraint_bounds(const ps_handle* h, double* lo, double* hi);
 int ps_jacobian_structure(const ps_handle* h, int64_t* row, int64_t* col);
 /* MOI.hessian_lagrangian_structure (src/opt/MOI_wrapper.jl:855): per-row blocks, lower-triangular tuples */
 int ps_hessian_structure(const ps_handle* h, int64_t* row, int64_t* col);
+/* ---- Hessian slot order -------------------------------------------------------------------------------------------
+ * JuMP lays every NL row's Hessian block out as [diagonal slots of the row's variables, ascending][off-diagonal slots in
+ * the order its acyclic-colouring recovery produces]; the second part depends on Julia's Set hash order and
+ * cannot be derived without running Julia.  ps_hessian_structure therefore reports a documented canonical order (diagonal
+ * slots ascending, then lower-triangular pairs (max, min) ascending) -- and these entry points let a caller that HAS the
+ * JuMP order (julia/make_golden.jl dumps it; julia/GpuNLPEvaluator.jl can fetch it from a throw-away JuMP evaluator)
+ * install it, so that structure and values cross the ABI in exactly JuMP's order.  The kernels are untouched: they keep
+ * writing the canonical order, a gather pass (device) applies the permutation to H before it leaves the library.
+ *
+ * ps_hessian_row_blocks: ptr[r] .. ptr[r+1] (0-based, m_nl + 1 entries) = the slots of NL row r in the canonical structure.
+ * ps_set_hessian_order: perm[i] (1-based, a permutation of 1..nnz_hess) = canonical position of the entry reported at
+ *   position i from now on, by ps_hessian_structure and by every evaluation entry point; NULL restores the canonical order.
+ * ps_match_hessian_structure: derive that permutation from a target structure (1-based (var, var) tuples, either triangle),
+ *   assumed -- like JuMP's -- to be the concatenation of the same per-row blocks in row order: inside every row block the
+ *   target must hold the same set of variable pairs; fails with PS_ERR_ARG naming the first row whose block differs.
+ * ps_hessian_order: the permutation in force (identity when none). */
+int ps_hessian_row_blocks(const ps_handle* h, int64_t* ptr);
+int ps_set_hessian_order(ps_handle* h, const int64_t* perm);
+int ps_match_hessian_structure(ps_handle* h, const int64_t* row, const int64_t* col);
+int ps_hessian_order(const ps_handle* h, int64_t* perm);
+
 /* 0-based offsets of the variable blocks (formulations.jl:20-67): out[0..15] =
  * a(theta|vi), b(V|vr), Wd, Wr, Wi, pg, qg, F0, F1, F2, F3, cg, bss, tgh, n_var, nx_nl ; -1 = absent */
 int ps_variable_offsets(const ps_handle* h, int64_t out[16]);
@@ -121,7 +142,12 @@ int ps_plan_info(const ps_handle* h, int64_t out[8]);
  * layouts are accepted and take the staged path. */
 int ps_preferred_layout(const ps_handle* h, int64_t ld[3], int64_t pad[3]);
 
-/* ---- single-scenario callbacks: host pointers, synchronous -------------------------------- */
+/* ---- single-scenario callbacks: host pointers, synchronous --------------------------------
+ * Like JuMP's evaluator (which keeps its forward pass while x is unchanged) the handle remembers the x of
+ * the last call: a callback at a new x evaluates g AND J in one launch (when the caller's previous point asked for both),
+ * keeps them on the device, and the sibling callback at the same x is served from there without a launch or an upload of
+ * x.  eval_hessian needs the multipliers, which arrive with it: one launch of its own (x is not uploaded again).
+ * ps_launch_count reports the kernel launches issued by these callbacks so far. */
 /* MOI.eval_constraint(d, g, x) (call site src/opt/MOI_wrapper.jl:969).  `g` may point into a larger
  * array (the wrapper passes view(g, row:length(g)), :967). */
 int ps_eval_constraint(ps_handle* h, const double* x, double* g);
@@ -137,9 +163,13 @@ int ps_eval_all(ps_handle* h, const double* x, const double* mu, double* g, doub
  * (has_objective = false, src/opt/MOI_wrapper.jl:897,938); the objective of formulations.jl:122-138 is
  * provided for the batched driver's scalars. */
 int ps_eval_objective(ps_handle* h, const double* x, double* f);
+int64_t ps_launch_count(const ps_handle* h);
 
 /* ---- batched, device-resident evaluation (the roofline path) ------------------------------ */
-/* Per-scenario data lives on `device` (defaults: the network's own loads, every branch in service). */
+/* Per-scenario data lives on `device` (defaults: the network's own loads, every branch in service).
+ * Lifetime: a ps_batch must be destroyed before its ps_handle, a ps_kkt may outlive its ps_csc (it copies what it needs).
+ * Concurrency: calls on one batch may use different streams as long as their scenario ranges do not overlap (the CB*
+ * models keep a per-scenario scratch between their two bus kernels); one in-flight evaluation per scenario range. */
 int ps_batch_create(ps_handle* h, int64_t S, ps_batch** out);
 void ps_batch_destroy(ps_batch* b);
 /* Pd, Qd: host [S][nbus] row-major (scenario loads: the only per-scenario constants of the NL rows) */
@@ -229,7 +259,7 @@ int ps_rows_eval_batch(ps_rows* r, int what, int64_t S, const double* x, int64_t
  * 4 phi = f + sum nu_i * viol_i, 5 D = df'p - sum nu_i * viol_i, 6 ||df||_2, 7 max_i |lambda_i| * ||J[i,:]||_2. */
 #define PS_NKKT 8
 typedef struct ps_kkt ps_kkt;
-/* bounds: g_L, g_U [m], x_L, x_U [n] (host; +-Inf allowed); the pattern must outlive the ps_kkt */
+/* bounds: g_L, g_U [m], x_L, x_U [n] (host; +-Inf allowed); the pattern's index arrays are copied */
 int ps_kkt_create(ps_csc* pattern, const double* g_L, const double* g_U, const double* x_L, const double* x_U, ps_kkt** out);
 void ps_kkt_destroy(ps_kkt* k);
 /* DEVICE pointers; row s of an array at ptr + s*ld; f [S]; nu / p may be NULL (out[4], out[5] are then f and 0);

@@ -48,6 +48,10 @@ _SIGS = {
     "ps_constraint_bounds": (C.c_int, [_VP, _PD, _PD]),
     "ps_jacobian_structure": (C.c_int, [_VP, _P64, _P64]),
     "ps_hessian_structure": (C.c_int, [_VP, _P64, _P64]),
+    "ps_hessian_row_blocks": (C.c_int, [_VP, _P64]),
+    "ps_set_hessian_order": (C.c_int, [_VP, _P64]),
+    "ps_match_hessian_structure": (C.c_int, [_VP, _P64, _P64]),
+    "ps_hessian_order": (C.c_int, [_VP, _P64]),
     "ps_variable_offsets": (C.c_int, [_VP, _P64]),
     "ps_plan_info": (C.c_int, [_VP, _P64]),
     "ps_preferred_layout": (C.c_int, [_VP, _P64, _P64]),
@@ -56,6 +60,7 @@ _SIGS = {
     "ps_eval_hessian": (C.c_int, [_VP, _PD, C.c_double, _PD, _PD]),
     "ps_eval_all": (C.c_int, [_VP, _PD, _PD, _PD, _PD, _PD]),
     "ps_eval_objective": (C.c_int, [_VP, _PD, _PD]),
+    "ps_launch_count": (C.c_int64, [_VP]),
     "ps_batch_create": (C.c_int, [_VP, C.c_int64, C.POINTER(_VP)]),
     "ps_batch_destroy": (None, [_VP]),
     "ps_batch_set_loads": (C.c_int, [_VP, _PD, _PD]),
@@ -192,6 +197,36 @@ class Handle:
         r, c = np.zeros(self.nnzH, np.int64), np.zeros(self.nnzH, np.int64)
         self._check(lib().ps_hessian_structure(self.h, _p64(r), _p64(c)))
         return r, c
+
+    def hessian_row_blocks(self):
+        """0-based offsets [m_nl + 1] of the per-row blocks of the Hessian structure."""
+        ptr = np.zeros(self.m_nl + 1, np.int64)
+        self._check(lib().ps_hessian_row_blocks(self.h, _p64(ptr)))
+        return ptr
+
+    def set_hessian_order(self, perm):
+        """perm[i] = 1-based canonical position of the entry reported at position i (None: canonical order)."""
+        if perm is None:
+            self._check(lib().ps_set_hessian_order(self.h, None))
+            return
+        perm = np.ascontiguousarray(perm, dtype=np.int64)
+        assert perm.size == self.nnzH
+        self._check(lib().ps_set_hessian_order(self.h, _p64(perm)))
+
+    def match_hessian_structure(self, row, col):
+        """Install the slot order of a target structure (e.g. JuMP's own, dumped by julia/make_golden.jl)."""
+        row, col = np.ascontiguousarray(row, dtype=np.int64), np.ascontiguousarray(col, dtype=np.int64)
+        assert row.size == self.nnzH and col.size == self.nnzH
+        self._check(lib().ps_match_hessian_structure(self.h, _p64(row), _p64(col)))
+
+    def hessian_order(self):
+        perm = np.zeros(self.nnzH, np.int64)
+        self._check(lib().ps_hessian_order(self.h, _p64(perm)))
+        return perm
+
+    def launch_count(self):
+        """kernel launches issued by the single-scenario callbacks so far"""
+        return int(lib().ps_launch_count(self.h))
 
     def variable_offsets(self):
         out = np.zeros(16, np.int64)

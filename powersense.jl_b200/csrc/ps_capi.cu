@@ -53,13 +53,24 @@ struct ps_handle {
   std::string err;
   ps_batch* single = nullptr;        // S = 1 batch behind the MOI-style callbacks
   double *h_in = nullptr, *h_out = nullptr;   // pinned staging for the single-scenario calls
+  // result cache of the single-scenario callbacks: h_in[0 .. n_var) / d_x hold the x of the last call,
+  // cache_dev says which of d_g / d_J belong to it; want_prev / want_cur = outputs asked for at the previous / current x
+  bool cache_x = false;
+  int cache_dev = 0, want_prev = EV_G | EV_J, want_cur = 0;
+  // Hessian slot order imposed by the caller (ps_set_hessian_order): reported slot i = canonical slot hperm[i]
+  std::vector<int32_t> hperm;
+  int32_t* d_hperm = nullptr;
   double *d_x = nullptr, *d_mu = nullptr, *d_g = nullptr, *d_J = nullptr, *d_H = nullptr, *d_scal = nullptr;
   cudaStream_t stream = nullptr;
 };
 
 struct ps_batch {
   ps_handle* h = nullptr;
+  int device = 0;                    // copied from the handle: ps_batch_destroy does not touch it
   int64_t S = 0;
+  bool status_active = false;        // a contingency mask is in force (ps_batch_set_branch_status(NULL) clears it)
+  double* d_Hs = nullptr;            // canonical-order Hessian slab when the handle carries a slot permutation
+  int64_t Hs_rows = 0;
   DevMem mem;
   double *d_Pd = nullptr, *d_Qd = nullptr;
   uint8_t* d_status = nullptr;
@@ -99,7 +110,7 @@ struct ps_rows {
 };
 
 struct ps_kkt {
-  ps_csc* pat = nullptr;
+  int64_t nnz = 0;                   // copied from the pattern (the ps_csc may be destroyed first)
   KktDev dev{};
   DevMem mem;
   int device = 0;
@@ -173,7 +184,7 @@ int do_eval(ps_batch* b, int what, int64_t s_begin, int64_t s_count, const doubl
   A.Pd = b->d_Pd ? b->d_Pd + s_begin * P.net.nbus : nullptr;
   A.Qd = b->d_Qd ? b->d_Qd + s_begin * P.net.nbus : nullptr;
   A.ldl = P.net.nbus;
-  A.status = b->d_status ? b->d_status + s_begin * P.net.nbr : nullptr;
+  A.status = (b->d_status && b->status_active) ? b->d_status + s_begin * P.net.nbr : nullptr;
   A.ldst = P.net.nbr;
   A.g = g; A.ldg = ldg; A.J = J; A.ldJ = ldJ; A.H = H; A.ldH = ldH;
   A.scal = scalars; A.viol_tol = b->viol_tol;
@@ -186,8 +197,37 @@ int do_eval(ps_batch* b, int what, int64_t s_begin, int64_t s_count, const doubl
     A.diag = b->d_diag + s_begin * 4 * P.net.nbus;
   }
   b->tmask = 0;
-  e = launch_eval(h->dev, A, P.smem_branch_bytes, P.smem_bus_bytes, stream, &b->launches, b->timing ? b->tev : nullptr, &b->tmask);
-  if (e != cudaSuccess) return cuda_fail(h, e, "eval_kernel launch");
+  if ((what & EV_H) && h->d_hperm) {
+    // a caller-imposed Hessian slot order: the kernels write their canonical order into a slab (laid out like
+    // ps_preferred_layout, so the fast store paths apply), one gather per slab moves it to the caller's rows
+    const int64_t ldHs = (P.nnzH + 3) / 4 * 4, pad = (4 - P.hptr[P.bus_rows] % 4) % 4;
+    const int64_t rows = std::max<int64_t>(1, std::min<int64_t>(s_count, (int64_t(256) << 20) / (ldHs * 8)));
+    if (b->Hs_rows < rows) {
+      // (the old slab, if any, stays owned by b->mem until the batch is destroyed; slabs only grow on the first calls)
+      b->d_Hs = b->mem.alloc<double>((size_t)(rows * ldHs + 4));
+      if (!b->d_Hs) return cuda_fail(h, b->mem.err, "cudaMalloc(Hessian slab)");
+      b->Hs_rows = rows;
+    }
+    for (int64_t c0 = 0; c0 < s_count; c0 += rows) {
+      const int64_t n = std::min<int64_t>(rows, s_count - c0);
+      EvalArgs As = A;
+      As.S = (int)n; As.chunk = pick_chunk(b, n, h->dev.ntiles);
+      As.x = x + c0 * ldx; As.mu = mu + c0 * ldmu;
+      if (As.Pd) { As.Pd += c0 * P.net.nbus; As.Qd += c0 * P.net.nbus; }
+      if (As.status) As.status += c0 * P.net.nbr;
+      if (As.g) As.g += c0 * ldg;
+      if (As.J) As.J += c0 * ldJ;
+      if (As.scal) As.scal += c0 * NSCAL;
+      if (As.diag) As.diag += c0 * As.lddiag;
+      As.H = b->d_Hs + pad; As.ldH = ldHs;
+      e = launch_eval(h->dev, As, P.smem_branch_bytes, P.smem_bus_bytes, stream, &b->launches, b->timing ? b->tev : nullptr, &b->tmask);
+      if (e == cudaSuccess) { e = launch_permute_rows(h->d_hperm, (int)P.nnzH, n, As.H, ldHs, H + c0 * ldH, ldH, stream); b->launches += 1; }
+      if (e != cudaSuccess) return cuda_fail(h, e, "eval_kernel launch (permuted Hessian)");
+    }
+  } else {
+    e = launch_eval(h->dev, A, P.smem_branch_bytes, P.smem_bus_bytes, stream, &b->launches, b->timing ? b->tev : nullptr, &b->tmask);
+    if (e != cudaSuccess) return cuda_fail(h, e, "eval_kernel launch");
+  }
   b->launches += (scalars ? 1 : 0);                  // the memset node
   return PS_OK;
 }
@@ -318,6 +358,8 @@ int ps_create(const ps_network* net, int formulation, int source_type, int flags
     D.pb_ht = M.upload(shifted(ht, sh)); D.pb_hi = M.upload(shifted(hi, sh));
     D.pb_jstride = (int)sj; D.pb_hstride = (int)sh;
   }
+  D.pbs_ok = P.pbs_ok ? 1 : 0;
+  if (P.pbs_ok) { D.pbs_code = M.upload(P.pbs_code); D.pbs_wmax = M.upload(P.pbs_wmax); }
   D.cb_slots = 0;
   if (is_CB(P.form) && nb > 0 && P.bus_rows == 2 * nb) {
     // CB* slot tables (same layout and kernel as the PB* ones).  Every entry of the bus block is coefficient * m:
@@ -405,7 +447,7 @@ int ps_create(const ps_network* net, int formulation, int source_type, int flags
   D.wt_owng = M.upload(P.wt_owng);
   D.wt_ownj_ptr = M.upload(P.wt_ownj_ptr); D.wt_ownh_ptr = M.upload(P.wt_ownh_ptr); D.wt_owng_ptr = M.upload(P.wt_owng_ptr);
   // single-scenario staging
-  const int64_t n_in = P.n_var + P.m_nl, n_out = P.m_nl + P.nnzJ + P.nnzH + NSCAL;
+  const int64_t n_in = P.n_var + P.m_nl, n_out = NSCAL;
   h->d_x = M.alloc<double>(P.n_var); h->d_mu = M.alloc<double>(P.m_nl);
   h->d_g = M.alloc<double>(P.m_nl); h->d_J = M.alloc<double>(P.nnzJ); h->d_H = M.alloc<double>(P.nnzH);
   h->d_scal = M.alloc<double>(NSCAL);
@@ -413,7 +455,7 @@ int ps_create(const ps_network* net, int formulation, int source_type, int flags
   if ((e = cudaHostAlloc((void**)&h->h_in, std::max<int64_t>(n_in, 1) * sizeof(double), cudaHostAllocDefault)) != cudaSuccess ||
       (e = cudaHostAlloc((void**)&h->h_out, std::max<int64_t>(n_out, 1) * sizeof(double), cudaHostAllocDefault)) != cudaSuccess ||
       (e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking)) != cudaSuccess ||
-      (e = configure_eval(P.form, P.src, P.smem_branch_bytes, P.smem_bus_bytes, wt_smem_bytes(D))) != cudaSuccess) {
+      (e = configure_eval(P.form, P.src, P.smem_branch_bytes, P.smem_bus_bytes, wt_smem_bytes(D), pbs_smem_bytes(D))) != cudaSuccess) {
     ps_destroy(h);
     return cuda_fail(nullptr, e, "handle setup");
   }
@@ -460,9 +502,84 @@ int ps_jacobian_structure(const ps_handle* h, int64_t* row, int64_t* col) {
 
 int ps_hessian_structure(const ps_handle* h, int64_t* row, int64_t* col) {
   if (!h || !row || !col) return PS_ERR_ARG;
-  std::copy(h->plan.hrow.begin(), h->plan.hrow.end(), row);
-  std::copy(h->plan.hcol.begin(), h->plan.hcol.end(), col);
+  const Plan& P = h->plan;
+  if (h->hperm.empty()) {
+    std::copy(P.hrow.begin(), P.hrow.end(), row);
+    std::copy(P.hcol.begin(), P.hcol.end(), col);
+  } else {
+    for (int64_t i = 0; i < P.nnzH; i++) { row[i] = P.hrow[h->hperm[i]]; col[i] = P.hcol[h->hperm[i]]; }
+  }
   return PS_OK;
+}
+
+int ps_hessian_row_blocks(const ps_handle* h, int64_t* ptr) {
+  if (!h || !ptr) return PS_ERR_ARG;
+  for (int64_t r = 0; r <= h->plan.m_nl; r++) ptr[r] = h->plan.hptr[r];
+  return PS_OK;
+}
+
+int ps_hessian_order(const ps_handle* h, int64_t* perm) {
+  if (!h || !perm) return PS_ERR_ARG;
+  for (int64_t i = 0; i < h->plan.nnzH; i++) perm[i] = h->hperm.empty() ? i + 1 : (int64_t)h->hperm[i] + 1;
+  return PS_OK;
+}
+
+int ps_set_hessian_order(ps_handle* hh, const int64_t* perm) {
+  if (!hh) return PS_ERR_ARG;
+  ps_handle* h = hh;
+  const int64_t n = h->plan.nnzH;
+  std::vector<int32_t> p;
+  if (perm) {
+    p.resize((size_t)n);
+    std::vector<uint8_t> seen((size_t)n, 0);
+    bool ident = true;
+    for (int64_t i = 0; i < n; i++) {
+      if (perm[i] < 1 || perm[i] > n || seen[perm[i] - 1]) return fail(h, PS_ERR_ARG, "Hessian order is not a permutation of 1..nnz_hess");
+      seen[perm[i] - 1] = 1;
+      p[i] = (int32_t)(perm[i] - 1);
+      ident = ident && perm[i] == i + 1;
+    }
+    if (ident) p.clear();
+  }
+  if (h->device != PS_DEVICE_NONE) {
+    cudaError_t e = cudaSetDevice(h->device);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+    if (e != cudaSuccess) return cuda_fail(h, e, "cudaSetDevice");
+    int32_t* d = nullptr;
+    if (!p.empty()) {
+      d = h->mem.upload(p);                          // (an earlier table stays owned by the handle until ps_destroy)
+      if (!d || h->mem.err != cudaSuccess) return cuda_fail(h, h->mem.err, "cudaMalloc(Hessian order)");
+    }
+    h->d_hperm = d;
+  }
+  h->hperm.swap(p);
+  return PS_OK;
+}
+
+int ps_match_hessian_structure(ps_handle* h, const int64_t* row, const int64_t* col) {
+  if (!h) return PS_ERR_ARG;
+  if (!row || !col) return fail(h, PS_ERR_ARG, "null structure");
+  const Plan& P = h->plan;
+  std::vector<int64_t> perm((size_t)P.nnzH);
+  std::vector<std::pair<std::pair<int64_t, int64_t>, int64_t>> blk;
+  for (int64_t r = 0; r < P.m_nl; r++) {
+    const int64_t e0 = P.hptr[r], e1 = P.hptr[r + 1];
+    blk.clear();
+    for (int64_t e = e0; e < e1; e++) blk.push_back({{std::max(P.hrow[e], P.hcol[e]), std::min(P.hrow[e], P.hcol[e])}, e});
+    std::sort(blk.begin(), blk.end());
+    std::vector<uint8_t> used(blk.size(), 0);
+    for (int64_t i = e0; i < e1; i++) {
+      const std::pair<int64_t, int64_t> key{std::max(row[i], col[i]), std::min(row[i], col[i])};
+      auto it = std::lower_bound(blk.begin(), blk.end(), std::make_pair(key, (int64_t)-1));
+      while (it != blk.end() && it->first == key && used[it - blk.begin()]) ++it;
+      if (it == blk.end() || it->first != key)
+        return fail(h, PS_ERR_ARG, "Hessian structure differs in the block of NL row " + std::to_string(r + 1) + ": pair (" +
+                                       std::to_string(row[i]) + ", " + std::to_string(col[i]) + ") at position " + std::to_string(i + 1));
+      used[it - blk.begin()] = 1;
+      perm[i] = it->second + 1;
+    }
+  }
+  return ps_set_hessian_order(h, perm.data());
 }
 
 int ps_variable_offsets(const ps_handle* h, int64_t out[16]) {
@@ -524,6 +641,9 @@ int64_t ps_algorithmic_bytes_branch(const ps_handle* h, int what) {
 }
 
 // ---- single-scenario callbacks ------------------------------------------------------------
+// The x of the last call stays in pinned h_in (the comparison key) and on the device, together with the g / J computed
+// from it: JuMP's evaluator reuses its forward pass while x is unchanged and solvers rely on that -- Ipopt
+// calls eval_g, eval_jac_g and eval_h at the same point.  Outputs go from the device straight to the caller's buffers.
 static int eval_single(ps_handle* h, int what, const double* x, const double* mu, double* g, double* J, double* H,
                        double* f) {
   if (!h) return PS_ERR_ARG;
@@ -533,32 +653,49 @@ static int eval_single(ps_handle* h, int what, const double* x, const double* mu
   cudaError_t e = cudaSetDevice(h->device);
   if (e != cudaSuccess) return cuda_fail(h, e, "cudaSetDevice");
   if ((what & EV_H) && !mu) return fail(h, PS_ERR_ARG, "mu is null");
-  std::memcpy(h->h_in, x, (size_t)P.n_var * sizeof(double));
-  e = cudaMemcpyAsync(h->d_x, h->h_in, (size_t)P.n_var * sizeof(double), cudaMemcpyHostToDevice, h->stream);
-  if (e == cudaSuccess && (what & EV_H)) {
+  const size_t xb = (size_t)P.n_var * sizeof(double);
+  const bool same_x = h->cache_x && !getenv("PS_NO_CACHE") && std::memcmp(h->h_in, x, xb) == 0;
+  if (!same_x) {
+    std::memcpy(h->h_in, x, xb);
+    e = cudaMemcpyAsync(h->d_x, h->h_in, xb, cudaMemcpyHostToDevice, h->stream);
+    if (e != cudaSuccess) { h->cache_x = false; return cuda_fail(h, e, "H2D copy"); }
+    h->cache_x = true; h->cache_dev = 0;
+    if (h->want_cur) h->want_prev = h->want_cur;
+    h->want_cur = 0;
+  }
+  h->want_cur |= what & (EV_G | EV_J);
+  // what has to be computed: the requested g / J that the device does not hold for this x -- widened to g + J when the
+  // caller's previous point asked for both -- and H, whose multipliers arrive with the call
+  int need = what & (EV_G | EV_J) & ~h->cache_dev;
+  if (need && (h->want_prev & (EV_G | EV_J)) == (EV_G | EV_J)) need = (EV_G | EV_J) & ~h->cache_dev;
+  if (P.m_nl == 0) need &= ~EV_G;
+  if (P.nnzJ == 0) need &= ~EV_J;
+  const int lw = need | (what & EV_H);
+  if (what & EV_H) {
     std::memcpy(h->h_in + P.n_var, mu, (size_t)P.m_nl * sizeof(double));
     e = cudaMemcpyAsync(h->d_mu, h->h_in + P.n_var, (size_t)P.m_nl * sizeof(double), cudaMemcpyHostToDevice, h->stream);
+    if (e != cudaSuccess) return cuda_fail(h, e, "H2D copy");
   }
-  if (e != cudaSuccess) return cuda_fail(h, e, "H2D copy");
-  int rc = do_eval(h->single, what, 0, 1, h->d_x, P.n_var, h->d_mu, P.m_nl, h->d_g, P.m_nl, h->d_J, P.nnzJ, h->d_H, P.nnzH,
-                   f ? h->d_scal : nullptr, h->stream);
-  if (rc != PS_OK) return rc;
-  double* ho = h->h_out;
-  if (what & EV_G) e = cudaMemcpyAsync(ho, h->d_g, (size_t)P.m_nl * sizeof(double), cudaMemcpyDeviceToHost, h->stream);
-  if (e == cudaSuccess && (what & EV_J))
-    e = cudaMemcpyAsync(ho + P.m_nl, h->d_J, (size_t)P.nnzJ * sizeof(double), cudaMemcpyDeviceToHost, h->stream);
-  if (e == cudaSuccess && (what & EV_H))
-    e = cudaMemcpyAsync(ho + P.m_nl + P.nnzJ, h->d_H, (size_t)P.nnzH * sizeof(double), cudaMemcpyDeviceToHost, h->stream);
+  if (lw || f) {
+    int rc = do_eval(h->single, lw, 0, 1, h->d_x, P.n_var, h->d_mu, P.m_nl, h->d_g, P.m_nl, h->d_J, P.nnzJ, h->d_H, P.nnzH,
+                     f ? h->d_scal : nullptr, h->stream);
+    if (rc != PS_OK) { h->cache_x = false; return rc; }
+    h->cache_dev |= need;
+  }
+  if ((what & EV_G) && P.m_nl) e = cudaMemcpyAsync(g, h->d_g, (size_t)P.m_nl * sizeof(double), cudaMemcpyDeviceToHost, h->stream);
+  if (e == cudaSuccess && (what & EV_J) && P.nnzJ)
+    e = cudaMemcpyAsync(J, h->d_J, (size_t)P.nnzJ * sizeof(double), cudaMemcpyDeviceToHost, h->stream);
+  if (e == cudaSuccess && (what & EV_H) && P.nnzH)
+    e = cudaMemcpyAsync(H, h->d_H, (size_t)P.nnzH * sizeof(double), cudaMemcpyDeviceToHost, h->stream);
   if (e == cudaSuccess && f)
-    e = cudaMemcpyAsync(ho + P.m_nl + P.nnzJ + P.nnzH, h->d_scal, NSCAL * sizeof(double), cudaMemcpyDeviceToHost, h->stream);
+    e = cudaMemcpyAsync(h->h_out, h->d_scal, NSCAL * sizeof(double), cudaMemcpyDeviceToHost, h->stream);
   if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);   // callers read the output immediately
-  if (e != cudaSuccess) return cuda_fail(h, e, "D2H copy / kernel");
-  if (what & EV_G) std::memcpy(g, ho, (size_t)P.m_nl * sizeof(double));
-  if (what & EV_J) std::memcpy(J, ho + P.m_nl, (size_t)P.nnzJ * sizeof(double));
-  if (what & EV_H) std::memcpy(H, ho + P.m_nl + P.nnzJ, (size_t)P.nnzH * sizeof(double));
-  if (f) *f = ho[P.m_nl + P.nnzJ + P.nnzH];
+  if (e != cudaSuccess) { h->cache_x = false; return cuda_fail(h, e, "D2H copy / kernel"); }
+  if (f) *f = h->h_out[0];
   return PS_OK;
 }
+
+int64_t ps_launch_count(const ps_handle* h) { return (h && h->single) ? h->single->launches : 0; }
 
 int ps_eval_constraint(ps_handle* h, const double* x, double* g) {
   if (h && !g) return fail(h, PS_ERR_ARG, "g is null");
@@ -592,14 +729,14 @@ int ps_batch_create(ps_handle* h, int64_t S, ps_batch** out) {
   cudaError_t e = cudaSetDevice(h->device);
   if (e != cudaSuccess) return cuda_fail(h, e, "cudaSetDevice");
   ps_batch* b = new ps_batch();
-  b->h = h; b->S = S;
+  b->h = h; b->S = S; b->device = h->device;
   *out = b;
   return PS_OK;
 }
 
 void ps_batch_destroy(ps_batch* b) {
   if (!b) return;
-  cudaSetDevice(b->h->device);
+  cudaSetDevice(b->device);
   for (int q = 0; q < 2; q++) {
     if (b->ev_in[q]) cudaEventDestroy(b->ev_in[q]);
     if (b->ev_k[q]) cudaEventDestroy(b->ev_k[q]);
@@ -634,14 +771,15 @@ int ps_batch_set_branch_status(ps_batch* b, const uint8_t* st) {
   cudaError_t e = cudaSetDevice(h->device);
   if (e != cudaSuccess) return cuda_fail(h, e, "cudaSetDevice");
   const size_t n = (size_t)b->S * h->plan.net.nbr;
-  if (!st) {                       // reset: every branch in service (the pointer stays allocated but unused)
-    if (b->d_status) { e = cudaMemset(b->d_status, 1, n); if (e != cudaSuccess) return cuda_fail(h, e, "cudaMemset(status)"); }
+  if (!st) {                       // reset: every branch in service (the buffer stays allocated; the kernels no longer read it)
+    b->status_active = false;
     return PS_OK;
   }
   for (size_t q = 0; q < n; q++) if (st[q] > 1) return fail(h, PS_ERR_ARG, "branch status must be 0 or 1");
   if (!b->d_status) b->d_status = b->mem.alloc<uint8_t>(n);
   if (!b->d_status) return cuda_fail(h, b->mem.err, "cudaMalloc(status)");
   if ((e = cudaMemcpy(b->d_status, st, n, cudaMemcpyHostToDevice)) != cudaSuccess) return cuda_fail(h, e, "cudaMemcpy(status)");
+  b->status_active = true;
   return PS_OK;
 }
 
@@ -996,7 +1134,7 @@ int ps_kkt_create(ps_csc* pattern, const double* g_L, const double* g_U, const d
   cudaError_t e = cudaSetDevice(pattern->device);
   if (e != cudaSuccess) return cuda_fail(nullptr, e, "cudaSetDevice");
   ps_kkt* k = new ps_kkt();
-  k->pat = pattern; k->device = pattern->device;
+  k->nnz = pattern->nnz; k->device = pattern->device;
   const int64_t m = pattern->m, n = pattern->n, nnz = pattern->nnz;
   std::vector<int32_t> colptr(n + 1), rowval(nnz), rptr(m + 1, 0), rperm(nnz);
   for (int64_t c = 0; c <= n; c++) colptr[c] = (int32_t)(pattern->colptr[c] - 1);
@@ -1029,7 +1167,7 @@ int ps_kkt_eval_batch(ps_kkt* k, int64_t S, const double* E, int64_t ldE, const 
   if (S == 0) return PS_OK;
   const int64_t m = k->dev.m, n = k->dev.n;
   if (!E || !x || !lambda || !mult_x_U || !mult_x_L || !df || !nzval || !out || ldE < m || ldx < n || ldl < m || ldm < n ||
-      lddf < n || ldnz < k->pat->nnz || (nu && ldnu < m) || (p && ldp < n)) {
+      lddf < n || ldnz < k->nnz || (nu && ldnu < m) || (p && ldp < n)) {
     g_create_error = "ps_kkt_eval_batch: null pointer or leading dimension too small";
     return PS_ERR_ARG;
   }

@@ -35,6 +35,22 @@ __device__ __forceinline__ void st_v4(double* p, double a, double b, double c, d
   asm volatile("st.global.cs.v4.f64 [%0], {%1, %2, %3, %4};" ::"l"(p), "d"(a), "d"(b), "d"(c), "d"(d) : "memory");
 }
 
+// V^3 and V^4 of the L4 current limits (formulations.jl:338-343).  JuMP evaluates `^` with a constant exponent other than
+// 2 through pow(), i.e. to within an ulp of the exact power, whereas repeated products carry up to two
+// roundings -- and on low-impedance branches those powers are multiplied by |y|^2 ~ 1e8.  These are the correctly rounded
+// powers (double-double products, the FMA residuals are exact): equal to glibc's pow() in 99.92 % of 2e7 random arguments
+// and to the exactly rounded power in all of them (tests/test_gpu_parity.py::test_correctly_rounded_powers).
+__device__ __forceinline__ double pow3_cr(double v) {
+  const double h = v * v, l = fma(v, v, -h);          // v^2 = h + l
+  const double p = h * v, e = fma(h, v, -p);          // h v = p + e
+  return p + (e + l * v);
+}
+__device__ __forceinline__ double pow4_cr(double v) {
+  const double h = v * v, l = fma(v, v, -h);
+  const double p = h * h, e = fma(h, h, -p);          // h^2 = p + e
+  return p + (e + 2.0 * (h * l));
+}
+
 // ------------------------------------------------------------------------------- branch rows
 // Thread lu of a branch tile stages its rows at sG[lu*NRP + r], sJ[lu*RJP + p], sH[lu*RHP + p];
 // the strides are odd so that the 8-byte shared-memory stores of a warp are conflict free.
@@ -338,8 +354,8 @@ struct Branch {
     sincos(psi, &s, &c);
     double val, dVa, dVb, dta, hVaVa, hVaVb, hVbVb, htt, htVa, htVb;
     if constexpr (MP) {
-      const double Va2 = Va * Va, Va3 = Va2 * Va, Vb2 = Vb * Vb;
-      val = (y1 * (Va2 * Va2) + y2 * Vb2 * Va2) + y3 * Va3 * Vb * c;
+      const double Va2 = Va * Va, Va3 = pow3_cr(Va), Vb2 = Vb * Vb;    // pow(V, 3), pow(V, 4): see pow3_cr
+      val = (y1 * pow4_cr(Va) + y2 * Vb2 * Va2) + y3 * Va3 * Vb * c;
       dVa = 4.0 * y1 * Va3 + 2.0 * y2 * Vb2 * Va + 3.0 * y3 * Va2 * Vb * c;
       dVb = 2.0 * y2 * Vb * Va2 + y3 * Va3 * c;
       dta = -y3 * Va3 * Vb * s;
@@ -1479,6 +1495,186 @@ __global__ void __launch_bounds__(PBT) pb_bus_g_kernel(const __grid_constant__ D
   pb_bus_g_body<FORM>(P, A, blockIdx.x);
 }
 
+// ---- PB* residuals, scenario-resident -----------------------------------------------------------------------------
+// pb_bus_g_kernel walks a bus's lists and gathers one 8-byte flow variable per 32-byte sector on a randomly numbered
+// network: it is bound by the L1 -> L2 request rate at 4.6x the useful sectors (profiles/r02_ncu_pb_bus_g_summary.txt).
+// Here the roles are swapped.  A CTA owns a whole scenario at a time and keeps the (P, Q) running sums of EVERY bus in
+// shared memory (16 bytes per bus: 218 KB for case13659pegase); the terms are visited in element order -- generators,
+// then the Sij side of every branch, then the Sji side -- PBS_WAVE consecutive elements per step, so pg / qg and the
+// four flow arrays are read with perfectly coalesced loads, each sector once.  A bus still receives its terms in the
+// reference's order (formulations.jl:171-196: generators, Sij ascending, Sji ascending): the adjacency lists are
+// ascending (checked at plan time), passes and steps are separated by CTA barriers, and the elements of one step that
+// share a bus are served in rank order (plan table pbs_code, one sub-round per rank; a random numbering needs one or two).
+// The shunt term and the load are subtracted by the thread that owns the bus in those passes, which then writes the row.
+// Bitwise identical to pb_bus_g_kernel (x - y == x + (-y); status 1.0 * v == v).
+#ifndef PS_PBS_R
+#define PS_PBS_R 4
+#endif
+constexpr int PBS_T = PBS_WAVE;
+constexpr int PBS_MAX_STEPS = 1024;
+constexpr int PBS_R = PS_PBS_R;    // steps whose inputs are in flight (a register ring: the CTA is alone on its SM -- the
+                                   // accumulators fill its shared memory -- so memory latency is hidden by depth, not by occupancy)
+
+// One pass over a term table: step j serves elements [j * PBS_T, (j + 1) * PBS_T) -- thread tid element j * PBS_T + tid --
+// with the inputs of the next PBS_R steps already in flight.
+template <bool HAS_ST>
+__device__ __forceinline__ void pbs_term_pass(double2* acc, const uint8_t* wmax, const int32_t* __restrict__ code, int n,
+                                              const double* __restrict__ v0p, const double* __restrict__ v1p,
+                                              const uint8_t* __restrict__ stp) {
+  const int tid = threadIdx.x;
+  // whole rings: the steps past the end have no terms (the loads are guarded) and cost one barrier each; unconditional
+  // ring bodies keep every slot in a fixed register (a guarded body makes the compiler rotate the ring through moves,
+  // which waits for a load one step after it was issued)
+  const int nsteps = ((n + PBS_T - 1) / PBS_T + PBS_R - 1) / PBS_R * PBS_R;
+  int c[PBS_R];
+  double a0[PBS_R], a1[PBS_R];
+  auto load = [&](int u, int j) {
+    const int e = j * PBS_T + tid;
+    c[u] = -1; a0[u] = 0.0; a1[u] = 0.0;
+    if (e < n) {
+      c[u] = code[e]; a0[u] = v0p[e]; a1[u] = v1p[e];
+      if constexpr (HAS_ST) { const double st = (double)stp[e]; a0[u] = st * a0[u]; a1[u] = st * a1[u]; }
+    }
+  };
+#pragma unroll
+  for (int u = 0; u < PBS_R; u++) load(u, u);
+  for (int j0 = 0; j0 < nsteps; j0 += PBS_R) {
+#pragma unroll
+    for (int u = 0; u < PBS_R; u++) {
+      const int j = j0 + u;
+      const int cc = c[u];
+      const double b0 = a0[u], b1 = a1[u];
+      load(u, j + PBS_R);                                      // refill: in flight while the next PBS_R - 1 steps are served
+      const int bus = cc & 0xffffff, rk = cc >> 24;            // no term: rk = -1
+      for (int r = 0, mr = wmax[j]; r <= mr; r++) {            // elements of the step that share a bus: rank order
+        if (rk == r) {
+          double2 a = acc[bus];
+          a.x = a.x + b0;
+          a.y = a.y + b1;
+          acc[bus] = a;
+        }
+        __syncthreads();
+      }
+    }
+  }
+}
+
+template <int FORM>
+__global__ void __launch_bounds__(PBS_T, 1) pb_bus_g_scn_kernel(const __grid_constant__ DevPlan P, const __grid_constant__ EvalArgs A) {
+  extern __shared__ __align__(16) double2 pbs_acc[];           // [nb] running (P, Q) sums of the scenario
+  __shared__ double redv[PBS_T / 32];
+  __shared__ int redn[PBS_T / 32];
+  __shared__ uint8_t wmax[PBS_MAX_STEPS];                      // highest rank per term-table step
+  const int tid = threadIdx.x;
+  const bool wg = (A.what & EV_G) != 0;
+  const int s_gen = (P.ng + PBS_T - 1) / PBS_T, s_br = (P.nr + PBS_T - 1) / PBS_T, s_bus = (P.nb + PBS_T - 1) / PBS_T;
+  for (int j = tid; j < PBS_MAX_STEPS; j += PBS_T) wmax[j] = j < s_gen + 2 * s_br ? P.pbs_wmax[j] : 0;
+  for (int s = blockIdx.x; s < A.S; s += gridDim.x) {
+    const double* __restrict__ x = A.x + (long long)s * A.ldx;
+    const uint8_t* __restrict__ stp = A.status ? A.status + (long long)s * A.ldst : nullptr;
+    const double* __restrict__ pd = A.Pd ? A.Pd + (long long)s * A.ldl : P.Pd0;
+    const double* __restrict__ qd = A.Qd ? A.Qd + (long long)s * A.ldl : P.Qd0;
+    double* __restrict__ gd = wg ? A.g + (long long)s * A.ldg : nullptr;
+    const bool al = (reinterpret_cast<unsigned long long>(gd) & 15) == 0;
+    for (int i = tid; i < P.nb; i += PBS_T) pbs_acc[i] = make_double2(0.0, 0.0);     // formulations.jl:171-172
+    __syncthreads();
+    pbs_term_pass<false>(pbs_acc, wmax, P.pbs_code, P.ng, x + P.o_pg, x + P.o_qg, nullptr);                        // :177-180
+    if (stp) {                                                                                                       // :188-196
+      pbs_term_pass<true>(pbs_acc, wmax + s_gen, P.pbs_code + P.ng, P.nr, x + P.o_f[0], x + P.o_f[1], stp);        // Sij side
+      pbs_term_pass<true>(pbs_acc, wmax + s_gen + s_br, P.pbs_code + P.ng + P.nr, P.nr, x + P.o_f[2], x + P.o_f[3], stp);   // Sji side
+    } else {
+      pbs_term_pass<false>(pbs_acc, wmax + s_gen, P.pbs_code + P.ng, P.nr, x + P.o_f[0], x + P.o_f[1], nullptr);
+      pbs_term_pass<false>(pbs_acc, wmax + s_gen + s_br, P.pbs_code + P.ng + P.nr, P.nr, x + P.o_f[2], x + P.o_f[3], nullptr);
+    }
+    // the bus's own shunt term (:256-258 | :264-266), then minus the load (:291-292) and out; thread tid owns bus
+    // j * PBS_T + tid in both passes: no barrier between them
+    {
+      double va[PBS_R], vb[PBS_R], gl[PBS_R], bl[PBS_R];
+      auto load = [&](int u, int j) {
+        const int e = j * PBS_T + tid;
+        va[u] = vb[u] = gl[u] = bl[u] = 0.0;
+        if (e < P.nb) {
+          if constexpr (FORM == PBRARV) va[u] = x[P.o_a + e];
+          vb[u] = x[P.o_b + e]; gl[u] = P.Gl[e]; bl[u] = P.Bl[e];
+        }
+      };
+      constexpr int R2 = PBS_R > 3 ? 3 : PBS_R;               // four values per bus: a shallower ring
+#pragma unroll
+      for (int u = 0; u < R2; u++) load(u, u);
+      for (int j0 = 0; j0 < s_bus; j0 += R2) {
+#pragma unroll
+        for (int u = 0; u < R2; u++) {
+          const int j = j0 + u, e = j * PBS_T + tid;
+          const double im = va[u], r = vb[u], Gl = gl[u], Bl = bl[u];
+          load(u, j + R2);
+          if (e < P.nb) {
+            double m2;
+            if constexpr (FORM == PBRARV) m2 = r * r + im * im;
+            else m2 = r * r;
+            double2 a = pbs_acc[e];
+            a.x = a.x - Gl * m2;
+            a.y = a.y + Bl * m2;
+            pbs_acc[e] = a;
+          }
+        }
+      }
+    }
+    double vmax = 0.0;
+    int nviol = 0;
+    {
+      double lp[PBS_R], lq[PBS_R];
+      auto load = [&](int u, int j) {
+        const int e = j * PBS_T + tid;
+        lp[u] = lq[u] = 0.0;
+        if (e < P.nb) { lp[u] = pd[e]; lq[u] = qd[e]; }
+      };
+#pragma unroll
+      for (int u = 0; u < PBS_R; u++) load(u, u);
+      for (int j0 = 0; j0 < s_bus; j0 += PBS_R) {
+#pragma unroll
+        for (int u = 0; u < PBS_R; u++) {
+          const int j = j0 + u, e = j * PBS_T + tid;
+          const double Pd = lp[u], Qd = lq[u];
+          load(u, j + PBS_R);
+          if (e < P.nb) {
+            const double2 a = pbs_acc[e];
+            const double gP = a.x - Pd, gQ = a.y - Qd;
+            if (wg) {
+              if (al) *reinterpret_cast<double2*>(gd + 2 * e) = make_double2(gP, gQ);
+              else { gd[2 * e] = gP; gd[2 * e + 1] = gQ; }
+            }
+            vmax = fmax(vmax, fmax(fabs(gP), fabs(gQ)));
+            nviol += (fabs(gP) > A.viol_tol ? 1 : 0) + (fabs(gQ) > A.viol_tol ? 1 : 0);
+          }
+        }
+      }
+    }
+    if (A.scal) {                                              // CTA-uniform
+#pragma unroll
+      for (int d = 16; d > 0; d >>= 1) {
+        vmax = fmax(vmax, __shfl_xor_sync(0xffffffffu, vmax, d));
+        nviol += __shfl_xor_sync(0xffffffffu, nviol, d);
+      }
+      if ((tid & 31) == 0) { redv[tid >> 5] = vmax; redn[tid >> 5] = nviol; }
+      __syncthreads();
+      if (tid < 32) {
+        vmax = tid < PBS_T / 32 ? redv[tid] : 0.0; nviol = tid < PBS_T / 32 ? redn[tid] : 0;
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) {
+          vmax = fmax(vmax, __shfl_xor_sync(0xffffffffu, vmax, d));
+          nviol += __shfl_xor_sync(0xffffffffu, nviol, d);
+        }
+        if (tid == 0) {
+          double* scal = A.scal + (long long)s * NSCAL;
+          if (vmax > 0.0) atomicMax((unsigned long long*)(scal + 1), (unsigned long long)__double_as_longlong(vmax));
+          if (nviol) atomicAdd(scal + 2, (double)nviol);
+        }
+      }
+    }
+    __syncthreads();                                           // the accumulators are reused by the next scenario
+  }
+}
+
 // objective scalar only (used with the PB* fast path, where no bus_kernel runs)
 // ---- CB* balances, fast path (CBRARV / CBRAWV without switched shunts and without a status mask) --------------------
 // The current-branch-flow balances are bilinear in (own voltage, branch current) (formulations.jl:206-214): every
@@ -1892,9 +2088,15 @@ cudaError_t launch_bus_warp_form(const DevPlan& P, const EvalArgs& A, size_t sme
 }
 
 template <int FORM>
-cudaError_t configure_form(int src, size_t smem_branch, size_t smem_bus, size_t smem_wt) {
+cudaError_t configure_form(int src, size_t smem_branch, size_t smem_bus, size_t smem_wt, size_t smem_pbs) {
   cudaError_t e = cudaFuncSetAttribute(bus_kernel<FORM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bus);
   if (e != cudaSuccess) return e;
+  if constexpr (FORM == PBRAPV || FORM == PBRARV) {
+    if (smem_pbs > 0) {
+      e = cudaFuncSetAttribute(pb_bus_g_scn_kernel<FORM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_pbs);
+      if (e != cudaSuccess) return e;
+    }
+  }
   if (smem_wt > 0) {
     e = cudaFuncSetAttribute(bus_warp_kernel<FORM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_wt);
     if (e != cudaSuccess) return e;
@@ -1926,6 +2128,15 @@ __global__ void __launch_bounds__(256) csc_assemble_kernel(const int32_t* __rest
   double acc = 0.0;                                           // common.jl:16-18: J[r,c] += dE[i], in COO order
   for (int q = q0; q < q1; q++) acc += e[perm[q]];
   nz[s * ldnz + j] = acc;
+}
+
+__global__ void __launch_bounds__(256) permute_rows_kernel(const int32_t* __restrict__ perm, int n, const double* __restrict__ in,
+                                                           long long ldin, double* __restrict__ out, long long ldout) {
+  const int i = blockIdx.x * 256 + threadIdx.x;
+  if (i >= n) return;
+  const int src = perm[i];
+  const long long s = blockIdx.y + (long long)blockIdx.z * gridDim.y;
+  out[s * ldout + i] = in[s * ldin + src];
 }
 
 // ---- affine + quadratic rows (MOI_wrapper.jl:864-891, 973-1002, 1030-1042) -------------------------------------
@@ -2068,18 +2279,26 @@ int64_t wt_smem_bytes(const DevPlan& P) {
   return (int64_t)WPC * wt_region_doubles(P) * 8;
 }
 
-cudaError_t configure_eval(int form, int src, int64_t smem_branch_bytes, int64_t smem_bus_bytes, int64_t smem_wt_bytes) {
-  const size_t sb = (size_t)smem_branch_bytes, su = (size_t)smem_bus_bytes, sw = (size_t)smem_wt_bytes;
+// the scenario-resident PB* residual kernel needs the (P, Q) sums of every bus in one CTA's shared memory
+int64_t pbs_smem_bytes(const DevPlan& P) {
+  const int64_t b = (int64_t)P.nb * 16;
+  const int64_t steps = (P.ng + PBS_T - 1) / PBS_T + 2 * ((P.nr + PBS_T - 1) / PBS_T);
+  return (P.pbs_ok && b <= 222 * 1024 && steps + 16 <= PBS_MAX_STEPS) ? b : 0;
+}
+
+cudaError_t configure_eval(int form, int src, int64_t smem_branch_bytes, int64_t smem_bus_bytes, int64_t smem_wt_bytes,
+                           int64_t smem_pbs_bytes) {
+  const size_t sb = (size_t)smem_branch_bytes, su = (size_t)smem_bus_bytes, sw = (size_t)smem_wt_bytes, sp = (size_t)smem_pbs_bytes;
   switch (form) {
-    case PBRAPV: return configure_form<PBRAPV>(src, sb, su, sw);
-    case PBRARV: return configure_form<PBRARV>(src, sb, su, sw);
-    case PBRAWV: return configure_form<PBRAWV>(src, sb, su, sw);
-    case CBRARV: return configure_form<CBRARV>(src, sb, su, sw);
-    case CBRAWV: return configure_form<CBRAWV>(src, sb, su, sw);
-    case PNPAPV: return configure_form<PNPAPV>(src, sb, su, sw);
-    case PNRAPV: return configure_form<PNRAPV>(src, sb, su, sw);
-    case PNRARV: return configure_form<PNRARV>(src, sb, su, sw);
-    case PNRAWV: return configure_form<PNRAWV>(src, sb, su, sw);
+    case PBRAPV: return configure_form<PBRAPV>(src, sb, su, sw, sp);
+    case PBRARV: return configure_form<PBRARV>(src, sb, su, sw, sp);
+    case PBRAWV: return configure_form<PBRAWV>(src, sb, su, sw, sp);
+    case CBRARV: return configure_form<CBRARV>(src, sb, su, sw, sp);
+    case CBRAWV: return configure_form<CBRAWV>(src, sb, su, sw, sp);
+    case PNPAPV: return configure_form<PNPAPV>(src, sb, su, sw, sp);
+    case PNRAPV: return configure_form<PNRAPV>(src, sb, su, sw, sp);
+    case PNRARV: return configure_form<PNRARV>(src, sb, su, sw, sp);
+    case PNRAWV: return configure_form<PNRAWV>(src, sb, su, sw, sp);
   }
   return cudaErrorInvalidValue;
 }
@@ -2120,7 +2339,19 @@ cudaError_t launch_pb_form(const DevPlan& P, const EvalArgs& A, cudaStream_t st,
   if constexpr (FORM == PBRAPV || FORM == PBRARV) {
     if ((A.what & EV_G) || A.scal) {
       rec(K_BUS, 0);
-      pb_bus_g_kernel<FORM><<<dim3((unsigned)((P.nb + PBT - 1) / PBT), (unsigned)nchunks), PBT, 0, st>>>(P, A);
+      // scenario-resident residuals when a batch fills the machine (a CTA works through whole scenarios one after the
+      // other: a handful of scenarios is faster with the list-walking kernel); PS_PBSCN=1 / PS_NO_PBSCN force either
+      const int64_t smem = pbs_smem_bytes(P);
+      const bool scn = smem > 0 && !getenv("PS_NO_PBSCN") && (A.S >= 32 || getenv("PS_PBSCN"));
+      if (scn) {
+        static int n_sm = 0;
+        if (n_sm == 0) { int dv = 0; cudaGetDevice(&dv); cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dv); if (n_sm <= 0) n_sm = 148; }
+        const int per_sm = (int)std::min<int64_t>(2, (220 * 1024) / smem);   // 1024-thread CTAs: at most 2 per SM
+        const int ncta = (int)std::min<int64_t>(A.S, (int64_t)n_sm * per_sm);
+        pb_bus_g_scn_kernel<FORM><<<dim3((unsigned)ncta), PBS_T, (size_t)smem, st>>>(P, A);
+      } else {
+        pb_bus_g_kernel<FORM><<<dim3((unsigned)((P.nb + PBT - 1) / PBT), (unsigned)nchunks), PBT, 0, st>>>(P, A);
+      }
       rec(K_BUS, 1);
       if (launches) *launches += 1;
     }
@@ -2216,16 +2447,15 @@ cudaError_t launch_eval(const DevPlan& P, const EvalArgs& A0, int64_t smem_branc
   cudaError_t e = cudaSuccess;
   const bool pb_fast = P.pb_slots && !getenv("PS_NO_PBFAST");
   const bool cb_fast = P.cb_slots && !A.status && (A.diag || !(A.what & EV_J)) && !getenv("PS_NO_CBFAST");
+  const int min_chunk = (A.S + 65534) / 65535;                 // gridDim.y <= 65535: very long batches take longer chunks
   if (cb_fast) {
-    A.chunk = env_int("PS_CHUNK_PB", 4);
+    A.chunk = std::max(env_int("PS_CHUNK_PB", 4), min_chunk);
     const int nchunks = (A.S + A.chunk - 1) / A.chunk;
-    if (nchunks > 65535) return cudaErrorInvalidConfiguration;
     e = launch_cb(P, A, stream, nchunks, launches, ev, ev_mask);
     if (e != cudaSuccess) return e;
   } else if (pb_fast) {
-    A.chunk = env_int("PS_CHUNK_PB", 4);
+    A.chunk = std::max(env_int("PS_CHUNK_PB", 4), min_chunk);
     const int nchunks = (A.S + A.chunk - 1) / A.chunk;
-    if (nchunks > 65535) return cudaErrorInvalidConfiguration;
     e = launch_pb(P, A, stream, nchunks, launches, ev, ev_mask);
     if (e != cudaSuccess) return e;
   } else if (P.n_bus_tiles > 0 || A.scal) {
@@ -2236,8 +2466,8 @@ cudaError_t launch_eval(const DevPlan& P, const EvalArgs& A0, int64_t smem_branc
     long long c = ((long long)A.S * (P.n_bus_tiles + 1)) / want;
     const long long cw = ((long long)A.S * ((P.n_wtiles + WPC - 1) / WPC)) / (148LL * PS_WT_MINB * 8);
     A.chunk = warp_tiles ? env_int("PS_CHUNK_WT", (int)(cw < 1 ? 1 : (cw > 16 ? 16 : cw))) : env_int("PS_CHUNK_BUS", (int)(c < 1 ? 1 : (c > 32 ? 32 : c)));
+    A.chunk = std::max(A.chunk, min_chunk);
     const int nchunks = (A.S + A.chunk - 1) / A.chunk;
-    if (nchunks > 65535) return cudaErrorInvalidConfiguration;
     if (P.n_bus_tiles > 0) {
       if (launches) *launches += 1;
       KTimer kt(ev, ev_mask, stream, K_BUS);
@@ -2265,9 +2495,8 @@ cudaError_t launch_eval(const DevPlan& P, const EvalArgs& A0, int64_t smem_branc
   if (P.nr == 0 || !(A.what & (EV_G | EV_J | EV_H)) ) {
     if (P.nr == 0 || !A.scal) return e;
   }
-  A.chunk = A0.chunk;
+  A.chunk = std::max(A0.chunk, min_chunk);
   const int nchunks = (A.S + A.chunk - 1) / A.chunk;
-  if (nchunks > 65535) return cudaErrorInvalidConfiguration;
   const unsigned nbt = (unsigned)((P.nr + TPB - 1) / TPB);
   bool direct = direct_ok(P.form, P.src) && !getenv("PS_NO_DIRECT");
   if (direct && (A.what & EV_J)) direct = sector_aligned(A.J, P.j_br0, A.ldJ);
@@ -2288,6 +2517,16 @@ cudaError_t launch_eval(const DevPlan& P, const EvalArgs& A0, int64_t smem_branc
   if (bulk) return launch_branch_bulk(P, A, stream, dim3(nbt, (unsigned)nchunks));
   if (direct) return launch_branch_direct(P, A, stream, dim3(nbt, (unsigned)nchunks));
   return launch_staged(P, A, (size_t)smem_branch_bytes, stream, dim3(nbt, (unsigned)nchunks));
+}
+
+cudaError_t launch_permute_rows(const int32_t* perm, int n, int64_t S, const double* in, long long ldin, double* out,
+                                long long ldout, cudaStream_t stream) {
+  if (n <= 0 || S <= 0) return cudaSuccess;
+  for (int64_t s0 = 0; s0 < S; s0 += 65535) {                  // gridDim.y limit
+    const unsigned ny = (unsigned)std::min<int64_t>(65535, S - s0);
+    permute_rows_kernel<<<dim3((n + 255) / 256, ny, 1), 256, 0, stream>>>(perm, n, in + s0 * ldin, ldin, out + s0 * ldout, ldout);
+  }
+  return cudaGetLastError();
 }
 
 cudaError_t launch_csc_assemble(const int32_t* segptr, const int32_t* perm, int nnz_csc, int64_t S, const double* dE,

@@ -30,6 +30,9 @@ struct DevPlan {                    // passed to kernels by value (constant bank
   const double *pb_jt, *pb_ht;                      // PB* slot tables (ps_capi.cu: upload): coefficients and
   const int32_t *pb_ji, *pb_hi;                     // indices, 4 shifted copies each:
   int pb_jstride, pb_hstride;                       // copy a at + a * stride + (4 - a) % 4 (aligned at entry a + 4q)
+  int pbs_ok;                                       // PB* scenario-resident residual kernel available (ps_plan.h: pbs_code)
+  const int32_t* pbs_code;                          // [ng | nr | nr] bus | rank << 24, -1 = no term
+  const uint8_t* pbs_wmax;                          // highest rank per step (generator, Sij, Sji steps)
   int cost_order;
   const int32_t *f, *t;
   const double *Gf, *Bf, *Gt, *Bt, *gf, *bf, *gt, *bt, *Imax, *Gl, *Bl, *Pd0, *Qd0;
@@ -73,9 +76,16 @@ enum KernelId : int { K_BUS = 0, K_BUS_JH = 1, K_OBJ = 2, K_BRANCH = 3, K_COUNT 
 cudaError_t launch_eval(const DevPlan& P, const EvalArgs& A, int64_t smem_branch_bytes, int64_t smem_bus_bytes,
                         cudaStream_t stream, int64_t* launches, cudaEvent_t* ev = nullptr, unsigned* ev_mask = nullptr);
 // opt the kernels of one formulation into the needed dynamic shared memory (once per device)
-cudaError_t configure_eval(int form, int src, int64_t smem_branch_bytes, int64_t smem_bus_bytes, int64_t smem_wt_bytes = 0);
+cudaError_t configure_eval(int form, int src, int64_t smem_branch_bytes, int64_t smem_bus_bytes, int64_t smem_wt_bytes = 0,
+                           int64_t smem_pbs_bytes = 0);
+// dynamic shared memory of pb_bus_g_scn_kernel (the bus accumulators of one scenario); 0 when it cannot run
+int64_t pbs_smem_bytes(const DevPlan& P);
 // dynamic shared memory of one bus_warp_kernel CTA (0 when the plan has no warp tiles)
 int64_t wt_smem_bytes(const DevPlan& P);
+
+// out[s][i] = in[s][perm[i]] (a caller-imposed Hessian slot order, ps_set_hessian_order)
+cudaError_t launch_permute_rows(const int32_t* perm, int n, int64_t S, const double* in, long long ldin, double* out,
+                                long long ldout, cudaStream_t stream);
 
 // COO -> CSC assembly (replaces src/opt/algorithms/common.jl:12-20): nz[j] = sum_{q in seg j} dE[perm[q]]
 cudaError_t launch_csc_assemble(const int32_t* segptr, const int32_t* perm, int nnz_csc, int64_t S,

@@ -387,6 +387,41 @@ std::string build_plan(const HostNet& net, int form, int src, int flags, int tpb
         }
       }
       P.pb_slots = true;
+      // element-ordered term tables of the scenario-resident residual kernel
+      const int64_t ng = net.ngen;
+      P.pbs_code.assign((size_t)(ng + 2 * nr), -1);
+      P.pbs_ok = nb < (1 << 24);
+      auto fill = [&](const std::vector<int32_t>& ptr, const std::vector<int32_t>& idx, int32_t* code) {
+        for (int64_t i = 0; i < nb && P.pbs_ok; i++)
+          for (int32_t q = ptr[i]; q < ptr[i + 1]; q++) {
+            if ((q > ptr[i] && idx[q] <= idx[q - 1]) || code[idx[q]] != -1) { P.pbs_ok = false; break; }   // list order == element order
+            code[idx[q]] = (int32_t)i;
+          }
+      };
+      fill(net.gen_ptr, net.gen_idx, P.pbs_code.data());
+      fill(net.sij_ptr, net.sij_idx, P.pbs_code.data() + ng);
+      fill(net.sji_ptr, net.sji_idx, P.pbs_code.data() + ng + nr);
+      std::vector<int32_t> seen((size_t)nb, -1), cnt((size_t)nb, 0);
+      auto ranks = [&](int32_t* code, int64_t n) {
+        for (int64_t w0 = 0; w0 < n && P.pbs_ok; w0 += PBS_WAVE) {
+          int mx = 0;
+          for (int64_t e = w0; e < std::min<int64_t>(n, w0 + PBS_WAVE); e++) {
+            const int32_t b = code[e];
+            if (b < 0) continue;
+            if (seen[b] != (int32_t)(w0 / PBS_WAVE)) { seen[b] = (int32_t)(w0 / PBS_WAVE); cnt[b] = 0; }
+            const int r = cnt[b]++;
+            if (r > 127) { P.pbs_ok = false; break; }
+            code[e] = b | (r << 24);
+            mx = std::max(mx, r);
+          }
+          P.pbs_wmax.push_back((uint8_t)mx);
+        }
+        std::fill(seen.begin(), seen.end(), -1);     // step ids restart with every pass
+      };
+      ranks(P.pbs_code.data(), ng);
+      ranks(P.pbs_code.data() + ng, nr);
+      ranks(P.pbs_code.data() + ng + nr, nr);
+      if (!P.pbs_ok) { P.pbs_code.clear(); P.pbs_wmax.clear(); }
     }
   }
   // bus tiles: greedy, at most tpb buses and at most `budget` bytes of shared memory per tile

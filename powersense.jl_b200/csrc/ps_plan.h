@@ -43,6 +43,8 @@ struct WTile {
   int32_t m0, mn;            // multi-slots of all three spaces, sorted by count (descending): Plan::wt_multi
 };
 
+constexpr int PBS_WAVE = 1024;   // elements per step of the scenario-resident PB* residual kernel (= its CTA size)
+
 struct Plan {
   int form = 0, src = 0, flags = 0;
   HostNet net;
@@ -78,6 +80,17 @@ struct Plan {
   //   H: 2*bus + (0: P row, 1: Q row)
   std::vector<int32_t> pb_jcode, pb_hcode;
   bool pb_slots = false;
+  // PB* balances, scenario-resident residual kernel (pb_bus_g_scn_kernel): the terms of a balance are visited in
+  // three element-ordered passes (generators, Sij side of every branch, Sji side of every branch) of PBS_WAVE
+  // consecutive elements per step, so that the injections / flow variables are read with coalesced loads.
+  //   pbs_code [ngen | nbr | nbr]: bus | rank << 24 of the element's term, -1 when the element is in no list;
+  //            rank = number of earlier elements of the same step that belong to the same bus (a bus's terms are
+  //            added in list order: ranks are served in sub-rounds)
+  //   pbs_wmax per step (generator steps, Sij steps, Sji steps): highest rank of the step
+  // pbs_ok: every adjacency list is ascending and ranks fit (else the list-walking pb_bus_g_kernel runs)
+  std::vector<int32_t> pbs_code;
+  std::vector<uint8_t> pbs_wmax;
+  bool pbs_ok = false;
   bool pb_implicit = false;                         // PB* bus rows: J slots follow [voltage][gens][Sij][Sji]
   int64_t smem_bytes = 0;                           // dynamic shared memory of the kernel (max over tile kinds)
   int64_t smem_bus_bytes = 0, smem_branch_bytes = 0; // bus kernel / staged branch kernel

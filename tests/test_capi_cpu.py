@@ -27,7 +27,7 @@ def test_library_exports_every_declared_symbol():
     for n in names:
         assert hasattr(L, n), f"{n} declared in include/powersense_b200.h but not exported"
     assert set(names) == set(capi.EXPORTS), set(names) ^ set(capi.EXPORTS)
-    assert L.ps_abi_version() == 1
+    assert L.ps_abi_version() == 2
 
 
 @pytest.mark.parametrize("F", ps.ALL_FORMULATIONS, ids=lambda f: f.name)
@@ -65,6 +65,55 @@ def test_structure_only_handle_matches_oracle(case, F):
     assert e.value.code == capi.PS_ERR_STATE
     with pytest.raises(capi.PowersenseError):
         capi.Batch(h, 4)
+    h.close()
+
+
+def _jump_like_order(h, seed):
+    """A structure in the shape JuMP's has: the same per-row blocks, the off-diagonal part of every block in
+    another order and with the other triangle for some pairs."""
+    rng = np.random.default_rng(seed)
+    hr, hc = h.hessian_structure()
+    ptr = h.hessian_row_blocks()
+    perm = np.arange(h.nnzH)
+    for r in range(h.m_nl):
+        e0, e1 = int(ptr[r]), int(ptr[r + 1])
+        off = np.flatnonzero(hr[e0:e1] != hc[e0:e1]) + e0
+        perm[off] = rng.permutation(off)
+    tr, tc = hr[perm].copy(), hc[perm].copy()
+    flip = (rng.random(h.nnzH) < 0.5) & (tr != tc)
+    tr[flip], tc[flip] = tc[flip], tr[flip]
+    return perm, tr, tc
+
+
+@pytest.mark.parametrize("F", ps.ALL_FORMULATIONS, ids=lambda f: f.name)
+def test_hessian_order_hook_on_the_structure(F):
+    """ps_set_hessian_order / ps_match_hessian_structure (the permutation-import hook for JuMP's intra-block order, SURVEY.md
+    section 7 "hard parts"): a JuMP-shaped target structure is matched block by block, reported back exactly, and reset."""
+    d = load_fixture("case14")
+    h = capi.Handle(d, F.code, device=-2)
+    hr0, hc0 = h.hessian_structure()
+    assert np.array_equal(h.hessian_order(), np.arange(1, h.nnzH + 1))
+    ptr = h.hessian_row_blocks()
+    assert ptr[0] == 0 and ptr[-1] == h.nnzH and np.all(np.diff(ptr) >= 0)
+    perm, tr, tc = _jump_like_order(h, 7 + F.code)
+    h.match_hessian_structure(tr, tc)
+    assert np.array_equal(h.hessian_order(), perm + 1)
+    hr, hc = h.hessian_structure()
+    assert np.array_equal(hr, hr0[perm]) and np.array_equal(hc, hc0[perm])      # our triangle convention, the target's order
+    assert np.array_equal(np.maximum(hr, hc), np.maximum(tr, tc)) and np.array_equal(np.minimum(hr, hc), np.minimum(tr, tc))
+    h.set_hessian_order(None)
+    assert np.array_equal(h.hessian_structure()[0], hr0)
+    h.set_hessian_order(perm + 1)
+    assert np.array_equal(h.hessian_structure()[1], hc0[perm])
+    # errors: not a permutation; a pair that does not belong to the row's block
+    bad = perm + 1
+    if h.nnzH > 1:
+        bad = bad.copy(); bad[0] = bad[1]
+        with pytest.raises(capi.PowersenseError):
+            h.set_hessian_order(bad)
+        tr2 = tr.copy(); tr2[0] = h.n_var
+        with pytest.raises(capi.PowersenseError, match="NL row 1"):
+            h.match_hessian_structure(tr2, tc)
     h.close()
 
 

@@ -508,3 +508,176 @@ def test_all_code_paths_agree_bitwise(F, case):
             assert np.array_equal(a, c), (F.name, env, layout, name)
     b.close()
     h.close()
+
+
+@pytest.mark.parametrize("F", [ps.PBRARVmodel, ps.PBRAPVmodel], ids=lambda v: v.name)
+@pytest.mark.parametrize("order", ["random", "file"])
+def test_scenario_resident_pb_residuals(F, order):
+    """pb_bus_g_scn_kernel (bus sums of a whole scenario in shared memory, terms visited in element order with coalesced
+    loads) is bitwise equal to the list-walking pb_bus_g_kernel: on a randomly numbered network (ranks 0-1), on a from-bus
+    ordered one (every step has chains of equal buses: one sub-round per rank), with a contingency mask, for g alone and
+    for g + J + H, with more scenarios than CTAs and with fewer."""
+    import os
+    torch = _torch()
+    dev = torch.device("cuda:0")
+    d = synth.named_case("case2869pegase", branch_order=order)
+    h = capi.Handle(d, F.code, device=0)
+    for S, masked in ((333, False), (40, True)):
+        x, Pd, Qd, _ = synth.scenario_batch(d, F, S, seed=5)
+        mu = np.random.default_rng(3).normal(size=(S, h.m_nl))
+        b = capi.Batch(h, S)
+        b.set_loads(Pd, Qd)
+        if masked:
+            st = np.ones((S, d.nbr), dtype=np.uint8)
+            st[np.arange(S), (np.arange(S) * 37) % d.nbr] = 0
+            b.set_branch_status(st)
+        tx, tmu = torch.from_numpy(x).to(dev), torch.from_numpy(mu).to(dev)
+
+        def run(what):
+            g = torch.full((S, h.m_nl), np.nan, dtype=torch.float64, device=dev)
+            J = torch.full((S, h.nnzJ), np.nan, dtype=torch.float64, device=dev)
+            H = torch.full((S, h.nnzH), np.nan, dtype=torch.float64, device=dev)
+            sc = torch.empty(S, capi.PS_NSCALARS, dtype=torch.float64, device=dev)
+            b.eval_torch(what, tx, tmu, g, J, H, sc)
+            torch.cuda.synchronize()
+            return g.cpu().numpy(), J.cpu().numpy(), H.cpu().numpy(), sc.cpu().numpy()
+        for what in (1, 7):
+            new = run(what)                                   # S >= 32: the scenario-resident kernel is the default
+            os.environ["PS_NO_PBSCN"] = "1"
+            try:
+                ref = run(what)
+            finally:
+                del os.environ["PS_NO_PBSCN"]
+            for name, a, c in zip("gJHs", ref, new):
+                assert np.array_equal(a, c, equal_nan=True), (F.name, order, S, what, name)
+            assert not np.isnan(new[0]).any()
+        b.close()
+    h.close()
+
+
+@pytest.mark.parametrize("F", [ps.PNPAPVmodel, ps.PBRARVmodel, ps.CBRARVmodel, ps.PNRAWVmodel], ids=lambda v: v.name)
+def test_hessian_order_hook_round_trips_bitwise(F):
+    """With a caller-imposed slot order (ps_match_hessian_structure) every entry point -- the single-scenario callback, the
+    batched device path (several slabs), the host-streaming path -- returns exactly canonical[perm]; the kernels are not
+    involved (they keep writing the canonical order).  Resetting restores the canonical output."""
+    import os
+    from test_capi_cpu import _jump_like_order
+    torch = _torch()
+    dev = torch.device("cuda:0")
+    d = synthetic("case118")
+    S = 7
+    x, Pd, Qd, _ = synth.scenario_batch(d, F, S, seed=3)
+    h = capi.Handle(d, F.code, device=0)
+    mu = np.random.default_rng(1).normal(size=(S, h.m_nl))
+    g0, J0, H0, _ = _batch_eval(h, x, mu, Pd, Qd)
+    perm, tr, tc = _jump_like_order(h, 11)
+    h.match_hessian_structure(tr, tc)
+    g1, J1, H1, _ = _batch_eval(h, x, mu, Pd, Qd)
+    assert np.array_equal(g1, g0) and np.array_equal(J1, J0) and np.array_equal(H1, H0[:, perm])
+    b = capi.Batch(h, S)
+    b.set_loads(Pd, Qd)
+    hx, hmu = capi.pinned_empty((S, h.n_var)), capi.pinned_empty((S, h.m_nl))
+    hx[:], hmu[:] = x, mu
+    hH = capi.pinned_empty((S, h.nnzH))
+    os.environ["PS_STAGE"] = "3"
+    try:
+        b.eval_host(4, hx, hmu, None, None, hH, None)
+    finally:
+        del os.environ["PS_STAGE"]
+    assert np.array_equal(np.asarray(hH), H0[:, perm])
+    b.close()
+    h2 = capi.Handle(d, F.code, device=0)          # network loads: the single-scenario callbacks use them
+    Hc = h2.eval_hessian(x[0], 1.0, mu[0]).copy()
+    h2.set_hessian_order(perm + 1)
+    assert np.array_equal(h2.eval_hessian(x[0], 1.0, mu[0]), Hc[perm])
+    g, J, Hp = h2.eval_all(x[0], mu[0])
+    assert np.array_equal(Hp, Hc[perm])
+    h2.set_hessian_order(None)
+    assert np.array_equal(h2.eval_hessian(x[0], 1.0, mu[0]), Hc)
+    h2.close()
+    h.set_hessian_order(None)
+    assert np.array_equal(_batch_eval(h, x, mu, Pd, Qd)[2], H0)
+    h.close()
+
+
+def test_single_scenario_cache_keyed_on_x():
+    """JuMP's evaluator keeps its forward pass while x is unchanged.  Here: eval_constraint at a new x runs
+    ONE fused g + J launch, eval_constraint_jacobian at the same x is served from the device without a launch,
+    eval_hessian_lagrangian (whose multipliers arrive with the call) costs one more; a g-only caller (the SLP line search)
+    stops paying for J after its first point; results equal the uncached path bitwise."""
+    import os
+    d = synthetic("case118")
+    F = ps.PNPAPVmodel
+    h = capi.Handle(d, F.code, device=0)
+    x, _, _, _ = synth.scenario_batch(d, F, 3, seed=8)
+    mu = np.random.default_rng(2).normal(size=h.m_nl)
+    os.environ["PS_NO_CACHE"] = "1"
+    try:
+        g_ref = [h.eval_constraint(x[k]).copy() for k in range(3)]
+        J_ref = [h.eval_jacobian(x[k]).copy() for k in range(3)]
+        H_ref = h.eval_hessian(x[0], 1.0, mu).copy()
+    finally:
+        del os.environ["PS_NO_CACHE"]
+    per_eval = 2                                    # PNPAPV: bus kernel + branch kernel per evaluation
+    h.eval_constraint(x[0]); h.eval_jacobian(x[0])  # a caller that asks for g and J at a point (Ipopt, the SLP's LP set-up) ...
+    n0 = h.launch_count()
+    g = h.eval_constraint(x[1])                     # ... gets both from ONE fused evaluation at the next new x
+    n1 = h.launch_count()
+    J = h.eval_jacobian(x[1])                       # same x: no launch
+    n2 = h.launch_count()
+    H = h.eval_hessian(x[1], 1.0, mu)               # multipliers arrive now: one evaluation (H only), no x upload
+    n3 = h.launch_count()
+    g2 = h.eval_constraint(x[1])                    # still cached
+    n4 = h.launch_count()
+    assert n1 - n0 == per_eval and n2 == n1 and n3 - n2 == per_eval and n4 == n3
+    assert np.array_equal(g, g_ref[1]) and np.array_equal(J, J_ref[1]) and np.array_equal(g2, g_ref[1])
+    assert np.array_equal(h.eval_hessian(x[0], 1.0, mu), H_ref)
+    xx = x[2].copy()                                # a caller that mutates its x in place is seen (the key is the content)
+    assert np.array_equal(h.eval_constraint(xx), g_ref[2])
+    xx[:] = x[0]
+    assert np.array_equal(h.eval_constraint(xx), g_ref[0]) and np.array_equal(h.eval_jacobian(xx), J_ref[0])
+    # g-only caller: after one point at which J was not asked for, a new x evaluates g alone
+    h.eval_constraint(x[1]); h.eval_constraint(x[2])
+    a = h.launch_count()
+    gg = h.eval_constraint(x[0])
+    Jl = h.eval_jacobian(x[0])                      # asked after all: a second launch, J only
+    assert np.array_equal(gg, g_ref[0]) and np.array_equal(Jl, J_ref[0]) and h.launch_count() - a == 2 * per_eval
+    h.close()
+
+
+def test_correctly_rounded_powers():
+    """The L4 limit rows hold V^4 and V^3 (formulations.jl:338-343); the reference evaluates them through pow() (JuMP's `^`
+    with a constant exponent other than 2).  The kernel's powers are the correctly rounded ones: on a network whose L4 rows
+    reduce to V_a^4 - 1 (g_s = 1, everything else 0, Imax = 1) g + 1 and J / 4 must equal the exactly rounded rational
+    powers, bit for bit (repeated products miss that in 25-50 % of the arguments; glibc's own pow() in 0.08 %)."""
+    import copy
+    from fractions import Fraction
+    d = copy.deepcopy(load_fixture("case3"))
+    for name in ("gf", "gt"):
+        getattr(d, name)[:] = 1.0
+    for name in ("bf", "bt", "Gf", "Bf", "Gt", "Bt"):
+        getattr(d, name)[:] = 0.0
+    d.Imax[:] = 1.0
+    F = ps.PNPAPVmodel
+    h = capi.Handle(d, F.code, device=0)
+    off = h.variable_offsets()
+    jr, jc = h.jacobian_structure()
+    rng = np.random.default_rng(12)
+    S = 2000
+    x, _, _, _ = synth.scenario_batch(d, F, S, seed=1)
+    V = rng.uniform(0.85, 1.18, size=(S, d.nbus))
+    x[:, off["b"]:off["b"] + d.nbus] = V
+    mu = np.zeros((S, h.m_nl))
+    g, J, _, _ = _batch_eval(h, x, mu, what=3)
+    bad4 = bad3 = 0
+    for k in range(d.nbr):
+        for side in range(2):
+            a = int(d.br[k][side]) - 1
+            row = 2 * d.nbus + 2 * k + side
+            e = int(np.flatnonzero((jr == row + 1) & (jc == off["b"] + a + 1))[0])
+            for s in range(0, S, 7):
+                v = Fraction(float(V[s, a]))
+                bad4 += (g[s, row] + 1.0) != float(v ** 4)
+                bad3 += (J[s, e] / 4.0) != float(v ** 3)
+    assert bad4 == 0 and bad3 == 0, (bad4, bad3)
+    h.close()

@@ -81,6 +81,16 @@ if __name__ == "__main__":
         run("case13659pegase", "CBRARVmodel", 512, [16])
     if sel == "ncu_pn":
         run("case9241pegase", "PNPAPVmodel", 256, [4], steps=1)
+    if sel == "pbs":
+        run("case13659pegase", "PBRARVmodel", 2048, [8])
+        run("case13659pegase", "PBRARVmodel", 2048, [8], what=1)
+        os.environ["PS_NO_PBSCN"] = "1"
+        run("case13659pegase", "PBRARVmodel", 2048, [8])
+        del os.environ["PS_NO_PBSCN"]
+    if sel == "ncu_g":
+        run("case13659pegase", "PBRARVmodel", 256, [4], what=1, steps=1)
+    if sel == "ncu_c3":
+        run("case2869pegase", "PNPAPVmodel", 512, [4], steps=1)
     if sel == "ncu_cb":
         run("case13659pegase", "CBRARVmodel", 256, [4], steps=1)
     if sel == "latency":

@@ -5,9 +5,11 @@
 
 A "step" is one pass of the hot path -- the fused g + Jacobian + Hessian-of-the-Lagrangian evaluation of every
 NL row -- over one batch of synthetic scenarios of case13659pegase in the rectangular branch-flow formulation
-(PBRARVmodel), through the C ABI (ps_batch_eval).  Weak scaling: every GPU owns `--scenarios` scenarios
-(4096 by default); scenarios are independent, so the only collective is the NCCL all_gather of the
-per-scenario scalars, which is inside the timed region.
+(PBRARVmodel), through the C ABI (ps_batch_eval).  BASELINE config 4 as written: `--scenarios` scenarios (4096) IN
+TOTAL, sharded over the N GPUs ("scaling": "strong"; N = 1 is the whole batch on one GPU); scenarios are independent, so
+the only collective is the NCCL all_gather of the per-scenario scalars, inside the timed region (issued on its own
+stream so that it overlaps the next evaluation).  For N > 1 the weak-scaled figure (4096 scenarios per GPU) is reported
+beside it under "weak".
 
 `value`   whole-job evaluations/s with inputs resident in HBM (CUDA events, max over ranks).
 `e2e`     the same metric through ps_batch_eval_host: pinned HOST buffers in, HOST buffers out, H2D/D2H copies
@@ -43,23 +45,29 @@ def parse_args():
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--case", default="case13659pegase")
     ap.add_argument("--formulation", default="PBRARVmodel")
-    ap.add_argument("--scenarios", type=int, default=4096, help="scenarios per GPU (weak scaling)")
-    ap.add_argument("--e2e-scenarios", type=int, default=256)
-    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--scenarios", type=int, default=4096, help="scenarios in total (config 4: sharded over the GPUs)")
+    ap.add_argument("--no-weak", action="store_true", help="N > 1: skip the extra weak-scaled pass (--scenarios per GPU)")
+    ap.add_argument("--e2e-scenarios", type=int, default=1024)
+    ap.add_argument("--e2e-steps", type=int, default=10)
+    ap.add_argument("--no-extra", action="store_true", help="skip the extra_configs block (config 3 and config 5's evaluator)")
     ap.add_argument("--what", type=int, default=7, help="bitmask G=1 J=2 H=4")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--callbacks", action="store_true", help="also time the g-only and g+J passes (outside the timed region)")
+    ap.add_argument("--no-callbacks", action="store_true", help="skip the g-only and g+J passes (timed outside the timed region)")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     return ap.parse_args()
 
 
-def workload_config(args, h=None):
+def workload_config(args, dims, world):
+    """The same dictionary for the native and the reference arm (dims = n_var, m_nl, nnz_jac, nnz_hess)."""
+    n_var, m_nl, nnzJ, nnzH = dims
     cfg = {"workload": f"{args.case} (synthetic topology, published dimensions) {args.formulation} g+J+H batched evaluation",
            "case": args.case, "formulation": args.formulation, "what": args.what,
-           "scenarios_per_gpu": args.scenarios, "l2": "inputs+outputs per step >> 126 MB L2 (no flush needed)",
+           "scenarios_total": args.scenarios, "l2": "inputs+outputs per step >> 126 MB L2 (no flush needed)",
            "synthetic_branch_order": os.environ.get("PS_SYNTH_ORDER", "random") + " (random = permuted branch list, the adversarial order "
-                                     "for the gathers; file = ascending from-bus like real case files)"}
+                                     "for the gathers; file = ascending from-bus like real case files)",
+           "n_var": int(n_var), "m_nl": int(m_nl), "nnz_jac": int(nnzJ), "nnz_hess": int(nnzH),
+           "parallelism": f"{args.scenarios} scenarios sharded over {world} GPU(s), all_gather of 4 scalars/scenario" if world > 1 else "1 GPU"}
     return cfg
 
 
@@ -185,9 +193,9 @@ def run_reference(args, rank):
         o.eval_batch(x, mu, Pd, Qd, what=args.what, nthreads=cores, out=out)
     dt = time.time() - t
     val = n * args.steps / dt
-    cfg = workload_config(args)
+    cfg = workload_config(args, (o.n_var, o.m_nl, o.nnzJ, o.nnzH), int(os.environ.get("WORLD_SIZE", "1")))
     line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
+            "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": cfg,
             "cpu_baseline": {"value": val, "unit": UNIT, "cores": int(cores), "kind": "port",
                              "sample": f"each step = {n} scenarios of {args.case} {F.name} (what={args.what}) on {cores} host threads"},
@@ -223,81 +231,93 @@ def main():
 
     d = synth.named_case(args.case)
     F = ps.BY_NAME[args.formulation]
-    S = args.scenarios
-    drv = ScenarioDriver(d, F, S * world, rank, world, device_index=local, what=args.what)
-    h = drv.handle
-    dev = drv.device
-    # ---- synthetic inputs: 16 seeded base scenarios, expanded and perturbed on the device per global scenario
-    xb, Pdb, Qdb, lay = make_inputs(d, F, S, seed=1000 + rank)
-    B = xb.shape[0]
-    gen = torch.Generator(device=dev)
-    gen.manual_seed(4242 + rank)
-    xbd = torch.from_numpy(xb).to(dev)
-    for s0 in range(0, S, 256):
-        n = min(256, S - s0)
-        idx = (torch.arange(s0, s0 + n, device=dev) % B)
-        noise = 1.0 + 1e-3 * (torch.rand(n, h.n_var, generator=gen, device=dev, dtype=torch.float64) - 0.5)
-        drv.x[s0:s0 + n] = xbd[idx] * noise
-        del noise
-    if drv.mu is not None:
+    peak, peak_src = measured_peak()
+
+    def fill_inputs(drv, seed_off=0):
+        """16 seeded base scenarios, expanded and perturbed on the device per global scenario"""
+        h, S, dev = drv.handle, drv.S, drv.device
+        xb, Pdb, Qdb, _ = make_inputs(d, F, S, seed=1000 + rank + seed_off)
+        B = xb.shape[0]
+        gen = torch.Generator(device=dev)
+        gen.manual_seed(4242 + rank + seed_off)
+        xbd = torch.from_numpy(xb).to(dev)
         for s0 in range(0, S, 256):
             n = min(256, S - s0)
-            drv.mu[s0:s0 + n] = torch.randn(n, h.m_nl, generator=gen, device=dev, dtype=torch.float64)
-    rng = np.random.default_rng(31 + rank)
-    reps = -(-S // B)
-    Pd = np.tile(Pdb, (reps, 1))[:S] * (1.0 + 0.01 * rng.standard_normal((S, 1)))
-    Qd = np.tile(Qdb, (reps, 1))[:S] * (1.0 + 0.01 * rng.standard_normal((S, 1)))
-    drv.set_loads(Pd, Qd)
-    del Pd, Qd
-    torch.cuda.synchronize()
+            idx = (torch.arange(s0, s0 + n, device=dev) % B)
+            noise = 1.0 + 1e-3 * (torch.rand(n, h.n_var, generator=gen, device=dev, dtype=torch.float64) - 0.5)
+            drv.x[s0:s0 + n] = xbd[idx] * noise
+            del noise
+        if drv.mu is not None:
+            for s0 in range(0, S, 256):
+                n = min(256, S - s0)
+                drv.mu[s0:s0 + n] = torch.randn(n, h.m_nl, generator=gen, device=dev, dtype=torch.float64)
+        rng = np.random.default_rng(31 + rank + seed_off)
+        reps = -(-S // B)
+        Pd = np.tile(Pdb, (reps, 1))[:S] * (1.0 + 0.01 * rng.standard_normal((S, 1)))
+        Qd = np.tile(Qdb, (reps, 1))[:S] * (1.0 + 0.01 * rng.standard_normal((S, 1)))
+        drv.set_loads(Pd, Qd)
+        torch.cuda.synchronize()
 
-    def step():
-        drv.evaluate()
+    def timed_steps(drv, steps, warmup, sampler=None):
+        """W warm-up steps, then K steps between a barrier + synchronize on both sides: one evaluation of the rank's shard +
+        the gather of its scalars per step; CUDA events; max over ranks.  No host synchronisation inside the loop."""
+        for _ in range(max(warmup, 3)):
+            drv.evaluate()
+            drv.gather_scalars_async()
+        drv.wait_gathers()
+        torch.cuda.synchronize()
         if world > 1:
-            drv.gather_scalars()
+            dist.barrier()
+        if sampler is not None:
+            sampler.start()
+        l0 = drv.batch.launch_count
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        t0 = time.time()
+        e0.record()
+        for _ in range(steps):
+            drv.evaluate()
+            drv.gather_scalars_async()
+        drv.wait_gathers()
+        e1.record()
+        torch.cuda.synchronize()
+        t1 = time.time()
+        if world > 1:
+            dist.barrier()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], dtype=torch.float64, device=drv.device)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms / steps, drv.batch.launch_count - l0, (t0, t1)
 
+    def kernel_pass(drv, n=3):
+        """per-kernel durations (CUDA events recorded around every kernel on the launching stream, inside the library) and
+        the whole evaluation, sampled in a separate pass so that the timed loop carries no host synchronisation"""
+        drv.batch.enable_timing(True)
+        kt, ev = [], []
+        for _ in range(n):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(); drv.evaluate(); b.record()
+            kt.append(drv.batch.kernel_times())
+            torch.cuda.synchronize()
+            ev.append(a.elapsed_time(b))
+        drv.batch.enable_timing(False)
+        return {k: float(np.mean([t[k] for t in kt])) for k in kt[0]}, float(np.mean(ev))
+
+    S_total = args.scenarios
+    drv = ScenarioDriver(d, F, S_total, rank, world, device_index=local, what=args.what)
+    h, S, dev = drv.handle, drv.S, drv.device
+    fill_inputs(drv)
     sampler = ClockSampler(local)
-    for _ in range(max(args.warmup, 3)):
-        step()
-    torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
-    launches0 = drv.batch.launch_count
-    drv.batch.enable_timing(True)          # CUDA events around every kernel, recorded on the launching stream
-    sampler.start()
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    ktimes = []
-    torch.cuda.synchronize()
-    t0 = time.time()
-    e0.record()
-    for k in range(args.steps):
-        ev[k][0].record()
-        drv.evaluate()
-        ev[k][1].record()
-        if world > 1:
-            drv.gather_scalars()
-        ktimes.append(drv.batch.kernel_times())      # waits for this step's kernels (event sync, no device idle of note)
-    e1.record()
-    torch.cuda.synchronize()
-    t1 = time.time()
-    if world > 1:
-        dist.barrier()
-    ms_total = e0.elapsed_time(e1)
-    kernel_ms = float(np.mean([a.elapsed_time(b) for a, b in ev]))
-    kavg = {k: float(np.mean([t[k] for t in ktimes])) for k in ktimes[0]}
-    launches = drv.batch.launch_count - launches0
-    if world > 1:
-        t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms_total = float(t.item())
+    ms_per_step, launches, (t0, t1) = timed_steps(drv, args.steps, args.warmup, sampler)
     clocks = sampler.summary(t0, t1)
-    ms_per_step = ms_total / args.steps
-    value = S * world / (ms_per_step * 1e-3)
+    value = S_total / (ms_per_step * 1e-3)
+    kavg, kernel_ms = kernel_pass(drv)
     alg_bytes = h.algorithmic_bytes(args.what)
     alg_branch = h.algorithmic_bytes_branch(args.what)
-    peak, peak_src = measured_peak()
-    achieved_step = alg_bytes * S / (kernel_ms * 1e-3) / 1e9
+    # the whole step, from the timed loop itself (what `value` measures; at N > 1 it includes the exposed part of the gather)
+    achieved_step = alg_bytes * S / (ms_per_step * 1e-3) / 1e9
     achieved = alg_branch * S / (kavg["branch"] * 1e-3) / 1e9      # the dominant kernel: branch rows
     info = h.plan_info()
     # ScenarioDriver allocates the preferred (sector-aligned) layout: the bulk (TMA store) branch kernel runs unless disabled
@@ -316,35 +336,36 @@ def main():
     if os.path.exists(tp):
         try:
             tj = json.load(open(tp))
-            key = f"{args.case}:{args.formulation}:{S}:{args.what}"
-            traffic = tj.get(key, {}).get("dram_bytes_per_launch")
+            e = tj.get(f"{args.case}:{args.formulation}:{args.what}", {})
+            if e.get("dram_bytes_per_scenario") is not None:
+                traffic = e["dram_bytes_per_scenario"] * S          # per launch, like `achieved`
         except Exception:
             traffic = None
-    # one scenario's scalars make a quick sanity line for the log (stderr)
     sc = drv.scalars[:2].cpu().numpy()
-    print(f"[rank {rank}] S={S} step {kernel_ms:.3f} ms ({achieved_step:.0f} GB/s algorithmic); kernels {kavg}; branch kernel "
-          f"{achieved:.0f} GB/s; scalars[0]={sc[0].tolist()}",
-          file=sys.stderr, flush=True)
+    print(f"[rank {rank}] S={S} of {S_total}: step {ms_per_step:.3f} ms; evaluation {kernel_ms:.3f} ms ({achieved_step:.0f} GB/s "
+          f"algorithmic); kernels {kavg}; branch kernel {achieved:.0f} GB/s; scalars[0]={sc[0].tolist()}", file=sys.stderr, flush=True)
 
-    # ---- the other callbacks of the boundary (SURVEY 8d): the SLP line search asks for g only, its LP set-up for g + J.
-    # Not part of `value` (opt-in, --callbacks, so that the default command launches the g + J + H pass only); per GPU,
-    # device-resident, CUDA events, 5 passes each after one warm-up pass
-    callbacks = {}
-    drv.batch.enable_timing(False)
-    for name, w in (("g", 1), ("g+J", 3)):
-        if not args.callbacks or (args.what & w) != w:
-            continue
-        drv.evaluate(w)
+    def passes(drv_, w, n=5):
+        drv_.evaluate(w)
         torch.cuda.synchronize()
         c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         c0.record()
-        for _ in range(5):
-            drv.evaluate(w)
+        for _ in range(n):
+            drv_.evaluate(w)
         c1.record()
         torch.cuda.synchronize()
-        ms = c0.elapsed_time(c1) / 5
+        return c0.elapsed_time(c1) / n
+
+    # ---- the other callbacks of the boundary (SURVEY 8d): the SLP line search asks for g only, its LP set-up for g + J.
+    # Outside the timed region; per GPU, device-resident, CUDA events, 5 passes each after one warm-up pass
+    callbacks = {}
+    for name, w in (("g", 1), ("g+J", 3)):
+        if args.no_callbacks or (args.what & w) != w:
+            continue
+        ms = passes(drv, w)
         ab = h.algorithmic_bytes(w)
-        callbacks[name] = {"evals_per_s_per_gpu": S / (ms * 1e-3), "ms_per_pass": ms, "algorithmic_gbs": ab * S / (ms * 1e-3) / 1e9}
+        callbacks[name] = {"evals_per_s_per_gpu": S / (ms * 1e-3), "ms_per_pass": ms, "algorithmic_gbs": ab * S / (ms * 1e-3) / 1e9,
+                           "frac_of_peak": ab * S / (ms * 1e-3) / 1e9 / peak}
     # ---- e2e: host buffers through ps_batch_eval_host
     e2e = None
     if not args.no_e2e:
@@ -355,18 +376,21 @@ def main():
         hJ = capi.pinned_empty((Se, h.nnzJ)) if args.what & 2 else None
         hH = capi.pinned_empty((Se, h.nnzH)) if args.what & 4 else None
         hs = capi.pinned_empty((Se, capi.PS_NSCALARS))
-        l0 = drv.batch.launch_count
-        drv.batch.eval_host(args.what, hx, hmu, hg, hJ, hH, hs)          # warm-up (allocates the staging buffers)
-        if world > 1:
-            dist.barrier()
-        ta = time.time()
-        for _ in range(args.e2e_steps):
-            drv.batch.eval_host(args.what, hx, hmu, hg, hJ, hH, hs)
-        tb = time.time() - ta
-        if world > 1:
-            t = torch.tensor([tb], dtype=torch.float64, device=dev)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            tb = float(t.item())
+
+        def host_steps(w, n):
+            drv.batch.eval_host(w, hx, hmu, hg if w & 1 else None, hJ if w & 2 else None, hH if w & 4 else None, hs)   # warm-up
+            if world > 1:
+                dist.barrier()
+            ta = time.time()
+            for _ in range(n):
+                drv.batch.eval_host(w, hx, hmu, hg if w & 1 else None, hJ if w & 2 else None, hH if w & 4 else None, hs)
+            tb = time.time() - ta
+            if world > 1:
+                t = torch.tensor([tb], dtype=torch.float64, device=dev)
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                tb = float(t.item())
+            return tb
+        tb = host_steps(args.what, args.e2e_steps)
         if args.what & 2:
             assert np.array_equal(hJ[0], drv.J[0].cpu().numpy()), "e2e path disagrees with the device path"
         h2d = Se * (h.n_var + (h.m_nl if args.what & 4 else 0)) * 8
@@ -374,33 +398,88 @@ def main():
                     capi.PS_NSCALARS) * 8
         e2e = {"value": Se * world * args.e2e_steps / tb, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                "scenarios_per_step_per_gpu": Se, "steps": args.e2e_steps,
-               "note": "ps_batch_eval_host: pinned host x/mu in, host g/J/H/scalars out, chunked 3-stream pipeline; PCIe-bound"}
+               "d2h_gbs_per_gpu": d2h * args.e2e_steps / tb / 1e9,
+               "note": "ps_batch_eval_host: pinned host x/mu in, host g/J/H/scalars out, chunked 3-stream pipeline; bound by the "
+                       "host link (PCIe 5 x16: ~56 GB/s per direction measured alone, tools/pcie_probe.py), at N > 1 by the host's "
+                       "aggregate copy bandwidth (profiles/r02_host_ceiling.txt)"}
+        if (args.what & 3) == 3 and not args.no_callbacks:
+            # what the SLP consumes per iteration (g + J: no Hessian crosses the link)
+            tgj = host_steps(3, max(3, args.e2e_steps // 2))
+            e2e["g+J"] = {"value": Se * world * max(3, args.e2e_steps // 2) / tgj, "unit": UNIT,
+                          "d2h_bytes_per_step": int(Se * (h.m_nl + h.nnzJ + capi.PS_NSCALARS) * 8)}
         del hx, hmu, hg, hJ, hH, hs
     sampler.stop()
+    n_var, m_nl, nnzJ, nnzH = h.n_var, h.m_nl, h.nnzJ, h.nnzH
+    drv.close()
+    del drv
+    torch.cuda.empty_cache()
+
+    # ---- N > 1: the weak-scaled figure (every GPU owns `--scenarios` scenarios) beside the strong-scaled headline
+    weak = None
+    if world > 1 and not args.no_weak:
+        drvw = ScenarioDriver(d, F, S_total * world, rank, world, device_index=local, what=args.what)
+        fill_inputs(drvw, seed_off=7)
+        msw, _, _ = timed_steps(drvw, max(5, args.steps // 2), 3)
+        weak = {"value": S_total * world / (msw * 1e-3), "unit": UNIT, "ms_per_step": msw, "scenarios_per_gpu": S_total,
+                "scaling": "weak"}
+        drvw.close()
+        del drvw
+        torch.cuda.empty_cache()
+
+    # ---- the BASELINE configs that use the nodal formulations, so that the driver's record carries them: 5 passes each,
+    # device-resident, outside the timed region, one GPU's worth (rank 0)
+    extra = {}
+    if rank == 0 and not args.no_extra:
+        for label, case, fname, Sx, masked in (("config3", "case2869pegase", "PNPAPVmodel", 1024, False),
+                                                ("config5_evaluator", "case9241pegase", "PNPAPVmodel", 512, True)):
+            dx = synth.named_case(case)
+            Fx = ps.BY_NAME[fname]
+            dr = ScenarioDriver(dx, Fx, Sx, 0, 1, device_index=local, what=7)
+            xb, Pdb, Qdb, _ = synth.scenario_batch(dx, Fx, 16, seed=5)
+            reps = -(-Sx // 16)
+            dr.x[:] = torch.from_numpy(np.tile(xb, (reps, 1))[:Sx]).to(dev)
+            dr.x *= 1.0 + 1e-3 * (torch.rand_like(dr.x) - 0.5)
+            dr.mu[:] = torch.randn(Sx, dr.handle.m_nl, dtype=torch.float64, device=dev)
+            dr.set_loads(np.tile(Pdb, (reps, 1))[:Sx], np.tile(Qdb, (reps, 1))[:Sx])
+            if masked:
+                from powersense_b200.driver import contingency_status
+                dr.set_branch_status(contingency_status(dx.nbr, 0, Sx))     # N-1 sweep: scenario s opens branch s
+            res = {"case": case, "formulation": fname, "scenarios": Sx, "contingency_mask": masked}
+            for name, w in (("g+J+H", 7), ("g", 1), ("g+J", 3)):
+                ms = passes(dr, w)
+                ab = dr.handle.algorithmic_bytes(w)
+                res[name] = {"evals_per_s": Sx / (ms * 1e-3), "ms_per_pass": ms, "algorithmic_gbs": ab * Sx / (ms * 1e-3) / 1e9,
+                             "frac_of_peak": ab * Sx / (ms * 1e-3) / 1e9 / peak}
+            kx, _ = kernel_pass(dr, 2)
+            res["kernels_ms"] = kx
+            extra[label] = res
+            dr.close()
+            del dr
+            torch.cuda.empty_cache()
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cpu = cpu_baseline(d, F, args, args.cpu_seconds)
 
     if rank == 0:
-        cfg = workload_config(args)
-        cfg.update({"n_var": h.n_var, "m_nl": h.m_nl, "nnz_jac": h.nnzJ, "nnz_hess": h.nnzH,
-                    "algorithmic_bytes_per_eval": alg_bytes, "scenarios_total": S * world,
-                    "parallelism": f"scenario-sharded x{world}, all_gather of {capi.PS_NSCALARS} scalars/scenario" if world > 1 else "1 GPU"})
+        cfg = workload_config(args, (n_var, m_nl, nnzJ, nnzH), world)
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
-                "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+                "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
                 "data": "synthetic", "config": cfg, "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
-                "callbacks": callbacks,
+                "callbacks": callbacks, "weak": weak, "extra_configs": extra,
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                              "traffic": traffic, "peak_source": peak_src, "kernel": kname,
                              "kernel_ms_per_launch": kavg["branch"], "units_per_launch": S,
                              "algorithmic_bytes_per_unit": alg_branch,
-                             "step": {"achieved": achieved_step, "frac": achieved_step / peak, "ms": kernel_ms,
-                                      "algorithmic_bytes_per_unit": alg_bytes, "kernels_ms": kavg,
-                                      "note": "all kernels of one evaluation (bus rows, bus J/H slots, objective, branch rows)"}},
+                             "note": "`frac` is the dominant kernel's (branch rows); the whole evaluation -- what `value` measures -- is under `step`",
+                             "step": {"achieved": achieved_step, "frac": achieved_step / peak, "ms": ms_per_step,
+                                      "algorithmic_bytes_per_unit": alg_bytes, "units_per_gpu": S, "kernels_ms": kavg,
+                                      "evaluation_ms_with_kernel_events": kernel_ms,
+                                      "note": "per GPU: algorithmic bytes of the rank's shard / ms_per_step of the timed loop; kernels_ms = the "
+                                              "kernels of one evaluation (bus rows, bus J/H slots, objective, branch rows), sampled in a "
+                                              "separate pass with CUDA events around every kernel (the events add gaps)"}},
                 "cpu_baseline": cpu}
         print(json.dumps(line), flush=True)
-    drv.close()
     if world > 1:
         dist.destroy_process_group()
 

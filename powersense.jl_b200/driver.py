@@ -65,7 +65,13 @@ class ScenarioDriver:
         self.g = rows(h.m_nl, ldg, pg) if what & EVAL_G else None
         self.J = rows(h.nnzJ, ldJ, pJ) if what & EVAL_J else None
         self.H = rows(h.nnzH, ldH, pH) if what & EVAL_H else None
-        self.scalars = torch.zeros(n, capi.PS_NSCALARS, dtype=f64, device=self.device)
+        # two sets of per-scenario scalars: the gather of evaluation k (NCCL, its own stream) overlaps evaluation k + 1
+        self._scal = [torch.zeros(n, capi.PS_NSCALARS, dtype=f64, device=self.device) for _ in range(2)]
+        self._flip = 0
+        self.scalars = self._scal[0]
+        self._comm_stream = None
+        self._gather_ev = [None, None]        # gather of buffer q finished (the next evaluation into q waits for it)
+        self._gather_out = None
 
     def set_loads(self, Pd: np.ndarray, Qd: np.ndarray):
         self.batch.set_loads(Pd, Qd)
@@ -77,6 +83,10 @@ class ScenarioDriver:
         """One pass of the hot path over this rank's shard (asynchronous on torch's current stream)."""
         if self.S == 0:
             return
+        ev = self._gather_ev[self._flip]
+        if ev is not None:                                # the gather that last read this scalar buffer
+            self.torch.cuda.current_stream().wait_event(ev)
+        self.scalars = self._scal[self._flip]
         self.batch.eval_torch(self.what if what is None else what, self.x, self.mu, self.g, self.J, self.H, self.scalars)
 
     def gather_scalars(self):
@@ -84,6 +94,47 @@ class ScenarioDriver:
         if self.world_size == 1:
             return self.scalars[:self.S]
         return all_gather_rows(self.scalars[:self.S], self.S_total, self.world_size)
+
+    def gather_scalars_async(self):
+        """The same exchange, off the evaluation's critical path: issued on a communication stream behind an event, into a
+        preallocated buffer, so that it overlaps the next evaluation (which writes the other scalar buffer).  Call
+        wait_gathers() before reading gathered_scalars.  Equal shards take one all_gather_into_tensor and nothing else."""
+        torch = self.torch
+        if self.world_size == 1:
+            self.gathered_scalars = self.scalars[:self.S]
+            return
+        import torch.distributed as dist
+        if self._comm_stream is None:
+            self._comm_stream = torch.cuda.Stream(device=self.device)
+            smax = -(-self.S_total // self.world_size)
+            self._gather_out = torch.empty(self.world_size * smax, capi.PS_NSCALARS, dtype=torch.float64, device=self.device)
+            self._gather_pad = torch.zeros(smax, capi.PS_NSCALARS, dtype=torch.float64, device=self.device)
+        done = torch.cuda.Event()
+        done.record()                                      # evaluation k has written its scalars
+        src = self.scalars
+        with torch.cuda.stream(self._comm_stream):
+            self._comm_stream.wait_event(done)
+            if self.S * self.world_size == self.S_total:
+                dist.all_gather_into_tensor(self._gather_out, src[:self.S])
+            else:
+                self._gather_pad[:self.S] = src[:self.S]
+                dist.all_gather_into_tensor(self._gather_out, self._gather_pad)
+            ev = torch.cuda.Event()
+            ev.record()
+        self._gather_ev[self._flip] = ev
+        self._flip ^= 1
+        self.gathered_scalars = None
+
+    def wait_gathers(self):
+        """Make torch's current stream wait for every outstanding gather; returns [S_total, PS_NSCALARS]."""
+        if self.world_size == 1:
+            return self.scalars[:self.S]
+        for ev in self._gather_ev:
+            if ev is not None:
+                self.torch.cuda.current_stream().wait_event(ev)
+        even = self.S * self.world_size == self.S_total
+        self.gathered_scalars = self._gather_out if even else gather_unpad(self._gather_out, self.S_total, self.world_size)
+        return self.gathered_scalars
 
     def close(self):
         self.batch.close()

@@ -17,7 +17,7 @@ def test_smoke():
 
 def test_bench_json_contract():
     out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--steps", "3", "--warmup", "3", "--scenarios", "64",
-                          "--e2e-scenarios", "16", "--cpu-seconds", "1"], capture_output=True, text=True, timeout=900, cwd=ROOT)
+                          "--e2e-scenarios", "16", "--e2e-steps", "3", "--cpu-seconds", "1", "--no-extra"], capture_output=True, text=True, timeout=900, cwd=ROOT)
     assert out.returncode == 0, out.stderr[-2000:]
     line = json.loads(out.stdout.strip().splitlines()[-1])
     for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline",
@@ -27,6 +27,12 @@ def test_bench_json_contract():
     assert line["roofline"]["bound"] == "hbm" and 0 < line["roofline"]["frac"] < 1.5
     assert line["e2e"]["h2d_bytes_per_step"] > 0 and line["e2e"]["d2h_bytes_per_step"] > 0
     assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
+    assert line["scaling"] == "strong" and set(line["callbacks"]) == {"g", "g+J"} and line["config"]["scenarios_total"] == 64
+    # the reference arm describes the same workload with the same keys (the driver compares the two config dicts)
+    ref = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0",
+                          "--scenarios", "64"], capture_output=True, text=True, timeout=900, cwd=ROOT)
+    assert ref.returncode == 0, ref.stderr[-2000:]
+    assert json.loads(ref.stdout.strip().splitlines()[-1])["config"] == line["config"]
 
 
 def test_reference_arm_contract():

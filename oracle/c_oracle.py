@@ -83,6 +83,8 @@ class COracle:
         self._has_bus_rows = formulation_code not in (2, 8)      # PBRAWV / PNRAWV have no NL bus rows
 
     def __del__(self):
+        if lib is None:
+            return
         if getattr(self, "h", None):
             lib().pso_destroy(self.h)
             self.h = None

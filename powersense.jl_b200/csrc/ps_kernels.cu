@@ -847,17 +847,21 @@ __device__ __forceinline__ void copy_out(double* __restrict__ dst, const double*
   copy_aligned<TPB>(dst, n, threadIdx.x, [&](int e) { return tile[e]; });
 }
 
+// per-scenario violation scalars of one warp: max over the lanes through two 32-bit REDUX (non-negative doubles order like
+// their bit patterns: high word first, then the low words of the lanes that hold the maximal high word) and the count
+// through a third -- three warp-wide instructions where a shuffle tree takes fifteen (on the residual-only pass the
+// shuffle version was a quarter of the branch kernel's time: profiles/r02_gonly_notes.txt)
 __device__ __forceinline__ void reduce_scalars(double* scal, double vmax, int nviol) {
   if (!scal) return;
-#pragma unroll
-  for (int d = 16; d > 0; d >>= 1) {
-    vmax = fmax(vmax, __shfl_xor_sync(0xffffffffu, vmax, d));
-    nviol += __shfl_xor_sync(0xffffffffu, nviol, d);
-  }
+  if (!(vmax >= 0.0)) vmax = 0.0;                               // NaN is ignored, like fmax does
+  const unsigned long long b = (unsigned long long)__double_as_longlong(vmax);
+  const unsigned hi = __reduce_max_sync(0xffffffffu, (unsigned)(b >> 32));
+  const unsigned lo = __reduce_max_sync(0xffffffffu, (unsigned)(b >> 32) == hi ? (unsigned)b : 0u);
+  const int nv = __reduce_add_sync(0xffffffffu, nviol);
   if ((threadIdx.x & 31) == 0) {
-    // non-negative doubles order like their bit patterns
-    if (vmax > 0.0) atomicMax((unsigned long long*)(scal + 1), (unsigned long long)__double_as_longlong(vmax));
-    if (nviol) atomicAdd(scal + 2, (double)nviol);             // small integers: exact, order independent
+    const unsigned long long m = ((unsigned long long)hi << 32) | lo;
+    if (m) atomicMax((unsigned long long*)(scal + 1), m);
+    if (nv) atomicAdd(scal + 2, (double)nv);                    // small integers: exact, order independent
   }
 }
 
@@ -1116,6 +1120,11 @@ struct RegW {                      // writer through register-held destinations 
   }
   __device__ __forceinline__ void zero() { k++; }               // structural zeros are never written (the plan drops them)
 };
+struct NullW {                     // a block that is not asked for: its values are never formed (compile-time dead)
+  static constexpr bool on = false;
+  __device__ __forceinline__ void put(double) {}
+  __device__ __forceinline__ void zero() {}
+};
 struct ListW {                     // writer through a destination list in shared memory
   double* base;
   const uint16_t* d;
@@ -1169,21 +1178,13 @@ __device__ __forceinline__ void wt_store_block(double* __restrict__ g, const dou
     for (int e = lane; e < b.n; e += 32) g[e] = img[e];
   }
 }
-__device__ __forceinline__ void reduce_scalars_redux(double* scal, double vmax, int nviol) {
-  if (!scal) return;
-  if (!(vmax >= 0.0)) vmax = 0.0;                               // NaN is ignored, like fmax does
-  const unsigned long long b = (unsigned long long)__double_as_longlong(vmax);   // non-negative doubles order like their bits
-  const unsigned hi = __reduce_max_sync(0xffffffffu, (unsigned)(b >> 32));
-  const unsigned lo = __reduce_max_sync(0xffffffffu, (unsigned)(b >> 32) == hi ? (unsigned)b : 0u);
-  const int nv = __reduce_add_sync(0xffffffffu, nviol);
-  if ((threadIdx.x & 31) == 0) {
-    const unsigned long long m = ((unsigned long long)hi << 32) | lo;
-    if (m) atomicMax((unsigned long long*)(scal + 1), m);
-    if (nv) atomicAdd(scal + 2, (double)nv);
-  }
-}
+__device__ __forceinline__ void reduce_scalars_redux(double* scal, double vmax, int nviol) { reduce_scalars(scal, vmax, nviol); }
 
-template <int FORM, bool FULL>
+// MODE: which outputs are compile-time constants.  WT_ANY: read from A.what / A.status at run time (any combination, status
+// masks); WT_FULL: g + J + H without a mask (the headline evaluation); WT_G: residuals only -- eval_constraint, every trial
+// point of the SLP line search: no derivative is formed at all; WT_GJ: g + J -- the SLP's LP set-up: no Hessian term is formed
+enum WtMode : int { WT_ANY = 0, WT_FULL = 1, WT_G = 2, WT_GJ = 3 };
+template <int FORM, int MODE>
 __device__ __forceinline__ void bus_warp_body(const DevPlan& P, const EvalArgs& A, double* region, int tile, int s0, int s1) {
   if constexpr (has_bus_rows(FORM)) {
     constexpr int NJ = he_nj(FORM), NH = he_nh(FORM), NG = he_npg(FORM);
@@ -1191,8 +1192,11 @@ __device__ __forceinline__ void bus_warp_body(const DevPlan& P, const EvalArgs& 
     constexpr bool PB = (FORM == PBRAPV || FORM == PBRARV);
     const WTile t = P.wtiles[tile];
     const int lane = threadIdx.x & 31;
-    const bool wg = FULL || (A.what & EV_G) != 0, wj = FULL || (A.what & EV_J) != 0, wh = FULL || (A.what & EV_H) != 0;
-    const bool has_status = !FULL && A.status != nullptr;
+    constexpr bool FULL = MODE == WT_FULL;
+    const bool wg = MODE != WT_ANY || (A.what & EV_G) != 0;
+    const bool wj = MODE == WT_FULL || MODE == WT_GJ || (MODE == WT_ANY && (A.what & EV_J) != 0);
+    const bool wh = MODE == WT_FULL || (MODE == WT_ANY && (A.what & EV_H) != 0);
+    const bool has_status = MODE == WT_ANY && A.status != nullptr;
     const bool need_g = wg || A.scal;
     const bool facts = (P.flags & FLAG_FACTS) != 0;
     double* const spJ = region;
@@ -1293,11 +1297,20 @@ __device__ __forceinline__ void bus_warp_body(const DevPlan& P, const EvalArgs& 
         HeIn in;
         in.side = side; in.st = cur.st; in.v0 = cur.v0; in.v1 = cur.v1; in.va0 = cur.va0; in.vb0 = cur.vb0;
         in.muP = cur.muP; in.muQ = cur.muQ; in.c0 = c0; in.c1 = c1; in.c2 = c2; in.c3 = c3;
-        RegW sj{imgJ, d, 0, wj}, sh{imgH, d, NJ, wh};
         auto gput = [&](int kk, double v) {
           imgG[(d[(NJ + NH + kk) >> 1] >> (((NJ + NH + kk) & 1) * 16)) & 0xffffu] = piece_neg(FORM, kk) ? -v : v;
         };
-        he_math<FORM>(in, sj, sh, gput, need_g);
+        if constexpr (MODE == WT_G) {
+          NullW sj, sh;
+          he_math<FORM>(in, sj, sh, gput, need_g);
+        } else if constexpr (MODE == WT_GJ) {
+          RegW sj{imgJ, d, 0, true};
+          NullW sh;
+          he_math<FORM>(in, sj, sh, gput, need_g);
+        } else {
+          RegW sj{imgJ, d, 0, wj}, sh{imgH, d, NJ, wh};
+          he_math<FORM>(in, sj, sh, gput, need_g);
+        }
         if constexpr (PB) {
           if (need_g) { gput(0, cur.st * cur.v0); gput(1, cur.st * cur.v1); }
         }
@@ -1370,15 +1383,25 @@ __device__ __forceinline__ void bus_warp_body(const DevPlan& P, const EvalArgs& 
 __host__ __device__ inline int wt_region_doubles(const DevPlan& P) {   // per-warp shared memory, doubles (even)
   return P.wt_jspace + P.wt_hspace + P.wt_gspace + ((P.wt_lists + 7) / 8) * 2;
 }
-template <int FORM>
+// one kernel per mode: each gets its own register allocation and code (the four bodies in ONE kernel cost the headline
+// g + J + H instantiation 8 %: gpurun_out/r2c13_ab.log)
+template <int FORM, int MODE>
 __global__ void __launch_bounds__(32 * WPC, PS_WT_MINB) bus_warp_kernel(const __grid_constant__ DevPlan P, const __grid_constant__ EvalArgs A) {
   extern __shared__ __align__(16) double smem[];
   const int tile = blockIdx.x * WPC + (threadIdx.x >> 5);
   if (tile >= P.n_wtiles) return;
   const int s0 = blockIdx.y * A.chunk, s1 = min(A.S, s0 + A.chunk);
   double* r = smem + (threadIdx.x >> 5) * wt_region_doubles(P);
-  if ((A.what & (EV_G | EV_J | EV_H)) == (EV_G | EV_J | EV_H) && A.status == nullptr) bus_warp_body<FORM, true>(P, A, r, tile, s0, s1);
-  else bus_warp_body<FORM, false>(P, A, r, tile, s0, s1);
+  bus_warp_body<FORM, MODE>(P, A, r, tile, s0, s1);
+}
+// which instantiation serves a call
+__host__ inline int wt_mode(const EvalArgs& A) {
+  const int w = A.what & (EV_G | EV_J | EV_H);
+  if (A.status != nullptr || A.force_any) return WT_ANY;
+  if (w == (EV_G | EV_J | EV_H)) return WT_FULL;
+  if (w == EV_G) return WT_G;
+  if (w == (EV_G | EV_J)) return WT_GJ;
+  return WT_ANY;
 }
 
 // ---- PB* balances, fast path (PBRAPV / PBRARV without switched shunts) ------------------------------------------
@@ -2009,8 +2032,11 @@ __global__ void __launch_bounds__(TPB, direct_minb(FORM)) branch_direct_kernel(c
 // Residual-only pass of the branch rows (eval_constraint alone: every trial point of the SLP line search, and the
 // violation scalars): the derivative tags are compile-time dead, so this is the flow / limit expressions and nothing
 // else; g leaves through a per-warp staging row as warp-contiguous, sector-aligned stores.  Any layout.
+#ifndef PS_BG_MINB
+#define PS_BG_MINB 1
+#endif
 template <int FORM, int SRC>
-__global__ void __launch_bounds__(TPB) branch_g_kernel(const __grid_constant__ DevPlan P, const __grid_constant__ EvalArgs A) {
+__global__ void __launch_bounds__(TPB, PS_BG_MINB) branch_g_kernel(const __grid_constant__ DevPlan P, const __grid_constant__ EvalArgs A) {
   using BR = Branch<FORM, SRC>;
   if constexpr (BR::NR > 0) {
     __shared__ __align__(16) double sW[TPB / 32][32 * BR::NR];
@@ -2034,9 +2060,13 @@ __global__ void __launch_bounds__(TPB) branch_g_kernel(const __grid_constant__ D
     const int nact = max(0, min(32, P.nr - ubase));
     const int ng = nact * BR::NR;
     const long long gb = P.bus_rows + (long long)ubase * BR::NR;
+    // inputs two scenarios ahead (the first use of a scenario's inputs was 32 % of this kernel's stall samples at depth 1:
+    // profiles/r02_ncu_gonly_summary.txt)
+    typename BR::In nx1{};
+    if (act && s0 + 1 < s1) nx1 = BR::load_in(P, A, s0 + 1, u, f, t);
     for (int s = s0; s < s1; s++) {
       typename BR::In nxt{};
-      if (act && s + 1 < s1) nxt = BR::load_in(P, A, s + 1, u, f, t);
+      if (act && s + 2 < s1) nxt = BR::load_in(P, A, s + 2, u, f, t);
       og.vmax = 0.0; og.nviol = 0;
       if (act) BR::run(og, cst, cur);
       if (wg) {
@@ -2050,7 +2080,7 @@ __global__ void __launch_bounds__(TPB) branch_g_kernel(const __grid_constant__ D
         __syncwarp();
       }
       reduce_scalars(A.scal ? A.scal + (long long)s * NSCAL : nullptr, og.vmax, og.nviol);
-      if (s + 1 < s1) cur = nxt;
+      cur = nx1; nx1 = nxt;
     }
   }
 }
@@ -2083,7 +2113,12 @@ cudaError_t launch_bus_form(const DevPlan& P, const EvalArgs& A, size_t smem, cu
 
 template <int FORM>
 cudaError_t launch_bus_warp_form(const DevPlan& P, const EvalArgs& A, size_t smem, cudaStream_t st, dim3 grid) {
-  bus_warp_kernel<FORM><<<grid, 32 * WPC, smem, st>>>(P, A);
+  switch (wt_mode(A)) {
+    case WT_FULL: bus_warp_kernel<FORM, WT_FULL><<<grid, 32 * WPC, smem, st>>>(P, A); break;
+    case WT_G: bus_warp_kernel<FORM, WT_G><<<grid, 32 * WPC, smem, st>>>(P, A); break;
+    case WT_GJ: bus_warp_kernel<FORM, WT_GJ><<<grid, 32 * WPC, smem, st>>>(P, A); break;
+    default: bus_warp_kernel<FORM, WT_ANY><<<grid, 32 * WPC, smem, st>>>(P, A); break;
+  }
   return cudaGetLastError();
 }
 
@@ -2098,7 +2133,10 @@ cudaError_t configure_form(int src, size_t smem_branch, size_t smem_bus, size_t 
     }
   }
   if (smem_wt > 0) {
-    e = cudaFuncSetAttribute(bus_warp_kernel<FORM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_wt);
+    e = cudaFuncSetAttribute(bus_warp_kernel<FORM, WT_ANY>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_wt);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(bus_warp_kernel<FORM, WT_FULL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_wt);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(bus_warp_kernel<FORM, WT_G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_wt);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(bus_warp_kernel<FORM, WT_GJ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_wt);
     if (e != cudaSuccess) return e;
   }
   {
@@ -2342,7 +2380,7 @@ cudaError_t launch_pb_form(const DevPlan& P, const EvalArgs& A, cudaStream_t st,
       // scenario-resident residuals when a batch fills the machine (a CTA works through whole scenarios one after the
       // other: a handful of scenarios is faster with the list-walking kernel); PS_PBSCN=1 / PS_NO_PBSCN force either
       const int64_t smem = pbs_smem_bytes(P);
-      const bool scn = smem > 0 && !getenv("PS_NO_PBSCN") && (A.S >= 32 || getenv("PS_PBSCN"));
+      const bool scn = smem > 0 && !getenv("PS_NO_PBSCN") && ((A.S >= 32 && P.pbs_prefer) || getenv("PS_PBSCN"));
       if (scn) {
         static int n_sm = 0;
         if (n_sm == 0) { int dv = 0; cudaGetDevice(&dv); cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dv); if (n_sm <= 0) n_sm = 148; }

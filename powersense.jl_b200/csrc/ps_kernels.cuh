@@ -30,6 +30,7 @@ struct DevPlan {                    // passed to kernels by value (constant bank
   const double *pb_jt, *pb_ht;                      // PB* slot tables (ps_capi.cu: upload): coefficients and
   const int32_t *pb_ji, *pb_hi;                     // indices, 4 shifted copies each:
   int pb_jstride, pb_hstride;                       // copy a at + a * stride + (4 - a) % 4 (aligned at entry a + 4q)
+  int pbs_prefer;                                   // the plan's choice between the two PB* residual kernels
   int pbs_ok;                                       // PB* scenario-resident residual kernel available (ps_plan.h: pbs_code)
   const int32_t* pbs_code;                          // [ng | nr | nr] bus | rank << 24, -1 = no term
   const uint8_t* pbs_wmax;                          // highest rank per step (generator, Sij, Sji steps)
@@ -68,6 +69,7 @@ struct EvalArgs {
   double* scal;                                        // [S][NSCAL] (nullptr -> skip); must be zeroed
   double* diag; long long lddiag;                      // CB* fast path: scratch [S][4*nb] own-voltage Jacobian sums (nullptr -> generic path)
   double viol_tol;
+  int force_any;                                       // development: bus_warp_kernel takes its run-time-flag instantiation (PS_WT_ANY)
 };
 
 // Launches one evaluation (bus kernel + branch kernel) on `stream`; *launches is incremented per kernel.

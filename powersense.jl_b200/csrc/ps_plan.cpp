@@ -421,6 +421,12 @@ std::string build_plan(const HostNet& net, int form, int src, int flags, int tpb
       ranks(P.pbs_code.data(), ng);
       ranks(P.pbs_code.data() + ng, nr);
       ranks(P.pbs_code.data() + ng + nr, nr);
+      // a bus's terms inside one step are served in rank order, one CTA barrier per rank: worth it on a randomly numbered
+      // branch list (1-3 ranks per step), not on a from-bus ordered one, where a step holds every outgoing branch of its
+      // buses (and where the list-walking kernel's gathers hit the same sectors anyway)
+      int64_t rounds = 0;
+      for (uint8_t w : P.pbs_wmax) rounds += w + 1;
+      P.pbs_prefer = P.pbs_ok && rounds <= 3 * (int64_t)P.pbs_wmax.size() + 8;
       if (!P.pbs_ok) { P.pbs_code.clear(); P.pbs_wmax.clear(); }
     }
   }

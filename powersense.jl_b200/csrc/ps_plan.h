@@ -91,6 +91,7 @@ struct Plan {
   std::vector<int32_t> pbs_code;
   std::vector<uint8_t> pbs_wmax;
   bool pbs_ok = false;
+  bool pbs_prefer = false;                          // ... and few enough ranks per step for it to be the faster kernel
   bool pb_implicit = false;                         // PB* bus rows: J slots follow [voltage][gens][Sij][Sji]
   int64_t smem_bytes = 0;                           // dynamic shared memory of the kernel (max over tile kinds)
   int64_t smem_bus_bytes = 0, smem_branch_bytes = 0; // bus kernel / staged branch kernel

@@ -542,7 +542,11 @@ def test_scenario_resident_pb_residuals(F, order):
             torch.cuda.synchronize()
             return g.cpu().numpy(), J.cpu().numpy(), H.cpu().numpy(), sc.cpu().numpy()
         for what in (1, 7):
-            new = run(what)                                   # S >= 32: the scenario-resident kernel is the default
+            os.environ["PS_PBSCN"] = "1"
+            try:
+                new = run(what)                               # S >= 32: the scenario-resident kernel (the default where the plan offers it)
+            finally:
+                del os.environ["PS_PBSCN"]
             os.environ["PS_NO_PBSCN"] = "1"
             try:
                 ref = run(what)
@@ -680,4 +684,35 @@ def test_correctly_rounded_powers():
                 bad4 += (g[s, row] + 1.0) != float(v ** 4)
                 bad3 += (J[s, e] / 4.0) != float(v ** 3)
     assert bad4 == 0 and bad3 == 0, (bad4, bad3)
+    h.close()
+
+
+@pytest.mark.parametrize("F", [ps.PNPAPVmodel, ps.PNRAPVmodel, ps.PNRARVmodel, ps.CBRARVmodel, ps.PBRARVmodel], ids=lambda v: v.name)
+def test_specialised_callback_kernels_match_the_general_one(F):
+    """bus_warp_kernel is instantiated for the callbacks a solver actually issues -- residuals only (eval_constraint: every
+    trial point of the SLP line search; no derivative is formed) and g + J (the LP set-up; no Hessian term is formed) -- next
+    to the run-time-flag version that serves status masks and odd combinations.  Same expressions, same order: bitwise equal."""
+    import os
+    torch = _torch()
+    dev = torch.device("cuda:0")
+    d = synthetic("case2869pegase")
+    S = 37
+    x, Pd, Qd, _ = synth.scenario_batch(d, F, S, seed=21)
+    h = capi.Handle(d, F.code, device=0)
+    mu = np.random.default_rng(2).normal(size=(S, h.m_nl))
+    base = {"PS_NO_CBFAST": "1", "PS_NO_PBFAST": "1"}           # the warp-tile kernel for every formulation
+    os.environ.update(base)
+    try:
+        for what in (1, 3, 7, 2, 5):
+            new = _batch_eval(h, x, mu, Pd, Qd, what=what)
+            os.environ["PS_WT_ANY"] = "1"
+            try:
+                ref = _batch_eval(h, x, mu, Pd, Qd, what=what)
+            finally:
+                del os.environ["PS_WT_ANY"]
+            for name, a, c in zip("gJHs", new, ref):
+                assert np.array_equal(a, c, equal_nan=True), (F.name, what, name)
+    finally:
+        for k in base:
+            del os.environ[k]
     h.close()

@@ -119,6 +119,24 @@ function MOI.eval_hessian_lagrangian(d::GpuNLPEvaluator, H, x, σ, μ)
     return
 end
 
+"""
+    adopt_hessian_order!(d, jump_evaluator)
+
+Make the library report its Hessian structure and values in exactly the order of a JuMP evaluator of the same model
+(`JuMP.NLPEvaluator(model)` of the reference's own `create_opf_model!`, initialised with `:Hess`): JuMP's intra-block
+off-diagonal order depends on its colouring / `Set` iteration order and cannot be derived outside Julia, so the order is
+IMPORTED (ps_match_hessian_structure: matched per NL-row block as sets of variable pairs, either triangle).  After this
+call `MOI.hessian_lagrangian_structure(d)` equals JuMP's pair for pair up to the triangle convention, and
+`eval_hessian_lagrangian` fills `H` in that order.  The kernels are untouched (a gather applies the permutation).
+"""
+function adopt_hessian_order!(d::GpuNLPEvaluator, jump_evaluator)
+    hs = MOI.hessian_lagrangian_structure(jump_evaluator)
+    length(hs) == d.nnz_hess || error("Hessian structures differ in length: $(length(hs)) vs $(d.nnz_hess)")
+    r = Int64[t[1] for t in hs]; c = Int64[t[2] for t in hs]
+    check(d.handle, ccall((:ps_match_hessian_structure, LIB), Cint, (Ptr{Cvoid}, Ptr{Int64}, Ptr{Int64}), d.handle, r, c))
+    return d
+end
+
 "NLPBlockData for MOI.set(backend, MOI.NLPBlock(), ...): bounds (0,0) for == rows, (-Inf,0) for <= rows"
 function nlp_block(d::GpuNLPEvaluator)
     lo = Vector{Float64}(undef, d.m_nl); hi = Vector{Float64}(undef, d.m_nl)

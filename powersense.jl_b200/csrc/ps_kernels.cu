@@ -1199,9 +1199,10 @@ __device__ __forceinline__ void bus_warp_body(const DevPlan& P, const EvalArgs& 
     const bool has_status = MODE == WT_ANY && A.status != nullptr;
     const bool need_g = wg || A.scal;
     const bool facts = (P.flags & FLAG_FACTS) != 0;
+    // the residual-only instantiation keeps no J / H image: its region is the G space and the lists
     double* const spJ = region;
-    double* const spH = spJ + P.wt_jspace;
-    double* const spG = spH + P.wt_hspace;
+    double* const spH = spJ + (MODE == WT_G ? 0 : P.wt_jspace);
+    double* const spG = spH + (MODE == WT_G ? 0 : P.wt_hspace);
     uint64_t* const multi = (uint64_t*)(spG + P.wt_gspace);     // multi-slot descriptors (ps_plan.h: wt_multi)
     const int oj0 = P.wt_ownj_ptr[t.u0], noj = P.wt_ownj_ptr[t.u1] - oj0;
     const int oh0 = P.wt_ownh_ptr[t.u0], noh = P.wt_ownh_ptr[t.u1] - oh0;
@@ -1211,7 +1212,8 @@ __device__ __forceinline__ void bus_warp_body(const DevPlan& P, const EvalArgs& 
     uint16_t* const owng = ownh + noh;
     // ---- scenario-independent set-up
     for (int q = lane; q < t.mn; q += 32) multi[q] = P.wt_multi[t.m0 + q];
-    for (int q = lane; q < P.wt_hspace; q += 32) spH[q] = 0.0;  // slots whose contributions are all structural zeros stay 0
+    if constexpr (MODE != WT_G)
+      for (int q = lane; q < P.wt_hspace; q += 32) spH[q] = 0.0;  // slots whose contributions are all structural zeros stay 0
     for (int q = lane; q < noj; q += 32) ownj[q] = P.wt_ownj[oj0 + q];
     for (int q = lane; q < noh; q += 32) ownh[q] = P.wt_ownh[oh0 + q];
     for (int q = lane; q < nog; q += 32) owng[q] = P.wt_owng[og0 + q];
@@ -1380,18 +1382,21 @@ __device__ __forceinline__ void bus_warp_body(const DevPlan& P, const EvalArgs& 
 #ifndef PS_WT_MINB
 #define PS_WT_MINB 16               // 16 warps / SM: 128 registers per thread
 #endif
-__host__ __device__ inline int wt_region_doubles(const DevPlan& P) {   // per-warp shared memory, doubles (even)
-  return P.wt_jspace + P.wt_hspace + P.wt_gspace + ((P.wt_lists + 7) / 8) * 2;
+__host__ __device__ inline int wt_region_doubles(const DevPlan& P, bool g_only = false) {   // per-warp shared memory, doubles (even)
+  return (g_only ? 0 : P.wt_jspace + P.wt_hspace) + P.wt_gspace + ((P.wt_lists + 7) / 8) * 2;
 }
+#ifndef PS_WT_MINB_G
+#define PS_WT_MINB_G 24             // residual-only: no destinations / multipliers in registers, 1-2 KB of shared memory per warp
+#endif
 // one kernel per mode: each gets its own register allocation and code (the four bodies in ONE kernel cost the headline
 // g + J + H instantiation 8 %: gpurun_out/r2c13_ab.log)
 template <int FORM, int MODE>
-__global__ void __launch_bounds__(32 * WPC, PS_WT_MINB) bus_warp_kernel(const __grid_constant__ DevPlan P, const __grid_constant__ EvalArgs A) {
+__global__ void __launch_bounds__(32 * WPC, MODE == WT_G ? PS_WT_MINB_G : PS_WT_MINB) bus_warp_kernel(const __grid_constant__ DevPlan P, const __grid_constant__ EvalArgs A) {
   extern __shared__ __align__(16) double smem[];
   const int tile = blockIdx.x * WPC + (threadIdx.x >> 5);
   if (tile >= P.n_wtiles) return;
   const int s0 = blockIdx.y * A.chunk, s1 = min(A.S, s0 + A.chunk);
-  double* r = smem + (threadIdx.x >> 5) * wt_region_doubles(P);
+  double* r = smem + (threadIdx.x >> 5) * wt_region_doubles(P, MODE == WT_G);
   bus_warp_body<FORM, MODE>(P, A, r, tile, s0, s1);
 }
 // which instantiation serves a call
@@ -2115,7 +2120,7 @@ template <int FORM>
 cudaError_t launch_bus_warp_form(const DevPlan& P, const EvalArgs& A, size_t smem, cudaStream_t st, dim3 grid) {
   switch (wt_mode(A)) {
     case WT_FULL: bus_warp_kernel<FORM, WT_FULL><<<grid, 32 * WPC, smem, st>>>(P, A); break;
-    case WT_G: bus_warp_kernel<FORM, WT_G><<<grid, 32 * WPC, smem, st>>>(P, A); break;
+    case WT_G: bus_warp_kernel<FORM, WT_G><<<grid, 32 * WPC, (size_t)WPC * wt_region_doubles(P, true) * 8, st>>>(P, A); break;
     case WT_GJ: bus_warp_kernel<FORM, WT_GJ><<<grid, 32 * WPC, smem, st>>>(P, A); break;
     default: bus_warp_kernel<FORM, WT_ANY><<<grid, 32 * WPC, smem, st>>>(P, A); break;
   }

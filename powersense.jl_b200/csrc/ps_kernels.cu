@@ -1538,13 +1538,16 @@ __global__ void __launch_bounds__(PBT) pb_bus_g_kernel(const __grid_constant__ D
 #ifndef PS_PBS_R
 #define PS_PBS_R 4
 #endif
-constexpr int PBS_T = PBS_WAVE;
+constexpr int PBS_T = PBS_THREADS;
+constexpr int PBS_E = PS_PBS_E;    // elements per thread and step (1: more per step -- fewer barriers, independent read-modify-writes --
+                                   // measured slower at every depth that fits 64 registers: gpurun_out/r2c16_ab.log)
 constexpr int PBS_MAX_STEPS = 1024;
+constexpr int PBS_RB = 4;           // ring depth of the two bus-ordered passes (one element per thread and step)
 constexpr int PBS_R = PS_PBS_R;    // steps whose inputs are in flight (a register ring: the CTA is alone on its SM -- the
                                    // accumulators fill its shared memory -- so memory latency is hidden by depth, not by occupancy)
 
-// One pass over a term table: step j serves elements [j * PBS_T, (j + 1) * PBS_T) -- thread tid element j * PBS_T + tid --
-// with the inputs of the next PBS_R steps already in flight.
+// One pass over a term table: step j serves elements [j * PBS_WAVE, (j + 1) * PBS_WAVE) -- thread tid the PBS_E elements
+// j * PBS_WAVE + e * PBS_T + tid -- with the inputs of the next PBS_R steps already in flight.
 template <bool HAS_ST>
 __device__ __forceinline__ void pbs_term_pass(double2* acc, const uint8_t* wmax, const int32_t* __restrict__ code, int n,
                                               const double* __restrict__ v0p, const double* __restrict__ v1p,
@@ -1553,15 +1556,18 @@ __device__ __forceinline__ void pbs_term_pass(double2* acc, const uint8_t* wmax,
   // whole rings: the steps past the end have no terms (the loads are guarded) and cost one barrier each; unconditional
   // ring bodies keep every slot in a fixed register (a guarded body makes the compiler rotate the ring through moves,
   // which waits for a load one step after it was issued)
-  const int nsteps = ((n + PBS_T - 1) / PBS_T + PBS_R - 1) / PBS_R * PBS_R;
-  int c[PBS_R];
-  double a0[PBS_R], a1[PBS_R];
+  const int nsteps = ((n + PBS_WAVE - 1) / PBS_WAVE + PBS_R - 1) / PBS_R * PBS_R;
+  int c[PBS_R][PBS_E];
+  double a0[PBS_R][PBS_E], a1[PBS_R][PBS_E];
   auto load = [&](int u, int j) {
-    const int e = j * PBS_T + tid;
-    c[u] = -1; a0[u] = 0.0; a1[u] = 0.0;
-    if (e < n) {
-      c[u] = code[e]; a0[u] = v0p[e]; a1[u] = v1p[e];
-      if constexpr (HAS_ST) { const double st = (double)stp[e]; a0[u] = st * a0[u]; a1[u] = st * a1[u]; }
+#pragma unroll
+    for (int q = 0; q < PBS_E; q++) {
+      const int e = j * PBS_WAVE + q * PBS_T + tid;
+      c[u][q] = -1; a0[u][q] = 0.0; a1[u][q] = 0.0;
+      if (e < n) {
+        c[u][q] = code[e]; a0[u][q] = v0p[e]; a1[u][q] = v1p[e];
+        if constexpr (HAS_ST) { const double st = (double)stp[e]; a0[u][q] = st * a0[u][q]; a1[u][q] = st * a1[u][q]; }
+      }
     }
   };
 #pragma unroll
@@ -1570,16 +1576,23 @@ __device__ __forceinline__ void pbs_term_pass(double2* acc, const uint8_t* wmax,
 #pragma unroll
     for (int u = 0; u < PBS_R; u++) {
       const int j = j0 + u;
-      const int cc = c[u];
-      const double b0 = a0[u], b1 = a1[u];
+      int cc[PBS_E];
+      double b0[PBS_E], b1[PBS_E];
+#pragma unroll
+      for (int q = 0; q < PBS_E; q++) { cc[q] = c[u][q]; b0[q] = a0[u][q]; b1[q] = a1[u][q]; }
       load(u, j + PBS_R);                                      // refill: in flight while the next PBS_R - 1 steps are served
-      const int bus = cc & 0xffffff, rk = cc >> 24;            // no term: rk = -1
       for (int r = 0, mr = wmax[j]; r <= mr; r++) {            // elements of the step that share a bus: rank order
-        if (rk == r) {
-          double2 a = acc[bus];
-          a.x = a.x + b0;
-          a.y = a.y + b1;
-          acc[bus] = a;
+        // one rank: every read-modify-write of the sub-round goes to a different bus (ranks are per bus and step), so the
+        // PBS_E of a thread are independent and overlap
+#pragma unroll
+        for (int q = 0; q < PBS_E; q++) {
+          if ((cc[q] >> 24) == r) {                            // no term: code -1, rank -1
+            double2* const p = acc + (cc[q] & 0xffffff);
+            double2 v = *p;
+            v.x = v.x + b0[q];
+            v.y = v.y + b1[q];
+            *p = v;
+          }
         }
         __syncthreads();
       }
@@ -1595,7 +1608,7 @@ __global__ void __launch_bounds__(PBS_T, 1) pb_bus_g_scn_kernel(const __grid_con
   __shared__ uint8_t wmax[PBS_MAX_STEPS];                      // highest rank per term-table step
   const int tid = threadIdx.x;
   const bool wg = (A.what & EV_G) != 0;
-  const int s_gen = (P.ng + PBS_T - 1) / PBS_T, s_br = (P.nr + PBS_T - 1) / PBS_T, s_bus = (P.nb + PBS_T - 1) / PBS_T;
+  const int s_gen = (P.ng + PBS_WAVE - 1) / PBS_WAVE, s_br = (P.nr + PBS_WAVE - 1) / PBS_WAVE, s_bus = (P.nb + PBS_T - 1) / PBS_T;
   for (int j = tid; j < PBS_MAX_STEPS; j += PBS_T) wmax[j] = j < s_gen + 2 * s_br ? P.pbs_wmax[j] : 0;
   for (int s = blockIdx.x; s < A.S; s += gridDim.x) {
     const double* __restrict__ x = A.x + (long long)s * A.ldx;
@@ -1617,7 +1630,7 @@ __global__ void __launch_bounds__(PBS_T, 1) pb_bus_g_scn_kernel(const __grid_con
     // the bus's own shunt term (:256-258 | :264-266), then minus the load (:291-292) and out; thread tid owns bus
     // j * PBS_T + tid in both passes: no barrier between them
     {
-      double va[PBS_R], vb[PBS_R], gl[PBS_R], bl[PBS_R];
+      double va[PBS_RB], vb[PBS_RB], gl[PBS_RB], bl[PBS_RB];
       auto load = [&](int u, int j) {
         const int e = j * PBS_T + tid;
         va[u] = vb[u] = gl[u] = bl[u] = 0.0;
@@ -1626,7 +1639,7 @@ __global__ void __launch_bounds__(PBS_T, 1) pb_bus_g_scn_kernel(const __grid_con
           vb[u] = x[P.o_b + e]; gl[u] = P.Gl[e]; bl[u] = P.Bl[e];
         }
       };
-      constexpr int R2 = PBS_R > 3 ? 3 : PBS_R;               // four values per bus: a shallower ring
+      constexpr int R2 = PBS_RB > 3 ? 3 : PBS_RB;               // four values per bus: a shallower ring
 #pragma unroll
       for (int u = 0; u < R2; u++) load(u, u);
       for (int j0 = 0; j0 < s_bus; j0 += R2) {
@@ -1650,20 +1663,20 @@ __global__ void __launch_bounds__(PBS_T, 1) pb_bus_g_scn_kernel(const __grid_con
     double vmax = 0.0;
     int nviol = 0;
     {
-      double lp[PBS_R], lq[PBS_R];
+      double lp[PBS_RB], lq[PBS_RB];
       auto load = [&](int u, int j) {
         const int e = j * PBS_T + tid;
         lp[u] = lq[u] = 0.0;
         if (e < P.nb) { lp[u] = pd[e]; lq[u] = qd[e]; }
       };
 #pragma unroll
-      for (int u = 0; u < PBS_R; u++) load(u, u);
-      for (int j0 = 0; j0 < s_bus; j0 += PBS_R) {
+      for (int u = 0; u < PBS_RB; u++) load(u, u);
+      for (int j0 = 0; j0 < s_bus; j0 += PBS_RB) {
 #pragma unroll
-        for (int u = 0; u < PBS_R; u++) {
+        for (int u = 0; u < PBS_RB; u++) {
           const int j = j0 + u, e = j * PBS_T + tid;
           const double Pd = lp[u], Qd = lq[u];
-          load(u, j + PBS_R);
+          load(u, j + PBS_RB);
           if (e < P.nb) {
             const double2 a = pbs_acc[e];
             const double gP = a.x - Pd, gQ = a.y - Qd;
@@ -2325,7 +2338,7 @@ int64_t wt_smem_bytes(const DevPlan& P) {
 // the scenario-resident PB* residual kernel needs the (P, Q) sums of every bus in one CTA's shared memory
 int64_t pbs_smem_bytes(const DevPlan& P) {
   const int64_t b = (int64_t)P.nb * 16;
-  const int64_t steps = (P.ng + PBS_T - 1) / PBS_T + 2 * ((P.nr + PBS_T - 1) / PBS_T);
+  const int64_t steps = (P.ng + PBS_WAVE - 1) / PBS_WAVE + 2 * ((P.nr + PBS_WAVE - 1) / PBS_WAVE);
   return (P.pbs_ok && b <= 222 * 1024 && steps + 16 <= PBS_MAX_STEPS) ? b : 0;
 }
 

@@ -43,7 +43,11 @@ struct WTile {
   int32_t m0, mn;            // multi-slots of all three spaces, sorted by count (descending): Plan::wt_multi
 };
 
-constexpr int PBS_WAVE = 1024;   // elements per step of the scenario-resident PB* residual kernel (= its CTA size)
+#ifndef PS_PBS_E
+#define PS_PBS_E 1
+#endif
+constexpr int PBS_THREADS = 1024;                 // CTA size of the scenario-resident PB* residual kernel
+constexpr int PBS_WAVE = PBS_THREADS * PS_PBS_E;  // elements per step: PS_PBS_E per thread
 
 struct Plan {
   int form = 0, src = 0, flags = 0;

@@ -86,7 +86,7 @@ def test_case300_gpu_backend_reproduces_the_cpu_checker_iterate_by_iterate():
     a = gpu.run()
     cpu = slp.BatchedSlpLS(None, S, backend=OracleBackend(model, S, status=st), options=opts)
     b = cpu.run()
-    assert len(a["history"]) == len(b["history"]) == 12
+    assert len(a["history"]) == len(b["history"]) >= 12        # lock-step iterations (a scenario's own count stops at max_iter)
     for ha, hb in zip(a["history"], b["history"]):
         np.testing.assert_allclose(ha["f"], hb["f"], rtol=1e-7, atol=1e-6)
         np.testing.assert_allclose(ha["alpha"], hb["alpha"], rtol=1e-9)
@@ -94,5 +94,6 @@ def test_case300_gpu_backend_reproduces_the_cpu_checker_iterate_by_iterate():
         np.testing.assert_allclose(ha["D"], hb["D"], rtol=1e-5, atol=1e-6)
     np.testing.assert_allclose(a["x"], b["x"], rtol=1e-6, atol=1e-8)
     tm = a["timing"]
-    assert tm["lp_calls"] == 12 * S and tm["trial_batches"] > 12
+    assert tm["lp_calls"] >= 12 * S and tm["trial_batches"] > 12
+    assert np.array_equal(a["status"], b["status"]) and np.array_equal(a["iter"], b["iter"])
     gpu.close(); cpu.close(); model.close()

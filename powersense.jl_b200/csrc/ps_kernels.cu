@@ -865,30 +865,41 @@ __device__ __forceinline__ void reduce_scalars(double* scal, double vmax, int nv
   }
 }
 
-// objective of formulations.jl:122-138: sum(cg) (obj_type = :linear) or the polynomial cost in pg
+// objective of formulations.jl:122-138: sum(cg) (obj_type = :linear) or the polynomial cost in pg.
+// The summation order is fixed independently of the CTA shape, so that every kernel that produces the scalar gives the same
+// bits: 1024 virtual lanes, lane t sums the generators t, t + 1024, ... in order; each group of 32 consecutive lanes is
+// folded by a xor-shuffle tree (16, 8, 4, 2, 1); the 32 group sums are added in order.
+constexpr int OBJ_LANES = 1024;
+__device__ __forceinline__ double objective_term(const DevPlan& P, const double* __restrict__ x, int i) {
+  if (P.flags & FLAG_OBJ_LINEAR) return x[P.o_cg + i];
+  const double p = x[P.o_pg + i];
+  double v = P.k0 ? P.k0[i] : 0.0;
+  if (P.cost_order >= 2 && P.k1) v += P.k1[i] * p;
+  if (P.cost_order == 3 && P.k2) v += P.k2[i] * (p * p);
+  return v;
+}
+__device__ __forceinline__ double objective_lane(const DevPlan& P, const double* __restrict__ x, int t) {
+  double acc = 0.0;
+  for (int i = t; i < P.ng; i += OBJ_LANES) acc += objective_term(P, x, i);
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, d);
+  return acc;                                                  // every lane of the group holds the group sum
+}
 __device__ __forceinline__ void objective_tile(const DevPlan& P, const EvalArgs& A, int s0, int s1, double* red) {
+  static_assert(OBJ_LANES % TPB == 0, "virtual lanes are dealt to the CTA's threads in whole rounds");
   for (int s = s0; s < s1; s++) {
     const double* __restrict__ x = A.x + (long long)s * A.ldx;
-    double acc = 0.0;
-    if (P.flags & FLAG_OBJ_LINEAR) {
-      for (int i = threadIdx.x; i < P.ng; i += TPB) acc += x[P.o_cg + i];
-    } else {
-      for (int i = threadIdx.x; i < P.ng; i += TPB) {
-        const double p = x[P.o_pg + i];
-        double v = P.k0 ? P.k0[i] : 0.0;
-        if (P.cost_order >= 2 && P.k1) v += P.k1[i] * p;
-        if (P.cost_order == 3 && P.k2) v += P.k2[i] * (p * p);
-        acc += v;
-      }
-    }
 #pragma unroll
-    for (int d = 16; d > 0; d >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, d);
-    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+    for (int j = 0; j < OBJ_LANES / TPB; j++) {                // thread tid plays the virtual lanes tid + TPB * j
+      const int t = threadIdx.x + TPB * j;
+      const double gsum = objective_lane(P, x, t);
+      if ((threadIdx.x & 31) == 0) red[t >> 5] = gsum;
+    }
     __syncthreads();
     if (threadIdx.x == 0) {
-      double t = 0.0;
-      for (int w = 0; w < TPB / 32; w++) t += red[w];
-      A.scal[(long long)s * NSCAL + 0] = t;
+      double tot = 0.0;
+      for (int w = 0; w < OBJ_LANES / 32; w++) tot += red[w];
+      A.scal[(long long)s * NSCAL + 0] = tot;
     }
     __syncthreads();
   }
@@ -1603,7 +1614,7 @@ __device__ __forceinline__ void pbs_term_pass(double2* acc, const uint8_t* wmax,
 template <int FORM>
 __global__ void __launch_bounds__(PBS_T, 1) pb_bus_g_scn_kernel(const __grid_constant__ DevPlan P, const __grid_constant__ EvalArgs A) {
   extern __shared__ __align__(16) double2 pbs_acc[];           // [nb] running (P, Q) sums of the scenario
-  __shared__ double redv[PBS_T / 32];
+  __shared__ double redv[PBS_T / 32], redo[PBS_T / 32];
   __shared__ int redn[PBS_T / 32];
   __shared__ uint8_t wmax[PBS_MAX_STEPS];                      // highest rank per term-table step
   const int tid = threadIdx.x;
@@ -1691,13 +1702,20 @@ __global__ void __launch_bounds__(PBS_T, 1) pb_bus_g_scn_kernel(const __grid_con
       }
     }
     if (A.scal) {                                              // CTA-uniform
+      static_assert(PBS_T == OBJ_LANES, "the CTA's threads are the objective's virtual lanes");
+      const double gsum = objective_lane(P, x, tid);           // the objective scalar, in objective_tile's order
 #pragma unroll
       for (int d = 16; d > 0; d >>= 1) {
         vmax = fmax(vmax, __shfl_xor_sync(0xffffffffu, vmax, d));
         nviol += __shfl_xor_sync(0xffffffffu, nviol, d);
       }
-      if ((tid & 31) == 0) { redv[tid >> 5] = vmax; redn[tid >> 5] = nviol; }
+      if ((tid & 31) == 0) { redv[tid >> 5] = vmax; redn[tid >> 5] = nviol; redo[tid >> 5] = gsum; }
       __syncthreads();
+      if (tid == 32) {
+        double tot = 0.0;
+        for (int w = 0; w < PBS_T / 32; w++) tot += redo[w];
+        A.scal[(long long)s * NSCAL + 0] = tot;
+      }
       if (tid < 32) {
         vmax = tid < PBS_T / 32 ? redv[tid] : 0.0; nviol = tid < PBS_T / 32 ? redn[tid] : 0;
 #pragma unroll
@@ -1803,7 +1821,7 @@ __global__ void __launch_bounds__(PBT) cb_bus_jh_kernel(const __grid_constant__ 
 }
 
 __global__ void __launch_bounds__(TPB) objective_kernel(const __grid_constant__ DevPlan P, const __grid_constant__ EvalArgs A) {
-  __shared__ double red[TPB / 32];
+  __shared__ double red[OBJ_LANES / 32];
   const int s0 = blockIdx.x * A.chunk, s1 = min(A.S, s0 + A.chunk);
   objective_tile(P, A, s0, s1, red);
 }
@@ -2393,6 +2411,7 @@ cudaError_t launch_pb_form(const DevPlan& P, const EvalArgs& A, cudaStream_t st,
                            cudaEvent_t* ev, unsigned* ev_mask) {
   auto rec = [&](int id, int end) { if (ev) { cudaEventRecord(ev[2 * id + end], st); if (end && ev_mask) *ev_mask |= 1u << id; } };
   if constexpr (FORM == PBRAPV || FORM == PBRARV) {
+    int obj_from = 0;                                          // scenarios [0, obj_from) got their objective scalar from the bus kernel
     if ((A.what & EV_G) || A.scal) {
       rec(K_BUS, 0);
       // scenario-resident residuals when a batch fills the machine (a CTA works through whole scenarios one after the
@@ -2403,8 +2422,30 @@ cudaError_t launch_pb_form(const DevPlan& P, const EvalArgs& A, cudaStream_t st,
         static int n_sm = 0;
         if (n_sm == 0) { int dv = 0; cudaGetDevice(&dv); cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dv); if (n_sm <= 0) n_sm = 148; }
         const int per_sm = (int)std::min<int64_t>(2, (220 * 1024) / smem);   // 1024-thread CTAs: at most 2 per SM
-        const int ncta = (int)std::min<int64_t>(A.S, (int64_t)n_sm * per_sm);
-        pb_bus_g_scn_kernel<FORM><<<dim3((unsigned)ncta), PBS_T, (size_t)smem, st>>>(P, A);
+        const int slots = n_sm * per_sm;
+        // a CTA works through whole scenarios: S scenarios take ceil(S / slots) rounds.  When the last round would be
+        // mostly empty (512 scenarios on 148 SMs: 3.46 rounds) the remainder goes to the list-walking kernel instead --
+        // same results bit for bit, disjoint scenario rows
+        const int rem = A.S % slots;
+        const int n_scn = (A.S > slots && rem > 0 && rem < (slots * 3) / 5) ? A.S - rem : A.S;
+        EvalArgs As = A;
+        As.S = n_scn;
+        pb_bus_g_scn_kernel<FORM><<<dim3((unsigned)std::min(n_scn, slots)), PBS_T, (size_t)smem, st>>>(P, As);
+        obj_from = n_scn;
+        if (n_scn < A.S) {
+          EvalArgs Ar = A;
+          const long long o = n_scn;
+          Ar.S = A.S - n_scn;
+          Ar.x += o * A.ldx;
+          if (Ar.Pd) Ar.Pd += o * A.ldl;
+          if (Ar.Qd) Ar.Qd += o * A.ldl;
+          if (Ar.status) Ar.status += o * A.ldst;
+          if (Ar.g) Ar.g += o * A.ldg;
+          if (Ar.scal) Ar.scal += o * NSCAL;
+          const int nch = (Ar.S + Ar.chunk - 1) / Ar.chunk;
+          pb_bus_g_kernel<FORM><<<dim3((unsigned)((P.nb + PBT - 1) / PBT), (unsigned)nch), PBT, 0, st>>>(P, Ar);
+          if (launches) *launches += 1;
+        }
       } else {
         pb_bus_g_kernel<FORM><<<dim3((unsigned)((P.nb + PBT - 1) / PBT), (unsigned)nchunks), PBT, 0, st>>>(P, A);
       }
@@ -2418,9 +2459,14 @@ cudaError_t launch_pb_form(const DevPlan& P, const EvalArgs& A, cudaStream_t st,
       rec(K_BUS_JH, 1);
       if (launches) *launches += 1;
     }
-    if (A.scal) {
+    if (A.scal && obj_from < A.S) {
+      EvalArgs Ao = A;
+      Ao.S = A.S - obj_from;
+      Ao.x += (long long)obj_from * A.ldx;
+      Ao.scal += (long long)obj_from * NSCAL;
+      Ao.chunk = Ao.S >= 65535 * 2 ? (Ao.S + 65534) / 65535 : (Ao.S > 1184 ? 2 : 1);   // one CTA per scenario while they fit a wave or two
       rec(K_OBJ, 0);
-      objective_kernel<<<dim3((unsigned)nchunks), TPB, 0, st>>>(P, A);
+      objective_kernel<<<dim3((unsigned)((Ao.S + Ao.chunk - 1) / Ao.chunk)), TPB, 0, st>>>(P, Ao);
       rec(K_OBJ, 1);
       if (launches) *launches += 1;
     }

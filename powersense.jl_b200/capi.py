@@ -274,9 +274,12 @@ class Handle:
         self._check(lib().ps_eval_hessian(self.h, _pd(x), float(sigma), _pd(mu), _pd(H)))
         return H
 
-    def eval_all(self, x, mu):
+    def eval_all(self, x, mu, g=None, J=None, H=None):
+        """g, J, H: optional preallocated outputs (a solver reuses its arrays; fresh ones cost their page faults)"""
         x, mu = _f64(x, self.n_var), _f64(mu, self.m_nl)
-        g, J, H = np.zeros(self.m_nl), np.zeros(self.nnzJ), np.zeros(self.nnzH)
+        g = np.zeros(self.m_nl) if g is None else g
+        J = np.zeros(self.nnzJ) if J is None else J
+        H = np.zeros(self.nnzH) if H is None else H
         self._check(lib().ps_eval_all(self.h, _pd(x), _pd(mu), _pd(g), _pd(J), _pd(H)))
         return g, J, H
 

@@ -94,7 +94,7 @@ if __name__ == "__main__":
     if sel == "ncu_cb":
         run("case13659pegase", "CBRARVmodel", 256, [4], steps=1)
     if sel == "latency":
-        for case, Fname in (("case14", "PNPAPVmodel"), ("case2869pegase", "PNPAPVmodel"), ("case13659pegase", "PBRARVmodel")):
+        for case, Fname in (("case14", "PNPAPVmodel"), ("case300", "PNPAPVmodel"), ("case13659pegase", "PBRARVmodel")):
             d = synth.named_case(case)
             F = ps.BY_NAME[Fname]
             h = capi.Handle(d, F.code, device=0)
@@ -102,8 +102,26 @@ if __name__ == "__main__":
             x = x[0]
             mu = np.random.default_rng(0).normal(size=h.m_nl)
             g, J, H = np.zeros(h.m_nl), np.zeros(h.nnzJ), np.zeros(h.nnzH)
-            for name, fn in (("eval_constraint", lambda: h.eval_constraint(x, g)), ("eval_jacobian", lambda: h.eval_jacobian(x, J)),
-                             ("eval_hessian", lambda: h.eval_hessian(x, 1.0, mu, H)), ("eval_all", lambda: h.eval_all(x, mu))):
+            x2 = x * (1.0 + 1e-9)
+
+            def triple():                       # what Ipopt does at a new point: eval_g, eval_jac_g, eval_h at the same x
+                triple.k ^= 1
+                xx = x2 if triple.k else x
+                h.eval_constraint(xx, g); h.eval_jacobian(xx, J); h.eval_hessian(xx, 1.0, mu, H)
+            triple.k = 0
+
+            def fresh(fn):                      # defeat the x-keyed cache: alternate between two points
+                def run():
+                    fresh.k ^= 1
+                    fn(x2 if fresh.k else x)
+                return run
+            fresh.k = 0
+            for name, fn in (("eval_constraint (new x)", fresh(lambda xx: h.eval_constraint(xx, g))),
+                             ("eval_jacobian (new x)", fresh(lambda xx: h.eval_jacobian(xx, J))),
+                             ("eval_jacobian (same x as the last eval_constraint: cached)", lambda: h.eval_jacobian(x, J)),
+                             ("eval_hessian (new x)", fresh(lambda xx: h.eval_hessian(xx, 1.0, mu, H))),
+                             ("eval_constraint + eval_jacobian + eval_hessian at one new x", triple),
+                             ("eval_all (new x)", fresh(lambda xx: h.eval_all(xx, mu, g, J, H)))):
                 for _ in range(5):
                     fn()
                 t0 = time.perf_counter()

@@ -1,0 +1,17 @@
+#!/bin/bash
+O=gpurun_out
+timeout 600 python -m pytest tests/test_gpu_parity.py -x -q -m gpu -k "scenario_resident" > $O/r2c24_tests.log 2>&1; tail -15 $O/r2c24_tests.log
+for S in 4096 512; do
+timeout 300 python - $S <<'P' 2>&1 | grep -v "^$"
+import os, sys
+sys.path.insert(0, "tools"); sys.path.insert(0, ".")
+import sweep
+S = int(sys.argv[1])
+for env in ({}, {"PS_NO_PBQ": "1"}):
+    os.environ.update(env)
+    print("--", env or "default (copy-engine-fed residual kernel)", flush=True)
+    for what in (7, 1):
+        sweep.run("case13659pegase", "PBRARVmodel", S, [16], what=what, steps=8)
+    for k in env: del os.environ[k]
+P
+done

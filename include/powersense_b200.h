@@ -208,6 +208,12 @@ int ps_batch_kernel_times(ps_batch* b, float ms[4]);
 /* pinned host memory for the *_host entry points */
 int ps_host_alloc(void** p, int64_t bytes);
 void ps_host_free(void* p);
+/* Page-lock an array the caller already owns (a solver's g / J / H / x vectors, which it reuses for every iteration):
+ * the single-scenario callbacks and ps_batch_eval_host then copy to / from it at the link's full rate instead of through
+ * the driver's staging of pageable memory (case13659pegase, 12.6 MB of g + J + H per call: see DESIGN.md).  Optional;
+ * unregister before the array is freed. */
+int ps_host_register(void* p, int64_t bytes);
+int ps_host_unregister(void* p);
 
 /* ---- COO -> CSC assembly with a fixed precomputed pattern ---------------------------------- */
 /* Replaces compute_jacobian_matrix(m, n, j_str, dE) (src/opt/algorithms/common.jl:12-20), which

@@ -77,6 +77,8 @@ _SIGS = {
     "ps_batch_kernel_times": (C.c_int, [_VP, C.POINTER(C.c_float)]),
     "ps_host_alloc": (C.c_int, [C.POINTER(_VP), C.c_int64]),
     "ps_host_free": (None, [_VP]),
+    "ps_host_register": (C.c_int, [_VP, C.c_int64]),
+    "ps_host_unregister": (C.c_int, [_VP]),
     "ps_csc_create": (C.c_int, [C.c_int64, C.c_int64, C.c_int64, _P64, _P64, C.c_int, C.POINTER(_VP)]),
     "ps_csc_destroy": (None, [_VP]),
     "ps_csc_dims": (C.c_int, [_VP, _P64]),
@@ -385,6 +387,31 @@ def pinned_empty(shape, dtype=np.float64):
     import weakref
     weakref.finalize(buf, lib().ps_host_free, p)
     return arr
+
+
+class host_registered:
+    """Context manager: page-lock numpy arrays the caller owns for the duration of the block (ps_host_register), e.g. the
+    g / J / H vectors a solver hands to the single-scenario callbacks at every iteration."""
+
+    def __init__(self, *arrays):
+        self.arrays = [a for a in arrays if a is not None and a.size]
+        self.done = []
+
+    def __enter__(self):
+        for a in self.arrays:
+            assert a.flags.c_contiguous
+            rc = lib().ps_host_register(a.ctypes.data_as(_VP), a.nbytes)
+            if rc != PS_OK:
+                self.__exit__(None, None, None)
+                raise PowersenseError(rc, (lib().ps_last_error(None) or b"").decode())
+            self.done.append(a)
+        return self
+
+    def __exit__(self, *exc):
+        for a in self.done:
+            lib().ps_host_unregister(a.ctypes.data_as(_VP))
+        self.done = []
+        return False
 
 
 class CscPattern:

@@ -954,6 +954,18 @@ int ps_host_alloc(void** p, int64_t bytes) {
   return PS_OK;
 }
 void ps_host_free(void* p) { if (p) cudaFreeHost(p); }
+int ps_host_register(void* p, int64_t bytes) {
+  if (!p || bytes <= 0) return PS_ERR_ARG;
+  cudaError_t e = cudaHostRegister(p, (size_t)bytes, cudaHostRegisterDefault);
+  if (e != cudaSuccess) { cudaGetLastError(); g_create_error = std::string("cudaHostRegister: ") + cudaGetErrorString(e); return PS_ERR_CUDA; }
+  return PS_OK;
+}
+int ps_host_unregister(void* p) {
+  if (!p) return PS_ERR_ARG;
+  cudaError_t e = cudaHostUnregister(p);
+  if (e != cudaSuccess) { cudaGetLastError(); g_create_error = std::string("cudaHostUnregister: ") + cudaGetErrorString(e); return PS_ERR_CUDA; }
+  return PS_OK;
+}
 
 // ---- COO -> CSC ----------------------------------------------------------------------------
 int ps_csc_create(int64_t m, int64_t n, int64_t nnz_coo, const int64_t* row, const int64_t* col, int device, ps_csc** out) {

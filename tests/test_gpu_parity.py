@@ -671,6 +671,28 @@ def test_single_scenario_cache_keyed_on_x():
     h.close()
 
 
+def test_callbacks_into_page_locked_caller_arrays():
+    """ps_host_register: the single-scenario callbacks write into arrays the caller page-locked (a solver's own g / J / H
+    vectors, views into larger arrays included) -- same values as into pageable ones; unregistering twice is an error."""
+    d = synthetic("case118")
+    F = ps.PBRARVmodel
+    h = capi.Handle(d, F.code, device=0)
+    x, _, _, _ = synth.scenario_batch(d, F, 2, seed=4)
+    mu = np.random.default_rng(5).normal(size=h.m_nl)
+    g0, J0, H0 = (a.copy() for a in h.eval_all(x[0], mu))
+    big = np.full(h.m_nl + h.nnzJ + h.nnzH + 7, np.nan)
+    g, J, H = big[3:3 + h.m_nl], big[3 + h.m_nl:3 + h.m_nl + h.nnzJ], big[5 + h.m_nl + h.nnzJ:5 + h.m_nl + h.nnzJ + h.nnzH]
+    with capi.host_registered(big):
+        h.eval_all(x[1], mu, g, J, H)               # another point first: nothing comes from the cache
+        h.eval_all(x[0], mu, g, J, H)
+        assert np.array_equal(g, g0) and np.array_equal(J, J0) and np.array_equal(H, H0)
+        assert np.isnan(big[:3]).all() and np.isnan(big[-2:]).all()
+    assert capi.lib().ps_host_unregister(big.ctypes.data_as(capi._VP)) != capi.PS_OK
+    h.eval_all(x[0], mu, g, J, H)                   # pageable again
+    assert np.array_equal(H, H0)
+    h.close()
+
+
 def test_correctly_rounded_powers():
     """The L4 limit rows hold V^4 and V^3 (formulations.jl:338-343); the reference evaluates them through pow() (JuMP's `^`
     with a constant exponent other than 2).  The kernel's powers are the correctly rounded ones: on a network whose L4 rows

@@ -53,22 +53,7 @@ for label, env in (("default", {}), ("PS_NO_BULK", {"PS_NO_BULK": "1"})):
     for k_ in env:
         del os.environ[k_]
 
-# device-resident S = 1 evaluation: the kernels alone
-b = capi.Batch(h, 1)
-dev = torch.device("cuda:0")
-tx, tmu = torch.from_numpy(x[None]).to(dev), torch.from_numpy(mu[None]).to(dev)
-tg, tJ, tH = (torch.empty(1, n, dtype=torch.float64, device=dev) for n in (h.m_nl, h.nnzJ, h.nnzH))
-for what in (1, 3, 4, 7):
-    for _ in range(3):
-        b.eval_torch(what, tx, tmu, tg, tJ, tH, None)
-    torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(20):
-        b.eval_torch(what, tx, tmu, tg, tJ, tH, None)
-    e1.record()
-    torch.cuda.synchronize()
-    print(f"{case} {Fname} device-resident S=1 what={what}: {e0.elapsed_time(e1) / 20 * 1e3:.0f} us", flush=True)
-# pinned destinations
-pg, pJ, pH = (torch.empty(n, dtype=torch.float64).pin_memory().numpy() for n in (h.m_nl, h.nnzJ, h.nnzH))
-timeit("[pinned outputs] eval_all g+J+H", lambda xx: lib.ps_eval_all(h.h, pd(xx), pd(mu), pd(pg), pd(pJ), pd(pH)))
+with capi.host_registered(g, J, H):
+    timeit("[caller's arrays page-locked: ps_host_register] eval_all g+J+H", lambda xx: lib.ps_eval_all(h.h, pd(xx), pd(mu), pd(g), pd(J), pd(H)))
+    timeit("[page-locked] eval_all g", lambda xx: lib.ps_eval_all(h.h, pd(xx), pd(mu), pd(g), N, N))
+    timeit("[page-locked] eval_all g+J", lambda xx: lib.ps_eval_all(h.h, pd(xx), pd(mu), pd(g), pd(J), N))

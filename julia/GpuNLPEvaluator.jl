@@ -137,6 +137,22 @@ function adopt_hessian_order!(d::GpuNLPEvaluator, jump_evaluator)
     return d
 end
 
+"""
+    pin!(arrays...) / unpin!(arrays...)
+
+Page-lock vectors the solver owns and reuses at every iteration (its constraint, Jacobian-value and Hessian-value arrays):
+the callbacks then copy into them at the link's full rate instead of through the driver's staging of pageable memory
+(ps_host_register; on case13659pegase `g + J + H` are 12.6 MB per call: 0.93 -> 0.49 ms).  Optional; `unpin!` before the
+arrays are freed or resized.
+"""
+function pin!(arrays::Vector{Float64}...)
+    for a in arrays
+        rc = ccall((:ps_host_register, LIB), Cint, (Ptr{Cvoid}, Int64), pointer(a), sizeof(a))
+        rc == 0 || error("powersense_b200: " * unsafe_string(ccall((:ps_last_error, LIB), Cstring, (Ptr{Cvoid},), C_NULL)))
+    end
+end
+unpin!(arrays::Vector{Float64}...) = foreach(a -> ccall((:ps_host_unregister, LIB), Cint, (Ptr{Cvoid},), pointer(a)), arrays)
+
 "NLPBlockData for MOI.set(backend, MOI.NLPBlock(), ...): bounds (0,0) for == rows, (-Inf,0) for <= rows"
 function nlp_block(d::GpuNLPEvaluator)
     lo = Vector{Float64}(undef, d.m_nl); hi = Vector{Float64}(undef, d.m_nl)

@@ -393,6 +393,30 @@ int ps_create(const ps_network* net, int formulation, int source_type, int flags
     }
     if (c4.empty()) c4.resize(PBS_WAVE, -1);
     D.pbs_code4 = M.upload(c4);
+    // pb_bus_g_gather_kernel: the half-edge list of a bus (Sij ascending, then Sji ascending: he_ks = 2 * branch + side) cut
+    // where the branch index crosses the half boundary on either side
+    const int64_t half = ((nbr + 1) / 2 + 1) & ~1LL;
+    D.pbg_half = (int)std::min<int64_t>(half, nbr);
+    std::vector<uint32_t> segs((size_t)(5 * nb), 0u);
+    bool seg_ok = P.he_ks.size() < (size_t(1) << 24) && (size_t)ng < (size_t(1) << 24);
+    auto put = [&](int ph, int64_t i, int64_t q0, int64_t q1) {
+      if (q1 - q0 > 255) seg_ok = false;
+      segs[(size_t)ph * nb + i] = (uint32_t)q0 | ((uint32_t)(q1 - q0) << 24);
+    };
+    for (int64_t i = 0; i < nb && seg_ok; i++) {
+      put(0, i, P.net.gen_ptr[i], P.net.gen_ptr[i + 1]);
+      int32_t q = P.he_ptr[i];
+      const int32_t q1 = P.he_ptr[i + 1];
+      int32_t c[5] = {q, q, q, q, q1};
+      while (q < q1 && !(P.he_ks[q] & 1) && (P.he_ks[q] >> 1) < D.pbg_half) q++;
+      c[1] = q;
+      while (q < q1 && !(P.he_ks[q] & 1)) q++;
+      c[2] = q;
+      while (q < q1 && (P.he_ks[q] >> 1) < D.pbg_half) q++;
+      c[3] = q;
+      for (int ph = 1; ph <= 4; ph++) put(ph, i, c[ph - 1], c[ph]);
+    }
+    D.pbg_seg = seg_ok ? M.upload(segs) : nullptr;
   }
   D.cb_slots = 0;
   if (is_CB(P.form) && nb > 0 && P.bus_rows == 2 * nb) {

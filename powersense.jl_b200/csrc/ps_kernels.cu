@@ -2022,6 +2022,206 @@ __global__ void __launch_bounds__(PBQ_T, 1) pb_bus_g_tma_kernel(const __grid_con
   }
 }
 
+// ---- PB* residuals, scenario-resident, gathered from shared memory ---------------------------------------------------
+// The list-walking kernel gathers every flow variable through its own 32-byte L2 sector; the element-ordered kernel
+// above avoids that with ~75 barrier-separated steps per scenario and pays for them in issue slots.  Third form: the P row
+// and the Q row of a scenario are separate work items, and an item's inputs come to the SM as a handful of LARGE
+// cp.async.bulk copies -- its generator injections, then each flow array in two halves (two buffers of nr / 2
+// doubles: together ~200 KB for case13659pegase) -- while thread-per-bus walks the bus's lists exactly like the
+// list-walking kernel (generators, Sij ascending, Sji ascending: the reference's order, accumulators in registers
+// across the phases), reading the terms from shared memory.  Six phases per item, one CTA barrier each; the copy of the
+// next phase's half (and of the next item's first arrays) is in flight while the current one is walked.
+//   phase 0 generators | 1 Sij, branches [0, h) | 2 Sij, [h, nr) | 3 Sji, [0, h) | 4 Sji, [h, nr) | 5 shunt, load, out
+// Plan table: the list segment of every bus for phases 0-4 (pbg_seg [5][nb]: first entry | length << 24; generators index
+// gen_idx, the others the half-edge list he_ks = 2 * branch + side, Sij ascending then Sji ascending, cut where the branch
+// index crosses h).  Bitwise identical to pb_bus_g_kernel.
+// ask the copy engine to bring elements [0, n) of p into L2 (whole 16-byte units inside the range)
+__device__ __forceinline__ void l2_prefetch(const double* p, int n) {
+  const unsigned long long a = reinterpret_cast<unsigned long long>(p);
+  const unsigned long long a0 = (a + 15ull) & ~15ull, a1 = (a + 8ull * (unsigned long long)n) & ~15ull;
+  if (a1 > a0) asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(a0), "r"((int)(a1 - a0)) : "memory");
+}
+constexpr int PBG_T = 1024;
+constexpr int PBG_KB = 16;          // buses per thread (registers): networks of up to PBG_T * PBG_KB buses
+static_assert(PBG_T == OBJ_LANES, "the CTA's threads are the objective's virtual lanes");
+
+template <int FORM>
+__global__ void __launch_bounds__(PBG_T, 1) pb_bus_g_gather_kernel(const __grid_constant__ DevPlan P, const __grid_constant__ EvalArgs A) {
+  extern __shared__ __align__(128) unsigned char pbg_smem[];
+  __shared__ double redv[PBG_T / 32], redo[PBG_T / 32];
+  __shared__ int redn[PBG_T / 32];
+  __shared__ __align__(8) uint64_t bar[3];                     // full: generator buffer, buffer A, buffer B
+  const int tid = threadIdx.x;
+  const int h = P.pbg_half, capb = ((max(h, P.nr - h) + 2) * 8 + 127) & ~127;
+  double* const bufA = reinterpret_cast<double*>(pbg_smem);
+  double* const bufB = reinterpret_cast<double*>(pbg_smem + capb);
+  double* const bufG = reinterpret_cast<double*>(pbg_smem + 2 * capb);
+  const bool wg = (A.what & EV_G) != 0;
+  const int n_items = 2 * A.S;
+  if (tid == 0) {
+    for (int q = 0; q < 3; q++) mbar_init(bar + q, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  // a copy of elements [0, n) of `arr` into `buf`: from arr - lo (16-byte aligned), an even number of doubles; returns lo.
+  // `open_end`: nothing readable is known to follow the array -- an odd total then leaves the last element out (its
+  // readers take it from global memory), otherwise the copy runs one element over (the next half, variable or scenario)
+  auto copy_in = [&](double* buf, uint64_t* b, const double* arr, int n, bool open_end) {
+    const int lo = (int)((reinterpret_cast<unsigned long long>(arr) >> 3) & 1ull);
+    int cnt = lo + n;
+    if (cnt & 1) cnt += open_end ? -1 : 1;
+    mbar_expect_tx(b, cnt * 8);
+    if (cnt > 0) bulk_load(buf, arr - lo, cnt * 8, b);
+  };
+  // the arrays of item `it`: 0 generators, 1 / 2 the Sij flow [0, h) / [h, nr), 3 / 4 the Sji flow
+  auto item_array = [&](int it, int a, int& n) -> const double* {
+    const int s = it >> 1, row = it & 1;
+    const double* x = A.x + (long long)s * A.ldx;
+    if (a == 0) { n = P.ng; return x + (row ? P.o_qg : P.o_pg); }
+    const double* f = x + P.o_f[(a >= 3 ? 2 : 0) + row];
+    if (a & 1) { n = h; return f; }
+    n = P.nr - h; return f + h;
+  };
+  auto issue = [&](int it, int a) {                            // thread 0
+    if (it >= n_items) return;
+    int n;
+    const double* arr = item_array(it, a, n);
+    const bool open_end = (a == 0 || a == 2 || a == 4) && (it >> 1) == A.S - 1;
+    copy_in(a == 0 ? bufG : ((a & 1) ? bufA : bufB), bar + (a == 0 ? 0 : ((a & 1) ? 1 : 2)), arr, n, open_end);
+  };
+  if (tid == 0) { issue(blockIdx.x, 0); issue(blockIdx.x, 1); issue(blockIdx.x, 2); }
+  unsigned phG = 0, phA = 0, phB = 0;                          // parities of the next completion of each buffer
+  for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
+    const int s = it >> 1, row = it & 1, nxt = it + gridDim.x;
+    const double* __restrict__ x = A.x + (long long)s * A.ldx;
+    const bool lastrow = s == A.S - 1;
+    double acc[PBG_KB];
+    int n;
+    const double* arr;
+    // one phase: the list segment of every owned bus (first entry | length << 24, plan table pbg_seg [5][nb]) is loaded for
+    // a group of buses, then the first two list entries of each (most segments hold one or two terms) -- all of a group's
+    // loads in flight together, two L2 latencies per group instead of one per term -- then the lists are walked
+    constexpr int GRP = 8;
+    auto phase = [&](int ph, const int32_t* __restrict__ list, int shift, int base, const double* buf, bool open_end) {
+      const int lo = (int)((reinterpret_cast<unsigned long long>(arr) >> 3) & 1ull);
+      const bool miss = open_end && ((lo + n) & 1);            // the array's last element is not in the buffer
+      auto term = [&](int e) { const int i = (e >> shift) - base; return (miss && i == n - 1) ? arr[i] : buf[i + lo]; };
+#pragma unroll
+      for (int k0 = 0; k0 < PBG_KB; k0 += GRP) {
+        unsigned sg[GRP];
+        int e0[GRP], e1[GRP];
+#pragma unroll
+        for (int u = 0; u < GRP; u++) { const int b = tid + (k0 + u) * PBG_T; sg[u] = b < P.nb ? P.pbg_seg[ph * P.nb + b] : 0u; }
+#pragma unroll
+        for (int u = 0; u < GRP; u++) {
+          const int q0 = (int)(sg[u] & 0xffffffu), len = (int)(sg[u] >> 24);
+          e0[u] = len > 0 ? list[q0] : 0;
+          e1[u] = len > 1 ? list[q0 + 1] : 0;
+        }
+#pragma unroll
+        for (int u = 0; u < GRP; u++) {
+          const int q0 = (int)(sg[u] & 0xffffffu), len = (int)(sg[u] >> 24);
+          double a = acc[k0 + u];
+          if (len > 0) a = a + term(e0[u]);
+          if (len > 1) a = a + term(e1[u]);
+          for (int q = q0 + 2; q < q0 + len; q++) a = a + term(list[q]);
+          acc[k0 + u] = a;
+        }
+      }
+    };
+    // ---- phase 0: generators (formulations.jl:177-180)
+    arr = item_array(it, 0, n);
+#pragma unroll
+    for (int k = 0; k < PBG_KB; k++) acc[k] = 0.0;
+    if (tid == 0) {                                            // phase 5 reads these per bus: have them in L2 by then
+      if constexpr (FORM == PBRARV) l2_prefetch(x + P.o_a, P.nb);
+      l2_prefetch(x + P.o_b, P.nb);
+      const double* l = row ? A.Qd : A.Pd;
+      if (l) l2_prefetch(l + (long long)s * A.ldl, P.nb);
+    }
+    mbar_wait(bar + 0, phG); phG ^= 1u;
+    phase(0, P.gen_idx, 0, 0, bufG, lastrow);
+    __syncthreads();
+    if (tid == 0) issue(nxt, 0);
+    // ---- phases 1-4: Sij then Sji (:188-196), each in two halves
+#pragma unroll 1
+    for (int ph = 1; ph <= 4; ph++) {
+      arr = item_array(it, ph, n);
+      const bool isA = ph & 1;
+      if (isA) { mbar_wait(bar + 1, phA); phA ^= 1u; } else { mbar_wait(bar + 2, phB); phB ^= 1u; }
+      phase(ph, P.he_ks, 1, isA ? 0 : h, isA ? bufA : bufB, !isA && lastrow);
+      __syncthreads();
+      if (tid == 0) { if (ph <= 2) issue(it, ph + 2); else issue(nxt, ph - 2); }
+    }
+    // ---- phase 5: the bus's own shunt term (:256-258 | :264-266), minus the load (:291-292), out
+    double* __restrict__ gd = wg ? A.g + (long long)s * A.ldg + row : nullptr;
+    const double* __restrict__ kk = row ? P.Bl : P.Gl;
+    const double* const ldp = row ? A.Qd : A.Pd;
+    const double* __restrict__ ld = ldp ? ldp + (long long)s * A.ldl : (row ? P.Qd0 : P.Pd0);
+    double vmax = 0.0;
+    int nviol = 0;
+    constexpr int PB5 = 2;                                     // buses whose inputs are in flight together (registers)
+#pragma unroll
+    for (int k0 = 0; k0 < PBG_KB; k0 += PB5) {
+      double vi[PB5], vr[PB5], kc[PB5], lv[PB5];
+#pragma unroll
+      for (int u = 0; u < PB5; u++) {
+        const int b = tid + (k0 + u) * PBG_T;
+        vi[u] = vr[u] = kc[u] = lv[u] = 0.0;
+        if (b < P.nb) {
+          if constexpr (FORM == PBRARV) vi[u] = x[P.o_a + b];
+          vr[u] = x[P.o_b + b]; kc[u] = kk[b]; lv[u] = ld[b];
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < PB5; u++) {
+        const int b = tid + (k0 + u) * PBG_T;
+        if (b < P.nb) {
+          double m2;
+          if constexpr (FORM == PBRARV) m2 = vr[u] * vr[u] + vi[u] * vi[u];
+          else m2 = vr[u] * vr[u];
+          double a = acc[k0 + u];
+          a = row ? a + kc[u] * m2 : a - kc[u] * m2;
+          const double gv = a - lv[u];
+          if (wg) gd[2 * b] = gv;
+          vmax = fmax(vmax, fabs(gv));
+          nviol += fabs(gv) > A.viol_tol ? 1 : 0;
+        }
+      }
+    }
+    if (A.scal) {                                              // CTA-uniform
+      double gsum = 0.0;
+      if (row == 0) gsum = objective_lane(P, x, tid);          // the objective scalar, in objective_tile's order
+#pragma unroll
+      for (int d = 16; d > 0; d >>= 1) {
+        vmax = fmax(vmax, __shfl_xor_sync(0xffffffffu, vmax, d));
+        nviol += __shfl_xor_sync(0xffffffffu, nviol, d);
+      }
+      if ((tid & 31) == 0) { redv[tid >> 5] = vmax; redn[tid >> 5] = nviol; redo[tid >> 5] = gsum; }
+      __syncthreads();
+      if (tid == 32 && row == 0) {
+        double tot = 0.0;
+        for (int w = 0; w < PBG_T / 32; w++) tot += redo[w];
+        A.scal[(long long)s * NSCAL + 0] = tot;
+      }
+      if (tid < 32) {
+        vmax = redv[tid]; nviol = redn[tid];
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) {
+          vmax = fmax(vmax, __shfl_xor_sync(0xffffffffu, vmax, d));
+          nviol += __shfl_xor_sync(0xffffffffu, nviol, d);
+        }
+        if (tid == 0) {
+          double* scal = A.scal + (long long)s * NSCAL;
+          if (vmax > 0.0) atomicMax((unsigned long long*)(scal + 1), (unsigned long long)__double_as_longlong(vmax));
+          if (nviol) atomicAdd(scal + 2, (double)nviol);
+        }
+      }
+      __syncthreads();                                         // the reduction arrays are reused by the next item
+    }
+  }
+}
+
 // objective scalar only (used with the PB* fast path, where no bus_kernel runs)
 // ---- CB* balances, fast path (CBRARV / CBRAWV without switched shunts and without a status mask) --------------------
 // The current-branch-flow balances are bilinear in (own voltage, branch current) (formulations.jl:206-214): every
@@ -2455,6 +2655,7 @@ cudaError_t configure_form(int src, size_t smem_branch, size_t smem_bus, size_t 
       e = cudaFuncSetAttribute(pb_bus_g_scn_kernel<FORM, 1024, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_pbs);
       if (e == cudaSuccess) e = cudaFuncSetAttribute(pb_bus_g_scn_kernel<FORM, 512, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_pbs);
       if (e == cudaSuccess) e = cudaFuncSetAttribute(pb_bus_g_tma_kernel<FORM>, cudaFuncAttributeMaxDynamicSharedMemorySize, 225 * 1024);
+      if (e == cudaSuccess) e = cudaFuncSetAttribute(pb_bus_g_gather_kernel<FORM>, cudaFuncAttributeMaxDynamicSharedMemorySize, 225 * 1024);
       if (e != cudaSuccess) return e;
     }
   }
@@ -2656,6 +2857,13 @@ static int env_int(const char* name, int dflt) {
   return v > 0 ? v : dflt;
 }
 
+// pb_bus_g_gather_kernel: two half-array buffers + the generator buffer; 0 when it cannot run
+static size_t pbg_smem_bytes(const DevPlan& P) {
+  if (!P.pbs_ok || !P.pbg_seg || P.nb > PBG_T * PBG_KB) return 0;
+  const int64_t h = P.pbg_half, capb = ((std::max<int64_t>(h, P.nr - h) + 2) * 8 + 127) & ~127LL;
+  const int64_t b = 2 * capb + (((int64_t)P.ng + 2) * 8 + 127);
+  return b <= 224 * 1024 ? (size_t)b : 0;
+}
 static int pbq_fills(const DevPlan& P) {
   const int s_gen = (P.ng + PBS_WAVE - 1) / PBS_WAVE, s_br = (P.nr + PBS_WAVE - 1) / PBS_WAVE, s_bus = (P.nb + PBS_WAVE - 1) / PBS_WAVE;
   return s_gen + 2 * s_br + (P.form == PBRARV ? 3 : 2) * s_bus;
@@ -2749,7 +2957,14 @@ cudaError_t launch_pb_form(const DevPlan& P, const EvalArgs& A, cudaStream_t st,
         // accumulators taking half of the shared memory, 16 consumer warps are left per SM and the step (wait, two
         // shared-memory read-modify-writes, barrier) becomes latency-bound (profiles/r02_ncu_pb_bus_summary.txt)
         const int nst = pbq_stages(P);
-        if (nst > 0 && !A.status && getenv("PS_PBQ")) {
+        const size_t smem_g = pbg_smem_bytes(P);
+        // the gather-from-shared-memory kernel: opt-in (PS_PBG=1).  Measured on case13659pegase, 4096 scenarios: 3.6-4.2 ms
+        // against 1.57 -- 70 list-segment visits per thread and item cost 474 k warp instructions per scenario, three times
+        // the element-ordered kernel's, and each visit waits for its L2-resident list entries (profiles/r02_ncu_pb_bus_summary.txt)
+        if (smem_g > 0 && !A.status && getenv("PS_PBG")) {
+          pb_bus_g_gather_kernel<FORM><<<dim3((unsigned)std::min(2 * A.S, n_sm)), PBG_T, smem_g, st>>>(P, A);
+          obj_from = A.S;
+        } else if (nst > 0 && !A.status && getenv("PS_PBQ")) {
           pb_bus_g_tma_kernel<FORM><<<dim3((unsigned)std::min(2 * A.S, n_sm)), PBQ_T, pbq_smem_bytes(P, nst), st>>>(P, A, nst);
           obj_from = A.S;
         } else {

@@ -36,6 +36,8 @@ struct DevPlan {                    // passed to kernels by value (constant bank
   const uint8_t* pbs_wmax;                          // highest rank per step (generator, Sij, Sji steps)
   const int32_t* pbs_code4;                         // the same codes, every segment on a 16-byte boundary and a step of padding
   int pbs_off4[3];                                  //   behind the table (pb_bus_g_tma_kernel copies whole steps); segment offsets
+  int pbg_half;                                     // pb_bus_g_gather_kernel: branches [0, pbg_half) | [pbg_half, nr) are the two halves
+  const uint32_t* pbg_seg;                          //   [5][nb] list segment (first | length << 24) of a bus per phase: generators, Sij lo / hi, Sji lo / hi
   int cost_order;
   const int32_t *f, *t;
   const double *Gf, *Bf, *Gt, *Bt, *gf, *bf, *gt, *bt, *Imax, *Gl, *Bl, *Pd0, *Qd0;

@@ -563,6 +563,14 @@ def test_scenario_resident_pb_residuals(F, order):
                 del os.environ["PS_PBSCN"], os.environ["PS_PBQ"]
             for name, a, c in zip("gJHs", ref, out):
                 assert np.array_equal(a, c, equal_nan=True), (F.name, order, S, what, name, "copy-engine-fed kernel")
+            # the gather-from-shared-memory kernel (forced here, the default on large networks)
+            os.environ.update({"PS_PBSCN": "1", "PS_PBG": "1"})
+            try:
+                out = run(what)
+            finally:
+                del os.environ["PS_PBSCN"], os.environ["PS_PBG"]
+            for name, a, c in zip("gJHs", ref, out):
+                assert np.array_equal(a, c, equal_nan=True), (F.name, order, S, what, name, "gather kernel")
             # beside another kernel (side lane; needs >= 256 scenarios): the 512-thread shape with the slot kernel on the other
             # half of every SM (g + J + H), the 1024-thread shape on 40 SMs of its own beside the branch kernel (g alone)
             if S >= 256:

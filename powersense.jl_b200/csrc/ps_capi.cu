@@ -201,8 +201,8 @@ int do_eval(ps_batch* b, int what, int64_t s_begin, int64_t s_count, const doubl
     A.diag = b->d_diag + s_begin * 4 * P.net.nbus;
   }
   b->tmask = 0;
-  if (!b->side_tried && h->dev.pbs_ok && s_count >= 256) {
-    // (a failure here only means that the evaluation runs on one stream)
+  if (!b->side_tried && h->dev.pbs_ok && s_count >= 256 && (getenv("PS_PBS_SIDE") || getenv("PS_PBCO"))) {
+    // the side lane serves opt-in experiments only (ps_kernels.cu: launch_pb_form); a failure here just means one stream
     b->side_tried = true;
     if (cudaStreamCreateWithFlags(&b->side.st, cudaStreamNonBlocking) != cudaSuccess ||
         cudaEventCreateWithFlags(&b->side.fork, cudaEventDisableTiming) != cudaSuccess ||

@@ -575,8 +575,7 @@ def test_scenario_resident_pb_residuals(F, order):
             # half of every SM (g + J + H), the 1024-thread shape on 40 SMs of its own beside the branch kernel (g alone)
             if S >= 256:
                 env = {"PS_PBSCN": "1", "PS_PBS_FORCE": "1"}
-                if what == 1:
-                    env["PS_PBS_SIDE"] = "40"
+                env["PS_PBS_SIDE" if what == 1 else "PS_PBCO"] = "40" if what == 1 else "1"
                 os.environ.update(env)
                 try:
                     out = run(what)

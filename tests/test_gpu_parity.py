@@ -742,7 +742,8 @@ def test_correctly_rounded_powers():
 def test_specialised_callback_kernels_match_the_general_one(F):
     """bus_warp_kernel is instantiated for the callbacks a solver actually issues -- residuals only (eval_constraint: every
     trial point of the SLP line search; no derivative is formed) and g + J (the LP set-up; no Hessian term is formed) -- next
-    to the run-time-flag version that serves status masks and odd combinations.  Same expressions, same order: bitwise equal."""
+    to the run-time-flag version that serves odd combinations, each kind also under a branch-status mask.  Same expressions,
+    same order: bitwise equal."""
     import os
     torch = _torch()
     dev = torch.device("cuda:0")
@@ -752,17 +753,20 @@ def test_specialised_callback_kernels_match_the_general_one(F):
     h = capi.Handle(d, F.code, device=0)
     mu = np.random.default_rng(2).normal(size=(S, h.m_nl))
     base = {"PS_NO_CBFAST": "1", "PS_NO_PBFAST": "1"}           # the warp-tile kernel for every formulation
+    st = np.ones((S, d.nbr), dtype=np.uint8)                    # an N-1 mask: the three kinds are also instantiated with one
+    st[np.arange(S), (np.arange(S) * 53) % d.nbr] = 0
     os.environ.update(base)
     try:
-        for what in (1, 3, 7, 2, 5):
-            new = _batch_eval(h, x, mu, Pd, Qd, what=what)
-            os.environ["PS_WT_ANY"] = "1"
-            try:
-                ref = _batch_eval(h, x, mu, Pd, Qd, what=what)
-            finally:
-                del os.environ["PS_WT_ANY"]
-            for name, a, c in zip("gJHs", new, ref):
-                assert np.array_equal(a, c, equal_nan=True), (F.name, what, name)
+        for status in (None, st):
+            for what in (1, 3, 7, 2, 5):
+                new = _batch_eval(h, x, mu, Pd, Qd, status=status, what=what)
+                os.environ["PS_WT_ANY"] = "1"
+                try:
+                    ref = _batch_eval(h, x, mu, Pd, Qd, status=status, what=what)
+                finally:
+                    del os.environ["PS_WT_ANY"]
+                for name, a, c in zip("gJHs", new, ref):
+                    assert np.array_equal(a, c, equal_nan=True), (F.name, what, name, status is not None)
     finally:
         for k in base:
             del os.environ[k]

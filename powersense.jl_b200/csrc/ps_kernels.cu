@@ -2424,6 +2424,25 @@ constexpr int bulk_row_stride(int r) { return ((r / 2) & 1) ? r : r + 2; }   // 
 #ifndef PS_BULK_MINB
 #define PS_BULK_MINB 2
 #endif
+// Rows handed to the copy engine together (one cp.async.bulk per group and block), and which lane evaluates which branch
+// of the warp's 32: lane l takes branch (l % NG) * GR + l / NG (NG = 32 / GR groups), so that the eight lanes of a
+// quarter-warp -- the unit a 16-byte shared-memory store is served in -- park their rows in eight DIFFERENT groups.  With
+// a group stride of GR * row + 2 doubles (an odd number of 16-byte units) the eight 16-byte chunks fall into the eight
+// bank groups: conflict-free for every row length when GR = 4; with GR = 8 (the default: half as many copies) a quarter-warp
+// holds two rows of each of four groups -- conflict-free for the 12-unit J rows of PBRARV, two-way for its 18-unit H rows.
+// (Lanes in branch order: row strides of 12 / 18 units put a quarter-warp on 2 / 4 bank groups -- 59 % of the kernel's
+// shared-memory wavefronts were conflicts, profiles/r02_ncu_branch_bulk_summary.txt.)  Measured (gpurun_out/r2c37_ab.log):
+// PBRAPV branch rows 4.87 -> 4.70 ms per 2048 scenarios (5.87 -> 6.09 TB/s), PBRARV 8.54 -> 8.51 per 4096 (not bound by
+// these stores); GR = 4 and 8 equal.  Global loads and the g rows see the same 32 consecutive branches either way.
+#ifndef PS_BULK_GROUP
+#define PS_BULK_GROUP 8
+#endif
+constexpr int BULK_GR = PS_BULK_GROUP, BULK_NG = 32 / BULK_GR;
+static_assert(BULK_GR == 4 || BULK_GR == 8, "eight lanes of a quarter-warp on eight (or four x two) groups");
+#ifndef PS_BULK_PERMUTE
+#define PS_BULK_PERMUTE 1
+#endif
+__device__ __forceinline__ int bulk_branch_of_lane(int l) { return PS_BULK_PERMUTE ? (l % BULK_NG) * BULK_GR + l / BULK_NG : l; }
 template <int FORM, int SRC>
 __global__ void __launch_bounds__(TPB, PS_BULK_MINB) branch_bulk_kernel(const __grid_constant__ DevPlan P, const __grid_constant__ EvalArgs A) {
   using BR = Branch<FORM, SRC>;
@@ -2433,15 +2452,20 @@ __global__ void __launch_bounds__(TPB, PS_BULK_MINB) branch_bulk_kernel(const __
     __shared__ __align__(16) double sW[TPB / 32][32 * BR::NR];     // per-warp staging row of g
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
 #if PS_BULK_WARP
-    // rows of 8 consecutive branches are contiguous (one copy per 8 rows); 16 bytes of padding between the groups of a
-    // warp spread the 16-byte row stores of the 32 lanes over all banks
-    double* const rj = rows + threadIdx.x * SJ + (threadIdx.x >> 3) * 2;
-    double* const rh = rows + TPB * SJ + (TPB / 8) * 2 + threadIdx.x * SH + (threadIdx.x >> 3) * 2;
+    // rows of BULK_GR consecutive branches are contiguous (one copy per group); 16 bytes of padding between the groups
+    const int bl = bulk_branch_of_lane(lane), tb = w * 32 + bl;    // this lane's branch within the warp / within the CTA
+    double* const rj = rows + tb * SJ + (tb / BULK_GR) * 2;
+    double* const rh = rows + TPB * SJ + (TPB / BULK_GR) * 2 + tb * SH + (tb / BULK_GR) * 2;
 #else
     double* const rj = rows + threadIdx.x * SJ;
     double* const rh = rows + TPB * SJ + threadIdx.x * SH;
 #endif
+#if PS_BULK_WARP
+    const int u = blockIdx.x * TPB + tb;
+#else
     const int u = blockIdx.x * TPB + threadIdx.x;
+    const int bl = lane;
+#endif
     const bool act = u < P.nr;
     const int s0 = blockIdx.y * A.chunk, s1 = min(A.S, s0 + A.chunk);
     const bool wg = (A.what & EV_G) != 0, wj = (A.what & EV_J) != 0, wh = (A.what & EV_H) != 0;
@@ -2462,8 +2486,8 @@ __global__ void __launch_bounds__(TPB, PS_BULK_MINB) branch_bulk_kernel(const __
     const int nact = max(0, min(32, P.nr - ubase));
     const int ng = nact * BR::NR;
     const long long gb = P.bus_rows + (long long)ubase * BR::NR;
-    const bool lead = (lane & 7) == 0;                             // issues (and waits for) the copies of its 8 rows
-    const int nrow8 = max(0, min(8, P.nr - u));                    // rows of this lane's group (meaningful on lead lanes)
+    const bool lead = (bl % BULK_GR) == 0;                         // issues (and waits for) the copies of its group's rows
+    const int nrow8 = max(0, min(BULK_GR, P.nr - u));              // rows of this lane's group (meaningful on lead lanes)
 #if PS_PREFETCH2
     typename BR::In nx1{};
     if (act && s0 + 1 < s1) nx1 = BR::load_in(P, A, s0 + 1, u, f, t);
@@ -2521,7 +2545,7 @@ __global__ void __launch_bounds__(TPB, PS_BULK_MINB) branch_bulk_kernel(const __
         double* sg = sW[w];
         if (act) {
 #pragma unroll
-          for (int r = 0; r < BR::NR; r++) sg[lane * BR::NR + r] = oj.gt[r];
+          for (int r = 0; r < BR::NR; r++) sg[bl * BR::NR + r] = oj.gt[r];
         }
         __syncwarp();
         copy_aligned<32>(A.g + (long long)s * A.ldg + gb, ng, lane, [&](int e) { return sg[e]; });
@@ -2542,11 +2566,11 @@ template <int FORM>
 cudaError_t launch_bulk(const DevPlan& P, const EvalArgs& A, cudaStream_t st, dim3 grid) {
   if (P.src == SRC_MATPOWER) {
     using BR = Branch<FORM, SRC_MATPOWER>;
-    const size_t smem = (size_t)(TPB * (bulk_row_stride(BR::RJ) + bulk_row_stride(BR::RH)) + (TPB / 8) * 4) * 8;
+    const size_t smem = (size_t)(TPB * (bulk_row_stride(BR::RJ) + bulk_row_stride(BR::RH)) + (TPB / BULK_GR) * 4) * 8;
     branch_bulk_kernel<FORM, SRC_MATPOWER><<<grid, TPB, smem, st>>>(P, A);
   } else {
     using BR = Branch<FORM, SRC_ARPAE>;
-    const size_t smem = (size_t)(TPB * (bulk_row_stride(BR::RJ) + bulk_row_stride(BR::RH)) + (TPB / 8) * 4) * 8;
+    const size_t smem = (size_t)(TPB * (bulk_row_stride(BR::RJ) + bulk_row_stride(BR::RH)) + (TPB / BULK_GR) * 4) * 8;
     branch_bulk_kernel<FORM, SRC_ARPAE><<<grid, TPB, smem, st>>>(P, A);
   }
   return cudaGetLastError();
@@ -2681,10 +2705,10 @@ cudaError_t configure_form(int src, size_t smem_branch, size_t smem_bus, size_t 
     using BA = Branch<FORM, SRC_ARPAE>;
     if (src == SRC_MATPOWER && BM::DIRECT_OK)
       e = cudaFuncSetAttribute(branch_bulk_kernel<FORM, SRC_MATPOWER>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                               (TPB * (bulk_row_stride(BM::RJ) + bulk_row_stride(BM::RH)) + (TPB / 8) * 4) * 8);
+                               (TPB * (bulk_row_stride(BM::RJ) + bulk_row_stride(BM::RH)) + (TPB / BULK_GR) * 4) * 8);
     if (src != SRC_MATPOWER && BA::DIRECT_OK)
       e = cudaFuncSetAttribute(branch_bulk_kernel<FORM, SRC_ARPAE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                               (TPB * (bulk_row_stride(BA::RJ) + bulk_row_stride(BA::RH)) + (TPB / 8) * 4) * 8);
+                               (TPB * (bulk_row_stride(BA::RJ) + bulk_row_stride(BA::RH)) + (TPB / BULK_GR) * 4) * 8);
     if (e != cudaSuccess) return e;
   }
   if (src == SRC_MATPOWER)

@@ -87,9 +87,6 @@ struct ps_batch {
          *sJ[2] = {nullptr, nullptr}, *sH[2] = {nullptr, nullptr}, *sscal[2] = {nullptr, nullptr};
   cudaStream_t st_in = nullptr, st_k = nullptr, st_out = nullptr;
   cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_k[2] = {nullptr, nullptr}, ev_out[2] = {nullptr, nullptr};
-  // side lane of launch_eval (ps_kernels.cuh): created with the first batched evaluation that can use it
-  SideLane side{nullptr, nullptr, nullptr};
-  bool side_tried = false;
 };
 
 struct ps_csc {
@@ -201,20 +198,6 @@ int do_eval(ps_batch* b, int what, int64_t s_begin, int64_t s_count, const doubl
     A.diag = b->d_diag + s_begin * 4 * P.net.nbus;
   }
   b->tmask = 0;
-  if (!b->side_tried && h->dev.pbs_ok && s_count >= 256 && (getenv("PS_PBS_SIDE") || getenv("PS_PBCO"))) {
-    // the side lane serves opt-in experiments only (ps_kernels.cu: launch_pb_form); a failure here just means one stream
-    b->side_tried = true;
-    if (cudaStreamCreateWithFlags(&b->side.st, cudaStreamNonBlocking) != cudaSuccess ||
-        cudaEventCreateWithFlags(&b->side.fork, cudaEventDisableTiming) != cudaSuccess ||
-        cudaEventCreateWithFlags(&b->side.join, cudaEventDisableTiming) != cudaSuccess) {
-      cudaGetLastError();
-      if (b->side.fork) cudaEventDestroy(b->side.fork);
-      if (b->side.join) cudaEventDestroy(b->side.join);
-      if (b->side.st) cudaStreamDestroy(b->side.st);
-      b->side = SideLane{nullptr, nullptr, nullptr};
-    }
-  }
-  const SideLane* side = b->side.st ? &b->side : nullptr;
   if ((what & EV_H) && h->d_hperm) {
     // a caller-imposed Hessian slot order: the kernels write their canonical order into a slab (laid out like
     // ps_preferred_layout, so the fast store paths apply), one gather per slab moves it to the caller's rows
@@ -238,12 +221,12 @@ int do_eval(ps_batch* b, int what, int64_t s_begin, int64_t s_count, const doubl
       if (As.scal) As.scal += c0 * NSCAL;
       if (As.diag) As.diag += c0 * As.lddiag;
       As.H = b->d_Hs + pad; As.ldH = ldHs;
-      e = launch_eval(h->dev, As, P.smem_branch_bytes, P.smem_bus_bytes, stream, &b->launches, b->timing ? b->tev : nullptr, &b->tmask, side);
+      e = launch_eval(h->dev, As, P.smem_branch_bytes, P.smem_bus_bytes, stream, &b->launches, b->timing ? b->tev : nullptr, &b->tmask);
       if (e == cudaSuccess) { e = launch_permute_rows(h->d_hperm, (int)P.nnzH, n, As.H, ldHs, H + c0 * ldH, ldH, stream); b->launches += 1; }
       if (e != cudaSuccess) return cuda_fail(h, e, "eval_kernel launch (permuted Hessian)");
     }
   } else {
-    e = launch_eval(h->dev, A, P.smem_branch_bytes, P.smem_bus_bytes, stream, &b->launches, b->timing ? b->tev : nullptr, &b->tmask, side);
+    e = launch_eval(h->dev, A, P.smem_branch_bytes, P.smem_bus_bytes, stream, &b->launches, b->timing ? b->tev : nullptr, &b->tmask);
     if (e != cudaSuccess) return cuda_fail(h, e, "eval_kernel launch");
   }
   b->launches += (scalars ? 1 : 0);                  // the memset node
@@ -378,46 +361,7 @@ int ps_create(const ps_network* net, int formulation, int source_type, int flags
   }
   D.pbs_ok = P.pbs_ok ? 1 : 0;
   D.pbs_prefer = P.pbs_prefer ? 1 : 0;
-  if (P.pbs_ok) {
-    D.pbs_code = M.upload(P.pbs_code); D.pbs_wmax = M.upload(P.pbs_wmax);
-    // copy for the copy-engine-fed kernel: every segment of [ngen | nbr | nbr] padded with -1 to whole steps (the kernel
-    // copies whole steps and reads them without bounds checks)
-    const int64_t ng = P.net.ngen, nbr = P.net.nbr, seg[3] = {ng, nbr, nbr}, src[3] = {0, ng, ng + nbr};
-    int64_t off = 0;
-    std::vector<int32_t> c4;
-    for (int q = 0; q < 3; q++) {
-      D.pbs_off4[q] = (int)off;
-      c4.resize((size_t)off + (size_t)((seg[q] + PBS_WAVE - 1) / PBS_WAVE) * PBS_WAVE, -1);
-      std::copy(P.pbs_code.begin() + src[q], P.pbs_code.begin() + src[q] + seg[q], c4.begin() + off);
-      off = (int64_t)c4.size();
-    }
-    if (c4.empty()) c4.resize(PBS_WAVE, -1);
-    D.pbs_code4 = M.upload(c4);
-    // pb_bus_g_gather_kernel: the half-edge list of a bus (Sij ascending, then Sji ascending: he_ks = 2 * branch + side) cut
-    // where the branch index crosses the half boundary on either side
-    const int64_t half = ((nbr + 1) / 2 + 1) & ~1LL;
-    D.pbg_half = (int)std::min<int64_t>(half, nbr);
-    std::vector<uint32_t> segs((size_t)(5 * nb), 0u);
-    bool seg_ok = P.he_ks.size() < (size_t(1) << 24) && (size_t)ng < (size_t(1) << 24);
-    auto put = [&](int ph, int64_t i, int64_t q0, int64_t q1) {
-      if (q1 - q0 > 255) seg_ok = false;
-      segs[(size_t)ph * nb + i] = (uint32_t)q0 | ((uint32_t)(q1 - q0) << 24);
-    };
-    for (int64_t i = 0; i < nb && seg_ok; i++) {
-      put(0, i, P.net.gen_ptr[i], P.net.gen_ptr[i + 1]);
-      int32_t q = P.he_ptr[i];
-      const int32_t q1 = P.he_ptr[i + 1];
-      int32_t c[5] = {q, q, q, q, q1};
-      while (q < q1 && !(P.he_ks[q] & 1) && (P.he_ks[q] >> 1) < D.pbg_half) q++;
-      c[1] = q;
-      while (q < q1 && !(P.he_ks[q] & 1)) q++;
-      c[2] = q;
-      while (q < q1 && (P.he_ks[q] >> 1) < D.pbg_half) q++;
-      c[3] = q;
-      for (int ph = 1; ph <= 4; ph++) put(ph, i, c[ph - 1], c[ph]);
-    }
-    D.pbg_seg = seg_ok ? M.upload(segs) : nullptr;
-  }
+  if (P.pbs_ok) { D.pbs_code = M.upload(P.pbs_code); D.pbs_wmax = M.upload(P.pbs_wmax); }
   D.cb_slots = 0;
   if (is_CB(P.form) && nb > 0 && P.bus_rows == 2 * nb) {
     // CB* slot tables (same layout and kernel as the PB* ones).  Every entry of the bus block is coefficient * m:
@@ -804,9 +748,6 @@ void ps_batch_destroy(ps_batch* b) {
   if (b->st_in) cudaStreamDestroy(b->st_in);
   if (b->st_k) cudaStreamDestroy(b->st_k);
   if (b->st_out) cudaStreamDestroy(b->st_out);
-  if (b->side.fork) cudaEventDestroy(b->side.fork);
-  if (b->side.join) cudaEventDestroy(b->side.join);
-  if (b->side.st) cudaStreamDestroy(b->side.st);
   b->mem.release();
   delete b;
 }

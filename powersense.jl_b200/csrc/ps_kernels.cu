@@ -1553,14 +1553,9 @@ __global__ void __launch_bounds__(PBT) pb_bus_g_kernel(const __grid_constant__ D
 #ifndef PS_PBS_R
 #define PS_PBS_R 4
 #endif
-#ifndef PS_PBS_SIDE_DEFAULT
-#define PS_PBS_SIDE_DEFAULT 0       // SMs of the side lane (0: the residual kernel precedes the others on the whole machine)
-#endif
-// Two shapes of the CTA serve the same PBS_WAVE elements per step: 1024 threads x 1 element (alone on the machine: more
-// per step -- fewer barriers, independent read-modify-writes -- measured slower at every depth that fits 64 registers,
-// gpurun_out/r2c16_ab.log) and 512 threads x 2 elements at <= 64 registers, which leaves half of the SM's threads and
-// registers to the slot kernel pb_bus_jh_kernel running beside it (launch_pb_form: the residual CTA is bound by issue
-// and barrier latency, the slot CTAs by the load/store path -- together they fill the SM).
+constexpr int PBS_T = PBS_THREADS;
+constexpr int PBS_E = PS_PBS_E;    // elements per thread and step (1: more per step -- fewer barriers, independent read-modify-writes --
+                                   // measured slower at every depth that fits 64 registers: gpurun_out/r2c16_ab.log)
 constexpr int PBS_MAX_STEPS = 1024;
 constexpr int PBS_RB = 4;           // ring depth of the two bus-ordered passes (one element per thread and step)
 constexpr int PBS_R = PS_PBS_R;    // steps whose inputs are in flight (a register ring: the CTA is alone on its SM -- the
@@ -1568,18 +1563,17 @@ constexpr int PBS_R = PS_PBS_R;    // steps whose inputs are in flight (a regist
 
 // One pass over a term table: step j serves elements [j * PBS_WAVE, (j + 1) * PBS_WAVE) -- thread tid the PBS_E elements
 // j * PBS_WAVE + e * PBS_T + tid -- with the inputs of the next PBS_R steps already in flight.
-template <bool HAS_ST, int PBS_T, int PBS_E>
+template <bool HAS_ST>
 __device__ __forceinline__ void pbs_term_pass(double2* acc, const uint8_t* wmax, const int32_t* __restrict__ code, int n,
                                               const double* __restrict__ v0p, const double* __restrict__ v1p,
                                               const uint8_t* __restrict__ stp) {
   const int tid = threadIdx.x;
-  constexpr int RING = PBS_E == 1 ? PBS_R : 2;                 // steps in flight: 2 elements per thread hold twice the registers per step
   // whole rings: the steps past the end have no terms (the loads are guarded) and cost one barrier each; unconditional
   // ring bodies keep every slot in a fixed register (a guarded body makes the compiler rotate the ring through moves,
   // which waits for a load one step after it was issued)
-  const int nsteps = ((n + PBS_WAVE - 1) / PBS_WAVE + RING - 1) / RING * RING;
-  int c[RING][PBS_E];
-  double a0[RING][PBS_E], a1[RING][PBS_E];
+  const int nsteps = ((n + PBS_WAVE - 1) / PBS_WAVE + PBS_R - 1) / PBS_R * PBS_R;
+  int c[PBS_R][PBS_E];
+  double a0[PBS_R][PBS_E], a1[PBS_R][PBS_E];
   auto load = [&](int u, int j) {
 #pragma unroll
     for (int q = 0; q < PBS_E; q++) {
@@ -1592,16 +1586,16 @@ __device__ __forceinline__ void pbs_term_pass(double2* acc, const uint8_t* wmax,
     }
   };
 #pragma unroll
-  for (int u = 0; u < RING; u++) load(u, u);
-  for (int j0 = 0; j0 < nsteps; j0 += RING) {
+  for (int u = 0; u < PBS_R; u++) load(u, u);
+  for (int j0 = 0; j0 < nsteps; j0 += PBS_R) {
 #pragma unroll
-    for (int u = 0; u < RING; u++) {
+    for (int u = 0; u < PBS_R; u++) {
       const int j = j0 + u;
       int cc[PBS_E];
       double b0[PBS_E], b1[PBS_E];
 #pragma unroll
       for (int q = 0; q < PBS_E; q++) { cc[q] = c[u][q]; b0[q] = a0[u][q]; b1[q] = a1[u][q]; }
-      load(u, j + RING);                                      // refill: in flight while the next RING - 1 steps are served
+      load(u, j + PBS_R);                                      // refill: in flight while the next PBS_R - 1 steps are served
       for (int r = 0, mr = wmax[j]; r <= mr; r++) {            // elements of the step that share a bus: rank order
         // one rank: every read-modify-write of the sub-round goes to a different bus (ranks are per bus and step), so the
         // PBS_E of a thread are independent and overlap
@@ -1621,11 +1615,10 @@ __device__ __forceinline__ void pbs_term_pass(double2* acc, const uint8_t* wmax,
   }
 }
 
-template <int FORM, int PBS_T, int PBS_E>
-__global__ void __launch_bounds__(PBS_T, 1024 / PBS_T) pb_bus_g_scn_kernel(const __grid_constant__ DevPlan P, const __grid_constant__ EvalArgs A) {
+template <int FORM>
+__global__ void __launch_bounds__(PBS_T, 1) pb_bus_g_scn_kernel(const __grid_constant__ DevPlan P, const __grid_constant__ EvalArgs A) {
   extern __shared__ __align__(16) double2 pbs_acc[];           // [nb] running (P, Q) sums of the scenario
-  static_assert(PBS_T * PBS_E == PBS_WAVE, "the plan's rank table is built for PBS_WAVE elements per step");
-  __shared__ double redv[PBS_T / 32], redo[OBJ_LANES / 32];
+  __shared__ double redv[PBS_T / 32], redo[PBS_T / 32];
   __shared__ int redn[PBS_T / 32];
   __shared__ uint8_t wmax[PBS_MAX_STEPS];                      // highest rank per term-table step
   const int tid = threadIdx.x;
@@ -1641,13 +1634,13 @@ __global__ void __launch_bounds__(PBS_T, 1024 / PBS_T) pb_bus_g_scn_kernel(const
     const bool al = (reinterpret_cast<unsigned long long>(gd) & 15) == 0;
     for (int i = tid; i < P.nb; i += PBS_T) pbs_acc[i] = make_double2(0.0, 0.0);     // formulations.jl:171-172
     __syncthreads();
-    pbs_term_pass<false, PBS_T, PBS_E>(pbs_acc, wmax, P.pbs_code, P.ng, x + P.o_pg, x + P.o_qg, nullptr);                        // :177-180
+    pbs_term_pass<false>(pbs_acc, wmax, P.pbs_code, P.ng, x + P.o_pg, x + P.o_qg, nullptr);                        // :177-180
     if (stp) {                                                                                                       // :188-196
-      pbs_term_pass<true, PBS_T, PBS_E>(pbs_acc, wmax + s_gen, P.pbs_code + P.ng, P.nr, x + P.o_f[0], x + P.o_f[1], stp);        // Sij side
-      pbs_term_pass<true, PBS_T, PBS_E>(pbs_acc, wmax + s_gen + s_br, P.pbs_code + P.ng + P.nr, P.nr, x + P.o_f[2], x + P.o_f[3], stp);   // Sji side
+      pbs_term_pass<true>(pbs_acc, wmax + s_gen, P.pbs_code + P.ng, P.nr, x + P.o_f[0], x + P.o_f[1], stp);        // Sij side
+      pbs_term_pass<true>(pbs_acc, wmax + s_gen + s_br, P.pbs_code + P.ng + P.nr, P.nr, x + P.o_f[2], x + P.o_f[3], stp);   // Sji side
     } else {
-      pbs_term_pass<false, PBS_T, PBS_E>(pbs_acc, wmax + s_gen, P.pbs_code + P.ng, P.nr, x + P.o_f[0], x + P.o_f[1], nullptr);
-      pbs_term_pass<false, PBS_T, PBS_E>(pbs_acc, wmax + s_gen + s_br, P.pbs_code + P.ng + P.nr, P.nr, x + P.o_f[2], x + P.o_f[3], nullptr);
+      pbs_term_pass<false>(pbs_acc, wmax + s_gen, P.pbs_code + P.ng, P.nr, x + P.o_f[0], x + P.o_f[1], nullptr);
+      pbs_term_pass<false>(pbs_acc, wmax + s_gen + s_br, P.pbs_code + P.ng + P.nr, P.nr, x + P.o_f[2], x + P.o_f[3], nullptr);
     }
     // the bus's own shunt term (:256-258 | :264-266), then minus the load (:291-292) and out; thread tid owns bus
     // j * PBS_T + tid in both passes: no barrier between them
@@ -1713,24 +1706,18 @@ __global__ void __launch_bounds__(PBS_T, 1024 / PBS_T) pb_bus_g_scn_kernel(const
       }
     }
     if (A.scal) {                                              // CTA-uniform
-      static_assert(OBJ_LANES % PBS_T == 0, "virtual lanes are dealt to the CTA's threads in whole rounds");
-      double gsum[OBJ_LANES / PBS_T];                          // the objective scalar, in objective_tile's order
-#pragma unroll
-      for (int j = 0; j < OBJ_LANES / PBS_T; j++) gsum[j] = objective_lane(P, x, tid + PBS_T * j);
+      static_assert(PBS_T == OBJ_LANES, "the CTA's threads are the objective's virtual lanes");
+      const double gsum = objective_lane(P, x, tid);           // the objective scalar, in objective_tile's order
 #pragma unroll
       for (int d = 16; d > 0; d >>= 1) {
         vmax = fmax(vmax, __shfl_xor_sync(0xffffffffu, vmax, d));
         nviol += __shfl_xor_sync(0xffffffffu, nviol, d);
       }
-      if ((tid & 31) == 0) {
-        redv[tid >> 5] = vmax; redn[tid >> 5] = nviol;
-#pragma unroll
-        for (int j = 0; j < OBJ_LANES / PBS_T; j++) redo[(tid + PBS_T * j) >> 5] = gsum[j];
-      }
+      if ((tid & 31) == 0) { redv[tid >> 5] = vmax; redn[tid >> 5] = nviol; redo[tid >> 5] = gsum; }
       __syncthreads();
       if (tid == 32) {
         double tot = 0.0;
-        for (int w = 0; w < OBJ_LANES / 32; w++) tot += redo[w];
+        for (int w = 0; w < PBS_T / 32; w++) tot += redo[w];
         A.scal[(long long)s * NSCAL + 0] = tot;
       }
       if (tid < 32) {
@@ -1748,481 +1735,6 @@ __global__ void __launch_bounds__(PBS_T, 1024 / PBS_T) pb_bus_g_scn_kernel(const
       }
     }
     __syncthreads();                                           // the accumulators are reused by the next scenario
-  }
-}
-
-// ---- PB* residuals, scenario-resident, fed by the copy engine -------------------------------------------------------
-// pb_bus_g_scn_kernel keeps its loads in registers: three per element and step, a ring of four steps -- and stalls on the
-// load/store unit's queue (lg_throttle) and on six pipeline drains per scenario (profiles/r02_ncu_pb_bus_summary.txt);
-// the 16 bytes per bus of its accumulators leave no room for anything else.  Here the P row and the Q row of a scenario
-// are two independent work items (they share nothing but the bus voltages), so an item's accumulators are 8 bytes per
-// bus and the other half of the SM's shared memory is a ring of PBQ stages that the copy engine fills
-// (cp.async.bulk global -> shared, completion on an mbarrier per stage; SASS UBLKCP): ~100 KB in flight per SM whatever
-// the threads do, one stream of fills across passes AND items (no drain anywhere), issued by a producer warp that the
-// consumers release stage by stage through a second mbarrier (a single issuing thread among the consumers put its
-// ~60 instructions per fill on every step's critical path: 3.2 ms against 1.85).  A stage =
-// one step: PBS_WAVE values (pg | Pij | Pji for a P item, the reactive ones for a Q item; own voltage / load in the
-// bus pass) and, for term steps, the step's PBS_WAVE codes (bus | rank << 24; copied from a 16-byte aligned, padded
-// copy of the plan table).  Value arrays start on any 8-byte boundary: the copy starts one element early and / or ends one
-// element late where that makes it 16-byte aligned (both neighbours belong to the same buffer: an odd start is not the
-// start of an allocation, and the element behind a step is the next step's, the next variable's or the next scenario's)
-// -- except behind the last step of the call's last scenario, whose final element its own thread reads from global memory.
-// Per bus the terms arrive in the reference's order exactly as in pb_bus_g_scn_kernel (same codes, same ranks, one CTA
-// barrier per rank) -- bitwise identical results.
-constexpr int PBQ_CT = 512, PBQ_E = 2;                         // consumer threads, elements per consumer thread and step
-constexpr int PBQ_T = PBQ_CT + 32;                             // + the producer warp
-static_assert(PBQ_CT * PBQ_E == PBS_WAVE, "the plan's rank table is built for PBS_WAVE elements per step");
-constexpr int PBQ_VALB = (PBS_WAVE + 2) * 8;                   // bytes of a step's values + one element on either side (alignment)
-constexpr int PBQ_STAGE = PBQ_VALB + PBS_WAVE * 4;             // + its codes
-constexpr int PBQ_MIN_STAGES = 6;
-
-__device__ __forceinline__ void mbar_init(uint64_t* b, int count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(b)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* b, int bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(b)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* b, unsigned parity) {
-  const unsigned a = (unsigned)__cvta_generic_to_shared(b);
-  unsigned done = 0;
-  while (!done) {
-    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-                 : "=r"(done) : "r"(a), "r"(parity) : "memory");
-  }
-}
-__device__ __forceinline__ void bulk_load(void* sdst, const void* gsrc, int bytes, uint64_t* b) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-               ::"r"((unsigned)__cvta_generic_to_shared(sdst)), "l"(gsrc), "r"(bytes), "r"((unsigned)__cvta_generic_to_shared(b)) : "memory");
-}
-
-// one fill of the stream, as the producer sees it (shared-memory table, built once per CTA for both rows): `n` elements at
-// element offset `off` of the scenario's x row (space 0), of its load row (1) or of the network's load array (2)
-struct PbqFill { int off, n, space, co; };                     // co: offset of the step's codes (-1: a bus-pass fill); n | lastseg << 16
-
-__device__ __forceinline__ void mbar_arrive(uint64_t* b) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"((unsigned)__cvta_generic_to_shared(b)) : "memory");
-}
-__device__ __forceinline__ void pbq_bar() { asm volatile("bar.sync 1, %0;" ::"n"(PBQ_CT) : "memory"); }   // the consumer warps only
-
-template <int FORM>
-__global__ void __launch_bounds__(PBQ_T, 1) pb_bus_g_tma_kernel(const __grid_constant__ DevPlan P, const __grid_constant__ EvalArgs A, const int nst) {
-  extern __shared__ __align__(128) unsigned char pbq_smem[];
-  constexpr int NB = FORM == PBRARV ? 3 : 2;                   // fills of a bus step: (vi, vr | V), load
-  constexpr int CT = PBQ_CT, E = PBQ_E;
-  __shared__ double redv[CT / 32], redo[OBJ_LANES / 32];
-  __shared__ int redn[CT / 32];
-  __shared__ uint8_t wmax[PBS_MAX_STEPS];
-  const int tid = threadIdx.x;
-  const int accb = (P.nb * 8 + 127) & ~127;
-  double* const acc = reinterpret_cast<double*>(pbq_smem);
-  unsigned char* const ring = pbq_smem + accb;
-  uint64_t* const full = reinterpret_cast<uint64_t*>(ring + (size_t)nst * PBQ_STAGE);
-  uint64_t* const empty = full + nst;
-  const bool wg = (A.what & EV_G) != 0;
-  const int s_gen = (P.ng + PBS_WAVE - 1) / PBS_WAVE, s_br = (P.nr + PBS_WAVE - 1) / PBS_WAVE, s_bus = (P.nb + PBS_WAVE - 1) / PBS_WAVE;
-  const int nterm = s_gen + 2 * s_br, nfill = nterm + NB * s_bus;
-  PbqFill* const tab = reinterpret_cast<PbqFill*>(empty + nst);   // [2][nfill], 16-byte aligned (2 * nst mbarriers before it)
-  const int n_items = 2 * A.S;
-  for (int j = tid; j < PBS_MAX_STEPS; j += PBQ_T) wmax[j] = j < nterm ? P.pbs_wmax[j] : 0;
-  for (int i = tid; i < P.nb; i += PBQ_T) acc[i] = 0.0;        // formulations.jl:171-172 (every item leaves them zeroed)
-  for (int e = tid; e < 2 * nfill; e += PBQ_T) {
-    const int row = e >= nfill, q = e - row * nfill;
-    PbqFill f;
-    f.space = 0; f.co = -1;
-    int nseg, j;
-    if (q < s_gen) { j = q; nseg = P.ng; f.off = row ? P.o_qg : P.o_pg; f.co = P.pbs_off4[0]; }
-    else if (q < s_gen + s_br) { j = q - s_gen; nseg = P.nr; f.off = P.o_f[row]; f.co = P.pbs_off4[1]; }
-    else if (q < nterm) { j = q - s_gen - s_br; nseg = P.nr; f.off = P.o_f[2 + row]; f.co = P.pbs_off4[2]; }
-    else {
-      const int b = q - nterm, a = b % NB;
-      j = b / NB; nseg = P.nb;
-      if (a == NB - 1) { f.off = 0; f.space = (row ? A.Qd : A.Pd) ? 1 : 2; }
-      else f.off = (FORM == PBRARV && a == 0) ? P.o_a : P.o_b;
-    }
-    f.off += j * PBS_WAVE;
-    if (f.co >= 0) f.co += j * PBS_WAVE;
-    f.n = min(PBS_WAVE, nseg - j * PBS_WAVE) | (((j + 1) * PBS_WAVE >= nseg) ? 1 << 16 : 0);
-    tab[e] = f;
-  }
-  if (tid == 0) {
-    for (int q = 0; q < nst; q++) { mbar_init(full + q, 1); mbar_init(empty + q, CT / 32); }
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  __syncthreads();
-  if (tid >= CT) {
-    // ---- producer warp (one lane): the stream of fills of this CTA's items, a stage behind the consumers' releases
-    if (tid != CT) return;
-    int stage = 0;
-    unsigned eph = 1;                                          // parity that passes on a fresh barrier: the first round finds every stage free
-    for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
-      const int s = it >> 1, row = it & 1;
-      const double* const xrow = A.x + (long long)s * A.ldx;
-      const double* const lrow = (row ? A.Qd : A.Pd) ? (row ? A.Qd : A.Pd) + (long long)s * A.ldl : (row ? P.Qd0 : P.Pd0);
-      const int4* t4p = reinterpret_cast<const int4*>(tab + row * nfill);
-      for (int q = 0; q < nfill; q++) {
-        const int4 t4 = t4p[q];                                // (off, n | lastseg << 16, space, co)
-        const double* arr = (t4.z == 0 ? xrow : lrow) + t4.x;
-        // nothing readable is known to follow the last step of an array in the call's last scenario (or of a network array)
-        const bool last = (t4.y >> 16) && (t4.z == 2 || s == A.S - 1);
-        const int n = t4.y & 0xffff, lo = (int)((reinterpret_cast<unsigned long long>(arr) >> 3) & 1ull);
-        int cnt = lo + n;
-        if (cnt & 1) cnt += last ? -1 : 1;
-        unsigned char* st = ring + (size_t)stage * PBQ_STAGE;
-        const int vb = cnt * 8, cb = t4.w >= 0 ? PBS_WAVE * 4 : 0;
-        mbar_wait(empty + stage, eph);
-        mbar_expect_tx(full + stage, vb + cb);
-        if (vb > 0) bulk_load(st, arr - lo, vb, full + stage);
-        if (cb > 0) bulk_load(st + PBQ_VALB, P.pbs_code4 + t4.w, cb, full + stage);
-        if (++stage == nst) { stage = 0; eph ^= 1u; }
-      }
-    }
-    return;
-  }
-  // ---- consumers: CT threads, E elements per thread and step (tid, tid + CT)
-  const int lane = tid & 31;
-  int cs = 0;
-  unsigned cph = 0;
-  const unsigned char* cst = ring;                             // = ring + cs * PBQ_STAGE
-  auto next_stage = [&]() { cst += PBQ_STAGE; if (++cs == nst) { cs = 0; cph ^= 1u; cst = ring; } };
-  auto release = [&]() { __syncwarp(); if (lane == 0) mbar_arrive(empty + cs); };   // this warp holds its elements in registers
-  auto misaligned = [](const double* p) { return (int)((reinterpret_cast<unsigned long long>(p) >> 3) & 1ull); };
-  for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
-    const int s = it >> 1, row = it & 1;
-    const double* __restrict__ x = A.x + (long long)s * A.ldx;
-    const bool lastrow = s == A.S - 1;
-    // ---- generators, Sij side, Sji side (formulations.jl:177-196): one fill per step.  Only the last step of an array is
-    // partial: every other one runs without bounds checks (the padded code table marks the elements behind an array with -1)
-    int q = 0;
-#pragma unroll 1
-    for (int pass = 0; pass < 3; pass++) {
-      const double* arr = x + (pass == 0 ? (row ? P.o_qg : P.o_pg) : P.o_f[2 * (pass - 1) + row]);
-      const int nseg = pass == 0 ? P.ng : P.nr, steps = pass == 0 ? s_gen : s_br, lo = misaligned(arr);
-      auto step = [&](const bool tail, int j) {
-        mbar_wait(full + cs, cph);
-        int c[E];
-        double v[E];
-#pragma unroll
-        for (int u = 0; u < E; u++) {
-          const int i = tid + u * CT;
-          c[u] = reinterpret_cast<const int32_t*>(cst + PBQ_VALB)[i];
-          v[u] = reinterpret_cast<const double*>(cst)[i + lo];
-          if (tail) {
-            const int n = nseg - j * PBS_WAVE;
-            if (lastrow && ((lo + n) & 1) && i == n - 1) v[u] = arr[(long long)j * PBS_WAVE + i];   // the one element the copy leaves out
-          }
-        }
-        release();
-        for (int r = 0, mr = wmax[q]; r <= mr; r++) {          // elements of the step that share a bus: rank order
-#pragma unroll
-          for (int u = 0; u < E; u++)
-            if ((c[u] >> 24) == r) {                           // no term: code -1, rank -1; equal ranks of a step are different buses
-              double* const p = acc + (c[u] & 0xffffff);
-              *p = *p + v[u];
-            }
-          pbq_bar();
-        }
-        next_stage();
-        q++;
-      };
-#pragma unroll 1
-      for (int j = 0; j < steps - 1; j++) step(false, j);
-      if (steps > 0) step(true, steps - 1);
-    }
-    // ---- the bus's own shunt term (:256-258 | :264-266), minus the load (:291-292), out; thread tid owns buses j * PBS_WAVE + tid (+ CT)
-    double* __restrict__ gd = wg ? A.g + (long long)s * A.ldg + row : nullptr;
-    const double* __restrict__ kk = row ? P.Bl : P.Gl;
-    const double* const ldp = row ? A.Qd : A.Pd;
-    const double* inp[NB];
-    int inlo[NB];
-    bool inlast[NB];
-#pragma unroll
-    for (int a = 0; a < NB; a++) {
-      if (a == NB - 1) { inp[a] = ldp ? ldp + (long long)s * A.ldl : (row ? P.Qd0 : P.Pd0); inlast[a] = !ldp || lastrow; }
-      else { inp[a] = x + ((FORM == PBRARV && a == 0) ? P.o_a : P.o_b); inlast[a] = lastrow; }
-      inlo[a] = misaligned(inp[a]);
-    }
-    double vmax = 0.0;
-    int nviol = 0;
-    double knext[E];
-#pragma unroll
-    for (int u = 0; u < E; u++) knext[u] = tid + u * CT < P.nb ? kk[tid + u * CT] : 0.0;
-    auto bus_step = [&](const bool tail, int j) {
-      const int n = tail ? P.nb - j * PBS_WAVE : PBS_WAVE;
-      double k[E], in[NB][E];
-#pragma unroll
-      for (int u = 0; u < E; u++) {
-        const int e = j * PBS_WAVE + tid + u * CT;
-        k[u] = knext[u];
-        if (!tail && e + PBS_WAVE < P.nb) knext[u] = kk[e + PBS_WAVE];
-      }
-#pragma unroll
-      for (int a = 0; a < NB; a++) {
-        mbar_wait(full + cs, cph);
-#pragma unroll
-        for (int u = 0; u < E; u++) {
-          const int i = tid + u * CT;
-          in[a][u] = reinterpret_cast<const double*>(cst)[i + inlo[a]];
-          if (tail && inlast[a] && ((inlo[a] + n) & 1) && i == n - 1) in[a][u] = inp[a][(long long)j * PBS_WAVE + i];
-        }
-        release();
-        next_stage();
-      }
-#pragma unroll
-      for (int u = 0; u < E; u++) {
-        const int i = tid + u * CT, e = j * PBS_WAVE + i;
-        if (!tail || i < n) {
-          double m2;
-          if constexpr (FORM == PBRARV) m2 = in[1][u] * in[1][u] + in[0][u] * in[0][u];
-          else m2 = in[0][u] * in[0][u];
-          double a = acc[e];
-          a = row ? a + k[u] * m2 : a - k[u] * m2;
-          const double gv = a - in[NB - 1][u];
-          if (wg) gd[2 * e] = gv;
-          acc[e] = 0.0;                                        // for the next item
-          vmax = fmax(vmax, fabs(gv));
-          nviol += fabs(gv) > A.viol_tol ? 1 : 0;
-        }
-      }
-    };
-#pragma unroll 1
-    for (int j = 0; j < s_bus - 1; j++) bus_step(false, j);
-    if (s_bus > 0) bus_step(true, s_bus - 1);
-    if (A.scal) {                                              // CTA-uniform
-      static_assert(OBJ_LANES % CT == 0, "virtual lanes are dealt to the consumer threads in whole rounds");
-      double gsum[OBJ_LANES / CT];
-#pragma unroll
-      for (int u = 0; u < OBJ_LANES / CT; u++) gsum[u] = row == 0 ? objective_lane(P, x, tid + CT * u) : 0.0;   // in objective_tile's order
-#pragma unroll
-      for (int d = 16; d > 0; d >>= 1) {
-        vmax = fmax(vmax, __shfl_xor_sync(0xffffffffu, vmax, d));
-        nviol += __shfl_xor_sync(0xffffffffu, nviol, d);
-      }
-      if (lane == 0) {
-        redv[tid >> 5] = vmax; redn[tid >> 5] = nviol;
-#pragma unroll
-        for (int u = 0; u < OBJ_LANES / CT; u++) redo[(tid + CT * u) >> 5] = gsum[u];
-      }
-      pbq_bar();
-      if (tid == 32 && row == 0) {
-        double tot = 0.0;
-        for (int w = 0; w < OBJ_LANES / 32; w++) tot += redo[w];
-        A.scal[(long long)s * NSCAL + 0] = tot;
-      }
-      if (tid < 32) {
-        vmax = tid < CT / 32 ? redv[tid] : 0.0; nviol = tid < CT / 32 ? redn[tid] : 0;
-#pragma unroll
-        for (int d = 16; d > 0; d >>= 1) {
-          vmax = fmax(vmax, __shfl_xor_sync(0xffffffffu, vmax, d));
-          nviol += __shfl_xor_sync(0xffffffffu, nviol, d);
-        }
-        if (tid == 0) {
-          double* scal = A.scal + (long long)s * NSCAL;
-          if (vmax > 0.0) atomicMax((unsigned long long*)(scal + 1), (unsigned long long)__double_as_longlong(vmax));
-          if (nviol) atomicAdd(scal + 2, (double)nviol);
-        }
-      }
-    }
-    pbq_bar();                                                 // the accumulators (zeroed by their owners) and the reduction arrays are reused by the next item
-  }
-}
-
-// ---- PB* residuals, scenario-resident, gathered from shared memory ---------------------------------------------------
-// The list-walking kernel gathers every flow variable through its own 32-byte L2 sector; the element-ordered kernel
-// above avoids that with ~75 barrier-separated steps per scenario and pays for them in issue slots.  Third form: the P row
-// and the Q row of a scenario are separate work items, and an item's inputs come to the SM as a handful of LARGE
-// cp.async.bulk copies -- its generator injections, then each flow array in two halves (two buffers of nr / 2
-// doubles: together ~200 KB for case13659pegase) -- while thread-per-bus walks the bus's lists exactly like the
-// list-walking kernel (generators, Sij ascending, Sji ascending: the reference's order, accumulators in registers
-// across the phases), reading the terms from shared memory.  Six phases per item, one CTA barrier each; the copy of the
-// next phase's half (and of the next item's first arrays) is in flight while the current one is walked.
-//   phase 0 generators | 1 Sij, branches [0, h) | 2 Sij, [h, nr) | 3 Sji, [0, h) | 4 Sji, [h, nr) | 5 shunt, load, out
-// Plan table: the list segment of every bus for phases 0-4 (pbg_seg [5][nb]: first entry | length << 24; generators index
-// gen_idx, the others the half-edge list he_ks = 2 * branch + side, Sij ascending then Sji ascending, cut where the branch
-// index crosses h).  Bitwise identical to pb_bus_g_kernel.
-// ask the copy engine to bring elements [0, n) of p into L2 (whole 16-byte units inside the range)
-__device__ __forceinline__ void l2_prefetch(const double* p, int n) {
-  const unsigned long long a = reinterpret_cast<unsigned long long>(p);
-  const unsigned long long a0 = (a + 15ull) & ~15ull, a1 = (a + 8ull * (unsigned long long)n) & ~15ull;
-  if (a1 > a0) asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(a0), "r"((int)(a1 - a0)) : "memory");
-}
-constexpr int PBG_T = 1024;
-constexpr int PBG_KB = 16;          // buses per thread (registers): networks of up to PBG_T * PBG_KB buses
-static_assert(PBG_T == OBJ_LANES, "the CTA's threads are the objective's virtual lanes");
-
-template <int FORM>
-__global__ void __launch_bounds__(PBG_T, 1) pb_bus_g_gather_kernel(const __grid_constant__ DevPlan P, const __grid_constant__ EvalArgs A) {
-  extern __shared__ __align__(128) unsigned char pbg_smem[];
-  __shared__ double redv[PBG_T / 32], redo[PBG_T / 32];
-  __shared__ int redn[PBG_T / 32];
-  __shared__ __align__(8) uint64_t bar[3];                     // full: generator buffer, buffer A, buffer B
-  const int tid = threadIdx.x;
-  const int h = P.pbg_half, capb = ((max(h, P.nr - h) + 2) * 8 + 127) & ~127;
-  double* const bufA = reinterpret_cast<double*>(pbg_smem);
-  double* const bufB = reinterpret_cast<double*>(pbg_smem + capb);
-  double* const bufG = reinterpret_cast<double*>(pbg_smem + 2 * capb);
-  const bool wg = (A.what & EV_G) != 0;
-  const int n_items = 2 * A.S;
-  if (tid == 0) {
-    for (int q = 0; q < 3; q++) mbar_init(bar + q, 1);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  __syncthreads();
-  // a copy of elements [0, n) of `arr` into `buf`: from arr - lo (16-byte aligned), an even number of doubles; returns lo.
-  // `open_end`: nothing readable is known to follow the array -- an odd total then leaves the last element out (its
-  // readers take it from global memory), otherwise the copy runs one element over (the next half, variable or scenario)
-  auto copy_in = [&](double* buf, uint64_t* b, const double* arr, int n, bool open_end) {
-    const int lo = (int)((reinterpret_cast<unsigned long long>(arr) >> 3) & 1ull);
-    int cnt = lo + n;
-    if (cnt & 1) cnt += open_end ? -1 : 1;
-    mbar_expect_tx(b, cnt * 8);
-    if (cnt > 0) bulk_load(buf, arr - lo, cnt * 8, b);
-  };
-  // the arrays of item `it`: 0 generators, 1 / 2 the Sij flow [0, h) / [h, nr), 3 / 4 the Sji flow
-  auto item_array = [&](int it, int a, int& n) -> const double* {
-    const int s = it >> 1, row = it & 1;
-    const double* x = A.x + (long long)s * A.ldx;
-    if (a == 0) { n = P.ng; return x + (row ? P.o_qg : P.o_pg); }
-    const double* f = x + P.o_f[(a >= 3 ? 2 : 0) + row];
-    if (a & 1) { n = h; return f; }
-    n = P.nr - h; return f + h;
-  };
-  auto issue = [&](int it, int a) {                            // thread 0
-    if (it >= n_items) return;
-    int n;
-    const double* arr = item_array(it, a, n);
-    const bool open_end = (a == 0 || a == 2 || a == 4) && (it >> 1) == A.S - 1;
-    copy_in(a == 0 ? bufG : ((a & 1) ? bufA : bufB), bar + (a == 0 ? 0 : ((a & 1) ? 1 : 2)), arr, n, open_end);
-  };
-  if (tid == 0) { issue(blockIdx.x, 0); issue(blockIdx.x, 1); issue(blockIdx.x, 2); }
-  unsigned phG = 0, phA = 0, phB = 0;                          // parities of the next completion of each buffer
-  for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
-    const int s = it >> 1, row = it & 1, nxt = it + gridDim.x;
-    const double* __restrict__ x = A.x + (long long)s * A.ldx;
-    const bool lastrow = s == A.S - 1;
-    double acc[PBG_KB];
-    int n;
-    const double* arr;
-    // one phase: the list segment of every owned bus (first entry | length << 24, plan table pbg_seg [5][nb]) is loaded for
-    // a group of buses, then the first two list entries of each (most segments hold one or two terms) -- all of a group's
-    // loads in flight together, two L2 latencies per group instead of one per term -- then the lists are walked
-    constexpr int GRP = 8;
-    auto phase = [&](int ph, const int32_t* __restrict__ list, int shift, int base, const double* buf, bool open_end) {
-      const int lo = (int)((reinterpret_cast<unsigned long long>(arr) >> 3) & 1ull);
-      const bool miss = open_end && ((lo + n) & 1);            // the array's last element is not in the buffer
-      auto term = [&](int e) { const int i = (e >> shift) - base; return (miss && i == n - 1) ? arr[i] : buf[i + lo]; };
-#pragma unroll
-      for (int k0 = 0; k0 < PBG_KB; k0 += GRP) {
-        unsigned sg[GRP];
-        int e0[GRP], e1[GRP];
-#pragma unroll
-        for (int u = 0; u < GRP; u++) { const int b = tid + (k0 + u) * PBG_T; sg[u] = b < P.nb ? P.pbg_seg[ph * P.nb + b] : 0u; }
-#pragma unroll
-        for (int u = 0; u < GRP; u++) {
-          const int q0 = (int)(sg[u] & 0xffffffu), len = (int)(sg[u] >> 24);
-          e0[u] = len > 0 ? list[q0] : 0;
-          e1[u] = len > 1 ? list[q0 + 1] : 0;
-        }
-#pragma unroll
-        for (int u = 0; u < GRP; u++) {
-          const int q0 = (int)(sg[u] & 0xffffffu), len = (int)(sg[u] >> 24);
-          double a = acc[k0 + u];
-          if (len > 0) a = a + term(e0[u]);
-          if (len > 1) a = a + term(e1[u]);
-          for (int q = q0 + 2; q < q0 + len; q++) a = a + term(list[q]);
-          acc[k0 + u] = a;
-        }
-      }
-    };
-    // ---- phase 0: generators (formulations.jl:177-180)
-    arr = item_array(it, 0, n);
-#pragma unroll
-    for (int k = 0; k < PBG_KB; k++) acc[k] = 0.0;
-    if (tid == 0) {                                            // phase 5 reads these per bus: have them in L2 by then
-      if constexpr (FORM == PBRARV) l2_prefetch(x + P.o_a, P.nb);
-      l2_prefetch(x + P.o_b, P.nb);
-      const double* l = row ? A.Qd : A.Pd;
-      if (l) l2_prefetch(l + (long long)s * A.ldl, P.nb);
-    }
-    mbar_wait(bar + 0, phG); phG ^= 1u;
-    phase(0, P.gen_idx, 0, 0, bufG, lastrow);
-    __syncthreads();
-    if (tid == 0) issue(nxt, 0);
-    // ---- phases 1-4: Sij then Sji (:188-196), each in two halves
-#pragma unroll 1
-    for (int ph = 1; ph <= 4; ph++) {
-      arr = item_array(it, ph, n);
-      const bool isA = ph & 1;
-      if (isA) { mbar_wait(bar + 1, phA); phA ^= 1u; } else { mbar_wait(bar + 2, phB); phB ^= 1u; }
-      phase(ph, P.he_ks, 1, isA ? 0 : h, isA ? bufA : bufB, !isA && lastrow);
-      __syncthreads();
-      if (tid == 0) { if (ph <= 2) issue(it, ph + 2); else issue(nxt, ph - 2); }
-    }
-    // ---- phase 5: the bus's own shunt term (:256-258 | :264-266), minus the load (:291-292), out
-    double* __restrict__ gd = wg ? A.g + (long long)s * A.ldg + row : nullptr;
-    const double* __restrict__ kk = row ? P.Bl : P.Gl;
-    const double* const ldp = row ? A.Qd : A.Pd;
-    const double* __restrict__ ld = ldp ? ldp + (long long)s * A.ldl : (row ? P.Qd0 : P.Pd0);
-    double vmax = 0.0;
-    int nviol = 0;
-    constexpr int PB5 = 2;                                     // buses whose inputs are in flight together (registers)
-#pragma unroll
-    for (int k0 = 0; k0 < PBG_KB; k0 += PB5) {
-      double vi[PB5], vr[PB5], kc[PB5], lv[PB5];
-#pragma unroll
-      for (int u = 0; u < PB5; u++) {
-        const int b = tid + (k0 + u) * PBG_T;
-        vi[u] = vr[u] = kc[u] = lv[u] = 0.0;
-        if (b < P.nb) {
-          if constexpr (FORM == PBRARV) vi[u] = x[P.o_a + b];
-          vr[u] = x[P.o_b + b]; kc[u] = kk[b]; lv[u] = ld[b];
-        }
-      }
-#pragma unroll
-      for (int u = 0; u < PB5; u++) {
-        const int b = tid + (k0 + u) * PBG_T;
-        if (b < P.nb) {
-          double m2;
-          if constexpr (FORM == PBRARV) m2 = vr[u] * vr[u] + vi[u] * vi[u];
-          else m2 = vr[u] * vr[u];
-          double a = acc[k0 + u];
-          a = row ? a + kc[u] * m2 : a - kc[u] * m2;
-          const double gv = a - lv[u];
-          if (wg) gd[2 * b] = gv;
-          vmax = fmax(vmax, fabs(gv));
-          nviol += fabs(gv) > A.viol_tol ? 1 : 0;
-        }
-      }
-    }
-    if (A.scal) {                                              // CTA-uniform
-      double gsum = 0.0;
-      if (row == 0) gsum = objective_lane(P, x, tid);          // the objective scalar, in objective_tile's order
-#pragma unroll
-      for (int d = 16; d > 0; d >>= 1) {
-        vmax = fmax(vmax, __shfl_xor_sync(0xffffffffu, vmax, d));
-        nviol += __shfl_xor_sync(0xffffffffu, nviol, d);
-      }
-      if ((tid & 31) == 0) { redv[tid >> 5] = vmax; redn[tid >> 5] = nviol; redo[tid >> 5] = gsum; }
-      __syncthreads();
-      if (tid == 32 && row == 0) {
-        double tot = 0.0;
-        for (int w = 0; w < PBG_T / 32; w++) tot += redo[w];
-        A.scal[(long long)s * NSCAL + 0] = tot;
-      }
-      if (tid < 32) {
-        vmax = redv[tid]; nviol = redn[tid];
-#pragma unroll
-        for (int d = 16; d > 0; d >>= 1) {
-          vmax = fmax(vmax, __shfl_xor_sync(0xffffffffu, vmax, d));
-          nviol += __shfl_xor_sync(0xffffffffu, nviol, d);
-        }
-        if (tid == 0) {
-          double* scal = A.scal + (long long)s * NSCAL;
-          if (vmax > 0.0) atomicMax((unsigned long long*)(scal + 1), (unsigned long long)__double_as_longlong(vmax));
-          if (nviol) atomicAdd(scal + 2, (double)nviol);
-        }
-      }
-      __syncthreads();                                         // the reduction arrays are reused by the next item
-    }
   }
 }
 
@@ -2683,10 +2195,7 @@ cudaError_t configure_form(int src, size_t smem_branch, size_t smem_bus, size_t 
   if (e != cudaSuccess) return e;
   if constexpr (FORM == PBRAPV || FORM == PBRARV) {
     if (smem_pbs > 0) {
-      e = cudaFuncSetAttribute(pb_bus_g_scn_kernel<FORM, 1024, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_pbs);
-      if (e == cudaSuccess) e = cudaFuncSetAttribute(pb_bus_g_scn_kernel<FORM, 512, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_pbs);
-      if (e == cudaSuccess) e = cudaFuncSetAttribute(pb_bus_g_tma_kernel<FORM>, cudaFuncAttributeMaxDynamicSharedMemorySize, 225 * 1024);
-      if (e == cudaSuccess) e = cudaFuncSetAttribute(pb_bus_g_gather_kernel<FORM>, cudaFuncAttributeMaxDynamicSharedMemorySize, 225 * 1024);
+      e = cudaFuncSetAttribute(pb_bus_g_scn_kernel<FORM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_pbs);
       if (e != cudaSuccess) return e;
     }
   }
@@ -2891,29 +2400,6 @@ static int env_int(const char* name, int dflt) {
   return v > 0 ? v : dflt;
 }
 
-// pb_bus_g_gather_kernel: two half-array buffers + the generator buffer; 0 when it cannot run
-static size_t pbg_smem_bytes(const DevPlan& P) {
-  if (!P.pbs_ok || !P.pbg_seg || P.nb > PBG_T * PBG_KB) return 0;
-  const int64_t h = P.pbg_half, capb = ((std::max<int64_t>(h, P.nr - h) + 2) * 8 + 127) & ~127LL;
-  const int64_t b = 2 * capb + (((int64_t)P.ng + 2) * 8 + 127);
-  return b <= 224 * 1024 ? (size_t)b : 0;
-}
-static int pbq_fills(const DevPlan& P) {
-  const int s_gen = (P.ng + PBS_WAVE - 1) / PBS_WAVE, s_br = (P.nr + PBS_WAVE - 1) / PBS_WAVE, s_bus = (P.nb + PBS_WAVE - 1) / PBS_WAVE;
-  return s_gen + 2 * s_br + (P.form == PBRARV ? 3 : 2) * s_bus;
-}
-// pb_bus_g_tma_kernel: accumulators (8 bytes per bus) + as many stages as fit (at most 12) + their mbarriers; 0 when it cannot run
-static int pbq_stages(const DevPlan& P) {
-  if (!P.pbs_ok || !P.pbs_code4 || pbs_smem_bytes(P) == 0) return 0;
-  const int64_t accb = ((int64_t)P.nb * 8 + 127) & ~127LL;
-  const int64_t n = (224 * 1024 - accb - 256 - 32 * (int64_t)pbq_fills(P)) / PBQ_STAGE;
-  if (n < PBQ_MIN_STAGES) return 0;
-  return (int)std::min<int64_t>(n, std::max(3, env_int("PS_PBQ_STAGES", 12)));
-}
-static size_t pbq_smem_bytes(const DevPlan& P, int nst) {      // accumulators | ring | mbarriers | fill table [2][fills]
-  return (size_t)((((int64_t)P.nb * 8 + 127) & ~127LL) + (int64_t)nst * PBQ_STAGE + 2 * nst * 8 + 2 * 16 * (int64_t)pbq_fills(P) + 64);
-}
-
 cudaError_t configure_eval(int form, int src, int64_t smem_branch_bytes, int64_t smem_bus_bytes, int64_t smem_wt_bytes,
                            int64_t smem_pbs_bytes) {
   const size_t sb = (size_t)smem_branch_bytes, su = (size_t)smem_bus_bytes, sw = (size_t)smem_wt_bytes, sp = (size_t)smem_pbs_bytes;
@@ -2962,12 +2448,10 @@ static cudaError_t launch_bus_warp(const DevPlan& P, const EvalArgs& A, size_t s
 }
 template <int FORM>
 cudaError_t launch_pb_form(const DevPlan& P, const EvalArgs& A, cudaStream_t st, int nchunks, int64_t* launches,
-                           cudaEvent_t* ev, unsigned* ev_mask, const SideLane* side, bool* forked) {
-  auto rec_on = [&](int id, int end, cudaStream_t s) { if (ev) { cudaEventRecord(ev[2 * id + end], s); if (end && ev_mask) *ev_mask |= 1u << id; } };
-  auto rec = [&](int id, int end) { rec_on(id, end, st); };
+                           cudaEvent_t* ev, unsigned* ev_mask) {
+  auto rec = [&](int id, int end) { if (ev) { cudaEventRecord(ev[2 * id + end], st); if (end && ev_mask) *ev_mask |= 1u << id; } };
   if constexpr (FORM == PBRAPV || FORM == PBRARV) {
     int obj_from = 0;                                          // scenarios [0, obj_from) got their objective scalar from the bus kernel
-    bool jh_done = false, bus_end_recorded = false;
     if ((A.what & EV_G) || A.scal) {
       rec(K_BUS, 0);
       // scenario-resident residuals when a batch fills the machine (a CTA works through whole scenarios one after the
@@ -2978,35 +2462,7 @@ cudaError_t launch_pb_form(const DevPlan& P, const EvalArgs& A, cudaStream_t st,
         static int n_sm = 0;
         if (n_sm == 0) { int dv = 0; cudaGetDevice(&dv); cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dv); if (n_sm <= 0) n_sm = 148; }
         const int per_sm = (int)std::min<int64_t>(2, (220 * 1024) / smem);   // 1024-thread CTAs: at most 2 per SM
-        // Two ways of running beside another kernel (side lane, batches that fill the machine several times over):
-        //  co-resident -- with the slot kernel of the same evaluation: the residual CTA takes the 512 x 2 shape (half of
-        //    the SM's threads and registers) and pb_bus_jh_kernel's CTAs fill the other half of every SM.  The residual CTA
-        //    is bound by issue / barrier latency, the slot CTAs by the load/store path: together they fill the SM
-        //    (PS_NO_PBCO: one after the other);
-        //  partitioned -- residual-only calls (nothing but the branch kernel runs beside): the 1024-thread CTAs take
-        //    `k_side` SMs for themselves -- nothing fits next to their accumulators -- and branch_g_kernel gets the rest at
-        //    once (PS_PBS_SIDE=k; measured: gpurun_out/r2c22_side.log -- it does not pay beside the HBM-bound branch_bulk_kernel)
-        // the copy-engine-fed kernel (P and Q rows as separate items): opt-in (PS_PBQ=1).  Measured on case13659pegase,
-        // 4096 scenarios: 1.85 ms against 1.57 ms for the register-fed kernel -- with one warp given to the producer and the
-        // accumulators taking half of the shared memory, 16 consumer warps are left per SM and the step (wait, two
-        // shared-memory read-modify-writes, barrier) becomes latency-bound (profiles/r02_ncu_pb_bus_summary.txt)
-        const int nst = pbq_stages(P);
-        const size_t smem_g = pbg_smem_bytes(P);
-        // the gather-from-shared-memory kernel: opt-in (PS_PBG=1).  Measured on case13659pegase, 4096 scenarios: 3.6-4.2 ms
-        // against 1.57 -- 70 list-segment visits per thread and item cost 474 k warp instructions per scenario, three times
-        // the element-ordered kernel's, and each visit waits for its L2-resident list entries (profiles/r02_ncu_pb_bus_summary.txt)
-        if (smem_g > 0 && !A.status && getenv("PS_PBG")) {
-          pb_bus_g_gather_kernel<FORM><<<dim3((unsigned)std::min(2 * A.S, n_sm)), PBG_T, smem_g, st>>>(P, A);
-          obj_from = A.S;
-        } else if (nst > 0 && !A.status && getenv("PS_PBQ")) {
-          pb_bus_g_tma_kernel<FORM><<<dim3((unsigned)std::min(2 * A.S, n_sm)), PBQ_T, pbq_smem_bytes(P, nst), st>>>(P, A, nst);
-          obj_from = A.S;
-        } else {
-        const bool big = side && ((per_sm == 1 && A.S >= 4 * n_sm) || getenv("PS_PBS_FORCE"));   // (PS_PBS_FORCE: tests, small networks)
-        const bool co = big && (A.what & (EV_J | EV_H)) && getenv("PS_PBCO");
-        int k_side = 0;
-        if (big && !co && (!(A.what & (EV_J | EV_H)) || getenv("PS_PBS_SIDE_ANY"))) k_side = std::min(env_int("PS_PBS_SIDE", PS_PBS_SIDE_DEFAULT), n_sm - 8);
-        const int slots = k_side > 0 ? k_side : n_sm * per_sm;
+        const int slots = n_sm * per_sm;
         // a CTA works through whole scenarios: S scenarios take ceil(S / slots) rounds.  When the last round would be
         // mostly empty (512 scenarios on 148 SMs: 3.46 rounds) the remainder goes to the list-walking kernel instead --
         // same results bit for bit, disjoint scenario rows
@@ -3014,29 +2470,8 @@ cudaError_t launch_pb_form(const DevPlan& P, const EvalArgs& A, cudaStream_t st,
         const int n_scn = (A.S > slots && rem > 0 && rem < (slots * 3) / 5) ? A.S - rem : A.S;
         EvalArgs As = A;
         As.S = n_scn;
-        cudaStream_t sb = st;
-        if (k_side > 0 || co) {                                // fork: the side lane starts where `st` is now
-          cudaEventRecord(side->fork, st);
-          cudaStreamWaitEvent(side->st, side->fork, 0);
-          *forked = true;
-        }
-        if (k_side > 0) {
-          sb = side->st;
-          rec_on(K_BUS, 0, sb);                                // (replaces the record on `st` above: same event, last record counts)
-        }
-        const dim3 gs((unsigned)std::min(n_scn, slots));
-        if (co) pb_bus_g_scn_kernel<FORM, 512, 2><<<gs, 512, (size_t)smem, sb>>>(P, As);
-        else pb_bus_g_scn_kernel<FORM, 1024, 1><<<gs, 1024, (size_t)smem, sb>>>(P, As);
+        pb_bus_g_scn_kernel<FORM><<<dim3((unsigned)std::min(n_scn, slots)), PBS_T, (size_t)smem, st>>>(P, As);
         obj_from = n_scn;
-        if (co) {                                              // the slot kernel beside it (launched second: the residual CTAs are resident first)
-          const int n = (P.j_br0 > P.h_br0 ? P.j_br0 : P.h_br0) / 4 + 1;
-          rec_on(K_BUS_JH, 0, side->st);
-          pb_bus_jh_kernel<FORM><<<dim3((unsigned)((n + PBT - 1) / PBT), (unsigned)nchunks), PBT, 0, side->st>>>(P, A);
-          rec_on(K_BUS_JH, 1, side->st);
-          if (launches) *launches += 1;
-          cudaEventRecord(side->join, side->st);               // launch_eval joins after the last kernel on `st`
-          jh_done = true;
-        }
         if (n_scn < A.S) {
           EvalArgs Ar = A;
           const long long o = n_scn;
@@ -3048,22 +2483,16 @@ cudaError_t launch_pb_form(const DevPlan& P, const EvalArgs& A, cudaStream_t st,
           if (Ar.g) Ar.g += o * A.ldg;
           if (Ar.scal) Ar.scal += o * NSCAL;
           const int nch = (Ar.S + Ar.chunk - 1) / Ar.chunk;
-          pb_bus_g_kernel<FORM><<<dim3((unsigned)((P.nb + PBT - 1) / PBT), (unsigned)nch), PBT, 0, sb>>>(P, Ar);
+          pb_bus_g_kernel<FORM><<<dim3((unsigned)((P.nb + PBT - 1) / PBT), (unsigned)nch), PBT, 0, st>>>(P, Ar);
           if (launches) *launches += 1;
-        }
-        if (k_side > 0) {
-          rec_on(K_BUS, 1, sb);
-          bus_end_recorded = true;
-          cudaEventRecord(side->join, sb);                     // launch_eval joins after the last kernel on `st`
-        }
         }
       } else {
         pb_bus_g_kernel<FORM><<<dim3((unsigned)((P.nb + PBT - 1) / PBT), (unsigned)nchunks), PBT, 0, st>>>(P, A);
       }
-      if (!bus_end_recorded) rec(K_BUS, 1);
+      rec(K_BUS, 1);
       if (launches) *launches += 1;
     }
-    if ((A.what & (EV_J | EV_H)) && !jh_done) {
+    if (A.what & (EV_J | EV_H)) {
       const int n = (P.j_br0 > P.h_br0 ? P.j_br0 : P.h_br0) / 4 + 1;
       rec(K_BUS_JH, 0);
       pb_bus_jh_kernel<FORM><<<dim3((unsigned)((n + PBT - 1) / PBT), (unsigned)nchunks), PBT, 0, st>>>(P, A);
@@ -3087,8 +2516,8 @@ cudaError_t launch_pb_form(const DevPlan& P, const EvalArgs& A, cudaStream_t st,
   }
 }
 static cudaError_t launch_pb(const DevPlan& P, const EvalArgs& A, cudaStream_t stream, int nchunks, int64_t* launches,
-                             cudaEvent_t* ev, unsigned* ev_mask, const SideLane* side, bool* forked) {
-#define PS_CALL(F) launch_pb_form<F>(P, A, stream, nchunks, launches, ev, ev_mask, side, forked)
+                             cudaEvent_t* ev, unsigned* ev_mask) {
+#define PS_CALL(F) launch_pb_form<F>(P, A, stream, nchunks, launches, ev, ev_mask)
   PS_FORM_SWITCH(PS_CALL)
 #undef PS_CALL
 }
@@ -3147,21 +2576,8 @@ struct KTimer {                        // records an event pair around one kerne
 // One evaluation = two launches on `stream`: the bus kernel (nodal balances + objective scalar) and the branch
 // kernel (flow definitions / limits / cones) -- direct when the branch blocks of J and H start on 32-byte
 // sectors in every scenario row, staged otherwise.
-static cudaError_t launch_eval_main(const DevPlan& P, const EvalArgs& A0, int64_t smem_branch_bytes, int64_t smem_bus_bytes,
-                                    cudaStream_t stream, int64_t* launches, cudaEvent_t* ev, unsigned* ev_mask,
-                                    const SideLane* side, bool* forked);
-
 cudaError_t launch_eval(const DevPlan& P, const EvalArgs& A0, int64_t smem_branch_bytes, int64_t smem_bus_bytes,
-                        cudaStream_t stream, int64_t* launches, cudaEvent_t* ev, unsigned* ev_mask, const SideLane* side) {
-  bool forked = false;
-  const cudaError_t e = launch_eval_main(P, A0, smem_branch_bytes, smem_bus_bytes, stream, launches, ev, ev_mask, side, &forked);
-  if (forked) cudaStreamWaitEvent(stream, side->join, 0);      // join: whatever follows on `stream` sees the side lane's rows
-  return e;
-}
-
-static cudaError_t launch_eval_main(const DevPlan& P, const EvalArgs& A0, int64_t smem_branch_bytes, int64_t smem_bus_bytes,
-                                    cudaStream_t stream, int64_t* launches, cudaEvent_t* ev, unsigned* ev_mask,
-                                    const SideLane* side, bool* forked) {
+                        cudaStream_t stream, int64_t* launches, cudaEvent_t* ev, unsigned* ev_mask) {
   if (A0.S <= 0) return cudaSuccess;
   EvalArgs A = A0;
   cudaError_t e = cudaSuccess;
@@ -3176,7 +2592,7 @@ static cudaError_t launch_eval_main(const DevPlan& P, const EvalArgs& A0, int64_
   } else if (pb_fast) {
     A.chunk = std::max(env_int("PS_CHUNK_PB", 4), min_chunk);
     const int nchunks = (A.S + A.chunk - 1) / A.chunk;
-    e = launch_pb(P, A, stream, nchunks, launches, ev, ev_mask, side, forked);
+    e = launch_pb(P, A, stream, nchunks, launches, ev, ev_mask);
     if (e != cudaSuccess) return e;
   } else if (P.n_bus_tiles > 0 || A.scal) {
     // bus tiles are few and pay a per-CTA staging cost: longer scenario chunks than the branch kernel

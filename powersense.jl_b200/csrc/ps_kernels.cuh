@@ -34,10 +34,6 @@ struct DevPlan {                    // passed to kernels by value (constant bank
   int pbs_ok;                                       // PB* scenario-resident residual kernel available (ps_plan.h: pbs_code)
   const int32_t* pbs_code;                          // [ng | nr | nr] bus | rank << 24, -1 = no term
   const uint8_t* pbs_wmax;                          // highest rank per step (generator, Sij, Sji steps)
-  const int32_t* pbs_code4;                         // the same codes, every segment on a 16-byte boundary and a step of padding
-  int pbs_off4[3];                                  //   behind the table (pb_bus_g_tma_kernel copies whole steps); segment offsets
-  int pbg_half;                                     // pb_bus_g_gather_kernel: branches [0, pbg_half) | [pbg_half, nr) are the two halves
-  const uint32_t* pbg_seg;                          //   [5][nb] list segment (first | length << 24) of a bus per phase: generators, Sij lo / hi, Sji lo / hi
   int cost_order;
   const int32_t *f, *t;
   const double *Gf, *Bf, *Gt, *Bt, *gf, *bf, *gt, *bt, *Imax, *Gl, *Bl, *Pd0, *Qd0;
@@ -79,13 +75,8 @@ struct EvalArgs {
 // Launches one evaluation (bus kernel + branch kernel) on `stream`; *launches is incremented per kernel.
 // kernel ids for the optional per-kernel timing: events ev[2*id], ev[2*id+1] are recorded around kernel `id`
 enum KernelId : int { K_BUS = 0, K_BUS_JH = 1, K_OBJ = 2, K_BRANCH = 3, K_COUNT = 4 };
-// A second stream (with its fork / join events) on which launch_eval may place a kernel that is to run BESIDE the
-// others of the evaluation: the PB* scenario-resident residual kernel keeps whole SMs to itself (its accumulators fill
-// their shared memory), so on a few of them it overlaps the HBM-bound branch kernel instead of preceding it.
-struct SideLane { cudaStream_t st; cudaEvent_t fork, join; };
 cudaError_t launch_eval(const DevPlan& P, const EvalArgs& A, int64_t smem_branch_bytes, int64_t smem_bus_bytes,
-                        cudaStream_t stream, int64_t* launches, cudaEvent_t* ev = nullptr, unsigned* ev_mask = nullptr,
-                        const SideLane* side = nullptr);
+                        cudaStream_t stream, int64_t* launches, cudaEvent_t* ev = nullptr, unsigned* ev_mask = nullptr);
 // opt the kernels of one formulation into the needed dynamic shared memory (once per device)
 cudaError_t configure_eval(int form, int src, int64_t smem_branch_bytes, int64_t smem_bus_bytes, int64_t smem_wt_bytes = 0,
                            int64_t smem_pbs_bytes = 0);

@@ -87,22 +87,6 @@ if __name__ == "__main__":
         os.environ["PS_NO_PBSCN"] = "1"
         run("case13659pegase", "PBRARVmodel", 2048, [8])
         del os.environ["PS_NO_PBSCN"]
-    if sel == "side":                      # the PB* residual kernel beside another kernel (launch_pb_form)
-        S = int(sys.argv[2]) if len(sys.argv) > 2 else 4096
-        for what in (7, 3):
-            for env in ({}, {"PS_NO_PBCO": "1"}):
-                os.environ.update(env)
-                print(f"-- what={what} {env or 'default (co-resident with the slot kernel)'}", flush=True)
-                run("case13659pegase", "PBRARVmodel", S, [16], what=what, steps=8)
-                for k in env:
-                    del os.environ[k]
-        for k in (0, 64, 74, 84, 96):
-            os.environ.pop("PS_PBS_SIDE", None)
-            if k:
-                os.environ["PS_PBS_SIDE"] = str(k)
-            print(f"-- g only, PS_PBS_SIDE={k}", flush=True)
-            run("case13659pegase", "PBRARVmodel", S, [16], what=1, steps=8)
-        os.environ.pop("PS_PBS_SIDE", None)
     if sel == "ncu_g":
         run("case13659pegase", "PBRARVmodel", 256, [4], what=1, steps=1)
     if sel == "ncu_c3":

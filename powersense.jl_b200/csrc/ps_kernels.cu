@@ -1424,6 +1424,82 @@ __host__ inline int wt_mode(const EvalArgs& A) {
   return WT_ANY;
 }
 
+// ---- residuals only, thread per bus (any formulation with nodal balances) -------------------------------------------
+// eval_constraint alone -- every trial point of the SLP line search -- writes 16 bytes per bus.  The warp-tile kernel's
+// residual-only instantiation still runs its phases (half-edge lanes, bus lanes, ordered slot sums, copy-out) once per
+// scenario: 245 SM cycles per 32 half-edges for one sincos and a dozen additions each.  Here a thread owns a bus and walks its
+// generator / half-edge / shunt lists like pb_bus_g_kernel does for the PB* models, forming each half-edge's pieces with the
+// same he_math and folding them with the same residual_math as the CTA-tile kernel (the reference's order and
+// association): no shared memory, no phases, any degree (hub buses included).  Bitwise equal to the other bus kernels.
+template <int FORM>
+__global__ void __launch_bounds__(PS_TPB) bus_g_list_kernel(const __grid_constant__ DevPlan P, const __grid_constant__ EvalArgs A) {
+  if constexpr (has_bus_rows(FORM)) {
+    constexpr bool PB = (FORM == PBRAPV || FORM == PBRARV);
+    const int s0 = blockIdx.y * A.chunk, s1 = min(A.S, s0 + A.chunk);
+    const int i = blockIdx.x * PS_TPB + threadIdx.x;
+    const bool act = i < P.nb;
+    const bool facts = (P.flags & FLAG_FACTS) != 0;
+    int g0 = 0, h0 = 0, f0 = 0;
+    OwnIn o{};
+    int deg = 0;
+    if (act) {
+      g0 = P.gen_ptr[i]; o.ngen = P.gen_ptr[i + 1] - g0;
+      h0 = P.he_ptr[i]; deg = P.he_ptr[i + 1] - h0;
+      if (facts) { f0 = P.sh_ptr[i]; o.nsh = P.sh_ptr[i + 1] - f0; }
+      o.Gl = P.Gl[i]; o.Bl = P.Bl[i];
+    }
+    const bool wg = (A.what & EV_G) != 0;
+    for (int s = s0; s < s1; s++) {
+      double vmax = 0.0;
+      int nviol = 0;
+      if (act) {
+        const double* __restrict__ x = A.x + (long long)s * A.ldx;
+        const uint8_t* __restrict__ stp = A.status ? A.status + (long long)s * A.ldst : nullptr;
+        const double* pd = A.Pd ? A.Pd + (long long)s * A.ldl : P.Pd0;
+        const double* qd = A.Qd ? A.Qd + (long long)s * A.ldl : P.Qd0;
+        o.va0 = x[P.o_a + i]; o.vb0 = x[P.o_b + i];
+        if constexpr (FORM == CBRAWV) o.W = x[P.o_Wd + i];
+        // the pieces of one half-edge, formed when the fold first asks for them
+        double pc[6];
+        int cq = -1;
+        auto pieces = [&](int q) {
+          const int e = h0 + q, ks = P.he_ks[e], k = ks >> 1;
+          HeIn in;
+          in.side = ks & 1;
+          in.st = stp ? (double)stp[k] : 1.0;
+          if constexpr (is_PN(FORM)) {
+            const int oth = P.he_other[e];
+            in.v0 = x[P.o_a + oth]; in.v1 = x[P.o_b + oth];
+            in.c0 = P.he_c[e]; in.c1 = P.he_c[(long long)P.nhe + e]; in.c2 = P.he_c[2LL * P.nhe + e]; in.c3 = P.he_c[3LL * P.nhe + e];
+          } else {
+            in.v0 = x[P.o_f[0 + 2 * in.side] + k]; in.v1 = x[P.o_f[1 + 2 * in.side] + k];
+            in.c0 = in.c1 = in.c2 = in.c3 = 0.0;
+          }
+          in.va0 = o.va0; in.vb0 = o.vb0; in.muP = in.muQ = 0.0;
+          NullW sj, sh;
+          he_math<FORM>(in, sj, sh, [&](int kk, double v) { pc[kk] = v; }, true);
+          if constexpr (PB) { pc[0] = in.st; pc[1] = in.v0; pc[2] = in.v1; }
+        };
+        double gP, gQ;
+        residual_math<FORM>(
+            o, deg, pd[i], qd[i],
+            [&](int q, double& pg, double& qg) { const int g = P.gen_idx[g0 + q]; pg = x[P.o_pg + g]; qg = x[P.o_qg + g]; },
+            [&](int q, double& st, double& fp, double& fq) { if (q != cq) { cq = q; pieces(q); } st = pc[0]; fp = pc[1]; fq = pc[2]; },
+            [&](int q, int k) { if (q != cq) { cq = q; pieces(q); } return pc[k]; },
+            [&](int q) { return x[P.o_bss + P.sh_idx[f0 + q]]; }, gP, gQ);
+        if (wg) {
+          double* gd = A.g + (long long)s * A.ldg + 2 * i;
+          if ((reinterpret_cast<unsigned long long>(gd) & 15) == 0) *reinterpret_cast<double2*>(gd) = make_double2(gP, gQ);
+          else { gd[0] = gP; gd[1] = gQ; }
+        }
+        vmax = fmax(fabs(gP), fabs(gQ));
+        nviol = (fabs(gP) > A.viol_tol ? 1 : 0) + (fabs(gQ) > A.viol_tol ? 1 : 0);
+      }
+      reduce_scalars(A.scal ? A.scal + (long long)s * NSCAL : nullptr, vmax, nviol);
+    }
+  }
+}
+
 // ---- PB* balances, fast path (PBRAPV / PBRARV without switched shunts) ------------------------------------------
 // The nodal balance of a power-branch-flow model is linear in the generator and flow variables
 // (formulations.jl:188-196): its Jacobian entries are the constant 1 (times the branch status) except the 1-2
@@ -2441,6 +2517,16 @@ static cudaError_t launch_bus(const DevPlan& P, const EvalArgs& A, size_t smem, 
   PS_FORM_SWITCH(PS_CALL)
 #undef PS_CALL
 }
+template <int FORM>
+cudaError_t launch_bus_g_list_form(const DevPlan& P, const EvalArgs& A, cudaStream_t st, dim3 grid) {
+  bus_g_list_kernel<FORM><<<grid, PS_TPB, 0, st>>>(P, A);
+  return cudaGetLastError();
+}
+static cudaError_t launch_bus_g_list(const DevPlan& P, const EvalArgs& A, cudaStream_t stream, dim3 grid) {
+#define PS_CALL(F) launch_bus_g_list_form<F>(P, A, stream, grid)
+  PS_FORM_SWITCH(PS_CALL)
+#undef PS_CALL
+}
 static cudaError_t launch_bus_warp(const DevPlan& P, const EvalArgs& A, size_t smem, cudaStream_t stream, dim3 grid) {
 #define PS_CALL(F) launch_bus_warp_form<F>(P, A, smem, stream, grid)
   PS_FORM_SWITCH(PS_CALL)
@@ -2604,7 +2690,15 @@ cudaError_t launch_eval(const DevPlan& P, const EvalArgs& A0, int64_t smem_branc
     A.chunk = warp_tiles ? env_int("PS_CHUNK_WT", (int)(cw < 1 ? 1 : (cw > 16 ? 16 : cw))) : env_int("PS_CHUNK_BUS", (int)(c < 1 ? 1 : (c > 32 ? 32 : c)));
     A.chunk = std::max(A.chunk, min_chunk);
     const int nchunks = (A.S + A.chunk - 1) / A.chunk;
-    if (P.n_bus_tiles > 0) {
+    // residuals only: thread per bus (PS_NO_GLIST: the warp-tile kernel's residual-only instantiation)
+    const bool g_list = !(A.what & (EV_J | EV_H)) && !A.force_any && !getenv("PS_NO_GLIST") && !getenv("PS_NO_WARPBUS") && P.n_bus_tiles > 0;
+    if (g_list) {
+      if (launches) *launches += 1;
+      KTimer kt(ev, ev_mask, stream, K_BUS);
+      EvalArgs Ag = A;
+      Ag.chunk = std::max(env_int("PS_CHUNK_GL", 4), min_chunk);
+      e = launch_bus_g_list(P, Ag, stream, dim3((unsigned)((P.nb + PS_TPB - 1) / PS_TPB), (unsigned)((A.S + Ag.chunk - 1) / Ag.chunk)));
+    } else if (P.n_bus_tiles > 0) {
       if (launches) *launches += 1;
       KTimer kt(ev, ev_mask, stream, K_BUS);
       if (warp_tiles) {

@@ -1191,12 +1191,12 @@ __device__ __forceinline__ void wt_store_block(double* __restrict__ g, const dou
 }
 __device__ __forceinline__ void reduce_scalars_redux(double* scal, double vmax, int nviol) { reduce_scalars(scal, vmax, nviol); }
 
-// MODE: which outputs are compile-time constants.  WT_ANY: read from A.what / A.status at run time (any combination, status
-// masks); WT_FULL: g + J + H without a mask (the headline evaluation); WT_G: residuals only -- eval_constraint, every trial
-// point of the SLP line search: no derivative is formed at all; WT_GJ: g + J -- the SLP's LP set-up: no Hessian term is formed
+// MODE: which outputs are compile-time constants.  WT_ANY: read from A.what / A.status at run time (any combination);
+// WT_FULL: g + J + H without a mask (the headline evaluation); WT_GJ: g + J -- the SLP's LP set-up: no Hessian term is formed.
+// (Residuals alone -- eval_constraint, every trial point of the SLP line search -- go to bus_g_list_kernel.)
 // WT_ST added to one of the three specialised kinds: the same with a branch-status mask (N-1 sweeps: config 5 evaluates,
 // and its SLP line search re-evaluates, under a mask -- the run-time-flag instantiation costs those calls 10-30 %)
-enum WtMode : int { WT_ANY = 0, WT_FULL = 1, WT_G = 2, WT_GJ = 3, WT_ST = 4 };
+enum WtMode : int { WT_ANY = 0, WT_FULL = 1, WT_GJ = 3, WT_ST = 4 };
 template <int FORM, int MODE>
 __device__ __forceinline__ void bus_warp_body(const DevPlan& P, const EvalArgs& A, double* region, int tile, int s0, int s1) {
   if constexpr (has_bus_rows(FORM)) {
@@ -1213,10 +1213,9 @@ __device__ __forceinline__ void bus_warp_body(const DevPlan& P, const EvalArgs& 
     const bool has_status = (MODE & WT_ST) != 0 || (KIND == WT_ANY && A.status != nullptr);
     const bool need_g = wg || A.scal;
     const bool facts = (P.flags & FLAG_FACTS) != 0;
-    // the residual-only instantiation keeps no J / H image: its region is the G space and the lists
     double* const spJ = region;
-    double* const spH = spJ + (KIND == WT_G ? 0 : P.wt_jspace);
-    double* const spG = spH + (KIND == WT_G ? 0 : P.wt_hspace);
+    double* const spH = spJ + P.wt_jspace;
+    double* const spG = spH + P.wt_hspace;
     uint64_t* const multi = (uint64_t*)(spG + P.wt_gspace);     // multi-slot descriptors (ps_plan.h: wt_multi)
     const int oj0 = P.wt_ownj_ptr[t.u0], noj = P.wt_ownj_ptr[t.u1] - oj0;
     const int oh0 = P.wt_ownh_ptr[t.u0], noh = P.wt_ownh_ptr[t.u1] - oh0;
@@ -1226,8 +1225,7 @@ __device__ __forceinline__ void bus_warp_body(const DevPlan& P, const EvalArgs& 
     uint16_t* const owng = ownh + noh;
     // ---- scenario-independent set-up
     for (int q = lane; q < t.mn; q += 32) multi[q] = P.wt_multi[t.m0 + q];
-    if constexpr (KIND != WT_G)
-      for (int q = lane; q < P.wt_hspace; q += 32) spH[q] = 0.0;  // slots whose contributions are all structural zeros stay 0
+    for (int q = lane; q < P.wt_hspace; q += 32) spH[q] = 0.0;    // slots whose contributions are all structural zeros stay 0
     for (int q = lane; q < noj; q += 32) ownj[q] = P.wt_ownj[oj0 + q];
     for (int q = lane; q < noh; q += 32) ownh[q] = P.wt_ownh[oh0 + q];
     for (int q = lane; q < nog; q += 32) owng[q] = P.wt_owng[og0 + q];
@@ -1316,10 +1314,7 @@ __device__ __forceinline__ void bus_warp_body(const DevPlan& P, const EvalArgs& 
         auto gput = [&](int kk, double v) {
           imgG[(d[(NJ + NH + kk) >> 1] >> (((NJ + NH + kk) & 1) * 16)) & 0xffffu] = piece_neg(FORM, kk) ? -v : v;
         };
-        if constexpr (KIND == WT_G) {
-          NullW sj, sh;
-          he_math<FORM>(in, sj, sh, gput, need_g);
-        } else if constexpr (KIND == WT_GJ) {
+        if constexpr (KIND == WT_GJ) {
           RegW sj{imgJ, d, 0, true};
           NullW sh;
           he_math<FORM>(in, sj, sh, gput, need_g);
@@ -1396,21 +1391,18 @@ __device__ __forceinline__ void bus_warp_body(const DevPlan& P, const EvalArgs& 
 #ifndef PS_WT_MINB
 #define PS_WT_MINB 16               // 16 warps / SM: 128 registers per thread
 #endif
-__host__ __device__ inline int wt_region_doubles(const DevPlan& P, bool g_only = false) {   // per-warp shared memory, doubles (even)
-  return (g_only ? 0 : P.wt_jspace + P.wt_hspace) + P.wt_gspace + ((P.wt_lists + 7) / 8) * 2;
+__host__ __device__ inline int wt_region_doubles(const DevPlan& P) {   // per-warp shared memory, doubles (even)
+  return P.wt_jspace + P.wt_hspace + P.wt_gspace + ((P.wt_lists + 7) / 8) * 2;
 }
-#ifndef PS_WT_MINB_G
-#define PS_WT_MINB_G 24             // residual-only: no destinations / multipliers in registers, 1-2 KB of shared memory per warp
-#endif
 // one kernel per mode: each gets its own register allocation and code (the four bodies in ONE kernel cost the headline
 // g + J + H instantiation 8 %: gpurun_out/r2c13_ab.log)
 template <int FORM, int MODE>
-__global__ void __launch_bounds__(32 * WPC, (MODE & 3) == WT_G ? PS_WT_MINB_G : PS_WT_MINB) bus_warp_kernel(const __grid_constant__ DevPlan P, const __grid_constant__ EvalArgs A) {
+__global__ void __launch_bounds__(32 * WPC, PS_WT_MINB) bus_warp_kernel(const __grid_constant__ DevPlan P, const __grid_constant__ EvalArgs A) {
   extern __shared__ __align__(16) double smem[];
   const int tile = blockIdx.x * WPC + (threadIdx.x >> 5);
   if (tile >= P.n_wtiles) return;
   const int s0 = blockIdx.y * A.chunk, s1 = min(A.S, s0 + A.chunk);
-  double* r = smem + (threadIdx.x >> 5) * wt_region_doubles(P, (MODE & 3) == WT_G);
+  double* r = smem + (threadIdx.x >> 5) * wt_region_doubles(P);
   bus_warp_body<FORM, MODE>(P, A, r, tile, s0, s1);
 }
 // which instantiation serves a call
@@ -1419,7 +1411,6 @@ __host__ inline int wt_mode(const EvalArgs& A) {
   const int st = A.status != nullptr ? WT_ST : 0;
   if (A.force_any) return WT_ANY;
   if (w == (EV_G | EV_J | EV_H)) return WT_FULL | st;
-  if (w == EV_G) return WT_G | st;
   if (w == (EV_G | EV_J)) return WT_GJ | st;
   return WT_ANY;
 }
@@ -2255,10 +2246,8 @@ template <int FORM>
 cudaError_t launch_bus_warp_form(const DevPlan& P, const EvalArgs& A, size_t smem, cudaStream_t st, dim3 grid) {
   switch (wt_mode(A)) {
     case WT_FULL: bus_warp_kernel<FORM, WT_FULL><<<grid, 32 * WPC, smem, st>>>(P, A); break;
-    case WT_G: bus_warp_kernel<FORM, WT_G><<<grid, 32 * WPC, (size_t)WPC * wt_region_doubles(P, true) * 8, st>>>(P, A); break;
     case WT_GJ: bus_warp_kernel<FORM, WT_GJ><<<grid, 32 * WPC, smem, st>>>(P, A); break;
     case WT_FULL | WT_ST: bus_warp_kernel<FORM, WT_FULL | WT_ST><<<grid, 32 * WPC, smem, st>>>(P, A); break;
-    case WT_G | WT_ST: bus_warp_kernel<FORM, WT_G | WT_ST><<<grid, 32 * WPC, (size_t)WPC * wt_region_doubles(P, true) * 8, st>>>(P, A); break;
     case WT_GJ | WT_ST: bus_warp_kernel<FORM, WT_GJ | WT_ST><<<grid, 32 * WPC, smem, st>>>(P, A); break;
     default: bus_warp_kernel<FORM, WT_ANY><<<grid, 32 * WPC, smem, st>>>(P, A); break;
   }
@@ -2278,10 +2267,8 @@ cudaError_t configure_form(int src, size_t smem_branch, size_t smem_bus, size_t 
   if (smem_wt > 0) {
     e = cudaFuncSetAttribute(bus_warp_kernel<FORM, WT_ANY>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_wt);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(bus_warp_kernel<FORM, WT_FULL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_wt);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(bus_warp_kernel<FORM, WT_G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_wt);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(bus_warp_kernel<FORM, WT_GJ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_wt);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(bus_warp_kernel<FORM, WT_FULL | WT_ST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_wt);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(bus_warp_kernel<FORM, WT_G | WT_ST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_wt);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(bus_warp_kernel<FORM, WT_GJ | WT_ST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_wt);
     if (e != cudaSuccess) return e;
   }

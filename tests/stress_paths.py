@@ -2,7 +2,8 @@
 `python tests/stress_paths.py 200` the long one): many small seeded networks -- parallel
 branches, out-of-service elements, switched shunts, both source types, hubs, isolated buses -- every formulation, random
 layouts; the default path, the warp-tile path (PS_NO_CBFAST / PS_NO_PBFAST) and the CTA-tile path (PS_NO_WARPBUS) must
-agree bitwise, with and without a status mask, and the default path must match the CPU oracle.
+agree bitwise, with and without a status mask, the residual-only and g + J calls must give the bits of the full evaluation,
+and the default path must match the CPU oracle.
 usage: python tests/stress_paths.py [n_networks]"""
 import os
 import sys
@@ -52,17 +53,25 @@ def main(n):
                 pads = [int(v) for v in rng.integers(0, 4, 3)]
                 odd = bool(rng.random() < 0.3)
 
-                def run():
+                def run(what=7):
                     def rows(width, pad):
                         ld = width + pad + ((width + pad + 1) % 2 if odd else (width + pad) % 2)
                         flat = torch.full((pad + S * max(ld, 1),), np.nan, dtype=torch.float64, device=dev)
                         return flat[pad:].view(S, max(ld, 1))[:, :width]
                     g, J, H = rows(h.m_nl, pads[0]), rows(h.nnzJ, pads[1]), rows(h.nnzH, pads[2])
                     sc = torch.empty(S, capi.PS_NSCALARS, dtype=torch.float64, device=dev)
-                    b.eval_torch(7, tx, tmu, g, J, H, sc)
+                    b.eval_torch(what, tx, tmu, g, J, H, sc)
                     torch.cuda.synchronize()
                     return [a.cpu().numpy() for a in (g, J, H, sc)]
                 ref = run()
+                # the callbacks a solver issues separately -- residuals alone (thread-per-bus kernel, residual-only branch
+                # kernel), g + J (their own instantiations) -- give the same bits as the full evaluation
+                for what, names in ((1, "gs"), (3, "gJs")):
+                    out = run(what)
+                    for name, a, c in zip("gJHs", ref, out):
+                        if name in names and not np.array_equal(a, c):
+                            bad += 1
+                            print(f"MISMATCH net {it} (nb {nb} nr {nr} {src} nbss {nbss}) {F.name} masked={masked} what={what} {name}", flush=True)
                 for env in ({"PS_NO_CBFAST": "1", "PS_NO_PBFAST": "1"}, {"PS_NO_CBFAST": "1", "PS_NO_PBFAST": "1", "PS_NO_WARPBUS": "1"},
                             {"PS_NO_BULK": "1", "PS_NO_DIRECT": "1"}):
                     os.environ.update(env)

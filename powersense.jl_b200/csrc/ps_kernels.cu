@@ -1146,21 +1146,35 @@ struct ListW {                     // writer through a destination list in share
   }
 };
 // slot += its extra cells, left to right; lane per multi-contribution slot of any of the three spaces (one list,
-// sorted by count, so the lanes of a round run about the same number of additions)
-__device__ __forceinline__ void reduce_multi_warp(double* imgJ, double* imgH, double* imgG, bool wj, bool wh, bool wgg,
-                                                  const uint64_t* multi, int mn, int lane) {
+// sorted by count, so the lanes of a round run about the same number of additions).  The descriptors are decoded ONCE per
+// CTA (wt_predecode: 32-bit shared-memory addresses of the slot and of its first extra cell, count in the top bits; slots
+// of a block that is not being computed get count 0), so a visit is one 8-byte load, the additions and one store --
+// decoding the plan's packed form and rebuilding the shared-window addresses on every visit was 30 of the ~55
+// instructions of a visit, and the visits 31 % of the kernel's instructions (profiles/r02_ncu_final_config3_summary.txt)
+__device__ __forceinline__ double lds_f64(unsigned a) { double v; asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(a) : "memory"); return v; }
+__device__ __forceinline__ void sts_f64(unsigned a, double v) { asm volatile("st.shared.f64 [%0], %1;" ::"r"(a), "d"(v) : "memory"); }
+__device__ __forceinline__ uint64_t wt_predecode(uint64_t w, const double* imgJ, const double* imgH, const double* imgG, bool wj, bool wh,
+                                                 bool wgg) {
+  const int kind = (int)(w >> 14) & 3;
+  const bool on = kind == 0 ? wj : (kind == 1 ? wh : wgg);
+  const unsigned base = (unsigned)__cvta_generic_to_shared(kind == 0 ? imgJ : (kind == 1 ? imgH : imgG));
+  const unsigned dst = base + 8u * ((unsigned)w & 0x3fffu), src = base + 8u * (((unsigned)w >> 16) & 0xffffu);
+  const unsigned n = on ? (unsigned)(w >> 32) & 0xfffu : 0u;
+  return (uint64_t)dst | ((uint64_t)(src | (n << 20)) << 32);
+}
+__device__ __forceinline__ void reduce_multi_warp(const uint64_t* multi, int mn, int lane) {
+  const unsigned mb = (unsigned)__cvta_generic_to_shared(multi);
   for (int m = lane; m < mn; m += 32) {
-    const uint64_t w = multi[m];
-    const int kind = (int)(w >> 14) & 3, n = (int)(w >> 32);
-    if (!(kind == 0 ? wj : (kind == 1 ? wh : wgg))) continue;
-    double* sp = kind == 0 ? imgJ : (kind == 1 ? imgH : imgG);
-    double* dp = sp + ((unsigned)w & 0x3fffu);
-    const double* xp = sp + (((unsigned)w >> 16) & 0xffffu);
-    double v = *dp;
+    unsigned dst, sn;
+    asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(dst), "=r"(sn) : "r"(mb + 8u * (unsigned)m) : "memory");
+    const unsigned src = sn & 0xfffffu;
+    const int n = (int)(sn >> 20);
+    if (n == 0) continue;
+    double v = lds_f64(dst);
     int q = 0;
-    for (; q + 1 < n; q += 2) { const double a = xp[q], b = xp[q + 1]; v = (v + a) + b; }
-    if (q < n) v = v + xp[q];
-    *dp = v;
+    for (; q + 1 < n; q += 2) { const double a = lds_f64(src + 8u * q), b2 = lds_f64(src + 8u * q + 8u); v = (v + a) + b2; }
+    if (q < n) v = v + lds_f64(src + 8u * q);
+    sts_f64(dst, v);
   }
 }
 // hand a finished block image to the copy engine: [head][mid doubles, 16-byte aligned on both sides][tail]; when the
@@ -1224,7 +1238,6 @@ __device__ __forceinline__ void bus_warp_body(const DevPlan& P, const EvalArgs& 
     uint16_t* const ownh = ownj + noj;
     uint16_t* const owng = ownh + noh;
     // ---- scenario-independent set-up
-    for (int q = lane; q < t.mn; q += 32) multi[q] = P.wt_multi[t.m0 + q];
     for (int q = lane; q < P.wt_hspace; q += 32) spH[q] = 0.0;    // slots whose contributions are all structural zeros stay 0
     for (int q = lane; q < noj; q += 32) ownj[q] = P.wt_ownj[oj0 + q];
     for (int q = lane; q < noh; q += 32) ownh[q] = P.wt_ownh[oh0 + q];
@@ -1282,6 +1295,7 @@ __device__ __forceinline__ void bus_warp_body(const DevPlan& P, const EvalArgs& 
     double* const imgG = spG;
     // image and destination share their 16-byte phase in every scenario iff the leading dimension is even
     const WtBlock blkJ = wt_block(imgJ, t.jn, (A.ldJ & 1) == 0), blkH = wt_block(imgH, t.hn, (A.ldH & 1) == 0);
+    for (int q = lane; q < t.mn; q += 32) multi[q] = wt_predecode(P.wt_multi[t.m0 + q], imgJ, imgH, imgG, wj, wh, need_g);
     // the generator entries of J are the constant 1 (:177-180): written once, the image persists across scenarios
     if (bact && wj) for (int q = 0; q < 2 * ngen; q++) imgJ[P.wt_ownj[oj0 + oj + q]] = 1.0;
     struct Raw { double v0, v1, va0, vb0, muP, muQ, st, Pd, Qd; };
@@ -1359,7 +1373,7 @@ __device__ __forceinline__ void bus_warp_body(const DevPlan& P, const EvalArgs& 
       }
       __syncwarp();
       // ---- 3. slots with several contributions
-      reduce_multi_warp(imgJ, imgH, imgG, wj, wh, need_g, multi, t.mn, lane);
+      reduce_multi_warp(multi, t.mn, lane);
       // ---- 4. the images go out
       fence_async_smem();
       __syncwarp();

@@ -610,6 +610,8 @@ std::string build_plan(const HostNet& net, int form, int src, int flags, int tpb
       spaces(1, lh_, cdh, t.hx);
       spaces(2, lg, cdg, t.gx);
       if (ncj + 2 >= 16384 || nch + 2 >= 16384 || ncg + 2 >= 16384) { ok = false; break; }
+      for (const MS& m : ms) if (m.cnt >= 4096) ok = false;           // the kernel's decoded descriptors keep 12 bits of count
+      if (!ok) break;
       std::stable_sort(ms.begin(), ms.end(), [](const MS& a, const MS& b) { return a.cnt > b.cnt; });
       t.m0 = (int32_t)P.wt_multi.size(); t.mn = (int32_t)ms.size();
       for (const MS& m : ms)

@@ -1171,9 +1171,14 @@ __device__ __forceinline__ void reduce_multi_warp(const uint64_t* multi, int mn,
     const int n = (int)(sn >> 20);
     if (n == 0) continue;
     double v = lds_f64(dst);
-    int q = 0;
-    for (; q + 1 < n; q += 2) { const double a = lds_f64(src + 8u * q), b2 = lds_f64(src + 8u * q + 8u); v = (v + a) + b2; }
-    if (q < n) v = v + lds_f64(src + 8u * q);
+    unsigned p = src;
+    int q = n;
+    for (; q >= 4; q -= 4, p += 32u) {                          // four loads in flight, then the additions in order
+      const double a0 = lds_f64(p), a1 = lds_f64(p + 8u), a2 = lds_f64(p + 16u), a3 = lds_f64(p + 24u);
+      v = (((v + a0) + a1) + a2) + a3;
+    }
+    if (q >= 2) { const double a0 = lds_f64(p), a1 = lds_f64(p + 8u); v = (v + a0) + a1; p += 16u; q -= 2; }
+    if (q) v = v + lds_f64(p);
     sts_f64(dst, v);
   }
 }
